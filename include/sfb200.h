@@ -1,0 +1,127 @@
+/*
+ * sfb200.h — C ABI of libsfb200.so: the B200-native (sm_100a) implementation of Starfish's per-step
+ * log-likelihood hot path.
+ *
+ * The reference (Starfish v0.4.2, pure Python) has no FFI for this path: the seam is a handful of Python
+ * call sites.  Each entry point below names the reference lines it replaces (paths relative to the
+ * reference root):
+ *
+ *   sfb_build_cov      Starfish/models/kernels.py:7-41   global_covariance_matrix (Matérn-3/2 × Hann)
+ *                      Starfish/models/kernels.py:44-81  local_covariance_matrix  (Gaussian × Hann)
+ *                      Starfish/models/spectrum_model.py:334-363  XᵀAX + diag(σ²) + global + Σ local
+ *   sfb_potrf          Starfish/models/spectrum_model.py:400  scipy.linalg.cho_factor  (LAPACK dpotrf)
+ *   sfb_loglike(_host) Starfish/models/spectrum_model.py:334-363 + :399-405
+ *                      (assembly, +1e-10·I, cho_factor, logdet, residual, cho_solve, quadratic form)
+ *   sfb_solve_lower    Starfish/models/spectrum_model.py:404  scipy.linalg.cho_solve (forward half;
+ *                      sqmah = ‖L⁻¹R‖²)
+ *
+ * Conventions
+ *   - All arithmetic is IEEE fp64.  Matrices are row-major ("C order", what numpy hands over).
+ *   - Pointers are DEVICE pointers unless the parameter name ends in _h (host; pinned recommended).
+ *   - `stream` is the caller's CUDA stream (cudaStream_t cast to void*; NULL = legacy default stream).
+ *     Work is ordered after everything already queued on `stream`, and `stream` waits for the result,
+ *     so the caller may enqueue consumers (or record timing events) on `stream` right after the call.
+ *     Calls return without waiting for the GPU (except the *_host variants' final copy, see below).
+ *   - Every function returns 0 on success, a negative sfb_status otherwise; never throws.
+ *     sfb_last_error() gives the text.  A handle is not thread-safe: serialise calls on it.
+ *   - Per-walker `info` follows LAPACK dpotrf: 0 = ok, i > 0 = leading minor of order i is not positive
+ *     definite (the reference raises numpy.linalg.LinAlgError there); lnL is NaN for such rows.
+ */
+#ifndef SFB200_H
+#define SFB200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sfb_ctx sfb_t;
+
+enum sfb_status {
+  SFB_OK = 0,
+  SFB_ERR_ARG = -1,     /* bad argument (sizes, NULL pointers)          */
+  SFB_ERR_CUDA = -2,    /* a CUDA runtime call failed                   */
+  SFB_ERR_NOMEM = -3,   /* workspace does not fit in device memory      */
+  SFB_ERR_STATE = -4    /* call order (e.g. loglike before set_static)  */
+};
+
+/* ABI version of this header; bumped on any signature change. */
+int sfb_abi_version(void);
+
+/*
+ * Create a handle on `device` for spectra of N pixels, up to M eigenspectra (rank of the emulator term),
+ * up to Kmax local kernels per walker and batches of up to Bmax walkers per call.
+ * `workspace_walkers` = how many N×N fp64 factorisation slots to allocate (0 = choose automatically:
+ * enough to keep the GPU full, bounded by free memory).
+ */
+int sfb_create(int device, int N, int M, int Kmax, int Bmax, int workspace_walkers, sfb_t** out);
+int sfb_destroy(sfb_t* h);
+
+/* Data shared by all walkers: wavelengths, per-pixel noise σ (NOT σ²) and observed flux (each N). */
+int sfb_set_static(sfb_t* h, const double* wave, const double* sigma, const double* data_flux, void* stream);
+int sfb_set_static_host(sfb_t* h, const double* wave_h, const double* sigma_h, const double* data_flux_h);
+
+/*
+ * Covariance only:  C[b] = X[b]ᵀ·A[b]·X[b] + diag(σ² + jitter) + K_global(glob[b]) + Σ_k K_local(loc[b,k])
+ *   X     B×M×N   (NULL ⇒ no emulator term; then A is ignored)
+ *   A     B×M×M   symmetric (parity mode: A = Σ_w⁻¹)
+ *   glob  B×2     (amplitude, lengthscale), already exponentiated; amplitude <= 0 ⇒ no global kernel
+ *   nloc  B       number of local kernels of walker b (<= Kmax);  loc  B×Kmax×3 (amplitude, mu, sigma)
+ *   shared_hyper != 0 ⇒ glob/nloc/loc hold ONE row used by every walker (frozen-kernel sharing)
+ *   C     B×N×N   row-major, both triangles written
+ */
+int sfb_build_cov(sfb_t* h, int B, const double* X, const double* A, const double* glob, const int* nloc,
+                  const double* loc, int shared_hyper, double jitter, double* C, void* stream);
+
+/*
+ * Batched in-place Cholesky of B row-major N×N SPD matrices (lower triangle read; on return the lower
+ * triangle holds L with C = L·Lᵀ, the strict upper triangle is left untouched).  logdet may be NULL;
+ * otherwise logdet[b] = 2·Σ log L_ii.
+ */
+int sfb_potrf(sfb_t* h, int B, double* C, int* info, double* logdet, void* stream);
+
+/* z[b] = L[b]⁻¹·r[b] for B lower-triangular row-major factors (forward substitution). */
+int sfb_solve_lower(sfb_t* h, int B, const double* L, const double* r, double* z, void* stream);
+
+/*
+ * The whole stage boundary, B walkers:
+ *   lnL[b] = −½·( log det(C_b + 1e-10·I) + R_bᵀ (C_b + 1e-10·I)⁻¹ R_b ),  R_b = model_flux[b] − data_flux
+ * Inputs as sfb_build_cov plus model_flux (B×N).  Outputs lnL (B), info (B), resid (B×N or NULL).
+ * No priors (they stay on the host, spectrum_model.py:387-395).
+ */
+int sfb_loglike(sfb_t* h, int B, const double* X, const double* A, const double* model_flux,
+                const double* glob, const int* nloc, const double* loc, int shared_hyper,
+                double* lnL, int* info, double* resid, void* stream);
+
+/*
+ * Same, with HOST buffers (the end-to-end path): inputs are copied host→device and lnL/info (and resid
+ * if not NULL) device→host inside the call, chunk by chunk, overlapped with the factorisation of the
+ * previous chunk.  Returns after the results are in the host buffers.
+ */
+int sfb_loglike_host(sfb_t* h, int B, const double* X_h, const double* A_h, const double* model_flux_h,
+                     const double* glob_h, const int* nloc_h, const double* loc_h, int shared_hyper,
+                     double* lnL_h, int* info_h, double* resid_h);
+
+/* Block the host until all work queued on the handle has finished. */
+int sfb_sync(sfb_t* h);
+
+/*
+ * Kernel-level timing for roofline reports.  With profiling on, the handle runs its kernels on ONE
+ * stream and brackets every launch with CUDA events.  sfb_profile_read fills, per kernel class,
+ * out[3*c+0] = number of launches, out[3*c+1] = total device milliseconds, out[3*c+2] = algorithmic work
+ * (bytes for SFB_K_BUILD, FLOPs otherwise), and resets the counters.  `n` = capacity of out in doubles.
+ */
+enum sfb_kernel_class { SFB_K_BUILD = 0, SFB_K_POTRF_DIAG = 1, SFB_K_TRSM = 2, SFB_K_SYRK = 3, SFB_K_NCLASS = 4 };
+int sfb_profile_enable(sfb_t* h, int on);
+int sfb_profile_read(sfb_t* h, double* out, int n);
+
+/* Introspection: number of workspace slots, padded leading dimension, kernel launches since creation. */
+int sfb_workspace_walkers(const sfb_t* h);
+int sfb_padded_n(const sfb_t* h);
+long long sfb_launch_count(const sfb_t* h);
+
+const char* sfb_last_error(const sfb_t* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SFB200_H */

@@ -1,0 +1,70 @@
+"""ctypes binding of libsfb200.so — the thin layer between Python and the sm_100a kernels.
+
+The signatures here are a 1:1 transcription of include/sfb200.h.  There is NO fallback: if the library
+is missing the import fails loudly (build it with ``python -m starfish_b200.build``).
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsfb200.so")
+
+EXPORTS = [
+    "sfb_abi_version", "sfb_create", "sfb_destroy", "sfb_set_static", "sfb_set_static_host",
+    "sfb_build_cov", "sfb_potrf", "sfb_solve_lower", "sfb_loglike", "sfb_loglike_host", "sfb_sync",
+    "sfb_profile_enable", "sfb_profile_read", "sfb_workspace_walkers", "sfb_padded_n",
+    "sfb_launch_count", "sfb_last_error",
+]
+
+KERNEL_CLASSES = ("build", "potrf_diag", "trsm", "syrk")
+
+_p = C.c_void_p
+_i = C.c_int
+_d = C.c_double
+
+
+class SfbError(RuntimeError):
+    pass
+
+
+def load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: the CUDA extension is required (no CPU fallback). "
+            "Build it with `python -m starfish_b200.build`."
+        )
+    lib = C.CDLL(LIB_PATH)
+    lib.sfb_abi_version.restype = _i
+    lib.sfb_create.argtypes = [_i, _i, _i, _i, _i, _i, C.POINTER(_p)]
+    lib.sfb_destroy.argtypes = [_p]
+    lib.sfb_set_static.argtypes = [_p, _p, _p, _p, _p]
+    lib.sfb_set_static_host.argtypes = [_p, _p, _p, _p]
+    lib.sfb_build_cov.argtypes = [_p, _i, _p, _p, _p, _p, _p, _i, _d, _p, _p]
+    lib.sfb_potrf.argtypes = [_p, _i, _p, _p, _p, _p]
+    lib.sfb_solve_lower.argtypes = [_p, _i, _p, _p, _p, _p]
+    lib.sfb_loglike.argtypes = [_p, _i, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p]
+    lib.sfb_loglike_host.argtypes = [_p, _i, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p]
+    lib.sfb_sync.argtypes = [_p]
+    lib.sfb_profile_enable.argtypes = [_p, _i]
+    lib.sfb_profile_read.argtypes = [_p, _p, _i]
+    lib.sfb_workspace_walkers.argtypes = [_p]
+    lib.sfb_padded_n.argtypes = [_p]
+    lib.sfb_launch_count.argtypes = [_p]
+    lib.sfb_launch_count.restype = C.c_longlong
+    lib.sfb_last_error.argtypes = [_p]
+    lib.sfb_last_error.restype = C.c_char_p
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if fn.restype is None:
+            fn.restype = _i
+    return lib
+
+
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = load()
+    return _LIB

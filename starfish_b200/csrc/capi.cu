@@ -1,0 +1,547 @@
+// extern "C" boundary of libsfb200.so (see include/sfb200.h for the contract and the reference lines
+// each entry point replaces).  Host-side orchestration only: workspace, streams, chunking of the walker
+// batch over factorisation slots, event timing.  No torch types cross this boundary.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+#include "sfb_internal.cuh"
+
+using namespace sfb;
+
+struct ProfEvent {
+  cudaEvent_t a, b;
+  int cls;
+  double work;
+};
+
+struct sfb_ctx {
+  int device = 0, N = 0, Np = 0, M = 0, Kmax = 0, Bmax = 0, slots = 0;
+  // factorisation workspace (per slot)
+  double* W = nullptr;
+  double* Minv = nullptr;
+  double* rhs = nullptr;
+  double* zk = nullptr;
+  double* logdet = nullptr;
+  double* sqmah = nullptr;
+  int* info_ws = nullptr;
+  // static data
+  double* wave = nullptr;
+  double* sigma = nullptr;
+  double* data_flux = nullptr;
+  int* sorted = nullptr;
+  bool have_static = false;
+  // device staging for the host-buffer path
+  double *dX = nullptr, *dA = nullptr, *dflux = nullptr, *dglob = nullptr, *dloc = nullptr, *dlnL = nullptr,
+         *dresid = nullptr;
+  int *dnloc = nullptr, *dinfo = nullptr;
+  cudaStream_t streams[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+  bool profile = false;
+  std::vector<ProfEvent> prof;
+  std::vector<cudaEvent_t> ev_pool;
+  long long launches = 0;
+  std::string err;
+};
+
+namespace {
+
+int fail(sfb_ctx* h, int code, const char* what, cudaError_t e = cudaSuccess) {
+  if (h) {
+    h->err = what;
+    if (e != cudaSuccess) {
+      h->err += ": ";
+      h->err += cudaGetErrorString(e);
+    }
+  }
+  return code;
+}
+
+#define SFB_CUDA(h, call)                                              \
+  do {                                                                 \
+    cudaError_t e__ = (call);                                          \
+    if (e__ != cudaSuccess) return fail(h, SFB_ERR_CUDA, #call, e__); \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    int cur;
+    cudaGetDevice(&cur);
+    if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+cudaEvent_t get_event(sfb_ctx* h) {
+  if (!h->ev_pool.empty()) {
+    cudaEvent_t e = h->ev_pool.back();
+    h->ev_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+
+struct ProfScope {  // brackets one launch with events when profiling is on
+  sfb_ctx* h;
+  cudaStream_t st;
+  ProfEvent pe;
+  bool on;
+  ProfScope(sfb_ctx* h_, cudaStream_t st_, int cls, double work) : h(h_), st(st_), on(h_->profile) {
+    if (on) {
+      pe.a = get_event(h);
+      pe.b = get_event(h);
+      pe.cls = cls;
+      pe.work = work;
+      cudaEventRecord(pe.a, st);
+    }
+  }
+  ~ProfScope() {
+    if (on) {
+      cudaEventRecord(pe.b, st);
+      h->prof.push_back(pe);
+    }
+  }
+};
+
+// fork: internal streams wait for everything queued on the caller's stream
+int fork_streams(sfb_ctx* h, cudaStream_t caller, int nstreams) {
+  SFB_CUDA(h, cudaEventRecord(h->ev_fork, caller));
+  for (int i = 0; i < nstreams; ++i) SFB_CUDA(h, cudaStreamWaitEvent(h->streams[i], h->ev_fork, 0));
+  return SFB_OK;
+}
+int join_streams(sfb_ctx* h, cudaStream_t caller, int nstreams) {
+  for (int i = 0; i < nstreams; ++i) {
+    SFB_CUDA(h, cudaEventRecord(h->ev_join[i], h->streams[i]));
+    SFB_CUDA(h, cudaStreamWaitEvent(caller, h->ev_join[i], 0));
+  }
+  return SFB_OK;
+}
+
+// Factor `nb` matrices sitting in slots [slot0, slot0+nb); rhs/logdet/sqmah/info already initialised.
+int run_cholesky(sfb_ctx* h, int slot0, int nb, double* lnL_out, int* info_out, cudaStream_t st) {
+  CholParams p;
+  p.Np = h->Np;
+  p.strideW = (long long)h->Np * h->Np;
+  p.W = h->W + (long long)slot0 * p.strideW;
+  p.Minv = h->Minv + (long long)slot0 * kTile * kTile;
+  p.rhs = h->rhs + (long long)slot0 * h->Np;
+  p.zk = h->zk + (long long)slot0 * kTile;
+  p.logdet = h->logdet + slot0;
+  p.sqmah = h->sqmah + slot0;
+  p.info = h->info_ws + slot0;
+  const int nt = h->Np / kTile;
+  for (int k = 0; k < nt; ++k) {
+    p.k0 = k * kTile;
+    const int last = (k == nt - 1);
+    const double rem = (double)(h->Np - p.k0 - kTile);
+    {
+      ProfScope ps(h, st, SFB_K_POTRF_DIAG, nb * (2.0 * kTile * kTile * kTile / 3.0));
+      SFB_CUDA(h, launch_potrf_diag(p, nb, last, lnL_out, info_out, st));
+      h->launches++;
+    }
+    if (!last) {
+      {
+        ProfScope ps(h, st, SFB_K_TRSM, nb * (rem * kTile * kTile));  // useful FLOPs of a triangular solve
+        SFB_CUDA(h, launch_trsm(p, nb, st));
+        h->launches++;
+      }
+      {
+        ProfScope ps(h, st, SFB_K_SYRK, nb * (rem * (rem + kTile) * kTile));  // lower tiles incl. diagonal
+        SFB_CUDA(h, launch_syrk(p, nb, st));
+        h->launches++;
+      }
+    }
+  }
+  return SFB_OK;
+}
+
+int check_batch(sfb_ctx* h, int B) {
+  if (!h) return SFB_ERR_ARG;
+  if (B < 0 || B > h->Bmax) return fail(h, SFB_ERR_ARG, "B out of range (0..Bmax)");
+  return SFB_OK;
+}
+
+BuildParams make_build_params(sfb_ctx* h, const double* X, const double* A, const double* glob, const int* nloc,
+                              const double* loc, int shared_hyper, double jitter) {
+  BuildParams bp;
+  bp.N = h->N;
+  bp.M = (X != nullptr) ? h->M : 0;
+  bp.Kmax = h->Kmax;
+  bp.hyper_stride = shared_hyper ? 0 : 1;
+  bp.jitter = jitter;
+  bp.wave = h->wave;
+  bp.sigma = h->sigma;
+  bp.X = X;
+  bp.A = A;
+  bp.glob = glob;
+  bp.nloc = nloc;
+  bp.loc = loc;
+  bp.sorted = h->sorted;
+  return bp;
+}
+
+// the device-resident log-likelihood over walkers [0,B), chunked over the slots of `nstreams` streams
+int loglike_device(sfb_ctx* h, int B, const double* X, const double* A, const double* model_flux,
+                   const double* glob, const int* nloc, const double* loc, int shared_hyper, double* lnL,
+                   int* info, double* resid, int nstreams,
+                   // optional host staging (host path): copies are issued per chunk on the chunk's stream
+                   const double* X_h, const double* A_h, const double* flux_h, const double* glob_h,
+                   const int* nloc_h, const double* loc_h, double* lnL_h, int* info_h, double* resid_h) {
+  const int N = h->N, M = h->M, K = h->Kmax;
+  const int per = std::max(1, h->slots / nstreams);
+  const bool host = (flux_h != nullptr);
+  if (host && shared_hyper) {  // one shared hyper-parameter row: copy once, up front, on stream 0
+    SFB_CUDA(h, cudaMemcpyAsync((void*)glob, glob_h, sizeof(double) * 2, cudaMemcpyHostToDevice, h->streams[0]));
+    SFB_CUDA(h, cudaMemcpyAsync((void*)nloc, nloc_h, sizeof(int), cudaMemcpyHostToDevice, h->streams[0]));
+    if (K > 0)
+      SFB_CUDA(h, cudaMemcpyAsync((void*)loc, loc_h, sizeof(double) * 3 * K, cudaMemcpyHostToDevice, h->streams[0]));
+    SFB_CUDA(h, cudaEventRecord(h->ev_fork, h->streams[0]));
+    for (int i = 1; i < nstreams; ++i) SFB_CUDA(h, cudaStreamWaitEvent(h->streams[i], h->ev_fork, 0));
+  }
+  int chunk = 0;
+  for (int b0 = 0; b0 < B; b0 += per, ++chunk) {
+    const int nb = std::min(per, B - b0);
+    const int si = chunk % nstreams;
+    cudaStream_t st = h->streams[si];
+    const int slot0 = si * per;
+    const int hb = shared_hyper ? 0 : b0;
+    if (host) {
+      if (X_h)
+        SFB_CUDA(h, cudaMemcpyAsync((void*)(X + (long long)b0 * M * N), X_h + (long long)b0 * M * N,
+                                    sizeof(double) * (size_t)nb * M * N, cudaMemcpyHostToDevice, st));
+      if (X_h)
+        SFB_CUDA(h, cudaMemcpyAsync((void*)(A + (long long)b0 * M * M), A_h + (long long)b0 * M * M,
+                                    sizeof(double) * (size_t)nb * M * M, cudaMemcpyHostToDevice, st));
+      SFB_CUDA(h, cudaMemcpyAsync((void*)(model_flux + (long long)b0 * N), flux_h + (long long)b0 * N,
+                                  sizeof(double) * (size_t)nb * N, cudaMemcpyHostToDevice, st));
+      if (!shared_hyper) {
+        SFB_CUDA(h, cudaMemcpyAsync((void*)(glob + 2LL * b0), glob_h + 2LL * b0, sizeof(double) * 2 * nb,
+                                    cudaMemcpyHostToDevice, st));
+        SFB_CUDA(h, cudaMemcpyAsync((void*)(nloc + b0), nloc_h + b0, sizeof(int) * nb, cudaMemcpyHostToDevice, st));
+        if (K > 0)
+          SFB_CUDA(h, cudaMemcpyAsync((void*)(loc + 3LL * K * b0), loc_h + 3LL * K * b0,
+                                      sizeof(double) * 3 * K * nb, cudaMemcpyHostToDevice, st));
+      }
+    }
+    SFB_CUDA(h, launch_residual(model_flux + (long long)b0 * N, h->data_flux, N, h->Np, nb,
+                                h->rhs + (long long)slot0 * h->Np, resid ? resid + (long long)b0 * N : nullptr,
+                                h->logdet + slot0, h->sqmah + slot0, h->info_ws + slot0, st));
+    h->launches++;
+    BuildParams bp = make_build_params(h, X ? X + (long long)b0 * M * N : nullptr,
+                                       A ? A + (long long)b0 * M * M : nullptr, glob + 2LL * hb, nloc + hb,
+                                       loc + 3LL * K * hb, shared_hyper, 1e-10);
+    bp.ldc = h->Np;
+    bp.strideC = (long long)h->Np * h->Np;
+    bp.padN = h->Np;
+    bp.lower_only = 1;
+    bp.vec2 = 1;
+    bp.C = h->W + (long long)slot0 * bp.strideC;
+    {
+      ProfScope ps(h, st, SFB_K_BUILD, nb * (4.0 * h->Np * ((double)h->Np + kTile)));  // lower tiles, 8 B each
+      SFB_CUDA(h, launch_cov_build(bp, nb, st));
+      h->launches++;
+    }
+    int rc = run_cholesky(h, slot0, nb, lnL + b0, info + b0, st);
+    if (rc != SFB_OK) return rc;
+    if (host) {
+      SFB_CUDA(h, cudaMemcpyAsync(lnL_h + b0, lnL + b0, sizeof(double) * nb, cudaMemcpyDeviceToHost, st));
+      SFB_CUDA(h, cudaMemcpyAsync(info_h + b0, info + b0, sizeof(int) * nb, cudaMemcpyDeviceToHost, st));
+      if (resid_h)
+        SFB_CUDA(h, cudaMemcpyAsync(resid_h + (long long)b0 * N, resid + (long long)b0 * N,
+                                    sizeof(double) * (size_t)nb * N, cudaMemcpyDeviceToHost, st));
+    }
+  }
+  return SFB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sfb_abi_version(void) { return 1; }
+
+int sfb_create(int device, int N, int M, int Kmax, int Bmax, int workspace_walkers, sfb_t** out) {
+  if (!out) return SFB_ERR_ARG;
+  *out = nullptr;
+  if (N < 1 || M < 0 || M > kMaxM || Kmax < 0 || Kmax > kMaxK || Bmax < 1) return SFB_ERR_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return SFB_ERR_CUDA;
+  sfb_ctx* h = new sfb_ctx();
+  h->device = device;
+  h->N = N;
+  h->Np = ((N + kTile - 1) / kTile) * kTile;
+  h->M = M;
+  h->Kmax = std::max(Kmax, 1);
+  h->Bmax = Bmax;
+  DeviceGuard guard(device);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) {
+    delete h;
+    return SFB_ERR_CUDA;  // sm_100a only
+  }
+  const size_t per_slot = sizeof(double) * (size_t)h->Np * h->Np;
+  size_t free_b = 0, total_b = 0;
+  cudaMemGetInfo(&free_b, &total_b);
+  long long slots = workspace_walkers;
+  if (slots <= 0) {
+    const size_t budget = std::min<size_t>((size_t)48 << 30, (size_t)(0.6 * (double)free_b));
+    slots = (long long)std::max<size_t>(2, std::min<size_t>(1024, budget / per_slot));
+    slots = std::min<long long>(slots, std::max(Bmax, 1));
+  }
+  if (slots > 1) slots -= slots % 2;  // two equal halves, one per stream
+  if ((size_t)slots * per_slot > (size_t)(0.9 * (double)free_b)) {
+    delete h;
+    return SFB_ERR_NOMEM;
+  }
+  h->slots = (int)slots;
+  auto alloc = [&](void** p, size_t bytes) { return cudaMalloc(p, std::max<size_t>(bytes, 16)) == cudaSuccess; };
+  bool ok = true;
+  ok &= alloc((void**)&h->W, per_slot * slots);
+  ok &= alloc((void**)&h->Minv, sizeof(double) * kTile * kTile * slots);
+  ok &= alloc((void**)&h->rhs, sizeof(double) * h->Np * slots);
+  ok &= alloc((void**)&h->zk, sizeof(double) * kTile * slots);
+  ok &= alloc((void**)&h->logdet, sizeof(double) * slots);
+  ok &= alloc((void**)&h->sqmah, sizeof(double) * slots);
+  ok &= alloc((void**)&h->info_ws, sizeof(int) * slots);
+  ok &= alloc((void**)&h->wave, sizeof(double) * N);
+  ok &= alloc((void**)&h->sigma, sizeof(double) * N);
+  ok &= alloc((void**)&h->data_flux, sizeof(double) * N);
+  ok &= alloc((void**)&h->sorted, sizeof(int));
+  for (int i = 0; i < 2 && ok; ++i) {
+    ok &= cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking) == cudaSuccess;
+    ok &= cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
+  }
+  ok = ok && cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && kernels_init() == cudaSuccess;
+  if (!ok) {
+    sfb_destroy(h);
+    return SFB_ERR_NOMEM;
+  }
+  *out = h;
+  return SFB_OK;
+}
+
+int sfb_destroy(sfb_t* h) {
+  if (!h) return SFB_OK;
+  DeviceGuard guard(h->device);
+  cudaDeviceSynchronize();
+  void* ptrs[] = {h->W,     h->Minv, h->rhs,  h->zk,   h->logdet, h->sqmah, h->info_ws, h->wave,  h->sigma,
+                  h->data_flux, h->sorted, h->dX, h->dA, h->dflux, h->dglob, h->dloc, h->dlnL, h->dresid,
+                  h->dnloc, h->dinfo};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  for (int i = 0; i < 2; ++i) {
+    if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
+    if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+  }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  for (auto& pe : h->prof) {
+    cudaEventDestroy(pe.a);
+    cudaEventDestroy(pe.b);
+  }
+  for (auto e : h->ev_pool) cudaEventDestroy(e);
+  delete h;
+  return SFB_OK;
+}
+
+int sfb_set_static(sfb_t* h, const double* wave, const double* sigma, const double* data_flux, void* stream) {
+  if (!h || !wave || !sigma || !data_flux) return fail(h, SFB_ERR_ARG, "sfb_set_static: NULL argument");
+  DeviceGuard guard(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  // earlier work on the handle's own streams may still read the old static data
+  for (int i = 0; i < 2; ++i) {
+    SFB_CUDA(h, cudaEventRecord(h->ev_join[i], h->streams[i]));
+    SFB_CUDA(h, cudaStreamWaitEvent(st, h->ev_join[i], 0));
+  }
+  const size_t nb = sizeof(double) * h->N;
+  SFB_CUDA(h, cudaMemcpyAsync(h->wave, wave, nb, cudaMemcpyDeviceToDevice, st));
+  SFB_CUDA(h, cudaMemcpyAsync(h->sigma, sigma, nb, cudaMemcpyDeviceToDevice, st));
+  SFB_CUDA(h, cudaMemcpyAsync(h->data_flux, data_flux, nb, cudaMemcpyDeviceToDevice, st));
+  SFB_CUDA(h, launch_check_sorted(h->wave, h->N, h->sorted, st));
+  h->launches += 2;
+  h->have_static = true;
+  return SFB_OK;
+}
+
+int sfb_set_static_host(sfb_t* h, const double* wave_h, const double* sigma_h, const double* data_flux_h) {
+  if (!h || !wave_h || !sigma_h || !data_flux_h) return fail(h, SFB_ERR_ARG, "sfb_set_static_host: NULL argument");
+  DeviceGuard guard(h->device);
+  for (int i = 0; i < 2; ++i) SFB_CUDA(h, cudaStreamSynchronize(h->streams[i]));
+  const size_t nb = sizeof(double) * h->N;
+  cudaStream_t st = h->streams[0];
+  SFB_CUDA(h, cudaMemcpyAsync(h->wave, wave_h, nb, cudaMemcpyHostToDevice, st));
+  SFB_CUDA(h, cudaMemcpyAsync(h->sigma, sigma_h, nb, cudaMemcpyHostToDevice, st));
+  SFB_CUDA(h, cudaMemcpyAsync(h->data_flux, data_flux_h, nb, cudaMemcpyHostToDevice, st));
+  SFB_CUDA(h, launch_check_sorted(h->wave, h->N, h->sorted, st));
+  h->launches += 2;
+  SFB_CUDA(h, cudaStreamSynchronize(st));
+  h->have_static = true;
+  return SFB_OK;
+}
+
+int sfb_build_cov(sfb_t* h, int B, const double* X, const double* A, const double* glob, const int* nloc,
+                  const double* loc, int shared_hyper, double jitter, double* C, void* stream) {
+  int rc = check_batch(h, B);
+  if (rc != SFB_OK) return rc;
+  if (!h->have_static) return fail(h, SFB_ERR_STATE, "sfb_build_cov: call sfb_set_static first");
+  if (!C || !glob || !nloc || !loc || (X && !A)) return fail(h, SFB_ERR_ARG, "sfb_build_cov: NULL argument");
+  if (B == 0) return SFB_OK;
+  DeviceGuard guard(h->device);
+  cudaStream_t caller = (cudaStream_t)stream, st = h->streams[0];
+  if ((rc = fork_streams(h, caller, 1)) != SFB_OK) return rc;
+  BuildParams bp = make_build_params(h, X, A, glob, nloc, loc, shared_hyper, jitter);
+  bp.ldc = h->N;
+  bp.strideC = (long long)h->N * h->N;
+  bp.padN = h->N;
+  bp.lower_only = 0;
+  bp.vec2 = ((h->N % 2) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+  bp.C = C;
+  {
+    ProfScope ps(h, st, SFB_K_BUILD, (double)B * 8.0 * h->N * h->N);
+    SFB_CUDA(h, launch_cov_build(bp, B, st));
+    h->launches++;
+  }
+  return join_streams(h, caller, 1);
+}
+
+int sfb_potrf(sfb_t* h, int B, double* C, int* info, double* logdet, void* stream) {
+  int rc = check_batch(h, B);
+  if (rc != SFB_OK) return rc;
+  if (!C || !info) return fail(h, SFB_ERR_ARG, "sfb_potrf: NULL argument");
+  if (B == 0) return SFB_OK;
+  DeviceGuard guard(h->device);
+  cudaStream_t caller = (cudaStream_t)stream;
+  const int nstreams = (h->profile || h->slots < 2) ? 1 : 2;
+  if ((rc = fork_streams(h, caller, nstreams)) != SFB_OK) return rc;
+  const int per = std::max(1, h->slots / nstreams);
+  const long long strideW = (long long)h->Np * h->Np;
+  int chunk = 0;
+  for (int b0 = 0; b0 < B; b0 += per, ++chunk) {
+    const int nb = std::min(per, B - b0);
+    const int si = chunk % nstreams;
+    cudaStream_t st = h->streams[si];
+    const int slot0 = si * per;
+    double* Cb = C + (long long)b0 * h->N * h->N;
+    SFB_CUDA(h, launch_copy_in_lower(Cb, h->N, h->W + slot0 * strideW, h->Np, strideW, nb, st));
+    SFB_CUDA(h, launch_residual(nullptr, nullptr, h->N, h->Np, nb, h->rhs + (long long)slot0 * h->Np, nullptr,
+                                h->logdet + slot0, h->sqmah + slot0, h->info_ws + slot0, st));
+    h->launches += 2;
+    if ((rc = run_cholesky(h, slot0, nb, nullptr, info + b0, st)) != SFB_OK) return rc;
+    SFB_CUDA(h, launch_copy_out_lower(Cb, h->N, h->W + slot0 * strideW, h->Np, strideW, nb, st));
+    h->launches++;
+    if (logdet)
+      SFB_CUDA(h, cudaMemcpyAsync(logdet + b0, h->logdet + slot0, sizeof(double) * nb, cudaMemcpyDeviceToDevice, st));
+  }
+  return join_streams(h, caller, nstreams);
+}
+
+int sfb_solve_lower(sfb_t* h, int B, const double* L, const double* r, double* z, void* stream) {
+  int rc = check_batch(h, B);
+  if (rc != SFB_OK) return rc;
+  if (!L || !r || !z) return fail(h, SFB_ERR_ARG, "sfb_solve_lower: NULL argument");
+  if (B == 0) return SFB_OK;
+  DeviceGuard guard(h->device);
+  cudaStream_t caller = (cudaStream_t)stream, st = h->streams[0];
+  if ((rc = fork_streams(h, caller, 1)) != SFB_OK) return rc;
+  SFB_CUDA(h, launch_solve_lower(L, (long long)h->N * h->N, h->N, r, z, h->N, B, st));
+  h->launches++;
+  return join_streams(h, caller, 1);
+}
+
+int sfb_loglike(sfb_t* h, int B, const double* X, const double* A, const double* model_flux, const double* glob,
+                const int* nloc, const double* loc, int shared_hyper, double* lnL, int* info, double* resid,
+                void* stream) {
+  int rc = check_batch(h, B);
+  if (rc != SFB_OK) return rc;
+  if (!h->have_static) return fail(h, SFB_ERR_STATE, "sfb_loglike: call sfb_set_static first");
+  if (!model_flux || !glob || !nloc || !loc || !lnL || !info || (X && !A))
+    return fail(h, SFB_ERR_ARG, "sfb_loglike: NULL argument");
+  if (B == 0) return SFB_OK;
+  DeviceGuard guard(h->device);
+  cudaStream_t caller = (cudaStream_t)stream;
+  const int nstreams = (h->profile || h->slots < 2) ? 1 : 2;
+  if ((rc = fork_streams(h, caller, nstreams)) != SFB_OK) return rc;
+  rc = loglike_device(h, B, X, A, model_flux, glob, nloc, loc, shared_hyper, lnL, info, resid, nstreams, nullptr,
+                      nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+  if (rc != SFB_OK) return rc;
+  return join_streams(h, caller, nstreams);
+}
+
+int sfb_loglike_host(sfb_t* h, int B, const double* X_h, const double* A_h, const double* model_flux_h,
+                     const double* glob_h, const int* nloc_h, const double* loc_h, int shared_hyper,
+                     double* lnL_h, int* info_h, double* resid_h) {
+  int rc = check_batch(h, B);
+  if (rc != SFB_OK) return rc;
+  if (!h->have_static) return fail(h, SFB_ERR_STATE, "sfb_loglike_host: call sfb_set_static first");
+  if (!model_flux_h || !glob_h || !nloc_h || !loc_h || !lnL_h || !info_h || (X_h && !A_h))
+    return fail(h, SFB_ERR_ARG, "sfb_loglike_host: NULL argument");
+  if (B == 0) return SFB_OK;
+  DeviceGuard guard(h->device);
+  const int N = h->N, M = h->M, K = h->Kmax, Bm = h->Bmax;
+  auto lazy = [&](void** p, size_t bytes) {
+    if (*p) return true;
+    return cudaMalloc(p, std::max<size_t>(bytes, 16)) == cudaSuccess;
+  };
+  bool ok = true;
+  ok &= lazy((void**)&h->dX, sizeof(double) * (size_t)Bm * std::max(M, 1) * N);
+  ok &= lazy((void**)&h->dA, sizeof(double) * (size_t)Bm * std::max(M * M, 1));
+  ok &= lazy((void**)&h->dflux, sizeof(double) * (size_t)Bm * N);
+  ok &= lazy((void**)&h->dglob, sizeof(double) * 2 * Bm);
+  ok &= lazy((void**)&h->dloc, sizeof(double) * 3 * (size_t)K * Bm);
+  ok &= lazy((void**)&h->dnloc, sizeof(int) * Bm);
+  ok &= lazy((void**)&h->dlnL, sizeof(double) * Bm);
+  ok &= lazy((void**)&h->dinfo, sizeof(int) * Bm);
+  if (resid_h) ok &= lazy((void**)&h->dresid, sizeof(double) * (size_t)Bm * N);
+  if (!ok) return fail(h, SFB_ERR_NOMEM, "sfb_loglike_host: staging allocation failed");
+  const int nstreams = (h->profile || h->slots < 2) ? 1 : 2;
+  rc = loglike_device(h, B, X_h ? h->dX : nullptr, X_h ? h->dA : nullptr, h->dflux, h->dglob, h->dnloc, h->dloc,
+                      shared_hyper, h->dlnL, h->dinfo, resid_h ? h->dresid : nullptr, nstreams, X_h, A_h,
+                      model_flux_h, glob_h, nloc_h, loc_h, lnL_h, info_h, resid_h);
+  if (rc != SFB_OK) return rc;
+  for (int i = 0; i < nstreams; ++i) SFB_CUDA(h, cudaStreamSynchronize(h->streams[i]));
+  return SFB_OK;
+}
+
+int sfb_sync(sfb_t* h) {
+  if (!h) return SFB_ERR_ARG;
+  DeviceGuard guard(h->device);
+  for (int i = 0; i < 2; ++i) SFB_CUDA(h, cudaStreamSynchronize(h->streams[i]));
+  return SFB_OK;
+}
+
+int sfb_profile_enable(sfb_t* h, int on) {
+  if (!h) return SFB_ERR_ARG;
+  h->profile = (on != 0);
+  return SFB_OK;
+}
+
+int sfb_profile_read(sfb_t* h, double* out, int n) {
+  if (!h || !out || n < 3 * SFB_K_NCLASS) return fail(h, SFB_ERR_ARG, "sfb_profile_read: buffer too small");
+  DeviceGuard guard(h->device);
+  for (int i = 0; i < 2; ++i) SFB_CUDA(h, cudaStreamSynchronize(h->streams[i]));
+  for (int i = 0; i < 3 * SFB_K_NCLASS; ++i) out[i] = 0.0;
+  for (auto& pe : h->prof) {
+    float ms = 0.f;
+    SFB_CUDA(h, cudaEventElapsedTime(&ms, pe.a, pe.b));
+    out[3 * pe.cls + 0] += 1.0;
+    out[3 * pe.cls + 1] += ms;
+    out[3 * pe.cls + 2] += pe.work;
+    h->ev_pool.push_back(pe.a);
+    h->ev_pool.push_back(pe.b);
+  }
+  h->prof.clear();
+  return SFB_OK;
+}
+
+int sfb_workspace_walkers(const sfb_t* h) { return h ? h->slots : 0; }
+int sfb_padded_n(const sfb_t* h) { return h ? h->Np : 0; }
+long long sfb_launch_count(const sfb_t* h) { return h ? h->launches : 0; }
+const char* sfb_last_error(const sfb_t* h) { return h ? h->err.c_str() : "null handle"; }
+
+}  // extern "C"

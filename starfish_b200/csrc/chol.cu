@@ -1,0 +1,502 @@
+// Batched blocked in-place fp64 Cholesky with the forward solve folded in (sm_100a).
+//
+// Replaces scipy.linalg.cho_factor / cho_solve at Starfish/models/spectrum_model.py:400-404 for a batch
+// of walkers.  Right-looking, panel width 128, lower triangle, row-major, leading dimension Np
+// (N padded to a multiple of 128 with an identity block so no kernel has ragged edges).  Per panel k:
+//
+//   potrf_diag  one CTA per walker: factor the 128×128 diagonal tile in shared memory, AND its inverse
+//               M = L_kk⁻¹ (kept in the unused upper triangle of the same tile), z_k = M·r_k,
+//               logdet += 2Σlog L_ii, sqmah += ‖z_k‖²;  reports LAPACK-style info on a non-positive pivot
+//   trsm        L_ik = A_ik·Mᵀ as a DMMA GEMM (64×128 tiles), and r_i −= L_ik·z_k in its epilogue
+//   syrk        A_ij −= L_ik·L_jkᵀ for i ≥ j > k, DMMA GEMM on 128×64 tiles — the dominant kernel
+//
+// so the residual vector rides along as an extra right-hand side: when the last panel is done
+// rhs = L⁻¹R and lnL = −(logdet + sqmah)/2 without a separate triangular-solve pass over L.
+//
+// Tensor cores: fp64 has no tcgen05 kind; the B200 fp64 tensor path is mma.sync m8n8k4 (SASS
+// DMMA.8x8x4), measured at 37.1 TFLOP/s = the nominal fp64 peak (tools/fp64_peak.cu) while plain DFMA
+// tops out at 33.8 — hence DMMA.  Operands are K-contiguous in memory for both factors (rows of L), so
+// tiles go global→shared with 16-byte cp.async through a 3-stage ring, rows padded to 20 doubles so
+// that the 8×4 fragment loads are bank-conflict-free.
+#include "sfb_internal.cuh"
+
+namespace sfb {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// small PTX helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp_async16(void* smem_ptr, const void* gmem_ptr) {
+  unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_ptr));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_ptr));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N));
+}
+
+// ------------------------------------------------------------------------------------------------
+// NT GEMM core:  acc[r][c] = Σ_k Aop[r][k]·Bop[c][k]   (both operands K-contiguous)
+//   CTA tile BM×BN, 8 warps, warp tile 32×32 = 4×4 DMMA tiles, BK = 16 doubles per stage.
+// ------------------------------------------------------------------------------------------------
+constexpr int BK = 16;
+constexpr int LDS = 20;  // padded smem row (doubles): bank = (40·g + 2·t) mod 32 -> conflict-free
+constexpr int STAGES = 3;
+constexpr int GEMM_THREADS = 256;
+
+template <int BM, int BN>
+struct GemmSmem {
+  static constexpr int kStageDoubles = (BM + BN) * LDS;
+  static constexpr size_t kBytes = sizeof(double) * kStageDoubles * STAGES;
+};
+
+template <int BM, int BN>
+__device__ __forceinline__ void gemm_load_stage(double* stage, const double* __restrict__ Ag, long long lda,
+                                                const double* __restrict__ Bg, long long ldb, int kk, int tid) {
+  // (BM+BN) rows × 8 chunks of 16 B
+  constexpr int CHUNKS = (BM + BN) * (BK / 2);
+#pragma unroll
+  for (int c = tid; c < CHUNKS; c += GEMM_THREADS) {
+    const int row = c >> 3, ch = c & 7;
+    const double* src = (row < BM) ? (Ag + (long long)row * lda + kk + 2 * ch)
+                                   : (Bg + (long long)(row - BM) * ldb + kk + 2 * ch);
+    cp_async16(stage + row * LDS + 2 * ch, src);
+  }
+}
+
+// acc layout: acc[mt][nt][2] for the warp's 4×4 grid of 8×8 DMMA tiles
+template <int BM, int BN>
+__device__ __forceinline__ void gemm_mainloop(double (&acc)[4][4][2], double* smem,
+                                              const double* __restrict__ Ag, long long lda,
+                                              const double* __restrict__ Bg, long long ldb, int K,
+                                              int kt_begin_skip_b /*unused*/) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int WN_CNT = BN / 32;
+  const int wm = warp / WN_CNT, wn = warp % WN_CNT;
+  const int g = lane >> 2, t = lane & 3;
+  const int KT = K / BK;
+  constexpr int SD = GemmSmem<BM, BN>::kStageDoubles;
+
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < KT) gemm_load_stage<BM, BN>(smem + s * SD, Ag, lda, Bg, ldb, s * BK, tid);
+    cp_async_commit();
+  }
+  for (int it = 0; it < KT; ++it) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    {
+      const int nx = it + STAGES - 1;
+      if (nx < KT) gemm_load_stage<BM, BN>(smem + (nx % STAGES) * SD, Ag, lda, Bg, ldb, nx * BK, tid);
+      cp_async_commit();
+    }
+    const double* As = smem + (it % STAGES) * SD + (wm * 32 + g) * LDS + t;
+    const double* Bs = smem + (it % STAGES) * SD + (BM + wn * 32 + g) * LDS + t;
+#pragma unroll
+    for (int q = 0; q < BK / 4; ++q) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        a[i] = As[i * 8 * LDS + 4 * q];
+        b[i] = Bs[i * 8 * LDS + 4 * q];
+      }
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+// syrk: A_ij −= L_ik·L_jkᵀ, tile 128 rows × 64 cols; grid (2T, T, B), tiles right of the diagonal exit
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GEMM_THREADS, 2) syrk_kernel(CholParams p) {
+  const int j64 = blockIdx.x, ti = blockIdx.y, s = blockIdx.z;
+  if (j64 > 2 * ti + 1) return;
+  if (p.info[s] != 0) return;
+  extern __shared__ __align__(16) double smem[];
+  double* Wm = p.W + (long long)s * p.strideW;
+  const long long ld = p.Np;
+  const int r0 = p.k0 + kTile + ti * 128;
+  const int c0 = p.k0 + kTile + j64 * 64;
+  const double* Ag = Wm + (long long)r0 * ld + p.k0;
+  const double* Bg = Wm + (long long)c0 * ld + p.k0;
+
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  gemm_mainloop<128, 64>(acc, smem, Ag, ld, Bg, ld, kTile, 0);
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wm = warp / 2, wn = warp % 2, g = lane >> 2, t = lane & 3;
+  double* Cg = Wm + (long long)(r0 + wm * 32 + g) * ld + c0 + wn * 32 + 2 * t;
+  double2 cv[4][4];
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+      cv[mt][nt] = *reinterpret_cast<const double2*>(Cg + (long long)mt * 8 * ld + nt * 8);
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      double2 v = cv[mt][nt];
+      v.x -= acc[mt][nt][0];
+      v.y -= acc[mt][nt][1];
+      *reinterpret_cast<double2*>(Cg + (long long)mt * 8 * ld + nt * 8) = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// trsm: L_ik = A_ik·Mᵀ (M = L_kk⁻¹, lower), tile 64 rows × 128 cols (whole panel width, so the in-place
+// overwrite is private to the CTA), then rhs_i −= L_ik·z_k.   grid (rows/64, B)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GEMM_THREADS, 2) trsm_kernel(CholParams p) {
+  const int rb = blockIdx.x, s = blockIdx.y;
+  if (p.info[s] != 0) return;
+  extern __shared__ __align__(16) double smem[];
+  double* Wm = p.W + (long long)s * p.strideW;
+  const long long ld = p.Np;
+  const int r0 = p.k0 + kTile + rb * 64;
+  const double* Ag = Wm + (long long)r0 * ld + p.k0;
+  const double* Bg = p.Minv + (long long)s * kTile * kTile;
+
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  gemm_mainloop<64, 128>(acc, smem, Ag, ld, Bg, kTile, kTile, 0);
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wm = warp / 4, wn = warp % 4, g = lane >> 2, t = lane & 3;
+  double* Cg = Wm + (long long)(r0 + wm * 32 + g) * ld + p.k0 + wn * 32 + 2 * t;
+  const double* zk = p.zk + (long long)s * kTile + wn * 32 + 2 * t;
+  double part[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    const double z0 = zk[nt * 8], z1 = zk[nt * 8 + 1];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+      *reinterpret_cast<double2*>(Cg + (long long)mt * 8 * ld + nt * 8) =
+          make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+      part[mt] = fma(acc[mt][nt][0], z0, part[mt]);
+      part[mt] = fma(acc[mt][nt][1], z1, part[mt]);
+    }
+  }
+  // reduce over the 4 lanes sharing a row, then over the 4 column-warps in a fixed order
+  double* red = smem;  // [4 wn][64 rows]  (mainloop ended with a __syncthreads, smem is free)
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt) {
+    double v = part[mt];
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    if (t == 0) red[wn * 64 + wm * 32 + mt * 8 + g] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int r = threadIdx.x;
+    double sum = ((red[r] + red[64 + r]) + red[128 + r]) + red[192 + r];
+    p.rhs[(long long)s * p.Np + r0 + r] -= sum;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// potrf_diag: factor + invert the diagonal tile, solve the panel's slice of the right-hand side
+// ------------------------------------------------------------------------------------------------
+constexpr int PD_THREADS = 512;
+constexpr int PD_LD = 129;  // odd stride: row and column sweeps are both conflict-free
+
+__global__ void __launch_bounds__(PD_THREADS) potrf_diag_kernel(CholParams p, int last, double* lnL_out,
+                                                                 int* info_out) {
+  const int s = blockIdx.x, tid = threadIdx.x;
+  extern __shared__ __align__(16) double smem[];
+  double* S = smem;                   // [128][129]: lower = A→L, strict upper = (L⁻¹)ᵀ under construction
+  double* dinv = S + kTile * PD_LD;   // [128] diagonal of L⁻¹
+  double* red = dinv + kTile;         // [32] reduction scratch
+  __shared__ int fail_col;
+
+  if (p.info[s] != 0) {
+    if (last && tid == 0) {
+      if (lnL_out) lnL_out[s] = __longlong_as_double(0x7ff8000000000000LL);
+      if (info_out) info_out[s] = p.info[s];
+    }
+    return;
+  }
+  double* Wm = p.W + (long long)s * p.strideW;
+  const long long ld = p.Np;
+  double* Ag = Wm + (long long)p.k0 * ld + p.k0;
+
+  for (int e = tid; e < kTile * kTile; e += PD_THREADS) {
+    const int r = e >> 7, c = e & 127;
+    S[r * PD_LD + c] = (c <= r) ? Ag[(long long)r * ld + c] : 0.0;
+  }
+  if (tid == 0) fail_col = -1;
+  __syncthreads();
+
+  const int x = tid & 127, iq = tid >> 7;  // element column, row phase (4 rows per sweep)
+  for (int j = 0; j < kTile; ++j) {
+    const double piv = S[j * PD_LD + j];
+    if (!(piv > 0.0) || isinf(piv)) {  // also catches NaN
+      if (tid == 0) fail_col = j;
+      break;                           // uniform: every thread reads the same pivot
+    }
+    const double d = sqrt(piv);
+    // phase 1: column j of L (rows > j), row j of L⁻¹ (cols < j, stored transposed), diagonals
+    if (tid < kTile) {
+      if (tid > j) S[tid * PD_LD + j] = S[tid * PD_LD + j] / d;
+      else if (tid == j) { S[j * PD_LD + j] = d; dinv[j] = 1.0 / d; }
+    } else if (tid < 2 * kTile) {
+      const int c = tid - kTile;
+      if (c < j) S[c * PD_LD + j] = S[c * PD_LD + j] / d;
+    }
+    __syncthreads();
+    // phase 2: rows i > j.  x in (j, i]: trailing update;  x < j: T[i][x] -= L[i][j]·M[j][x];
+    //          x == j: T[i][j] = -L[i][j]/d
+    const double dj = dinv[j];
+    for (int i = j + 1 + iq; i < kTile; i += 4) {
+      const double lij = S[i * PD_LD + j];
+      if (x > j) {
+        if (x <= i) S[i * PD_LD + x] = fma(-lij, S[x * PD_LD + j], S[i * PD_LD + x]);
+      } else if (x < j) {
+        S[x * PD_LD + i] = fma(-lij, S[x * PD_LD + j], S[x * PD_LD + i]);
+      } else {
+        S[j * PD_LD + i] = -lij * dj;
+      }
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  if (fail_col >= 0) {
+    if (tid == 0) {
+      const int code = p.k0 + fail_col + 1;
+      p.info[s] = code;
+      if (last) {
+        if (lnL_out) lnL_out[s] = __longlong_as_double(0x7ff8000000000000LL);
+        if (info_out) info_out[s] = code;
+      }
+    }
+    return;
+  }
+
+  // write L (lower incl. diagonal) back, and M = L⁻¹ to the per-slot buffer (row-major, ld 128)
+  double* Mg = p.Minv + (long long)s * kTile * kTile;
+  for (int e = tid; e < kTile * kTile; e += PD_THREADS) {
+    const int r = e >> 7, c = e & 127;
+    if (c <= r) Ag[(long long)r * ld + c] = S[r * PD_LD + c];
+    Mg[e] = (c < r) ? S[c * PD_LD + r] : ((c == r) ? dinv[r] : 0.0);
+  }
+  // z_k = M·r_k ; logdet ; sqmah
+  double zz = 0.0, lg = 0.0;
+  if (tid < kTile) {
+    const double* rk = p.rhs + (long long)s * p.Np + p.k0;
+    double acc0 = dinv[tid] * rk[tid], acc1 = 0.0;
+    int c = 0;
+    for (; c + 1 < tid; c += 2) {
+      acc0 = fma(S[c * PD_LD + tid], rk[c], acc0);
+      acc1 = fma(S[(c + 1) * PD_LD + tid], rk[c + 1], acc1);
+    }
+    if (c < tid) acc0 = fma(S[c * PD_LD + tid], rk[c], acc0);
+    const double z = acc0 + acc1;
+    zz = z * z;
+    lg = log(S[tid * PD_LD + tid]);
+    __syncwarp();
+    p.zk[(long long)s * kTile + tid] = z;
+  }
+  __syncthreads();  // all reads of rk done before it is overwritten with z
+  if (tid < kTile) p.rhs[(long long)s * p.Np + p.k0 + tid] = p.zk[(long long)s * kTile + tid];
+  // block reduction of (zz, lg) over the first 4 warps, fixed order
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    zz += __shfl_xor_sync(0xffffffffu, zz, o);
+    lg += __shfl_xor_sync(0xffffffffu, lg, o);
+  }
+  if (tid < kTile && (tid & 31) == 0) {
+    red[tid >> 5] = zz;
+    red[8 + (tid >> 5)] = lg;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const double zsum = ((red[0] + red[1]) + red[2]) + red[3];
+    const double lsum = ((red[8] + red[9]) + red[10]) + red[11];
+    const double sq = p.sqmah[s] + zsum;
+    const double ldt = p.logdet[s] + 2.0 * lsum;
+    p.sqmah[s] = sq;
+    p.logdet[s] = ldt;
+    if (last) {
+      if (lnL_out) lnL_out[s] = -(ldt + sq) / 2;
+      if (info_out) info_out[s] = 0;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+__global__ void residual_kernel(const double* __restrict__ model_flux, const double* __restrict__ data_flux,
+                                int N, int Np, double* rhs, double* resid_out, double* logdet, double* sqmah,
+                                int* info) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < Np) {
+    double r = 0.0;
+    if (i < N) {
+      r = model_flux[(long long)b * N + i] - data_flux[i];
+      if (resid_out) resid_out[(long long)b * N + i] = r;
+    }
+    rhs[(long long)b * Np + i] = r;
+  }
+  if (i == 0) {
+    logdet[b] = 0.0;
+    sqmah[b] = 0.0;
+    info[b] = 0;
+  }
+}
+
+__global__ void copy_in_lower_kernel(const double* __restrict__ C, int N, double* W, int Np, long long strideW) {
+  const int b = blockIdx.z;
+  const int i = blockIdx.y;
+  const double* src = C + (long long)b * N * N + (long long)i * N;
+  double* dst = W + (long long)b * strideW + (long long)i * Np;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j <= i; j += gridDim.x * blockDim.x)
+    dst[j] = (i < N) ? src[j] : ((j == i) ? 1.0 : 0.0);
+}
+
+__global__ void copy_out_lower_kernel(double* C, int N, const double* __restrict__ W, int Np, long long strideW) {
+  const int b = blockIdx.z;
+  const int i = blockIdx.y;
+  double* dst = C + (long long)b * N * N + (long long)i * N;
+  const double* src = W + (long long)b * strideW + (long long)i * Np;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j <= i; j += gridDim.x * blockDim.x) dst[j] = src[j];
+}
+
+__global__ void zero_rhs_kernel(double* rhs, int Np, double* logdet, double* sqmah, int* info) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < Np) rhs[(long long)b * Np + i] = 0.0;
+  if (i == 0) { logdet[b] = 0.0; sqmah[b] = 0.0; info[b] = 0; }
+}
+
+// Forward substitution z = L⁻¹ r, one CTA per matrix (the cho_solve seam; not on the fused path).
+// Blocks of 64 rows: all warps accumulate the dot products with the already-solved prefix (coalesced row
+// reads), then warp 0 solves the 64×64 triangle.
+__global__ void __launch_bounds__(256) solve_lower_kernel(const double* __restrict__ L, long long strideL, int ldl,
+                                                          const double* __restrict__ r, double* z, int N) {
+  extern __shared__ __align__(16) double zs[];  // [N] solution so far
+  __shared__ double partial[64];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double* Lb = L + (long long)b * strideL;
+  for (int i0 = 0; i0 < N; i0 += 64) {
+    const int nb = min(64, N - i0);
+    for (int rr = warp; rr < nb; rr += 8) {
+      const double* row = Lb + (long long)(i0 + rr) * ldl;
+      double acc = 0.0;
+      for (int c = lane; c < i0; c += 32) acc = fma(row[c], zs[c], acc);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) partial[rr] = r[(long long)b * N + i0 + rr] - acc;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      for (int rr = 0; rr < nb; ++rr) {
+        const double* row = Lb + (long long)(i0 + rr) * ldl + i0;
+        double acc = 0.0;
+        for (int c = lane; c < rr; c += 32) acc = fma(row[c], zs[i0 + c], acc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) zs[i0 + rr] = (partial[rr] - acc) / row[rr];
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < N; i += 256) z[(long long)b * N + i] = zs[i];
+}
+
+constexpr size_t kPotrfSmem = sizeof(double) * (kTile * PD_LD + kTile + 32);
+
+}  // namespace
+
+cudaError_t kernels_init() {
+  cudaError_t e;
+  e = cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)GemmSmem<128, 64>::kBytes);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)GemmSmem<64, 128>::kBytes);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPotrfSmem);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(solve_lower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  return e;
+}
+
+cudaError_t launch_residual(const double* model_flux, const double* data_flux, int N, int Np, int B,
+                            double* rhs, double* resid_out, double* logdet, double* sqmah, int* info,
+                            cudaStream_t st) {
+  dim3 grid((Np + 255) / 256, B);
+  if (model_flux == nullptr) {
+    zero_rhs_kernel<<<grid, 256, 0, st>>>(rhs, Np, logdet, sqmah, info);
+  } else {
+    residual_kernel<<<grid, 256, 0, st>>>(model_flux, data_flux, N, Np, rhs, resid_out, logdet, sqmah, info);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_potrf_diag(const CholParams& p, int B, int last, double* lnL_out, int* info_out,
+                              cudaStream_t st) {
+  potrf_diag_kernel<<<B, PD_THREADS, kPotrfSmem, st>>>(p, last, lnL_out, info_out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_trsm(const CholParams& p, int B, cudaStream_t st) {
+  const int rows = p.Np - p.k0 - kTile;
+  if (rows <= 0) return cudaSuccess;
+  dim3 grid(rows / 64, B);
+  trsm_kernel<<<grid, GEMM_THREADS, GemmSmem<64, 128>::kBytes, st>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_syrk(const CholParams& p, int B, cudaStream_t st) {
+  const int T = (p.Np - p.k0 - kTile) / kTile;
+  if (T <= 0) return cudaSuccess;
+  dim3 grid(2 * T, T, B);
+  syrk_kernel<<<grid, GEMM_THREADS, GemmSmem<128, 64>::kBytes, st>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_copy_in_lower(const double* C, int N, double* W, int Np, long long strideW, int B,
+                                 cudaStream_t st) {
+  dim3 grid(min(64, (Np + 255) / 256), Np, B);
+  copy_in_lower_kernel<<<grid, 256, 0, st>>>(C, N, W, Np, strideW);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_copy_out_lower(double* C, int N, const double* W, int Np, long long strideW, int B,
+                                  cudaStream_t st) {
+  dim3 grid(min(64, (N + 255) / 256), N, B);
+  copy_out_lower_kernel<<<grid, 256, 0, st>>>(C, N, W, Np, strideW);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_solve_lower(const double* L, long long strideL, int ldl, const double* r, double* z, int N,
+                               int B, cudaStream_t st) {
+  solve_lower_kernel<<<B, 256, sizeof(double) * N, st>>>(L, strideL, ldl, r, z, N);
+  return cudaGetLastError();
+}
+
+}  // namespace sfb

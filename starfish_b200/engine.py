@@ -1,0 +1,257 @@
+"""`LikelihoodEngine` — Python owner of one libsfb200 handle (one GPU, one process).
+
+This is the stage boundary of SURVEY §8d: per-walker ``X[M,N]``, ``A[M,M]``, ``model_flux[N]`` and
+kernel hyper-parameters in, ``lnL[B]`` / ``info[B]`` out.  torch tensors are used purely as device
+memory containers (allocation, ``data_ptr()``, current stream); there are no torch ops on the path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from .constants import JITTER
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+class LikelihoodEngine:
+    """Batched covariance build + Cholesky + solve on one B200.
+
+    Parameters
+    ----------
+    n_pix, n_comp, max_local, max_walkers : sizes (N, M, Kmax, Bmax) the handle is created for
+    device : CUDA device index
+    workspace_walkers : number of N×N factorisation slots (0 = automatic)
+    """
+
+    def __init__(self, n_pix: int, n_comp: int, max_local: int, max_walkers: int, device: int = 0,
+                 workspace_walkers: int = 0):
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise RuntimeError("starfish_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self._lib = _lib.lib()
+        self.N, self.M, self.K, self.B = int(n_pix), int(n_comp), max(int(max_local), 1), int(max_walkers)
+        self.device = torch.device("cuda", device)
+        torch.cuda.init()
+        with torch.cuda.device(self.device):
+            torch.empty(1, device=self.device)  # make sure the primary context exists
+        h = C.c_void_p()
+        rc = self._lib.sfb_create(device, self.N, self.M, self.K, self.B, int(workspace_walkers), C.byref(h))
+        if rc != 0:
+            raise _lib.SfbError(f"sfb_create failed with status {rc} (N={n_pix}, M={n_comp}, "
+                                f"Kmax={max_local}, Bmax={max_walkers})")
+        self._h = h
+        self._static = None
+
+    # -- plumbing ---------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.sfb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            msg = self._lib.sfb_last_error(self._h)
+            raise _lib.SfbError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    def _stream(self):
+        return C.c_void_p(_torch().cuda.current_stream(self.device).cuda_stream)
+
+    def _dev(self, a, dtype=None, shape=None):
+        """numpy / torch (any device) -> contiguous device tensor of the wanted dtype."""
+        torch = _torch()
+        dtype = dtype or torch.float64
+        if a is None:
+            return None
+        if isinstance(a, torch.Tensor):
+            t = a.to(device=self.device, dtype=dtype).contiguous()
+        else:
+            np_dtype = np.float64 if dtype == torch.float64 else np.int32
+            t = torch.from_numpy(np.ascontiguousarray(a, dtype=np_dtype)).to(self.device)
+        if shape is not None and tuple(t.shape) != tuple(shape):
+            raise ValueError(f"expected shape {tuple(shape)}, got {tuple(t.shape)}")
+        return t
+
+    @staticmethod
+    def _ptr(t):
+        return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+    @property
+    def workspace_walkers(self) -> int:
+        return self._lib.sfb_workspace_walkers(self._h)
+
+    @property
+    def padded_n(self) -> int:
+        return self._lib.sfb_padded_n(self._h)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.sfb_launch_count(self._h))
+
+    def synchronize(self):
+        self._check(self._lib.sfb_sync(self._h), "sfb_sync")
+        _torch().cuda.synchronize(self.device)
+
+    # -- static data --------------------------------------------------------------------------------
+    def set_data(self, wave, sigma, data_flux):
+        """Upload the walker-independent arrays (wavelengths, σ, observed flux), each of length N."""
+        w = self._dev(wave, shape=(self.N,))
+        s = self._dev(sigma, shape=(self.N,))
+        f = self._dev(data_flux, shape=(self.N,))
+        self._check(self._lib.sfb_set_static(self._h, self._ptr(w), self._ptr(s), self._ptr(f), self._stream()),
+                    "sfb_set_static")
+        self._static = (w, s, f)  # keep alive until the async copies have run
+
+    # -- hyper-parameter packing ----------------------------------------------------------------------
+    def pack_hyper(self, B, glob, nloc, loc, shared):
+        """-> device tensors glob[Bh,2], nloc[Bh] (int32), loc[Bh,Kmax,3];  Bh = 1 if shared else B."""
+        torch = _torch()
+        Bh = 1 if shared else B
+        g = np.zeros((Bh, 2)) if glob is None else glob
+        g = self._dev(g).reshape(Bh, 2)
+        if loc is None:
+            l = torch.zeros((Bh, self.K, 3), dtype=torch.float64, device=self.device)
+            n = torch.zeros((Bh,), dtype=torch.int32, device=self.device)
+        else:
+            l = self._dev(loc)
+            if l.dim() == 2:
+                l = l.unsqueeze(0)
+            if l.shape[0] != Bh or l.shape[2] != 3 or l.shape[1] > self.K:
+                raise ValueError(f"loc must be [{Bh}, <= {self.K}, 3], got {tuple(l.shape)}")
+            kk = l.shape[1]
+            if kk < self.K:
+                pad = torch.zeros((Bh, self.K, 3), dtype=torch.float64, device=self.device)
+                pad[:, :kk] = l
+                l = pad
+            n = (torch.full((Bh,), kk, dtype=torch.int32, device=self.device) if nloc is None
+                 else self._dev(nloc, dtype=torch.int32).reshape(Bh))
+        return g.contiguous(), n.contiguous(), l.contiguous()
+
+    def _xa(self, B, X, A):
+        if X is None or self.M == 0:
+            return None, None
+        X = self._dev(X, shape=(B, self.M, self.N))
+        A = self._dev(A, shape=(B, self.M, self.M))
+        return X, A
+
+    # -- entry points -------------------------------------------------------------------------------
+    def build_covariance(self, X, A, glob=None, nloc=None, loc=None, shared_hyper=False,
+                         jitter: float = 0.0, n_walkers: Optional[int] = None):
+        """C[b] = XᵀAX + diag(σ²+jitter) + K_global + ΣK_local  → device tensor [B,N,N] (both triangles)."""
+        torch = _torch()
+        B = int(n_walkers if n_walkers is not None else (X.shape[0] if X is not None else np.shape(glob)[0]))
+        X, A = self._xa(B, X, A)
+        g, n, l = self.pack_hyper(B, glob, nloc, loc, shared_hyper)
+        Cm = torch.empty((B, self.N, self.N), dtype=torch.float64, device=self.device)
+        self._check(self._lib.sfb_build_cov(self._h, B, self._ptr(X), self._ptr(A), self._ptr(g), self._ptr(n),
+                                            self._ptr(l), int(shared_hyper), float(jitter), self._ptr(Cm),
+                                            self._stream()), "sfb_build_cov")
+        self._keep = (X, A, g, n, l)
+        return Cm
+
+    def log_likelihood(self, X, A, model_flux, glob=None, nloc=None, loc=None, shared_hyper=False,
+                       return_residuals=False):
+        """Device path: inputs numpy or torch; returns device tensors (lnL[B], info[B][, resid[B,N]])."""
+        torch = _torch()
+        F = self._dev(model_flux)
+        if F.dim() == 1:
+            F = F.unsqueeze(0)
+        B = F.shape[0]
+        if F.shape[1] != self.N:
+            raise ValueError(f"model_flux must be [B,{self.N}]")
+        X, A = self._xa(B, X, A)
+        g, n, l = self.pack_hyper(B, glob, nloc, loc, shared_hyper)
+        lnL = torch.empty((B,), dtype=torch.float64, device=self.device)
+        info = torch.empty((B,), dtype=torch.int32, device=self.device)
+        resid = torch.empty((B, self.N), dtype=torch.float64, device=self.device) if return_residuals else None
+        self._check(self._lib.sfb_loglike(self._h, B, self._ptr(X), self._ptr(A), self._ptr(F), self._ptr(g),
+                                          self._ptr(n), self._ptr(l), int(shared_hyper), self._ptr(lnL),
+                                          self._ptr(info), self._ptr(resid), self._stream()), "sfb_loglike")
+        self._keep = (X, A, F, g, n, l)
+        return (lnL, info, resid) if return_residuals else (lnL, info)
+
+    def log_likelihood_resident(self, B, X, A, F, g, n, l, lnL, info, shared_hyper=False):
+        """Zero-overhead variant for benchmarks: every argument is already a packed device tensor."""
+        self._check(self._lib.sfb_loglike(self._h, B, self._ptr(X), self._ptr(A), self._ptr(F), self._ptr(g),
+                                          self._ptr(n), self._ptr(l), int(shared_hyper), self._ptr(lnL),
+                                          self._ptr(info), C.c_void_p(0), self._stream()), "sfb_loglike")
+
+    def log_likelihood_host(self, X, A, model_flux, glob, nloc, loc, lnL_out, info_out, shared_hyper=False,
+                            resid_out=None):
+        """End-to-end path on HOST buffers (numpy arrays, ideally views of pinned memory).
+
+        Host→device copies of the inputs and the device→host read of lnL/info happen inside the call,
+        pipelined chunk by chunk behind the factorisation.  Arrays must be C-contiguous fp64 / int32 with
+        ``loc`` already padded to [Bh, Kmax, 3].
+        """
+        def hp(a, dt):
+            if a is None:
+                return C.c_void_p(0)
+            if not (isinstance(a, np.ndarray) and a.dtype == dt and a.flags["C_CONTIGUOUS"]):
+                raise ValueError("host buffers must be C-contiguous numpy arrays of the documented dtype")
+            return C.c_void_p(a.ctypes.data)
+
+        B = model_flux.shape[0]
+        self._check(self._lib.sfb_loglike_host(self._h, B, hp(X, np.float64), hp(A, np.float64),
+                                               hp(model_flux, np.float64), hp(glob, np.float64),
+                                               hp(nloc, np.int32), hp(loc, np.float64), int(shared_hyper),
+                                               hp(lnL_out, np.float64), hp(info_out, np.int32),
+                                               hp(resid_out, np.float64)), "sfb_loglike_host")
+        return lnL_out, info_out
+
+    def cho_factor(self, Cmat, return_logdet=False):
+        """Batched in-place lower Cholesky of device tensor [B,N,N] (row-major; lower triangle read and
+        overwritten with L; strict upper untouched).  Returns (Cmat, info[, logdet])."""
+        torch = _torch()
+        if not (isinstance(Cmat, torch.Tensor) and Cmat.is_cuda and Cmat.dtype == torch.float64
+                and Cmat.is_contiguous()):
+            raise ValueError("cho_factor needs a contiguous fp64 CUDA tensor [B,N,N]")
+        if Cmat.dim() == 2:
+            Cmat = Cmat.unsqueeze(0)
+        B = Cmat.shape[0]
+        info = torch.empty((B,), dtype=torch.int32, device=self.device)
+        logdet = torch.empty((B,), dtype=torch.float64, device=self.device)
+        self._check(self._lib.sfb_potrf(self._h, B, self._ptr(Cmat), self._ptr(info), self._ptr(logdet),
+                                        self._stream()), "sfb_potrf")
+        return (Cmat, info, logdet) if return_logdet else (Cmat, info)
+
+    def solve_lower(self, L, r):
+        """z = L⁻¹ r for device tensors L[B,N,N] (lower, row-major) and r[B,N]."""
+        torch = _torch()
+        L = self._dev(L)
+        r = self._dev(r)
+        if L.dim() == 2:
+            L, r = L.unsqueeze(0), r.reshape(1, -1)
+        z = torch.empty_like(r)
+        self._check(self._lib.sfb_solve_lower(self._h, L.shape[0], self._ptr(L), self._ptr(r), self._ptr(z),
+                                              self._stream()), "sfb_solve_lower")
+        self._keep = (L, r)
+        return z
+
+    # -- profiling ----------------------------------------------------------------------------------
+    def profile(self, on: bool):
+        self._check(self._lib.sfb_profile_enable(self._h, int(on)), "sfb_profile_enable")
+
+    def profile_read(self):
+        """{class: dict(launches, ms, work)} accumulated since the last read (work: bytes for 'build',
+        FLOPs otherwise)."""
+        buf = (C.c_double * (3 * len(_lib.KERNEL_CLASSES)))()
+        self._check(self._lib.sfb_profile_read(self._h, buf, len(buf)), "sfb_profile_read")
+        return {name: dict(launches=int(buf[3 * i]), ms=buf[3 * i + 1], work=buf[3 * i + 2])
+                for i, name in enumerate(_lib.KERNEL_CLASSES)}
+
+
+JITTER_DEFAULT = JITTER
