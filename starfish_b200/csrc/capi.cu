@@ -152,7 +152,7 @@ int run_cholesky(sfb_ctx* h, int slot0, int nb, double* lnL_out, int* info_out, 
         h->launches++;
       }
       {
-        ProfScope ps(h, st, SFB_K_SYRK, nb * (rem * (rem + kTile) * kTile));  // lower tiles incl. diagonal
+        ProfScope ps(h, st, SFB_K_SYRK, nb * (rem * (rem + 1.0) * kTile));  // algorithmic syrk FLOPs: n(n+1)k
         SFB_CUDA(h, launch_syrk(p, nb, st));
         h->launches++;
       }
