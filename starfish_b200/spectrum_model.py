@@ -1,0 +1,519 @@
+"""Drop-in ``SpectrumModel`` whose covariance assembly, Cholesky and solve run on the B200.
+
+Mirrors the object API of the reference's ``Starfish.models.SpectrumModel``
+(Starfish/models/spectrum_model.py): constructor :126-181, ``grid_params``/``cheb``/``labels`` :183-222,
+item access :224-275, ``__call__`` :277-365, ``log_likelihood`` :367-407, parameter dict/vector
+get/set :409-493, ``freeze``/``thaw`` :495-590, ``save``/``load`` :592-633, ``train`` :635-696,
+``__repr__`` :789-822 — same names, argument meaning, parameter-vector order and error behaviour
+(``KeyError`` for unknown parameters, ``ValueError`` for multi-order data / wrong vector length,
+``numpy.linalg.LinAlgError`` when the covariance is not positive definite).
+
+What differs is where the work happens.  Everything from the rank-M emulator term onwards
+(:334-363, :399-405) is one call into libsfb200 (``LikelihoodEngine``); the dense N×N covariance only
+comes back to the host when ``model()`` is asked for it.  ``log_likelihood_batch(P)`` is new: it evaluates
+a whole ensemble of parameter vectors in one GPU pass and plugs into ``emcee.EnsembleSampler(...,
+vectorize=True)``.  The spectral transforms upstream of the path stay on the host.
+"""
+from __future__ import annotations
+
+import logging
+from collections import deque
+from typing import Optional, Sequence
+
+import numpy as np
+from scipy.linalg import cho_factor, cho_solve
+from scipy.optimize import minimize
+
+from .constants import JITTER
+from .paramtree import ParamTree
+from .transforms import (_get_renorm_factor, chebyshev_correct, doppler_shift, rescale, resample,
+                         rotational_broaden)
+from .utils import calculate_dv, create_log_lam_grid
+
+_TRANSFORM_KEYS = ("vz", "vsini", "Av", "Rv", "log_scale", "global_cov", "local_cov", "cheb")
+_GLOBAL_KEYS = ("log_amp", "log_ls")
+_LOCAL_KEYS = ("mu", "log_amp", "log_sigma")
+
+
+class _CachedKernel:
+    """What ``model._glob_cov`` / ``model._loc_cov`` hold: the (exponentiated) hyper-parameters the cached
+    kernel was built from.  Behaves like the reference's cached N×N array where it is looked at
+    (``.shape``, ``numpy.asarray``), materialising the matrix on the GPU only on demand."""
+
+    def __init__(self, model, glob=None, loc=None):
+        self._model = model
+        self.glob = glob            # (amp, ls) or None
+        self.loc = loc              # array [K,3] or None
+        n = len(model.data.wave)
+        self.shape = (n, n)
+
+    def __array__(self, dtype=None, copy=None):
+        eng = self._model._get_engine(1)
+        self._model._sync_static(eng)
+        zeros = np.zeros(self.shape[0])
+        # kernels only: σ is part of the static data, so build with the kernel terms and subtract σ²
+        C = eng.build_covariance(None, None, glob=None if self.glob is None else np.array([self.glob]),
+                                 loc=None if self.loc is None else self.loc[None], n_walkers=1)[0]
+        out = C.cpu().numpy()
+        out[np.diag_indices_from(out)] -= np.asarray(self._model.data.sigma) ** 2
+        return out if dtype is None else out.astype(dtype)
+
+
+class SpectrumModel:
+    """A single-order spectrum model evaluated on the GPU (see module docstring)."""
+
+    _PARAMS = list(_TRANSFORM_KEYS)
+    _GLOBAL_PARAMS = list(_GLOBAL_KEYS)
+    _LOCAL_PARAMS = list(_LOCAL_KEYS)
+
+    def __init__(self, emulator, data, grid_params: Sequence[float], max_deque_len: int = 100, norm=False,
+                 name: str = "SpectrumModel", device: int = 0, emulator_term: str = "reference", **params):
+        if isinstance(emulator, str) or isinstance(data, str):
+            raise NotImplementedError("loading from HDF5 paths needs h5py; pass in-memory Emulator/Spectrum")
+        if len(data) > 1:
+            raise ValueError("Multiple orders detected in data, please use EchelleModel")
+        if emulator_term not in ("reference", "paper"):
+            raise ValueError("emulator_term must be 'reference' (XᵀΣ_w⁻¹X, as coded) or 'paper' (XᵀΣ_wX)")
+        self.emulator = emulator
+        self.data_name = data.name
+        self.data = data[0]
+        self.device = device
+        self.emulator_term = emulator_term
+
+        # internal fine log-λ grid on which broadening happens (power-of-two length)
+        dv = calculate_dv(self.data.wave)
+        self.min_dv_wave = create_log_lam_grid(dv, self.emulator.wl.min(), self.emulator.wl.max())["wl"]
+        self.bulk_fluxes = resample(self.emulator.wl, self.emulator.bulk_fluxes, self.min_dv_wave)
+        self.residuals = deque(maxlen=max_deque_len)
+
+        params = dict(params)
+        if "cheb" in params:  # c0 is pinned to 1; stored coefficients are c1, c2, ... (re-inserted last,
+            # which fixes the position of cheb:* in `labels` exactly as the reference does)
+            coeffs = params.pop("cheb")
+            params["cheb"] = {str(i + 1): c for i, c in enumerate(coeffs)}
+        self.params = ParamTree(params)
+        self.frozen = []
+        self.name = name
+        self.norm = norm
+        self.n_grid_params = len(grid_params)
+        self.grid_params = grid_params
+
+        self._lnprob = None
+        self._glob_cov = None
+        self._loc_cov = None
+        self._log_scale = params.get("log_scale", None)
+        self._engine = None
+        self._static_sig = None
+        self.log = logging.getLogger(self.__class__.__name__)
+
+    # ------------------------------------------------------------------------------------------------
+    # parameter bookkeeping
+    # ------------------------------------------------------------------------------------------------
+    @property
+    def grid_params(self):
+        return np.array([self.params[k] for k in self.emulator.param_names])
+
+    @grid_params.setter
+    def grid_params(self, values):
+        for key, val in zip(self.emulator.param_names, values):
+            if key not in self.frozen:
+                self.params[key] = val
+
+    @property
+    def cheb(self):
+        return np.array(self.params["cheb"].values())
+
+    @cheb.setter
+    def cheb(self, values):
+        if "cheb" in self.frozen:
+            return
+        for key, val in zip(self.params["cheb"], values):
+            if key not in self.frozen:
+                self.params["cheb"][key] = val
+
+    @property
+    def labels(self):
+        return tuple(self.get_param_dict(flat=True).keys())
+
+    def __getitem__(self, key):
+        if key == "cheb":
+            return list(self.params[key].values())
+        return self.params[key]
+
+    def __setitem__(self, key, value):
+        if ":" not in key:
+            if key == "cheb":
+                self.params[key] = {str(i + 1): c for i, c in enumerate(value)}
+            elif key in self._PARAMS or key in self.emulator.param_names:
+                self.params[key] = value
+            else:
+                raise KeyError(f"{key} not recognized")
+            return
+        group, rest = key.split(":", 1)
+        leaf = rest.rsplit(":", 1)[-1]
+        if group == "global_cov" and leaf in self._GLOBAL_PARAMS:
+            self.params[key] = value
+        elif group == "local_cov" and leaf in self._LOCAL_PARAMS:
+            self.params[key] = value
+        elif group == "cheb":
+            idx = int(rest)
+            if idx == 0:
+                raise KeyError("cannot change constant Chebyshev term")
+            if "cheb" in self.params:  # fill skipped orders with zeros
+                for i in range(len(self.params["cheb"]) + 1, idx + 1):
+                    self.params[f"cheb:{i}"] = 0
+            self.params[key] = value
+        else:
+            raise KeyError(f"{key} not recognized")
+
+    def __delitem__(self, key):
+        if key not in self.params:
+            raise KeyError(f"{key} not in params")
+        if key in ("global_cov", "local_cov"):
+            if key == "global_cov":
+                self._glob_cov = None
+            else:
+                self._loc_cov = None
+            self.frozen = [k for k in self.frozen if not k.startswith(key)]
+        del self.params[key]
+        if key in self.frozen:
+            self.frozen.remove(key)
+
+    def get_param_dict(self, flat: bool = False):
+        thawed = ParamTree()
+        for key, val in self.params.items():
+            if key not in self.frozen:
+                thawed[key] = val
+        if not flat:
+            return thawed.as_dict()
+        return thawed
+
+    def set_param_dict(self, params):
+        for key, val in ParamTree(params).items():
+            if key not in self.frozen:
+                self.params[key] = val
+
+    def get_param_vector(self):
+        return np.array(self.get_param_dict(flat=True).values())
+
+    def set_param_vector(self, params):
+        labels = self.labels
+        if len(params) != len(labels):
+            raise ValueError("Param Vector does not match length of thawed parameters")
+        self.set_param_dict(dict(zip(labels, params)))
+
+    def _group_flat_keys(self, name):
+        sub = self.params.as_dict()[name]
+        if name == "local_cov":
+            return [f"local_cov:{i}:{k}" for i, kern in enumerate(sub) for k in kern]
+        return [f"{name}:{k}" for k in sub]
+
+    def freeze(self, names):
+        names = [str(n) for n in np.atleast_1d(names)]
+        if names[0] == "all":
+            for key in self.labels:
+                if key not in self.frozen:
+                    self.frozen.append(key)
+            for group in ("global_cov", "local_cov", "cheb"):
+                if group in self.params:
+                    self.frozen.append(group)
+            return
+        for name in names:
+            if name in ("global_cov", "local_cov", "cheb"):
+                self.frozen.append(name)
+                if name == "global_cov":
+                    self._glob_cov = None
+                elif name == "local_cov":
+                    self._loc_cov = None
+                for flat in self._group_flat_keys(name):
+                    if flat not in self.frozen:
+                        self.frozen.append(flat)
+            elif name not in self.frozen and name in self.params:
+                self.frozen.append(name)
+
+    def thaw(self, names):
+        names = [str(n) for n in np.atleast_1d(names)]
+        if names[0] == "all":
+            self.frozen = []
+            return
+        for name in names:
+            if name in ("global_cov", "local_cov", "cheb"):
+                self.frozen.remove(name)
+                for flat in self._group_flat_keys(name):
+                    self.frozen.remove(flat)
+            elif name in self.frozen:
+                self.frozen.remove(name)
+
+    # ------------------------------------------------------------------------------------------------
+    # host side of the evaluation: everything upstream of the covariance (spectrum_model.py:287-332)
+    # ------------------------------------------------------------------------------------------------
+    def _upstream(self):
+        """-> (flux[N], X[M,N], weights_cov[M,M]) for the current parameters."""
+        wave, fluxes = self.min_dv_wave, self.bulk_fluxes
+        if "vsini" in self.params:
+            fluxes = rotational_broaden(wave, fluxes, self.params["vsini"])
+        if "vz" in self.params:
+            wave = doppler_shift(wave, self.params["vz"])
+        fluxes = resample(wave, fluxes, self.data.wave)
+        if "Av" in self.params:
+            if self.params["Av"] != 0:
+                raise NotImplementedError("extinction needs the `extinction` package, absent from this image")
+        if "cheb" in self.params:
+            fluxes = chebyshev_correct(self.data.wave, fluxes, [1, *self.cheb])
+        weights, weights_cov = self.emulator(self.grid_params)
+        *eigenspectra, flux_mean, flux_std = fluxes
+        X = eigenspectra * flux_std
+        flux = weights @ X + flux_mean
+        norm = self.emulator.norm_factor(self.grid_params) if self.norm else 1
+        if "log_scale" not in self.params:
+            scale = _get_renorm_factor(self.data.wave, flux * norm, self.data.flux)
+            self._log_scale = np.log(scale)
+            scale *= norm
+            self.log.debug(f"fit scale factor using integrated flux ratio: {scale}")
+        else:
+            self._log_scale = self.params["log_scale"]
+            scale = np.exp(self.params["log_scale"]) * norm
+        return rescale(flux, scale), rescale(X, scale), weights_cov
+
+    def _emulator_matrix(self, weights_cov):
+        """The M×M matrix A of the rank-M term XᵀAX: Σ_w⁻¹ as the reference codes it (:334-335), or Σ_w
+        as the paper/docs state it (``emulator_term='paper'``)."""
+        weights_cov = np.array(weights_cov, dtype=np.float64)
+        if self.emulator_term == "paper":
+            return weights_cov
+        fac = cho_factor(weights_cov)
+        return cho_solve(fac, np.eye(weights_cov.shape[0]))
+
+    def _kernel_hyper(self):
+        """(glob (amp, ls) | None, loc [K,3] | None) honouring the frozen-group cache semantics of
+        spectrum_model.py:341-363: a group is re-read from the parameters on every call unless it is
+        frozen and already cached."""
+        if "global_cov" in self.params:
+            if "global_cov" not in self.frozen or self._glob_cov is None:
+                self._glob_cov = _CachedKernel(self, glob=(float(np.exp(self.params["global_cov:log_amp"])),
+                                                           float(np.exp(self.params["global_cov:log_ls"]))))
+        if "local_cov" in self.params:
+            if "local_cov" not in self.frozen or self._loc_cov is None:
+                rows = [(np.exp(k["log_amp"]), k["mu"], np.exp(k["log_sigma"]))
+                        for k in self.params.as_dict()["local_cov"]]
+                self._loc_cov = _CachedKernel(self, loc=np.array(rows, dtype=np.float64).reshape(-1, 3))
+        glob = self._glob_cov.glob if self._glob_cov is not None else None
+        loc = self._loc_cov.loc if self._loc_cov is not None else None
+        return glob, loc
+
+    # ------------------------------------------------------------------------------------------------
+    # GPU plumbing
+    # ------------------------------------------------------------------------------------------------
+    def _get_engine(self, n_walkers, n_local=None):
+        from .engine import LikelihoodEngine
+
+        n = len(self.data.wave)
+        m = self.emulator.ncomps
+        k = max(1, n_local if n_local is not None else
+                (len(self.params.as_dict()["local_cov"]) if "local_cov" in self.params else 0))
+        eng = self._engine
+        if eng is None or eng.N != n or eng.M != m or eng.K < k or eng.B < n_walkers:
+            if eng is not None:
+                k = max(k, eng.K)
+                n_walkers = max(n_walkers, eng.B)
+                eng.close()
+            self._engine = eng = LikelihoodEngine(n, m, k, n_walkers, device=self.device)
+            self._static_sig = None
+        return eng
+
+    def _sync_static(self, eng):
+        """Re-upload wave/σ/flux when the user swapped or edited them (tests overwrite ``data._flux``)."""
+        cur = (np.array(self.data.wave, dtype=np.float64), np.array(self.data.sigma, dtype=np.float64),
+               np.array(self.data.flux, dtype=np.float64))
+        old = self._static_sig
+        if old is None or any(a.shape != b.shape or not np.array_equal(a, b) for a, b in zip(cur, old)):
+            eng.set_data(*cur)
+            self._static_sig = cur
+
+    @staticmethod
+    def _check_finite(*arrays):
+        for a in arrays:
+            if not np.all(np.isfinite(a)):
+                raise ValueError("array must not contain infs or NaNs")
+
+    # ------------------------------------------------------------------------------------------------
+    # evaluation
+    # ------------------------------------------------------------------------------------------------
+    def __call__(self):
+        """-> (flux[N], cov[N,N]) like the reference; the covariance is assembled on the GPU."""
+        flux, X, weights_cov = self._upstream()
+        glob, loc = self._kernel_hyper()
+        eng = self._get_engine(1)
+        self._sync_static(eng)
+        A = self._emulator_matrix(weights_cov)
+        C = eng.build_covariance(X[None], A[None], glob=None if glob is None else np.array([glob]),
+                                 loc=None if loc is None or len(loc) == 0 else loc[None], n_walkers=1)
+        return flux, C[0].cpu().numpy()
+
+    def log_likelihood(self, priors: Optional[dict] = None) -> float:
+        prior_lp = 0
+        if priors is not None:
+            for key, prior in priors.items():
+                if key in self.params:
+                    prior_lp += prior.logpdf(self[key])
+        if not np.isfinite(prior_lp):
+            return -np.inf
+        flux, X, weights_cov = self._upstream()
+        glob, loc = self._kernel_hyper()
+        self._check_finite(flux, X, weights_cov)
+        eng = self._get_engine(1)
+        self._sync_static(eng)
+        A = self._emulator_matrix(weights_cov)
+        lnL, info, resid = eng.log_likelihood(
+            X[None], A[None], flux[None], glob=None if glob is None else np.array([glob]),
+            loc=None if loc is None or len(loc) == 0 else loc[None], return_residuals=True)
+        code = int(info.cpu().numpy()[0])
+        self.residuals.append(resid[0].cpu().numpy())
+        if code > 0:
+            raise np.linalg.LinAlgError(f"{code}-th leading minor of the array is not positive definite")
+        self._lnprob = float(lnL.cpu().numpy()[0])
+        return self._lnprob + prior_lp
+
+    def log_likelihood_batch(self, P, priors: Optional[dict] = None, on_not_pd: str = "-inf"):
+        """Log-probability of B parameter vectors (rows of ``P``, columns in ``self.labels`` order).
+
+        Rows whose priors are non-finite or whose grid parameters fall outside the emulator grid get
+        ``-inf`` without any GPU work (mirrors spectrum_model.py:394-395 and the priors' usual role);
+        rows whose covariance is not positive definite get ``-inf`` (``on_not_pd='-inf'``) or raise
+        ``LinAlgError`` (``on_not_pd='raise'``).  The model's own parameters are left unchanged.
+        """
+        P = np.atleast_2d(np.asarray(P, dtype=np.float64))
+        labels = self.labels
+        if P.shape[1] != len(labels):
+            raise ValueError("Param Vector does not match length of thawed parameters")
+        B = P.shape[0]
+        out = np.full(B, -np.inf)
+        saved = self.get_param_vector()
+        saved_cache = (self._glob_cov, self._loc_cov, self._log_scale)
+        rows, fluxes, Xs, As, globs, locs, plp = [], [], [], [], [], [], []
+        try:
+            for b in range(B):
+                self.set_param_vector(P[b])
+                lp = 0.0
+                if priors is not None:
+                    for key, prior in priors.items():
+                        if key in self.params:
+                            lp += prior.logpdf(self[key])
+                if not np.isfinite(lp):
+                    continue
+                gp = self.grid_params
+                if np.any(gp < self.emulator.min_params) or np.any(gp > self.emulator.max_params):
+                    continue
+                flux, X, wcov = self._upstream()
+                glob, loc = self._kernel_hyper()
+                if not (np.all(np.isfinite(flux)) and np.all(np.isfinite(X)) and np.all(np.isfinite(wcov))):
+                    continue
+                rows.append(b); plp.append(lp); fluxes.append(flux); Xs.append(X)
+                As.append(self._emulator_matrix(wcov))
+                globs.append((0.0, 1.0) if glob is None else glob)
+                locs.append(np.zeros((0, 3)) if loc is None else loc)
+        finally:
+            self.set_param_vector(saved)
+            self._glob_cov, self._loc_cov, self._log_scale = saved_cache
+        if not rows:
+            return out
+        nb = len(rows)
+        kmax = max(1, max(len(l) for l in locs))
+        loc_arr = np.zeros((nb, kmax, 3))
+        nloc = np.zeros(nb, dtype=np.int32)
+        for i, l in enumerate(locs):
+            loc_arr[i, :len(l)] = l
+            nloc[i] = len(l)
+        eng = self._get_engine(nb, n_local=kmax)
+        self._sync_static(eng)
+        lnL, info, resid = eng.log_likelihood(np.array(Xs), np.array(As), np.array(fluxes),
+                                              glob=np.array(globs), nloc=nloc, loc=loc_arr,
+                                              return_residuals=True)
+        lnL, info = lnL.cpu().numpy(), info.cpu().numpy()
+        self.residuals.append(resid[-1].cpu().numpy())
+        if on_not_pd == "raise" and (info > 0).any():
+            bad = int(np.flatnonzero(info > 0)[0])
+            raise np.linalg.LinAlgError(f"walker {rows[bad]}: {int(info[bad])}-th leading minor of the array "
+                                        "is not positive definite")
+        good = info == 0
+        out[np.array(rows)[good]] = lnL[good] + np.array(plp)[good]
+        return out
+
+    # ------------------------------------------------------------------------------------------------
+    # persistence, optimisation, display
+    # ------------------------------------------------------------------------------------------------
+    def save(self, filename, metadata=None):
+        import toml
+
+        meta = {"name": self.name, "data": self.data_name}
+        if self.emulator.name is not None:
+            meta["emulator"] = self.emulator.name
+        if metadata is not None:
+            meta.update(metadata)
+        doc = {"parameters": self.params.as_dict(), "frozen": self.frozen, "metadata": meta}
+        with open(filename, "w") as fh:
+            toml.dump(doc, fh, encoder=toml.TomlNumpyEncoder(doc.__class__))
+        self.log.info(f"Saved current state at {filename}")
+
+    def load(self, filename):
+        import toml
+
+        with open(filename, "r") as fh:
+            doc = toml.load(fh)
+        self.params = ParamTree(doc["parameters"])
+        self.frozen = doc["frozen"]
+
+    def train(self, priors: Optional[dict] = None, **kwargs):
+        """MAP estimate with ``scipy.optimize.minimize`` (Nelder-Mead by default), as the reference."""
+        priors = {} if priors is None else priors
+        for key, val in priors.items():
+            if key not in self.params and not key.startswith("cheb"):
+                raise ValueError(f"Invalid priors. {key} not a vlid key.")
+            if not callable(getattr(val, "logpdf", None)):
+                raise ValueError(f"Invalid priors. {key} does not have a `logpdf` method")
+            lp = val.logpdf(self[key])
+            if not np.isfinite(lp):
+                raise RuntimeError(f"{key}'s logpdf evaluated to {lp}")
+
+        def nll(P):
+            self.set_param_vector(P)
+            return -self.log_likelihood(priors)
+
+        opts = {"method": "Nelder-Mead"}
+        opts.update(kwargs)
+        soln = minimize(nll, self.get_param_vector(), **opts)
+        if soln.success:
+            self.set_param_vector(soln.x)
+        return soln
+
+    def __repr__(self):
+        lines = [self.name, "-" * len(self.name), f"Data: {self.data_name}", f"Emulator: {self.emulator.name}",
+                 f"Log Likelihood: {self._lnprob}", "", "Parameters"]
+        thawed = self.get_param_dict(flat=True)
+        top = []
+        for key in thawed.keys():
+            head = key.split(":", 1)[0]
+            if head not in top:
+                top.append(head)
+        nested = self.get_param_dict()
+        for key in top:
+            value = nested[key]
+            if key == "global_cov":
+                lines.append("  global_cov:")
+                lines += [f"    {k}: {v}" for k, v in value.items()]
+            elif key == "local_cov":
+                lines.append("  local_cov:")
+                kerns = value.values() if isinstance(value, dict) else value
+                for i, kern in enumerate(kerns):
+                    lines.append(f"    {i}: " + ", ".join(f"{k}: {v}" for k, v in kern.items()))
+            elif key == "cheb":
+                lines.append(f"  cheb: {list(value.values())}")
+            else:
+                lines.append(f"  {key}: {value}")
+        if "log_scale" not in self.params:
+            self._upstream()
+            lines.append(f"  log_scale: {self._log_scale} (fit)")
+        shown = [k for k in self.frozen if k not in ("global_cov", "local_cov")]
+        if self.frozen:
+            lines += ["", "Frozen Parameters"] + [f"  {k}: {self[k]}" for k in shown]
+        return "\n".join(lines)

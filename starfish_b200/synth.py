@@ -1,7 +1,7 @@
 """Seeded synthetic workload of SURVEY.md §8d (there is no network for PHOENIX libraries).
 
-Pure numpy, no Starfish objects: ``tests/`` and ``oracle/make_golden.py`` feed the *same* arrays to
-the reference's classes, to the oracle and to this package, so "identical inputs" is literal.
+Pure numpy, no Starfish objects: the tests and the golden-fixture generator feed the *same* arrays to
+the reference classes, to the CPU checker and to this package, so "identical inputs" is literal.
 """
 from __future__ import annotations
 

@@ -1,0 +1,23 @@
+import copy
+import warnings
+
+from starfish_b200 import synth
+
+
+def make_model(n_pix=256, walker=0, wave=None, mus=None, **over):
+    """Our SpectrumModel on the seeded synthetic set-up (same arrays the golden generator fed the reference)."""
+    from starfish_b200.emulator import Emulator
+    from starfish_b200.spectrum import Spectrum
+    from starfish_b200.spectrum_model import SpectrumModel
+
+    emu = Emulator(**copy.deepcopy(synth.make_emulator_arrays()))
+    emu._trained = True
+    w, f, s = synth.make_data(n_pix, wave=wave)
+    grid, p = synth.walker_params(walker)
+    if mus is not None:
+        for k, mu in enumerate(mus):
+            p["local_cov"][k]["mu"] = float(mu)
+    p.update(over)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return SpectrumModel(emu, Spectrum(w, f, sigmas=s, name="synthetic"), grid_params=grid, **p)
