@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 #include "sfb_internal.cuh"
 
@@ -35,9 +36,14 @@ struct sfb_ctx {
   double *dX = nullptr, *dA = nullptr, *dflux = nullptr, *dglob = nullptr, *dloc = nullptr, *dlnL = nullptr,
          *dresid = nullptr;
   int *dnloc = nullptr, *dinfo = nullptr;
+  // two lanes; each lane = a main stream (bulk trailing updates, copies) + a high-priority stream for the
+  // panel work that is on the critical path (look-ahead)
   cudaStream_t streams[2] = {nullptr, nullptr};
+  cudaStream_t hi[2] = {nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+  cudaEvent_t ev_hi[2] = {nullptr, nullptr}, ev_lo[2] = {nullptr, nullptr};
   bool profile = false;
+  int debug_mode = 0;  // SFB_DEBUG_MODE: bit0 = no high-priority stream, bit1 = single lane
   std::vector<ProfEvent> prof;
   std::vector<cudaEvent_t> ev_pool;
   long long launches = 0;
@@ -124,7 +130,22 @@ int join_streams(sfb_ctx* h, cudaStream_t caller, int nstreams) {
 }
 
 // Factor `nb` matrices sitting in slots [slot0, slot0+nb); rhs/logdet/sqmah/info already initialised.
-int run_cholesky(sfb_ctx* h, int slot0, int nb, double* lnL_out, int* info_out, cudaStream_t st) {
+//
+// Two-level blocking with one block of look-ahead.  Tile columns are grouped into outer blocks of
+// kOuterTiles.  PANEL(J): inside block J each column is brought up to date left-looking (strip update by
+// the block's earlier columns), factored (potrf_diag) and solved (trsm).  The trailing matrix is updated
+// once per block with K = kOuterTiles·128 — split into NEXT(J), the tile columns of block J+1, and REST(J),
+// everything right of them.  PANEL and NEXT run on the lane's high-priority stream, REST on its main stream:
+//
+//     hi :  PANEL(J) ─┬─ wait REST(J-1) ─ NEXT(J) ─ PANEL(J+1) ─┬─ ...
+//     lo :            └─ REST(J) ────────────────────────────────┴─ REST(J+1) ...
+//
+// so the latency-bound panel work of block J+1 hides under the bulk update of block J (they touch
+// disjoint tile columns).  On entry and exit all ordering is expressed on the main stream `lo`.
+int run_cholesky(sfb_ctx* h, int lane, int slot0, int nb, double* lnL_out, int* info_out) {
+  cudaStream_t lo = h->streams[lane];
+  cudaStream_t hi = (h->profile || (h->debug_mode & 1)) ? lo : h->hi[lane];
+  const bool two = (hi != lo);
   CholParams p;
   p.Np = h->Np;
   p.strideW = (long long)h->Np * h->Np;
@@ -135,28 +156,64 @@ int run_cholesky(sfb_ctx* h, int slot0, int nb, double* lnL_out, int* info_out, 
   p.logdet = h->logdet + slot0;
   p.sqmah = h->sqmah + slot0;
   p.info = h->info_ws + slot0;
+  p.k0 = 0;
   const int nt = h->Np / kTile;
-  for (int k = 0; k < nt; ++k) {
-    p.k0 = k * kTile;
-    const int last = (k == nt - 1);
-    const double rem = (double)(h->Np - p.k0 - kTile);
-    {
-      ProfScope ps(h, st, SFB_K_POTRF_DIAG, nb * (2.0 * kTile * kTile * kTile / 3.0));
-      SFB_CUDA(h, launch_potrf_diag(p, nb, last, lnL_out, info_out, st));
+  if (two) {  // hi starts after whatever produced the matrices on lo (build / copy-in)
+    SFB_CUDA(h, cudaEventRecord(h->ev_lo[lane], lo));
+    SFB_CUDA(h, cudaStreamWaitEvent(hi, h->ev_lo[lane], 0));
+  }
+  for (int J0 = 0; J0 < nt; J0 += kOuterTiles) {
+    const int q = std::min(kOuterTiles, nt - J0);
+    const int kb = J0 * kTile;
+    // ---- PANEL(J) on hi
+    for (int c = 0; c < q; ++c) {
+      const int jt = J0 + c;
+      p.k0 = jt * kTile;
+      const int last = (jt == nt - 1);
+      const double rem = (double)(h->Np - p.k0 - kTile);
+      if (c > 0) {
+        const double rows = (double)(h->Np - p.k0), K = (double)c * kTile;
+        ProfScope ps(h, hi, SFB_K_SYRK, nb * (2.0 * K * kTile * rows - K * kTile * (kTile - 1.0)));
+        SFB_CUDA(h, launch_syrk_strip(p, kb, c * kTile, jt, 1, nb, hi));
+        h->launches++;
+      }
+      {
+        ProfScope ps(h, hi, SFB_K_POTRF_DIAG, nb * (2.0 * kTile * kTile * kTile / 3.0));
+        SFB_CUDA(h, launch_potrf_diag(p, nb, last, lnL_out, info_out, hi));
+        h->launches++;
+      }
+      if (!last) {
+        ProfScope ps(h, hi, SFB_K_TRSM, nb * (rem * kTile * kTile));  // useful FLOPs of a triangular solve
+        SFB_CUDA(h, launch_trsm(p, nb, hi));
+        h->launches++;
+      }
+    }
+    const int jn = J0 + q;  // first tile column right of this block
+    if (jn >= nt) break;
+    const int qn = std::min(kOuterTiles, nt - jn);  // width of the next block
+    const double K = (double)q * kTile;
+    if (two) {
+      SFB_CUDA(h, cudaEventRecord(h->ev_hi[lane], hi));        // PANEL(J) done
+      SFB_CUDA(h, cudaStreamWaitEvent(lo, h->ev_hi[lane], 0));
+      SFB_CUDA(h, cudaStreamWaitEvent(hi, h->ev_lo[lane], 0));  // REST(J-1) done (or the build, for J=0)
+    }
+    {  // ---- NEXT(J): tile columns [jn, jn+qn), on hi
+      const double rows = (double)(h->Np - jn * kTile), w = (double)qn * kTile;
+      ProfScope ps(h, hi, SFB_K_SYRK, nb * (2.0 * K * w * rows - K * w * (w - 1.0)));
+      SFB_CUDA(h, launch_syrk_strip(p, kb, q * kTile, jn, qn, nb, hi));
       h->launches++;
     }
-    if (!last) {
-      {
-        ProfScope ps(h, st, SFB_K_TRSM, nb * (rem * kTile * kTile));  // useful FLOPs of a triangular solve
-        SFB_CUDA(h, launch_trsm(p, nb, st));
-        h->launches++;
-      }
-      {
-        ProfScope ps(h, st, SFB_K_SYRK, nb * (rem * (rem + 1.0) * kTile));  // algorithmic syrk FLOPs: n(n+1)k
-        SFB_CUDA(h, launch_syrk(p, nb, st));
-        h->launches++;
-      }
+    if (jn + qn < nt) {  // ---- REST(J): everything right of the next block, on lo
+      const double n = (double)(h->Np - (jn + qn) * kTile);
+      ProfScope ps(h, lo, SFB_K_SYRK, nb * (n * (n + 1.0) * K));  // algorithmic syrk FLOPs: n(n+1)k
+      SFB_CUDA(h, launch_syrk_tri(p, kb, q * kTile, jn + qn, nb, lo));
+      h->launches++;
     }
+    if (two) SFB_CUDA(h, cudaEventRecord(h->ev_lo[lane], lo));
+  }
+  if (two) {  // fold hi back into lo
+    SFB_CUDA(h, cudaEventRecord(h->ev_hi[lane], hi));
+    SFB_CUDA(h, cudaStreamWaitEvent(lo, h->ev_hi[lane], 0));
   }
   return SFB_OK;
 }
@@ -247,7 +304,7 @@ int loglike_device(sfb_ctx* h, int B, const double* X, const double* A, const do
       SFB_CUDA(h, launch_cov_build(bp, nb, st));
       h->launches++;
     }
-    int rc = run_cholesky(h, slot0, nb, lnL + b0, info + b0, st);
+    int rc = run_cholesky(h, si, slot0, nb, lnL + b0, info + b0);
     if (rc != SFB_OK) return rc;
     if (host) {
       SFB_CUDA(h, cudaMemcpyAsync(lnL_h + b0, lnL + b0, sizeof(double) * nb, cudaMemcpyDeviceToHost, st));
@@ -279,6 +336,7 @@ int sfb_create(int device, int N, int M, int Kmax, int Bmax, int workspace_walke
   h->M = M;
   h->Kmax = std::max(Kmax, 1);
   h->Bmax = Bmax;
+  if (const char* dbg = getenv("SFB_DEBUG_MODE")) h->debug_mode = atoi(dbg);
   DeviceGuard guard(device);
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) {
@@ -313,9 +371,14 @@ int sfb_create(int device, int N, int M, int Kmax, int Bmax, int workspace_walke
   ok &= alloc((void**)&h->sigma, sizeof(double) * N);
   ok &= alloc((void**)&h->data_flux, sizeof(double) * N);
   ok &= alloc((void**)&h->sorted, sizeof(int));
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
   for (int i = 0; i < 2 && ok; ++i) {
-    ok &= cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking) == cudaSuccess;
+    ok &= cudaStreamCreateWithPriority(&h->streams[i], cudaStreamNonBlocking, prio_lo) == cudaSuccess;
+    ok &= cudaStreamCreateWithPriority(&h->hi[i], cudaStreamNonBlocking, prio_hi) == cudaSuccess;
     ok &= cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
+    ok &= cudaEventCreateWithFlags(&h->ev_hi[i], cudaEventDisableTiming) == cudaSuccess;
+    ok &= cudaEventCreateWithFlags(&h->ev_lo[i], cudaEventDisableTiming) == cudaSuccess;
   }
   ok = ok && cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess;
   ok = ok && kernels_init() == cudaSuccess;
@@ -338,7 +401,10 @@ int sfb_destroy(sfb_t* h) {
     if (p) cudaFree(p);
   for (int i = 0; i < 2; ++i) {
     if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
+    if (h->hi[i]) cudaStreamDestroy(h->hi[i]);
     if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+    if (h->ev_hi[i]) cudaEventDestroy(h->ev_hi[i]);
+    if (h->ev_lo[i]) cudaEventDestroy(h->ev_lo[i]);
   }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   for (auto& pe : h->prof) {
@@ -417,7 +483,7 @@ int sfb_potrf(sfb_t* h, int B, double* C, int* info, double* logdet, void* strea
   if (B == 0) return SFB_OK;
   DeviceGuard guard(h->device);
   cudaStream_t caller = (cudaStream_t)stream;
-  const int nstreams = (h->profile || h->slots < 2) ? 1 : 2;
+  const int nstreams = (h->profile || h->slots < 2 || (h->debug_mode & 2)) ? 1 : 2;
   if ((rc = fork_streams(h, caller, nstreams)) != SFB_OK) return rc;
   const int per = std::max(1, h->slots / nstreams);
   const long long strideW = (long long)h->Np * h->Np;
@@ -432,7 +498,7 @@ int sfb_potrf(sfb_t* h, int B, double* C, int* info, double* logdet, void* strea
     SFB_CUDA(h, launch_residual(nullptr, nullptr, h->N, h->Np, nb, h->rhs + (long long)slot0 * h->Np, nullptr,
                                 h->logdet + slot0, h->sqmah + slot0, h->info_ws + slot0, st));
     h->launches += 2;
-    if ((rc = run_cholesky(h, slot0, nb, nullptr, info + b0, st)) != SFB_OK) return rc;
+    if ((rc = run_cholesky(h, si, slot0, nb, nullptr, info + b0)) != SFB_OK) return rc;
     SFB_CUDA(h, launch_copy_out_lower(Cb, h->N, h->W + slot0 * strideW, h->Np, strideW, nb, st));
     h->launches++;
     if (logdet)
@@ -465,7 +531,7 @@ int sfb_loglike(sfb_t* h, int B, const double* X, const double* A, const double*
   if (B == 0) return SFB_OK;
   DeviceGuard guard(h->device);
   cudaStream_t caller = (cudaStream_t)stream;
-  const int nstreams = (h->profile || h->slots < 2) ? 1 : 2;
+  const int nstreams = (h->profile || h->slots < 2 || (h->debug_mode & 2)) ? 1 : 2;
   if ((rc = fork_streams(h, caller, nstreams)) != SFB_OK) return rc;
   rc = loglike_device(h, B, X, A, model_flux, glob, nloc, loc, shared_hyper, lnL, info, resid, nstreams, nullptr,
                       nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
@@ -499,7 +565,7 @@ int sfb_loglike_host(sfb_t* h, int B, const double* X_h, const double* A_h, cons
   ok &= lazy((void**)&h->dinfo, sizeof(int) * Bm);
   if (resid_h) ok &= lazy((void**)&h->dresid, sizeof(double) * (size_t)Bm * N);
   if (!ok) return fail(h, SFB_ERR_NOMEM, "sfb_loglike_host: staging allocation failed");
-  const int nstreams = (h->profile || h->slots < 2) ? 1 : 2;
+  const int nstreams = (h->profile || h->slots < 2 || (h->debug_mode & 2)) ? 1 : 2;
   rc = loglike_device(h, B, X_h ? h->dX : nullptr, X_h ? h->dA : nullptr, h->dflux, h->dglob, h->dnloc, h->dloc,
                       shared_hyper, h->dlnL, h->dinfo, resid_h ? h->dresid : nullptr, nstreams, X_h, A_h,
                       model_flux_h, glob_h, nloc_h, loc_h, lnL_h, info_h, resid_h);

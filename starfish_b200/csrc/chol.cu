@@ -118,19 +118,35 @@ __device__ __forceinline__ void gemm_mainloop(double (&acc)[4][4][2], double* sm
 }
 
 // ------------------------------------------------------------------------------------------------
-// syrk: A_ij −= L_ik·L_jkᵀ, tile 128 rows × 64 cols; grid (2T, T, B), tiles right of the diagonal exit
+// syrk: A_ij −= Σ_{k in [kb, kb+K)} L_ik·L_jkᵀ on 128×64 tiles.  Two grid shapes:
+//   strip    (update of a few whole tile columns jt0.. by the K columns [kb, kb+K)): grid (2·ncols, rows, B)
+//   triangle (trailing update of every tile column >= jt0):  grid (T(T+1), 1, B), T = nt − jt0, the
+//            linear block index is decoded to (row tile, 64-column block) so no CTA is launched for the
+//            upper triangle
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(GEMM_THREADS, 2) syrk_kernel(CholParams p) {
-  const int j64 = blockIdx.x, ti = blockIdx.y, s = blockIdx.z;
-  if (j64 > 2 * ti + 1) return;
+__global__ void __launch_bounds__(GEMM_THREADS, 2) syrk_kernel(CholParams p, int kb, int K, int jt0, int strip) {
+  const int s = blockIdx.z;
   if (p.info[s] != 0) return;
+  int it, c0;  // row tile (absolute), first column (absolute)
+  if (strip) {
+    const int jt = jt0 + (blockIdx.x >> 1);
+    it = jt0 + blockIdx.y;
+    if (it < jt) return;  // above the diagonal of this tile column
+    c0 = jt * kTile + (blockIdx.x & 1) * 64;
+  } else {
+    const int L = blockIdx.x;
+    int t = (int)((sqrtf(4.0f * (float)L + 1.0f) - 1.0f) * 0.5f);
+    while (t * (t + 1) > L) --t;
+    while ((t + 1) * (t + 2) <= L) ++t;
+    it = jt0 + t;
+    c0 = jt0 * kTile + (L - t * (t + 1)) * 64;
+  }
   extern __shared__ __align__(16) double smem[];
   double* Wm = p.W + (long long)s * p.strideW;
   const long long ld = p.Np;
-  const int r0 = p.k0 + kTile + ti * 128;
-  const int c0 = p.k0 + kTile + j64 * 64;
-  const double* Ag = Wm + (long long)r0 * ld + p.k0;
-  const double* Bg = Wm + (long long)c0 * ld + p.k0;
+  const int r0 = it * kTile;
+  const double* Ag = Wm + (long long)r0 * ld + kb;
+  const double* Bg = Wm + (long long)c0 * ld + kb;
 
   double acc[4][4][2];
 #pragma unroll
@@ -138,7 +154,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) syrk_kernel(CholParams p) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  gemm_mainloop<128, 64>(acc, smem, Ag, ld, Bg, ld, kTile, 0);
+  gemm_mainloop<128, 64>(acc, smem, Ag, ld, Bg, ld, K, 0);
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wm = warp / 2, wn = warp % 2, g = lane >> 2, t = lane & 3;
@@ -227,7 +243,8 @@ __global__ void __launch_bounds__(PD_THREADS) potrf_diag_kernel(CholParams p, in
   extern __shared__ __align__(16) double smem[];
   double* S = smem;                   // [128][129]: lower = A→L, strict upper = (L⁻¹)ᵀ under construction
   double* dinv = S + kTile * PD_LD;   // [128] diagonal of L⁻¹
-  double* red = dinv + kTile;         // [32] reduction scratch
+  double* ddiag = dinv + kTile;       // [128] diagonal of L
+  double* red = ddiag + kTile;        // [32] reduction scratch
   __shared__ int fail_col;
 
   if (p.info[s] != 0) {
@@ -259,7 +276,8 @@ __global__ void __launch_bounds__(PD_THREADS) potrf_diag_kernel(CholParams p, in
     // phase 1: column j of L (rows > j), row j of L⁻¹ (cols < j, stored transposed), diagonals
     if (tid < kTile) {
       if (tid > j) S[tid * PD_LD + j] = S[tid * PD_LD + j] / d;
-      else if (tid == j) { S[j * PD_LD + j] = d; dinv[j] = 1.0 / d; }
+      else if (tid == j) { ddiag[j] = d; dinv[j] = 1.0 / d; }  // S[j][j] itself is left alone: other
+      // warps may still be reading it as this column's pivot (it is patched after the sweep)
     } else if (tid < 2 * kTile) {
       const int c = tid - kTile;
       if (c < j) S[c * PD_LD + j] = S[c * PD_LD + j] / d;
@@ -280,6 +298,8 @@ __global__ void __launch_bounds__(PD_THREADS) potrf_diag_kernel(CholParams p, in
     }
     __syncthreads();
   }
+  __syncthreads();
+  if (fail_col < 0 && tid < kTile) S[tid * PD_LD + tid] = ddiag[tid];
   __syncthreads();
   if (fail_col >= 0) {
     if (tid == 0) {
@@ -427,22 +447,24 @@ __global__ void __launch_bounds__(256) solve_lower_kernel(const double* __restri
   for (int i = tid; i < N; i += 256) z[(long long)b * N + i] = zs[i];
 }
 
-constexpr size_t kPotrfSmem = sizeof(double) * (kTile * PD_LD + kTile + 32);
+constexpr size_t kPotrfSmem = sizeof(double) * (kTile * PD_LD + 2 * kTile + 32);
 
 }  // namespace
 
 cudaError_t kernels_init() {
-  cudaError_t e;
-  e = cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)GemmSmem<128, 64>::kBytes);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)GemmSmem<64, 128>::kBytes);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPotrfSmem);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(solve_lower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  return e;
+  // Opt in to > 48 KB of dynamic shared memory.  (Forcing the maximum carve-out so that panel CTAs can
+  // co-reside with syrk CTAs was measured to cost the syrk kernel 3.5 % — its epilogue's C tiles go through
+  // L1 — and is therefore not done.)
+  struct Item { const void* fn; int bytes; };
+  const Item items[] = {{(const void*)syrk_kernel, (int)GemmSmem<128, 64>::kBytes},
+                        {(const void*)trsm_kernel, (int)GemmSmem<64, 128>::kBytes},
+                        {(const void*)potrf_diag_kernel, (int)kPotrfSmem},
+                        {(const void*)solve_lower_kernel, 200 * 1024}};
+  for (const Item& it : items) {
+    cudaError_t e = cudaFuncSetAttribute(it.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, it.bytes);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
 }
 
 cudaError_t launch_residual(const double* model_flux, const double* data_flux, int N, int Np, int B,
@@ -466,16 +488,23 @@ cudaError_t launch_potrf_diag(const CholParams& p, int B, int last, double* lnL_
 cudaError_t launch_trsm(const CholParams& p, int B, cudaStream_t st) {
   const int rows = p.Np - p.k0 - kTile;
   if (rows <= 0) return cudaSuccess;
-  dim3 grid(rows / 64, B);
-  trsm_kernel<<<grid, GEMM_THREADS, GemmSmem<64, 128>::kBytes, st>>>(p);
+  trsm_kernel<<<dim3(rows / 64, B), GEMM_THREADS, GemmSmem<64, 128>::kBytes, st>>>(p);
   return cudaGetLastError();
 }
 
-cudaError_t launch_syrk(const CholParams& p, int B, cudaStream_t st) {
-  const int T = (p.Np - p.k0 - kTile) / kTile;
-  if (T <= 0) return cudaSuccess;
-  dim3 grid(2 * T, T, B);
-  syrk_kernel<<<grid, GEMM_THREADS, GemmSmem<128, 64>::kBytes, st>>>(p);
+// update of tile columns [jt0, jt0+njt) (each from its diagonal tile down) by columns [kb, kb+K)
+cudaError_t launch_syrk_strip(const CholParams& p, int kb, int K, int jt0, int njt, int B, cudaStream_t st) {
+  const int rows = p.Np / kTile - jt0;
+  if (rows <= 0 || K <= 0 || njt <= 0) return cudaSuccess;
+  syrk_kernel<<<dim3(2 * njt, rows, B), GEMM_THREADS, GemmSmem<128, 64>::kBytes, st>>>(p, kb, K, jt0, 1);
+  return cudaGetLastError();
+}
+
+// trailing update of every tile column >= jt0 by columns [kb, kb+K)
+cudaError_t launch_syrk_tri(const CholParams& p, int kb, int K, int jt0, int B, cudaStream_t st) {
+  const int T = p.Np / kTile - jt0;
+  if (T <= 0 || K <= 0) return cudaSuccess;
+  syrk_kernel<<<dim3(T * (T + 1), 1, B), GEMM_THREADS, GemmSmem<128, 64>::kBytes, st>>>(p, kb, K, jt0, 0);
   return cudaGetLastError();
 }
 

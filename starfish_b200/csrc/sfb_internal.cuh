@@ -15,6 +15,7 @@ namespace sfb {
 
 constexpr double kC_KMS = 2.99792458e5;  // Starfish/constants.py:7
 constexpr int kTile = 128;               // factorisation panel width / tile edge
+constexpr int kOuterTiles = 4;           // tile columns per outer block: trailing updates run with K = 512
 constexpr int kMaxM = 16;                // max eigenspectra handled by the fused build kernel
 constexpr int kMaxK = 32;                // max local kernels per walker
 
@@ -67,7 +68,8 @@ cudaError_t launch_residual(const double* model_flux, const double* data_flux, i
 cudaError_t launch_potrf_diag(const CholParams& p, int B, int last, double* lnL_out, int* info_out,
                               cudaStream_t st);
 cudaError_t launch_trsm(const CholParams& p, int B, cudaStream_t st);
-cudaError_t launch_syrk(const CholParams& p, int B, cudaStream_t st);
+cudaError_t launch_syrk_strip(const CholParams& p, int kb, int K, int jt0, int njt, int B, cudaStream_t st);
+cudaError_t launch_syrk_tri(const CholParams& p, int kb, int K, int jt0, int B, cudaStream_t st);
 cudaError_t launch_copy_in_lower(const double* C, int N, double* W, int Np, long long strideW, int B,
                                  cudaStream_t st);
 cudaError_t launch_copy_out_lower(double* C, int N, const double* W, int Np, long long strideW, int B,
