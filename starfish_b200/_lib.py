@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsfb200.so")
+LIB_PATH = os.environ.get("SFB200_LIB", os.path.join(_HERE, "libsfb200.so"))  # override: dev experiments only
 
 EXPORTS = [
     "sfb_abi_version", "sfb_create", "sfb_destroy", "sfb_set_static", "sfb_set_static_host",

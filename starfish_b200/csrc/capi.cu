@@ -32,6 +32,7 @@ struct sfb_ctx {
   double* data_flux = nullptr;
   int* sorted = nullptr;
   bool have_static = false;
+  GemmMaps maps;
   // device staging for the host-buffer path
   double *dX = nullptr, *dA = nullptr, *dflux = nullptr, *dglob = nullptr, *dloc = nullptr, *dlnL = nullptr,
          *dresid = nullptr;
@@ -174,7 +175,7 @@ int run_cholesky(sfb_ctx* h, int lane, int slot0, int nb, double* lnL_out, int* 
       if (c > 0) {
         const double rows = (double)(h->Np - p.k0), K = (double)c * kTile;
         ProfScope ps(h, hi, SFB_K_SYRK, nb * (2.0 * K * kTile * rows - K * kTile * (kTile - 1.0)));
-        SFB_CUDA(h, launch_syrk_strip(p, kb, c * kTile, jt, 1, nb, hi));
+        SFB_CUDA(h, launch_syrk_strip(p, h->maps, slot0, kb, c * kTile, jt, 1, nb, hi));
         h->launches++;
       }
       {
@@ -184,7 +185,7 @@ int run_cholesky(sfb_ctx* h, int lane, int slot0, int nb, double* lnL_out, int* 
       }
       if (!last) {
         ProfScope ps(h, hi, SFB_K_TRSM, nb * (rem * kTile * kTile));  // useful FLOPs of a triangular solve
-        SFB_CUDA(h, launch_trsm(p, nb, hi));
+        SFB_CUDA(h, launch_trsm(p, h->maps, slot0, nb, hi));
         h->launches++;
       }
     }
@@ -200,13 +201,13 @@ int run_cholesky(sfb_ctx* h, int lane, int slot0, int nb, double* lnL_out, int* 
     {  // ---- NEXT(J): tile columns [jn, jn+qn), on hi
       const double rows = (double)(h->Np - jn * kTile), w = (double)qn * kTile;
       ProfScope ps(h, hi, SFB_K_SYRK, nb * (2.0 * K * w * rows - K * w * (w - 1.0)));
-      SFB_CUDA(h, launch_syrk_strip(p, kb, q * kTile, jn, qn, nb, hi));
+      SFB_CUDA(h, launch_syrk_strip(p, h->maps, slot0, kb, q * kTile, jn, qn, nb, hi));
       h->launches++;
     }
     if (jn + qn < nt) {  // ---- REST(J): everything right of the next block, on lo
       const double n = (double)(h->Np - (jn + qn) * kTile);
       ProfScope ps(h, lo, SFB_K_SYRK, nb * (n * (n + 1.0) * K));  // algorithmic syrk FLOPs: n(n+1)k
-      SFB_CUDA(h, launch_syrk_tri(p, kb, q * kTile, jn + qn, nb, lo));
+      SFB_CUDA(h, launch_syrk_tri(p, h->maps, slot0, kb, q * kTile, jn + qn, nb, lo));
       h->launches++;
     }
     if (two) SFB_CUDA(h, cudaEventRecord(h->ev_lo[lane], lo));
@@ -382,6 +383,7 @@ int sfb_create(int device, int N, int M, int Kmax, int Bmax, int workspace_walke
   }
   ok = ok && cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess;
   ok = ok && kernels_init() == cudaSuccess;
+  ok = ok && make_gemm_maps(&h->maps, h->W, h->Np, h->Minv, h->slots) == cudaSuccess;
   if (!ok) {
     sfb_destroy(h);
     return SFB_ERR_NOMEM;
@@ -407,6 +409,7 @@ int sfb_destroy(sfb_t* h) {
     if (h->ev_lo[i]) cudaEventDestroy(h->ev_lo[i]);
   }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  free_gemm_maps(&h->maps);
   for (auto& pe : h->prof) {
     cudaEventDestroy(pe.a);
     cudaEventDestroy(pe.b);

@@ -16,8 +16,10 @@
 // Tensor cores: fp64 has no tcgen05 kind; the B200 fp64 tensor path is mma.sync m8n8k4 (SASS
 // DMMA.8x8x4), measured at 37.1 TFLOP/s = the nominal fp64 peak (tools/fp64_peak.cu) while plain DFMA
 // tops out at 33.8 — hence DMMA.  Operands are K-contiguous in memory for both factors (rows of L), so
-// tiles go global→shared with 16-byte cp.async through a 3-stage ring, rows padded to 20 doubles so
-// that the 8×4 fragment loads are bank-conflict-free.
+// tiles go global→shared by TMA (cp.async.bulk.tensor, SWIZZLE_128B) through a 4-stage mbarrier ring; a
+// row permutation of the fragments makes the swizzled 16-byte loads bank-conflict-free.
+#include <cuda.h>
+
 #include "sfb_internal.cuh"
 
 namespace sfb {
@@ -32,89 +34,187 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "+d"(c0), "+d"(c1)
                : "d"(a), "d"(b));
 }
-__device__ __forceinline__ void cp_async16(void* smem_ptr, const void* gmem_ptr) {
-  unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_ptr));
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_ptr));
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N));
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_test(bar, parity)) {
+  }
+}
+// Explicit shared-space 16-byte load.  Must be a real LDS: shared loads and mbarrier arrives go through
+// the same in-order pipe, which is what makes "arrive on the empty barrier after the last read" safe; a
+// generic-address load (which the compiler emits for pointers that went through integer arithmetic) can
+// still be in flight when the arrive lands and the slot is refilled by TMA.
+__device__ __forceinline__ double2 lds128(uint32_t addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
+// TMA: 3-D tiled bulk tensor load global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------
-// NT GEMM core:  acc[r][c] = Σ_k Aop[r][k]·Bop[c][k]   (both operands K-contiguous)
-//   CTA tile BM×BN, 8 warps, warp tile 32×32 = 4×4 DMMA tiles, BK = 16 doubles per stage.
+// NT GEMM core:  acc[r][c] = Σ_k Aop[r][k]·Bop[c][k]   (both operands K-contiguous rows of L or L_kk⁻¹)
+//
+//   CTA tile BM×BN with BM+BN = 192, 8 warps, warp tile 32×32 = 4×4 DMMA tiles.
+//   Operands arrive by TMA: per k-slab of 16 doubles one elected thread issues three 64-row × 128-byte
+//   boxes (SWIZZLE_128B) into a 4-deep ring of 24 KB stages; `full` mbarriers count the bytes, `empty`
+//   mbarriers count the 8 consumer warps.  No __syncthreads in the loop: warps drift by up to a slab.
+//
+//   Shared-memory layout of a stage: row r (128 B) of the box at r·128, its 16-byte chunk c at
+//   ((c ^ (r & 7)) << 4).  Thread (g = lane/4, t = lane%4) reads, for each of its 8-row tiles, chunk t and
+//   chunk t+4 of row ρ(g) = (g>>1)|((g&1)<<2) with one LDS.128 each: within every quarter-warp the two
+//   rows differ in bit 2, so the eight 16-byte chunks are distinct -> conflict-free.  A chunk holds
+//   k = 2c, 2c+1; DMMA "k-group" (h, e) therefore uses k = 2(t+4h)+e for both operands.
+//   Consequence for the accumulators: fragment row g is tile row ρ(g), fragment columns 2t, 2t+1 are
+//   tile columns t and t+4.
 // ------------------------------------------------------------------------------------------------
 constexpr int BK = 16;
-constexpr int LDS = 20;  // padded smem row (doubles): bank = (40·g + 2·t) mod 32 -> conflict-free
-constexpr int STAGES = 3;
+constexpr int ROW_BYTES = 128;
+constexpr int STAGES = 4;
+constexpr int STAGE_BYTES = 192 * ROW_BYTES;  // 24 KB
 constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 2 * STAGES * 8;
 
-template <int BM, int BN>
-struct GemmSmem {
-  static constexpr int kStageDoubles = (BM + BN) * LDS;
-  static constexpr size_t kBytes = sizeof(double) * kStageDoubles * STAGES;
+struct GemmOperand {
+  const CUtensorMap* map;
+  int col0;   // first k column
+  int row0;   // first row of the operand tile
+  int slot;   // walker slot (3rd tensor coordinate)
 };
 
 template <int BM, int BN>
-__device__ __forceinline__ void gemm_load_stage(double* stage, const double* __restrict__ Ag, long long lda,
-                                                const double* __restrict__ Bg, long long ldb, int kk, int tid) {
-  // (BM+BN) rows × 8 chunks of 16 B
-  constexpr int CHUNKS = (BM + BN) * (BK / 2);
-#pragma unroll
-  for (int c = tid; c < CHUNKS; c += GEMM_THREADS) {
-    const int row = c >> 3, ch = c & 7;
-    const double* src = (row < BM) ? (Ag + (long long)row * lda + kk + 2 * ch)
-                                   : (Bg + (long long)(row - BM) * ldb + kk + 2 * ch);
-    cp_async16(stage + row * LDS + 2 * ch, src);
-  }
-}
-
-// acc layout: acc[mt][nt][2] for the warp's 4×4 grid of 8×8 DMMA tiles
-template <int BM, int BN>
-__device__ __forceinline__ void gemm_mainloop(double (&acc)[4][4][2], double* smem,
-                                              const double* __restrict__ Ag, long long lda,
-                                              const double* __restrict__ Bg, long long ldb, int K,
-                                              int kt_begin_skip_b /*unused*/) {
+__device__ __forceinline__ void gemm_mainloop(double (&acc)[4][4][2], uint8_t* smem_raw, const GemmOperand A,
+                                              const GemmOperand B, int K, int warp_slabs) {
+  static_assert(BM + BN == 192 && BM % 64 == 0 && BN % 64 == 0, "tile shape");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int WN_CNT = BN / 32;
   const int wm = warp / WN_CNT, wn = warp % WN_CNT;
   const int g = lane >> 2, t = lane & 3;
   const int KT = K / BK;
-  constexpr int SD = GemmSmem<BM, BN>::kStageDoubles;
 
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;  // full[s] at +8s, empty[s] at +8(STAGES+s)
+
+  if (tid == 0) {
 #pragma unroll
-  for (int s = 0; s < STAGES - 1; ++s) {
-    if (s < KT) gemm_load_stage<BM, BN>(smem + s * SD, Ag, lda, Bg, ldb, s * BK, tid);
-    cp_async_commit();
-  }
-  for (int it = 0; it < KT; ++it) {
-    cp_async_wait<STAGES - 2>();
-    __syncthreads();
-    {
-      const int nx = it + STAGES - 1;
-      if (nx < KT) gemm_load_stage<BM, BN>(smem + (nx % STAGES) * SD, Ag, lda, Bg, ldb, nx * BK, tid);
-      cp_async_commit();
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_base + 8 * s, 1);
+      mbar_init(bar_base + 8 * (STAGES + s), GEMM_THREADS / 32);
     }
-    const double* As = smem + (it % STAGES) * SD + (wm * 32 + g) * LDS + t;
-    const double* Bs = smem + (it % STAGES) * SD + (BM + wn * 32 + g) * LDS + t;
-#pragma unroll
-    for (int q = 0; q < BK / 4; ++q) {
-      double a[4], b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        a[i] = As[i * 8 * LDS + 4 * q];
-        b[i] = Bs[i * 8 * LDS + 4 * q];
-      }
-#pragma unroll
-      for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
-    }
+    mbar_fence_init();
   }
-  cp_async_wait<0>();
   __syncthreads();
+
+  auto issue = [&](int slab) {
+    const int slot = slab % STAGES;
+    const uint32_t dst = smem_base + slot * STAGE_BYTES;
+    const uint32_t bar = bar_base + 8 * slot;
+    mbar_arrive_expect_tx(bar, STAGE_BYTES);
+#pragma unroll
+    for (int rb = 0; rb < BM / 64; ++rb)
+      tma_load_3d(dst + rb * 64 * ROW_BYTES, A.map, bar, A.col0 + slab * BK, A.row0 + rb * 64, A.slot);
+#pragma unroll
+    for (int rb = 0; rb < BN / 64; ++rb)
+      tma_load_3d(dst + (BM + rb * 64) * ROW_BYTES, B.map, bar, B.col0 + slab * BK, B.row0 + rb * 64, B.slot);
+  };
+
+  int next_issue = 0;  // only meaningful in thread 0
+  if (tid == 0) {
+    for (; next_issue < STAGES - 1 && next_issue < KT; ++next_issue) issue(next_issue);
+  }
+  // slab j may be (re)issued into its slot once slab j-STAGES has been released by all 8 warps
+  auto try_issue = [&](bool block) {
+    if (next_issue >= KT) return;
+    if (next_issue >= STAGES) {
+      const int prev = next_issue - STAGES;
+      const uint32_t bar = bar_base + 8 * (STAGES + prev % STAGES);
+      const uint32_t par = (prev / STAGES) & 1;
+      if (block) mbar_wait(bar, par);
+      else if (!mbar_test(bar, par)) return;
+    }
+    issue(next_issue);
+    ++next_issue;
+  };
+
+  const int rho = (g >> 1) | ((g & 1) << 2);
+  const uint32_t a_off = (wm * 32 + rho) * ROW_BYTES;
+  const uint32_t b_off = (BM + wn * 32 + rho) * ROW_BYTES;
+  const uint32_t x0 = (t ^ rho) << 4, x1 = ((t + 4) ^ rho) << 4;
+
+  for (int it = 0; it < KT; ++it) {
+    const int slot = it % STAGES;
+    if (tid == 0) {
+      while (next_issue <= it) try_issue(true);  // the slab about to be consumed must be in flight
+      try_issue(false);
+    }
+    mbar_wait(bar_base + 8 * slot, (it / STAGES) & 1);
+    if (it < warp_slabs) {
+      const uint32_t st = smem_base + slot * STAGE_BYTES;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t x = h ? x1 : x0;
+        double2 a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          a[i] = lds128(st + a_off + i * 8 * ROW_BYTES + x);
+          b[i] = lds128(st + b_off + i * 8 * ROW_BYTES + x);
+        }
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt].x, b[nt].x);
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt].y, b[nt].y);
+        if (h == 0 && tid == 0) try_issue(false);
+      }
+    }
+    // Release the slot.  The fence is load-bearing: without it ptxas hoists the arrive above the last
+    // DMMA group (they have no register dependence), i.e. right behind the *issue* of the last LDS, and an
+    // arrive can then overtake shared-memory reads that are still queued in the LSU — the producer refills
+    // the slot by TMA and those reads return the next slab's data (seen as sporadic 1e-6…1e-1 errors once
+    // the workspace no longer fits L2 and warps drift apart).  The CTA-scope fence completes this thread's
+    // outstanding loads first; it costs nothing measurable (syrk went from 88 % to 92 % of DMMA peak with
+    // the TMA ring including it).
+    asm volatile("fence.acq_rel.cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_base + 8 * (STAGES + slot));
+  }
+  __syncthreads();  // every warp is past its last shared-memory read: the ring may be reused by the caller
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -124,7 +224,8 @@ __device__ __forceinline__ void gemm_mainloop(double (&acc)[4][4][2], double* sm
 //            linear block index is decoded to (row tile, 64-column block) so no CTA is launched for the
 //            upper triangle
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(GEMM_THREADS, 2) syrk_kernel(CholParams p, int kb, int K, int jt0, int strip) {
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+    syrk_kernel(const __grid_constant__ CUtensorMap tmW, CholParams p, int slot0, int kb, int K, int jt0, int strip) {
   const int s = blockIdx.z;
   if (p.info[s] != 0) return;
   int it, c0;  // row tile (absolute), first column (absolute)
@@ -141,12 +242,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) syrk_kernel(CholParams p, int
     it = jt0 + t;
     c0 = jt0 * kTile + (L - t * (t + 1)) * 64;
   }
-  extern __shared__ __align__(16) double smem[];
+  extern __shared__ uint8_t smem_raw[];
   double* Wm = p.W + (long long)s * p.strideW;
   const long long ld = p.Np;
   const int r0 = it * kTile;
-  const double* Ag = Wm + (long long)r0 * ld + kb;
-  const double* Bg = Wm + (long long)c0 * ld + kb;
 
   double acc[4][4][2];
 #pragma unroll
@@ -154,41 +253,45 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) syrk_kernel(CholParams p, int
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  gemm_mainloop<128, 64>(acc, smem, Ag, ld, Bg, ld, K, 0);
+  const GemmOperand opA{&tmW, kb, r0, slot0 + s}, opB{&tmW, kb, c0, slot0 + s};
+  gemm_mainloop<128, 64>(acc, smem_raw, opA, opB, K, K / BK);
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wm = warp / 2, wn = warp % 2, g = lane >> 2, t = lane & 3;
-  double* Cg = Wm + (long long)(r0 + wm * 32 + g) * ld + c0 + wn * 32 + 2 * t;
-  double2 cv[4][4];
-#pragma unroll
-  for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
-      cv[mt][nt] = *reinterpret_cast<const double2*>(Cg + (long long)mt * 8 * ld + nt * 8);
+  const int rho = (g >> 1) | ((g & 1) << 2);
+  double* Cg = Wm + (long long)(r0 + wm * 32 + rho) * ld + c0 + wn * 32 + t;
+  double cv[4][4][2];
 #pragma unroll
   for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
-      double2 v = cv[mt][nt];
-      v.x -= acc[mt][nt][0];
-      v.y -= acc[mt][nt][1];
-      *reinterpret_cast<double2*>(Cg + (long long)mt * 8 * ld + nt * 8) = v;
+      cv[mt][nt][0] = Cg[(long long)mt * 8 * ld + nt * 8];
+      cv[mt][nt][1] = Cg[(long long)mt * 8 * ld + nt * 8 + 4];
+    }
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      Cg[(long long)mt * 8 * ld + nt * 8] = cv[mt][nt][0] - acc[mt][nt][0];
+      Cg[(long long)mt * 8 * ld + nt * 8 + 4] = cv[mt][nt][1] - acc[mt][nt][1];
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // trsm: L_ik = A_ik·Mᵀ (M = L_kk⁻¹, lower), tile 64 rows × 128 cols (whole panel width, so the in-place
-// overwrite is private to the CTA), then rhs_i −= L_ik·z_k.   grid (rows/64, B)
+// overwrite is private to the CTA), then rhs_i −= L_ik·z_k.   grid (rows/64, B).
+// M is lower triangular: output columns [32·wn, 32·wn+32) only need k < 32·(wn+1), so each warp skips the
+// k-slabs beyond its columns.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(GEMM_THREADS, 2) trsm_kernel(CholParams p) {
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+    trsm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmM, CholParams p,
+                int slot0) {
   const int rb = blockIdx.x, s = blockIdx.y;
   if (p.info[s] != 0) return;
-  extern __shared__ __align__(16) double smem[];
+  extern __shared__ uint8_t smem_raw[];
   double* Wm = p.W + (long long)s * p.strideW;
   const long long ld = p.Np;
   const int r0 = p.k0 + kTile + rb * 64;
-  const double* Ag = Wm + (long long)r0 * ld + p.k0;
-  const double* Bg = p.Minv + (long long)s * kTile * kTile;
 
   double acc[4][4][2];
 #pragma unroll
@@ -196,32 +299,35 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) trsm_kernel(CholParams p) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  gemm_mainloop<64, 128>(acc, smem, Ag, ld, Bg, kTile, kTile, 0);
-
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wm = warp / 4, wn = warp % 4, g = lane >> 2, t = lane & 3;
-  double* Cg = Wm + (long long)(r0 + wm * 32 + g) * ld + p.k0 + wn * 32 + 2 * t;
-  const double* zk = p.zk + (long long)s * kTile + wn * 32 + 2 * t;
+  const GemmOperand opA{&tmW, p.k0, r0, slot0 + s}, opB{&tmM, 0, 0, slot0 + s};
+  gemm_mainloop<64, 128>(acc, smem_raw, opA, opB, kTile, 2 * (wn + 1));
+
+  const int rho = (g >> 1) | ((g & 1) << 2);
+  double* Cg = Wm + (long long)(r0 + wm * 32 + rho) * ld + p.k0 + wn * 32 + t;
+  const double* zk = p.zk + (long long)s * kTile + wn * 32 + t;
   double part[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
   for (int nt = 0; nt < 4; ++nt) {
-    const double z0 = zk[nt * 8], z1 = zk[nt * 8 + 1];
+    const double z0 = zk[nt * 8], z1 = zk[nt * 8 + 4];
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt) {
-      *reinterpret_cast<double2*>(Cg + (long long)mt * 8 * ld + nt * 8) =
-          make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+      Cg[(long long)mt * 8 * ld + nt * 8] = acc[mt][nt][0];
+      Cg[(long long)mt * 8 * ld + nt * 8 + 4] = acc[mt][nt][1];
       part[mt] = fma(acc[mt][nt][0], z0, part[mt]);
       part[mt] = fma(acc[mt][nt][1], z1, part[mt]);
     }
   }
   // reduce over the 4 lanes sharing a row, then over the 4 column-warps in a fixed order
-  double* red = smem;  // [4 wn][64 rows]  (mainloop ended with a __syncthreads, smem is free)
+  double* red = reinterpret_cast<double*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));  // [4 wn][64 rows], ring is idle now
 #pragma unroll
   for (int mt = 0; mt < 4; ++mt) {
     double v = part[mt];
     v += __shfl_xor_sync(0xffffffffu, v, 1);
     v += __shfl_xor_sync(0xffffffffu, v, 2);
-    if (t == 0) red[wn * 64 + wm * 32 + mt * 8 + g] = v;
+    if (t == 0) red[wn * 64 + wm * 32 + mt * 8 + rho] = v;
   }
   __syncthreads();
   if (threadIdx.x < 64) {
@@ -456,8 +562,8 @@ cudaError_t kernels_init() {
   // co-reside with syrk CTAs was measured to cost the syrk kernel 3.5 % — its epilogue's C tiles go through
   // L1 — and is therefore not done.)
   struct Item { const void* fn; int bytes; };
-  const Item items[] = {{(const void*)syrk_kernel, (int)GemmSmem<128, 64>::kBytes},
-                        {(const void*)trsm_kernel, (int)GemmSmem<64, 128>::kBytes},
+  const Item items[] = {{(const void*)syrk_kernel, GEMM_SMEM_BYTES},
+                        {(const void*)trsm_kernel, GEMM_SMEM_BYTES},
                         {(const void*)potrf_diag_kernel, (int)kPotrfSmem},
                         {(const void*)solve_lower_kernel, 200 * 1024}};
   for (const Item& it : items) {
@@ -485,27 +591,68 @@ cudaError_t launch_potrf_diag(const CholParams& p, int B, int last, double* lnL_
   return cudaGetLastError();
 }
 
-cudaError_t launch_trsm(const CholParams& p, int B, cudaStream_t st) {
+cudaError_t launch_trsm(const CholParams& p, const GemmMaps& m, int slot0, int B, cudaStream_t st) {
   const int rows = p.Np - p.k0 - kTile;
   if (rows <= 0) return cudaSuccess;
-  trsm_kernel<<<dim3(rows / 64, B), GEMM_THREADS, GemmSmem<64, 128>::kBytes, st>>>(p);
+  trsm_kernel<<<dim3(rows / 64, B), GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(*m.W, *m.Minv, p, slot0);
   return cudaGetLastError();
 }
 
 // update of tile columns [jt0, jt0+njt) (each from its diagonal tile down) by columns [kb, kb+K)
-cudaError_t launch_syrk_strip(const CholParams& p, int kb, int K, int jt0, int njt, int B, cudaStream_t st) {
+cudaError_t launch_syrk_strip(const CholParams& p, const GemmMaps& m, int slot0, int kb, int K, int jt0, int njt,
+                              int B, cudaStream_t st) {
   const int rows = p.Np / kTile - jt0;
   if (rows <= 0 || K <= 0 || njt <= 0) return cudaSuccess;
-  syrk_kernel<<<dim3(2 * njt, rows, B), GEMM_THREADS, GemmSmem<128, 64>::kBytes, st>>>(p, kb, K, jt0, 1);
+  syrk_kernel<<<dim3(2 * njt, rows, B), GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(*m.W, p, slot0, kb, K, jt0, 1);
   return cudaGetLastError();
 }
 
 // trailing update of every tile column >= jt0 by columns [kb, kb+K)
-cudaError_t launch_syrk_tri(const CholParams& p, int kb, int K, int jt0, int B, cudaStream_t st) {
+cudaError_t launch_syrk_tri(const CholParams& p, const GemmMaps& m, int slot0, int kb, int K, int jt0, int B,
+                            cudaStream_t st) {
   const int T = p.Np / kTile - jt0;
   if (T <= 0 || K <= 0) return cudaSuccess;
-  syrk_kernel<<<dim3(T * (T + 1), 1, B), GEMM_THREADS, GemmSmem<128, 64>::kBytes, st>>>(p, kb, K, jt0, 0);
+  syrk_kernel<<<dim3(T * (T + 1), 1, B), GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(*m.W, p, slot0, kb, K, jt0, 0);
   return cudaGetLastError();
+}
+
+// Tensor maps for TMA: 3-D {k (inner), row, slot}, box {16 doubles, 64 rows, 1}, 128-byte swizzle.
+cudaError_t make_gemm_maps(GemmMaps* out, double* W, int Np, double* Minv, int slots) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                               const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+  if (e != cudaSuccess) return e;
+  if (!fn || q != cudaDriverEntryPointSuccess) return cudaErrorNotSupported;
+  EncodeFn encode = reinterpret_cast<EncodeFn>(fn);
+  out->W = new CUtensorMap;
+  out->Minv = new CUtensorMap;
+  const cuuint32_t box[3] = {BK, 64, 1}, estr[3] = {1, 1, 1};
+  {
+    const cuuint64_t dims[3] = {(cuuint64_t)Np, (cuuint64_t)Np, (cuuint64_t)slots};
+    const cuuint64_t strides[2] = {(cuuint64_t)Np * 8, (cuuint64_t)Np * Np * 8};
+    CUresult r = encode(out->W, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, W, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+  }
+  {
+    const cuuint64_t dims[3] = {(cuuint64_t)kTile, (cuuint64_t)kTile, (cuuint64_t)slots};
+    const cuuint64_t strides[2] = {(cuuint64_t)kTile * 8, (cuuint64_t)kTile * kTile * 8};
+    CUresult r = encode(out->Minv, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, Minv, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+  }
+  return cudaSuccess;
+}
+
+void free_gemm_maps(GemmMaps* m) {
+  delete m->W;
+  delete m->Minv;
+  m->W = m->Minv = nullptr;
 }
 
 cudaError_t launch_copy_in_lower(const double* C, int N, double* W, int Np, long long strideW, int B,

@@ -11,6 +11,8 @@
 #error "libsfb200 is written for sm_100a (B200) only"
 #endif
 
+struct CUtensorMap_st;  // <cuda.h>
+
 namespace sfb {
 
 constexpr double kC_KMS = 2.99792458e5;  // Starfish/constants.py:7
@@ -67,9 +69,17 @@ cudaError_t launch_residual(const double* model_flux, const double* data_flux, i
                             cudaStream_t st);
 cudaError_t launch_potrf_diag(const CholParams& p, int B, int last, double* lnL_out, int* info_out,
                               cudaStream_t st);
-cudaError_t launch_trsm(const CholParams& p, int B, cudaStream_t st);
-cudaError_t launch_syrk_strip(const CholParams& p, int kb, int K, int jt0, int njt, int B, cudaStream_t st);
-cudaError_t launch_syrk_tri(const CholParams& p, int kb, int K, int jt0, int B, cudaStream_t st);
+struct GemmMaps {  // TMA tensor maps over the factorisation workspace and the per-slot L_kk⁻¹ buffers
+  CUtensorMap_st* W = nullptr;
+  CUtensorMap_st* Minv = nullptr;
+};
+cudaError_t make_gemm_maps(GemmMaps* out, double* W, int Np, double* Minv, int slots);
+void free_gemm_maps(GemmMaps* m);
+cudaError_t launch_trsm(const CholParams& p, const GemmMaps& m, int slot0, int B, cudaStream_t st);
+cudaError_t launch_syrk_strip(const CholParams& p, const GemmMaps& m, int slot0, int kb, int K, int jt0, int njt,
+                              int B, cudaStream_t st);
+cudaError_t launch_syrk_tri(const CholParams& p, const GemmMaps& m, int slot0, int kb, int K, int jt0, int B,
+                            cudaStream_t st);
 cudaError_t launch_copy_in_lower(const double* C, int N, double* W, int Np, long long strideW, int B,
                                  cudaStream_t st);
 cudaError_t launch_copy_out_lower(double* C, int N, const double* W, int Np, long long strideW, int B,
