@@ -20,6 +20,8 @@
 // row permutation of the fragments makes the swizzled 16-byte loads bank-conflict-free.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "sfb_internal.cuh"
 
 namespace sfb {
@@ -105,7 +107,7 @@ constexpr int ROW_BYTES = 128;
 constexpr int STAGES = 4;
 constexpr int STAGE_BYTES = 192 * ROW_BYTES;  // 24 KB
 constexpr int GEMM_THREADS = 256;
-constexpr int GEMM_SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 2 * STAGES * 8;
+constexpr int GEMM_SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STAGES * 8;  // ring + mbarriers, no slack
 
 struct GemmOperand {
   const CUtensorMap* map;
@@ -124,8 +126,11 @@ __device__ __forceinline__ void gemm_mainloop(double (&acc)[4][4][2], uint8_t* s
   const int g = lane >> 2, t = lane & 3;
   const int KT = K / BK;
 
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t smem_base = smem_u32(smem);
+  // SWIZZLE_128B needs the ring 1024-byte aligned.  The kernels have no static shared memory, so the
+  // dynamic window starts at the CTA's (1 KB-granular) allocation base; verified rather than padded,
+  // because every KB counts for co-residency with the panel kernels.
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if (smem_base & 1023u) __trap();
   const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;  // full[s] at +8s, empty[s] at +8(STAGES+s)
 
   if (tid == 0) {
@@ -242,7 +247,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2)
     it = jt0 + t;
     c0 = jt0 * kTile + (L - t * (t + 1)) * 64;
   }
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   double* Wm = p.W + (long long)s * p.strideW;
   const long long ld = p.Np;
   const int r0 = it * kTile;
@@ -288,7 +293,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2)
                 int slot0) {
   const int rb = blockIdx.x, s = blockIdx.y;
   if (p.info[s] != 0) return;
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   double* Wm = p.W + (long long)s * p.strideW;
   const long long ld = p.Np;
   const int r0 = p.k0 + kTile + rb * 64;
@@ -320,8 +325,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2)
     }
   }
   // reduce over the 4 lanes sharing a row, then over the 4 column-warps in a fixed order
-  double* red = reinterpret_cast<double*>(
-      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));  // [4 wn][64 rows], ring is idle now
+  double* red = reinterpret_cast<double*>(smem_raw);  // [4 wn][64 rows], the ring is idle now
 #pragma unroll
   for (int mt = 0; mt < 4; ++mt) {
     double v = part[mt];
@@ -341,17 +345,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2)
 // potrf_diag: factor + invert the diagonal tile, solve the panel's slice of the right-hand side
 // ------------------------------------------------------------------------------------------------
 constexpr int PD_THREADS = 512;
-constexpr int PD_LD = 129;  // odd stride: row and column sweeps are both conflict-free
+// The tile lives in shared memory UNPADDED (128 KB) with an XOR swizzle — element (r, c) at r·128 + (c ^ r) —
+// so that row sweeps and column sweeps are both bank-conflict-free.  The footprint matters: together with
+// one resident syrk/trsm CTA (96 KB ring) it must fit the SM's 228 KB, otherwise the high-priority panel
+// stream can never slip a potrf CTA in between the trailing-update CTAs (look-ahead would be moot).
+#define PD_AT(r, c) ((((r)) << 7) | (((c)) ^ ((r))))
 
-__global__ void __launch_bounds__(PD_THREADS) potrf_diag_kernel(CholParams p, int last, double* lnL_out,
-                                                                 int* info_out) {
+__global__ void __launch_bounds__(PD_THREADS, 1) potrf_diag_kernel(CholParams p, int last, double* lnL_out,
+                                                                    int* info_out) {
   const int s = blockIdx.x, tid = threadIdx.x;
   extern __shared__ __align__(16) double smem[];
-  double* S = smem;                   // [128][129]: lower = A→L, strict upper = (L⁻¹)ᵀ under construction
-  double* dinv = S + kTile * PD_LD;   // [128] diagonal of L⁻¹
-  double* ddiag = dinv + kTile;       // [128] diagonal of L
+  double* S = smem;                   // [128×128]: lower = A→L, strict upper = (L⁻¹)ᵀ under construction
+  double* ddiag = S + kTile * kTile;  // [128] diagonal of L (S[j][j] keeps the pivot until the sweep ends)
   double* red = ddiag + kTile;        // [32] reduction scratch
-  __shared__ int fail_col;
+  int& fail_col = *reinterpret_cast<int*>(red + 32);  // (no static shared memory: keeps the footprint exact)
 
   if (p.info[s] != 0) {
     if (last && tid == 0) {
@@ -366,46 +373,46 @@ __global__ void __launch_bounds__(PD_THREADS) potrf_diag_kernel(CholParams p, in
 
   for (int e = tid; e < kTile * kTile; e += PD_THREADS) {
     const int r = e >> 7, c = e & 127;
-    S[r * PD_LD + c] = (c <= r) ? Ag[(long long)r * ld + c] : 0.0;
+    S[PD_AT(r, c)] = (c <= r) ? Ag[(long long)r * ld + c] : 0.0;
   }
   if (tid == 0) fail_col = -1;
   __syncthreads();
 
   const int x = tid & 127, iq = tid >> 7;  // element column, row phase (4 rows per sweep)
   for (int j = 0; j < kTile; ++j) {
-    const double piv = S[j * PD_LD + j];
+    const double piv = S[PD_AT(j, j)];
     if (!(piv > 0.0) || isinf(piv)) {  // also catches NaN
       if (tid == 0) fail_col = j;
-      break;                           // uniform: every thread reads the same pivot
+      break;                           // uniform: every thread reads the same, untouched pivot
     }
     const double d = sqrt(piv);
-    // phase 1: column j of L (rows > j), row j of L⁻¹ (cols < j, stored transposed), diagonals
+    // phase 1: column j of L (rows > j), row j of L⁻¹ (cols < j, stored transposed), diagonal
     if (tid < kTile) {
-      if (tid > j) S[tid * PD_LD + j] = S[tid * PD_LD + j] / d;
-      else if (tid == j) { ddiag[j] = d; dinv[j] = 1.0 / d; }  // S[j][j] itself is left alone: other
-      // warps may still be reading it as this column's pivot (it is patched after the sweep)
+      if (tid > j) S[PD_AT(tid, j)] = S[PD_AT(tid, j)] / d;
+      else if (tid == j) ddiag[j] = d;  // S[j][j] itself is left alone: other warps may still be
+                                        // reading it as this column's pivot (patched after the sweep)
     } else if (tid < 2 * kTile) {
       const int c = tid - kTile;
-      if (c < j) S[c * PD_LD + j] = S[c * PD_LD + j] / d;
+      if (c < j) S[PD_AT(c, j)] = S[PD_AT(c, j)] / d;
     }
     __syncthreads();
     // phase 2: rows i > j.  x in (j, i]: trailing update;  x < j: T[i][x] -= L[i][j]·M[j][x];
     //          x == j: T[i][j] = -L[i][j]/d
-    const double dj = dinv[j];
+    const double dj = 1.0 / d;
     for (int i = j + 1 + iq; i < kTile; i += 4) {
-      const double lij = S[i * PD_LD + j];
+      const double lij = S[PD_AT(i, j)];
       if (x > j) {
-        if (x <= i) S[i * PD_LD + x] = fma(-lij, S[x * PD_LD + j], S[i * PD_LD + x]);
+        if (x <= i) S[PD_AT(i, x)] = fma(-lij, S[PD_AT(x, j)], S[PD_AT(i, x)]);
       } else if (x < j) {
-        S[x * PD_LD + i] = fma(-lij, S[x * PD_LD + j], S[x * PD_LD + i]);
+        S[PD_AT(x, i)] = fma(-lij, S[PD_AT(x, j)], S[PD_AT(x, i)]);
       } else {
-        S[j * PD_LD + i] = -lij * dj;
+        S[PD_AT(j, i)] = -lij * dj;
       }
     }
     __syncthreads();
   }
   __syncthreads();
-  if (fail_col < 0 && tid < kTile) S[tid * PD_LD + tid] = ddiag[tid];
+  if (fail_col < 0 && tid < kTile) S[PD_AT(tid, tid)] = ddiag[tid];
   __syncthreads();
   if (fail_col >= 0) {
     if (tid == 0) {
@@ -423,23 +430,23 @@ __global__ void __launch_bounds__(PD_THREADS) potrf_diag_kernel(CholParams p, in
   double* Mg = p.Minv + (long long)s * kTile * kTile;
   for (int e = tid; e < kTile * kTile; e += PD_THREADS) {
     const int r = e >> 7, c = e & 127;
-    if (c <= r) Ag[(long long)r * ld + c] = S[r * PD_LD + c];
-    Mg[e] = (c < r) ? S[c * PD_LD + r] : ((c == r) ? dinv[r] : 0.0);
+    if (c <= r) Ag[(long long)r * ld + c] = S[PD_AT(r, c)];
+    Mg[e] = (c < r) ? S[PD_AT(c, r)] : ((c == r) ? 1.0 / ddiag[r] : 0.0);
   }
   // z_k = M·r_k ; logdet ; sqmah
   double zz = 0.0, lg = 0.0;
   if (tid < kTile) {
     const double* rk = p.rhs + (long long)s * p.Np + p.k0;
-    double acc0 = dinv[tid] * rk[tid], acc1 = 0.0;
+    double acc0 = rk[tid] / ddiag[tid], acc1 = 0.0;
     int c = 0;
     for (; c + 1 < tid; c += 2) {
-      acc0 = fma(S[c * PD_LD + tid], rk[c], acc0);
-      acc1 = fma(S[(c + 1) * PD_LD + tid], rk[c + 1], acc1);
+      acc0 = fma(S[PD_AT(c, tid)], rk[c], acc0);
+      acc1 = fma(S[PD_AT(c + 1, tid)], rk[c + 1], acc1);
     }
-    if (c < tid) acc0 = fma(S[c * PD_LD + tid], rk[c], acc0);
+    if (c < tid) acc0 = fma(S[PD_AT(c, tid)], rk[c], acc0);
     const double z = acc0 + acc1;
     zz = z * z;
-    lg = log(S[tid * PD_LD + tid]);
+    lg = log(ddiag[tid]);
     __syncwarp();
     p.zk[(long long)s * kTile + tid] = z;
   }
@@ -553,7 +560,7 @@ __global__ void __launch_bounds__(256) solve_lower_kernel(const double* __restri
   for (int i = tid; i < N; i += 256) z[(long long)b * N + i] = zs[i];
 }
 
-constexpr size_t kPotrfSmem = sizeof(double) * (kTile * PD_LD + 2 * kTile + 32);
+constexpr size_t kPotrfSmem = sizeof(double) * (kTile * kTile + kTile + 32 + 2);
 
 }  // namespace
 
@@ -569,6 +576,10 @@ cudaError_t kernels_init() {
   for (const Item& it : items) {
     cudaError_t e = cudaFuncSetAttribute(it.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, it.bytes);
     if (e != cudaSuccess) return e;
+    if (getenv("SFB_MAX_CARVEOUT")) {
+      e = cudaFuncSetAttribute(it.fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      if (e != cudaSuccess) return e;
+    }
   }
   return cudaSuccess;
 }
