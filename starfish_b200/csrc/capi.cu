@@ -44,6 +44,7 @@ struct sfb_ctx {
   cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
   cudaEvent_t ev_hi[2] = {nullptr, nullptr}, ev_lo[2] = {nullptr, nullptr};
   bool profile = false;
+  int outer_tiles = kOuterTiles;  // SFB_OUTER_TILES overrides (experiments)
   int debug_mode = 0;  // SFB_DEBUG_MODE: bit0 = no high-priority stream, bit1 = single lane
   std::vector<ProfEvent> prof;
   std::vector<cudaEvent_t> ev_pool;
@@ -163,8 +164,9 @@ int run_cholesky(sfb_ctx* h, int lane, int slot0, int nb, double* lnL_out, int* 
     SFB_CUDA(h, cudaEventRecord(h->ev_lo[lane], lo));
     SFB_CUDA(h, cudaStreamWaitEvent(hi, h->ev_lo[lane], 0));
   }
-  for (int J0 = 0; J0 < nt; J0 += kOuterTiles) {
-    const int q = std::min(kOuterTiles, nt - J0);
+  const int OT = h->outer_tiles;
+  for (int J0 = 0; J0 < nt; J0 += OT) {
+    const int q = std::min(OT, nt - J0);
     const int kb = J0 * kTile;
     // ---- PANEL(J) on hi
     for (int c = 0; c < q; ++c) {
@@ -191,7 +193,7 @@ int run_cholesky(sfb_ctx* h, int lane, int slot0, int nb, double* lnL_out, int* 
     }
     const int jn = J0 + q;  // first tile column right of this block
     if (jn >= nt) break;
-    const int qn = std::min(kOuterTiles, nt - jn);  // width of the next block
+    const int qn = std::min(OT, nt - jn);  // width of the next block
     const double K = (double)q * kTile;
     if (two) {
       SFB_CUDA(h, cudaEventRecord(h->ev_hi[lane], hi));        // PANEL(J) done
@@ -252,7 +254,9 @@ int loglike_device(sfb_ctx* h, int B, const double* X, const double* A, const do
                    const double* X_h, const double* A_h, const double* flux_h, const double* glob_h,
                    const int* nloc_h, const double* loc_h, double* lnL_h, int* info_h, double* resid_h) {
   const int N = h->N, M = h->M, K = h->Kmax;
-  const int per = std::max(1, h->slots / nstreams);
+  const int per_max = std::max(1, h->slots / nstreams);
+  const int nchunks = (B + per_max - 1) / per_max;
+  const int per = (B + nchunks - 1) / nchunks;  // balanced chunks: no small tail chunk
   const bool host = (flux_h != nullptr);
   if (host && shared_hyper) {  // one shared hyper-parameter row: copy once, up front, on stream 0
     SFB_CUDA(h, cudaMemcpyAsync((void*)glob, glob_h, sizeof(double) * 2, cudaMemcpyHostToDevice, h->streams[0]));
@@ -267,7 +271,7 @@ int loglike_device(sfb_ctx* h, int B, const double* X, const double* A, const do
     const int nb = std::min(per, B - b0);
     const int si = chunk % nstreams;
     cudaStream_t st = h->streams[si];
-    const int slot0 = si * per;
+    const int slot0 = si * per_max;
     const int hb = shared_hyper ? 0 : b0;
     if (host) {
       if (X_h)
@@ -338,6 +342,7 @@ int sfb_create(int device, int N, int M, int Kmax, int Bmax, int workspace_walke
   h->Kmax = std::max(Kmax, 1);
   h->Bmax = Bmax;
   if (const char* dbg = getenv("SFB_DEBUG_MODE")) h->debug_mode = atoi(dbg);
+  if (const char* ot = getenv("SFB_OUTER_TILES")) h->outer_tiles = std::max(1, atoi(ot));
   DeviceGuard guard(device);
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) {
