@@ -243,6 +243,7 @@ BuildParams make_build_params(sfb_ctx* h, const double* X, const double* A, cons
   bp.nloc = nloc;
   bp.loc = loc;
   bp.sorted = h->sorted;
+  bp.bulk_ok = 0;
   return bp;
 }
 

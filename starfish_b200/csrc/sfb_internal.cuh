@@ -34,6 +34,7 @@ struct BuildParams {
   int lower_only;      // 1: only tiles on/below the diagonal are produced
   int hyper_stride;    // 1: per-walker glob/nloc/loc rows, 0: one shared row
   int vec2;            // 1: C rows are 16 B aligned (ldc, strideC even and base aligned) -> double2 stores
+  int bulk_ok;         // 1: wave/X rows are 16 B aligned -> column slices prefetched with cp.async.bulk (set by the launcher)
   double jitter;
   const double* wave;
   const double* sigma;
