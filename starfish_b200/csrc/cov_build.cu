@@ -70,6 +70,8 @@ struct ColBuf {  // one stage of the column double buffer
   double Xc[(MT > 0 ? MT : 1) * BT];
 };
 
+// MT = register/unroll width of the rank-M term; for MT <= 8 the kernel is instantiated with MT == M exactly
+// (no predication in the hot loop), wider models use MT = 12 or 16 with the tail predicated.
 template <int MT>
 __global__ void __launch_bounds__(NTHREADS) cov_build_kernel(BuildParams p) {
   const int nt = (p.padN + BT - 1) / BT;
@@ -78,7 +80,8 @@ __global__ void __launch_bounds__(NTHREADS) cov_build_kernel(BuildParams p) {
   const int i0 = ti * BT;
   const int ntj = p.lower_only ? ti + 1 : nt;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int N = p.N, M = p.M;
+  const int N = p.N;
+  const int M = (MT <= 8) ? MT : p.M;  // compile-time constant on the common path
 
   extern __shared__ __align__(16) uint8_t smem_raw[];
   ColBuf<MT>* cbuf = reinterpret_cast<ColBuf<MT>*>(smem_raw);          // [2]
@@ -173,7 +176,8 @@ __global__ void __launch_bounds__(NTHREADS) cov_build_kernel(BuildParams p) {
   const double r0g = 6 * g_ls;
   const double sqrt3 = sqrt(3.0);
   const bool sorted = (*p.sorted != 0);
-  const int cc[4] = {2 * lane, 2 * lane + 1, 64 + 2 * lane, 65 + 2 * lane};
+  const int cA = 2 * lane, cB = 64 + 2 * lane;  // this thread's column pairs (cA, cA+1) and (cB, cB+1)
+  auto col_of = [&](int q) { return (q < 2 ? cA : cB) + (q & 1); };
   double* Cb = p.C + (long long)b * p.strideC;
   const int padN = p.padN;
 
@@ -234,17 +238,44 @@ __global__ void __launch_bounds__(NTHREADS) cov_build_kernel(BuildParams p) {
       }
     }
     const bool diag_tile = (i0 == j0);
+    const bool interior = p.vec2 && (i0 + BT <= N) && (j0 + BT <= N);
 
     double wj[4];
     double yj[MT > 0 ? MT : 1][4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      wj[q] = (cc[q] < ncol) ? cb.wc[cc[q]] : 0.0;
+      wj[q] = (col_of(q) < ncol) ? cb.wc[col_of(q)] : 0.0;
 #pragma unroll
-      for (int m = 0; m < MT; ++m) yj[m][q] = (m < M) ? Yc[m * BT + cc[q]] : 0.0;
+      for (int m = 0; m < MT; ++m) yj[m][q] = (m < M) ? Yc[m * BT + col_of(q)] : 0.0;
     }
 
-#pragma unroll 1
+    // Fast path — the overwhelming majority of tiles: fully inside the N×N block, away from the diagonal,
+    // outside the Matérn band and every local block.  Only the rank-M term is left: M shared loads, 4·M
+    // DFMA and two 16-byte stores per row, with the row pointer carried as an induction variable.
+    const bool fast = interior && !band && !n_active && !diag_tile;
+    if (fast) {
+      double* rowp = Cb + (long long)(i0 + warp) * p.ldc + j0;
+      const long long step = 8 * p.ldc;
+#pragma unroll 4
+      for (int rr = 0; rr < BT / 8; ++rr) {
+        const int r = warp + 8 * rr;
+        double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+          if (m < M) {
+            const double x = Xr[m * BT + r];
+            v0 = fma(x, yj[m][0], v0);
+            v1 = fma(x, yj[m][1], v1);
+            v2 = fma(x, yj[m][2], v2);
+            v3 = fma(x, yj[m][3], v3);
+          }
+        }
+        *reinterpret_cast<double2*>(rowp + cA) = make_double2(v0, v1);
+        *reinterpret_cast<double2*>(rowp + cB) = make_double2(v2, v3);
+        rowp += step;
+      }
+    } else
+#pragma unroll 2
     for (int rr = 0; rr < BT / 8; ++rr) {
       const int r = warp + 8 * rr;
       const int i = i0 + r;
@@ -264,7 +295,7 @@ __global__ void __launch_bounds__(NTHREADS) cov_build_kernel(BuildParams p) {
       if (diag_tile) {
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          if (cc[q] == r) v[q] += s2[r];
+          if (col_of(q) == r) v[q] += s2[r];
       }
       if (band) {
 #pragma unroll
@@ -285,7 +316,7 @@ __global__ void __launch_bounds__(NTHREADS) cov_build_kernel(BuildParams p) {
           const double r0 = 4 * lk[k].sigma, sg2 = lk[k].sigma * lk[k].sigma, amp = lk[k].amp;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const double mj = colm[k * BT + cc[q]];
+            const double mj = colm[k * BT + col_of(q)];
             if (mj >= 0.0) {
               const double rt = fmax(mi, mj);
               const double taper = 0.5 + 0.5 * cos(kPi * rt / r0);
@@ -299,27 +330,32 @@ __global__ void __launch_bounds__(NTHREADS) cov_build_kernel(BuildParams p) {
       if (diag_tile) {
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          if (cc[q] == r) v[q] += p.jitter;
+          if (col_of(q) == r) v[q] += p.jitter;
       }
       if (i >= N) {  // identity padding of the factorisation workspace
 #pragma unroll
-        for (int q = 0; q < 4; ++q) v[q] = (j0 + cc[q] == i) ? 1.0 : 0.0;
+        for (int q = 0; q < 4; ++q) v[q] = (j0 + col_of(q) == i) ? 1.0 : 0.0;
       }
       double* row = Cb + (long long)i * p.ldc + j0;
+      if (interior) {  // whole tile inside the N×N block and 16-byte aligned rows: two unconditional 16 B stores
+        *reinterpret_cast<double2*>(row + cA) = make_double2(v[0], v[1]);
+        *reinterpret_cast<double2*>(row + cB) = make_double2(v[2], v[3]);
+      } else {
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int c = cc[2 * h];
-        const int j = j0 + c;
-        double a = v[2 * h], c1 = v[2 * h + 1];
-        if (i < N) {  // columns beyond N inside a padded workspace are zero
-          if (j >= N) a = 0.0;
-          if (j + 1 >= N) c1 = 0.0;
-        }
-        if (j + 1 < padN && p.vec2) {
-          *reinterpret_cast<double2*>(row + c) = make_double2(a, c1);
-        } else {
-          if (j < padN) row[c] = a;
-          if (j + 1 < padN) row[c + 1] = c1;
+        for (int h = 0; h < 2; ++h) {
+          const int c = h ? cB : cA;
+          const int j = j0 + c;
+          double a = v[2 * h], c1 = v[2 * h + 1];
+          if (i < N) {  // columns beyond N inside a padded workspace are zero
+            if (j >= N) a = 0.0;
+            if (j + 1 >= N) c1 = 0.0;
+          }
+          if (j + 1 < padN && p.vec2) {
+            *reinterpret_cast<double2*>(row + c) = make_double2(a, c1);
+          } else {
+            if (j < padN) row[c] = a;
+            if (j + 1 < padN) row[c + 1] = c1;
+          }
         }
       }
     }
@@ -362,7 +398,18 @@ cudaError_t launch_cov_build(const BuildParams& p, int B, cudaStream_t st) {
     q.X = nullptr;
     return launch_build_t<0>(q, B, st);
   }
-  if (p.M <= 8) return launch_build_t<8>(q, B, st);
+  switch (p.M) {
+    case 1: return launch_build_t<1>(q, B, st);
+    case 2: return launch_build_t<2>(q, B, st);
+    case 3: return launch_build_t<3>(q, B, st);
+    case 4: return launch_build_t<4>(q, B, st);
+    case 5: return launch_build_t<5>(q, B, st);
+    case 6: return launch_build_t<6>(q, B, st);
+    case 7: return launch_build_t<7>(q, B, st);
+    case 8: return launch_build_t<8>(q, B, st);
+    default: break;
+  }
+  if (p.M <= 12) return launch_build_t<12>(q, B, st);
   return launch_build_t<kMaxM>(q, B, st);
 }
 
