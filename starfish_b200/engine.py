@@ -172,6 +172,13 @@ class LikelihoodEngine:
         B = F.shape[0]
         if F.shape[1] != self.N:
             raise ValueError(f"model_flux must be [B,{self.N}]")
+        if B > self.B:
+            raise _lib.SfbError(f"batch of {B} walkers exceeds the handle's Bmax={self.B}")
+        if B == 0:  # nothing to do (and empty tensors have no device pointer to hand over)
+            empty = torch.empty((0,), dtype=torch.float64, device=self.device)
+            out = (empty, torch.empty((0,), dtype=torch.int32, device=self.device))
+            return out + (torch.empty((0, self.N), dtype=torch.float64, device=self.device),) \
+                if return_residuals else out
         X, A = self._xa(B, X, A)
         g, n, l = self.pack_hyper(B, glob, nloc, loc, shared_hyper)
         lnL = torch.empty((B,), dtype=torch.float64, device=self.device)

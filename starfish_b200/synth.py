@@ -139,3 +139,20 @@ def stage_inputs_direct(n_pix, n_walkers, n_comp=6, n_local=2, with_global=True,
             loc[i, k] = np.exp(kk["log_amp"]), kk["mu"], np.exp(kk["log_sigma"])
     return dict(wave=wave, sigma=sigma, data_flux=data_flux, X=X, A=A, model_flux=model_flux,
                 glob=glob, nloc=nloc, loc=loc)
+
+
+def stage_inputs_orders(n_walkers, n_orders=8, n_per_order=2048, n_comp=6, n_local_per_order=2, first_walker=0):
+    """Config 5 of BASELINE.json: one concatenated multi-order spectrum (8 × 2048 = 16384 px) with
+    ``n_local_per_order`` local kernels inside every order (16 per walker)."""
+    wave = multi_order_wave(n_orders, n_per_order)
+    d = stage_inputs_direct(wave.size, n_walkers, n_comp=n_comp, n_local=0, wave=wave, first_walker=first_walker)
+    centres = [wave[o * n_per_order:(o + 1) * n_per_order].mean() for o in range(n_orders)]
+    K = n_orders * n_local_per_order
+    loc = np.zeros((n_walkers, K, 3))
+    for i in range(n_walkers):
+        _, p = walker_params_orders(first_walker + i, centres, n_local_per_order)
+        for k, kk in enumerate(p["local_cov"]):
+            loc[i, k] = np.exp(kk["log_amp"]), kk["mu"], np.exp(kk["log_sigma"])
+    d["loc"] = loc
+    d["nloc"] = np.full(n_walkers, K, dtype=np.int32)
+    return d

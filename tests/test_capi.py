@@ -64,8 +64,9 @@ def test_create_fails_cleanly_without_gpu(built_lib):
         LikelihoodEngine(256, 6, 2, 4)
 
 
-def test_sass_uses_dmma_and_async_copies(built_lib):
-    """The fp64 tensor path (DMMA.8x8x4) and cp.async (LDGSTS) must be in the shipped SASS."""
+def test_sass_uses_dmma_and_tma(built_lib):
+    """The fp64 tensor path (DMMA.8x8x4), TMA tensor loads (UTMALDG), bulk async copies (UBLKCP) and the
+    mbarrier pipeline (SYNCS) must be in the shipped SASS."""
     import shutil
     import subprocess
 
@@ -73,5 +74,5 @@ def test_sass_uses_dmma_and_async_copies(built_lib):
     if not os.path.exists(cuobjdump):
         pytest.skip("cuobjdump not available")
     sass = subprocess.run([cuobjdump, "-sass", built_lib], capture_output=True, text=True).stdout
-    assert "DMMA.8x8x4" in sass
-    assert "LDGSTS" in sass
+    for mnemonic in ("DMMA.8x8x4", "UTMALDG.3D", "UBLKCP", "SYNCS.ARRIVE.TRANS64", "LDS.128"):
+        assert mnemonic in sass, mnemonic

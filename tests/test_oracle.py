@@ -101,3 +101,25 @@ def test_live_reference_agrees():
     assert np.abs(cov - r["cov"]).max() <= 1e-15 * r["cov"].diagonal().max()
     lnl = O.log_likelihood(cov, r["model_flux"], r["data_flux"])[0]
     assert abs(lnl - r["lnL"]) <= 1e-12 * abs(r["lnL"])
+
+
+def test_structured_oracle_matches_dense():
+    """The banded-Cholesky + Woodbury checker used for the full-size GPU tests agrees with the dense oracle."""
+    from oracle import structured_oracle as SO
+    from starfish_b200 import synth
+
+    d = synth.stage_inputs_direct(768, 3)
+    for b in range(3):
+        cov = O.assemble_covariance(d["wave"], d["sigma"], None, None, d["glob"][b], d["loc"][b])
+        cov += d["X"][b].T @ d["A"][b] @ d["X"][b]
+        ref = O.log_likelihood(cov, d["model_flux"][b], d["data_flux"])[0]
+        got = SO.stage_log_likelihood(d["wave"], d["sigma"], d["data_flux"], d["X"][b], d["A"][b],
+                                      d["model_flux"][b], d["glob"][b], d["loc"][b])
+        assert abs(got - ref) <= 1e-11 * abs(ref)
+    # multi-order grid with many local kernels, no emulator term
+    d = synth.stage_inputs_orders(1, n_orders=2, n_per_order=256, n_comp=0)
+    cov = O.assemble_covariance(d["wave"], d["sigma"], None, None, d["glob"][0], d["loc"][0])
+    ref = O.log_likelihood(cov, d["model_flux"][0], d["data_flux"])[0]
+    got = SO.stage_log_likelihood(d["wave"], d["sigma"], d["data_flux"], None, None, d["model_flux"][0],
+                                  d["glob"][0], d["loc"][0])
+    assert abs(got - ref) <= 1e-11 * abs(ref)
