@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--walkers", type=int, default=WORKLOAD["n_walkers"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-model", action="store_true", help="skip the parameter-level (drop-in model) legs")
     ap.add_argument("--cpu-sample", type=int, default=0, help="walkers in the CPU sample (0 = auto)")
     return ap.parse_args()
 
@@ -259,6 +260,64 @@ def run_b200(args, rank, world, local_rank):
                "api": "LikelihoodEngine.log_likelihood_host -> sfb_loglike_host (pinned host buffers)"}
         assert np.allclose(hb["lnL"], lnL.cpu().numpy(), rtol=0, atol=0), "host and device paths disagree"
 
+    # ---- the parameter-level step (rows f1/f2/f3): theta -> transforms + emulator + covariance path ------
+    model_leg = None
+    if not args.no_model:
+        import copy
+        import warnings
+
+        from starfish_b200.emulator import Emulator
+        from starfish_b200.spectrum import Spectrum
+        from starfish_b200.spectrum_model import SpectrumModel
+
+        emu = Emulator(**copy.deepcopy(synth.make_emulator_arrays(n_comp=M)))
+        emu._trained = True
+        grid0, p0 = synth.walker_params(lo, n_local=K)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            model = SpectrumModel(emu, Spectrum(stage["wave"], stage["data_flux"], sigmas=stage["sigma"],
+                                                name="synthetic"), grid_params=grid0, device=local_rank, **p0)
+        model._engine = eng   # share the workspace of this process' handle
+        model._static_sig = None
+        labels = list(model.labels)
+        P = np.empty((nb, len(labels)))
+        for i in range(nb):
+            grid_i, p_i = synth.walker_params(lo + i, n_local=K)
+            flat = dict(zip(emu.param_names, grid_i))
+            flat.update({k: v for k, v in p_i.items() if k not in ("cheb", "global_cov", "local_cov")})
+            flat.update({f"cheb:{j + 1}": c for j, c in enumerate(p_i["cheb"])})
+            flat.update({f"global_cov:{k}": v for k, v in p_i["global_cov"].items()})
+            for j, kern in enumerate(p_i["local_cov"]):
+                flat.update({f"local_cov:{j}:{k}": v for k, v in kern.items()})
+            P[i] = [flat[k] for k in labels]
+        lnl_model = [None]
+
+        def step_model():
+            lnl_model[0] = model.log_likelihood_batch(P)
+            if world > 1:
+                return gather_lnl(torch.from_numpy(lnl_model[0]).to(dev), B)
+            return lnl_model[0]
+
+        m_steps = max(2, min(args.steps, 3))
+        ms_model, launches_model, _ = timed(step_model, m_steps, 1)
+        nf = len(model.min_dv_wave)
+        model_leg = {"value": B / (ms_model / m_steps * 1e-3), "unit": "evals/s", "steps": m_steps,
+                     "h2d_bytes_per_step": int(P.nbytes + nb * (2 + 3 * eng.K) * 8 + nb * 4),
+                     "d2h_bytes_per_step": int(nb * 12),
+                     "api": "SpectrumModel.log_likelihood_batch(P[B,ndim]) -> sfb_loglike_params_host: emulator GP, "
+                            "rotational broadening, Doppler shift, spline resampling, Chebyshev, covariance build, "
+                            "Cholesky, solve — all on the device; only parameters and lnL cross PCIe",
+                     "n_fine": nf, "ndim": len(labels), "gpu_launches": int(launches_model),
+                     "not_finite": int((~np.isfinite(lnl_model[0])).sum())}
+        if rank == 0:
+            eng.profile(True)
+            model.log_likelihood_batch(P)
+            up = eng.profile_read()["upstream"]
+            eng.profile(False)
+            model_leg["upstream_ms_per_step"] = up["ms"]
+            model_leg["upstream_gbs"] = up["work"] / (up["ms"] * 1e-3) / 1e9 if up["ms"] > 0 else None
+        model._engine = None
+
     # ---- roofline of the dominant kernel: one extra profiled step (single stream, events per launch)
     roof = None
     prof = None
@@ -291,7 +350,7 @@ def run_b200(args, rank, world, local_rank):
                                       "achieved": (v["work"] / (v["ms"] * 1e-3) / (1e9 if k == "build" else 1e12))
                                       if v["ms"] > 0 else None,
                                       "unit": "GB/s" if k == "build" else "TFLOP/s"}
-                                  for k, v in prof.items() if k != "syrk"}}
+                                  for k, v in prof.items() if k not in ("syrk", "upstream")}}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
             roof["other_kernels"]["build"]["peak_hbm_gbs"] = peaks.get("hbm_gbs")
@@ -307,7 +366,7 @@ def run_b200(args, rank, world, local_rank):
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(args, world),
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks, "e2e": e2e, "e2e_model": model_leg, "gpu_launches": int(launches),
             "roofline": roof,
             "path_tflops": value * flops_eval / 1e12,
             "path_frac_of_fp64_peak": value * flops_eval / 1e12 / (FP64_DMMA_PEAK_TFLOPS * world),

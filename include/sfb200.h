@@ -101,6 +101,70 @@ int sfb_loglike_host(sfb_t* h, int B, const double* X_h, const double* A_h, cons
                      const double* glob_h, const int* nloc_h, const double* loc_h, int shared_hyper,
                      double* lnL_h, int* info_h, double* resid_h);
 
+/*
+ * ---- Upstream of the covariance (scope-table rows f1/f2/f3): parameters in, log-likelihood out ----
+ *
+ * sfb_set_model_host   what SpectrumModel.__init__ prepares          Starfish/models/spectrum_model.py:149-156
+ *                      + the static part of Emulator.__call__        Starfish/emulator/emulator.py:382-388
+ * sfb_upstream         SpectrumModel.__call__ up to the rank-M term  Starfish/models/spectrum_model.py:287-332:
+ *                        rotational_broaden   Starfish/transforms.py:93-134
+ *                        doppler_shift        Starfish/transforms.py:137-158
+ *                        resample (k=5)       Starfish/transforms.py:11-42
+ *                        chebyshev_correct    Starfish/transforms.py:271-304
+ *                        Emulator.__call__    Starfish/emulator/emulator.py:330-394 (weights, Σ_w)
+ *                        X = eig·std, flux = w·X + mean, rescale / renorm   spectrum_model.py:306-332
+ *                        A = Σ_w⁻¹            spectrum_model.py:334-335
+ * sfb_loglike_params(_host)  sfb_upstream followed by sfb_loglike — one call per ensemble step; with the
+ *                      _host variant only B×ntheta parameter values cross the PCIe bus.
+ *
+ * Model flags say which optional parameters the model has (the reference tests `"vsini" in self.params` ...).
+ */
+enum sfb_model_flags {
+  SFB_MODEL_VSINI = 1,      /* rotational broadening (theta column D)                                  */
+  SFB_MODEL_VZ = 2,         /* Doppler shift (theta column D+1)                                        */
+  SFB_MODEL_LOG_SCALE = 4,  /* log_scale given (column D+2); otherwise renormalise to the data flux    */
+  SFB_MODEL_NORM = 8,       /* multiply by the emulator's norm factor (column D+3, host-interpolated)   */
+  SFB_MODEL_PAPER_TERM = 16 /* A = Σ_w (paper) instead of Σ_w⁻¹ (as the reference codes it)            */
+};
+
+/*
+ * Static model data (host pointers; copied).  M (eigenspectra) and N come from sfb_create.
+ *   nf            power-of-two length of the model's internal log-λ grid (create_log_lam_grid)
+ *   fine_wave_h   nf         that grid (SpectrumModel.min_dv_wave)
+ *   bulk_h        (M+2)×nf   eigenspectra, flux_mean, flux_std on it (SpectrumModel.bulk_fluxes)
+ *   G, D          emulator grid points and their dimension;  grid_points_h G×D
+ *   variances_h   M;  lengthscales_h M×D;  v11_h (M·G)×(M·G) row-major;  w_hat_h M·G
+ *   ncheb_max     most Chebyshev coefficients (c1..) a call will pass
+ */
+int sfb_set_model_host(sfb_t* h, int nf, const double* fine_wave_h, const double* bulk_h, int G, int D,
+                       const double* grid_points_h, const double* variances_h, const double* lengthscales_h,
+                       const double* v11_h, const double* w_hat_h, int ncheb_max, int flags);
+
+/*
+ * theta: B×ntheta (ntheta = D+4+ncheb), row b = [grid params (D) | vsini | vz | log_scale | norm | c1..c_ncheb];
+ * columns the model's flags do not use are ignored.  Outputs (device): X B×M×N, A B×M×M, model_flux B×N,
+ * log_scale_out B (the fitted value when SFB_MODEL_LOG_SCALE is off), status B (0 ok, 1 = Σ_w not
+ * positive definite — the reference raises LinAlgError there).  weights/weights_cov (B×M, B×M×M) may be NULL.
+ */
+int sfb_upstream(sfb_t* h, int B, const double* theta, int ncheb, double* X, double* A, double* model_flux,
+                 double* log_scale_out, int* status, double* weights, double* weights_cov, void* stream);
+
+/* sfb_upstream + sfb_loglike on device buffers.  info[b] = -1 where status[b] != 0. */
+int sfb_loglike_params(sfb_t* h, int B, const double* theta, int ncheb, const double* glob, const int* nloc,
+                       const double* loc, int shared_hyper, double* lnL, int* info, double* resid,
+                       double* log_scale_out, void* stream);
+
+/* The end-to-end entry: HOST buffers in and out (theta, hyper-parameters; lnL, info, log_scale, resid). */
+int sfb_loglike_params_host(sfb_t* h, int B, const double* theta_h, int ncheb, const double* glob_h,
+                            const int* nloc_h, const double* loc_h, int shared_hyper, double* lnL_h, int* info_h,
+                            double* resid_h, double* log_scale_h);
+
+/* Pure host helpers used at set-up, exported so that they can be checked without a GPU. */
+int sfb_host_rfft(int n, const double* x_h, double* out_complex_h /* 2·(n/2+1) */);
+int sfb_host_spline_inverse_band(int nf, const double* fine_wave_h, int W, double* out_h /* (2W+1)×nf */);
+int sfb_host_cholesky_lower(int n, double* a_h /* n×n row-major, in place */);
+int sfb_spline_halfwidth(void);
+
 /* Block the host until all work queued on the handle has finished. */
 int sfb_sync(sfb_t* h);
 
@@ -110,7 +174,8 @@ int sfb_sync(sfb_t* h);
  * out[3*c+0] = number of launches, out[3*c+1] = total device milliseconds, out[3*c+2] = algorithmic work
  * (bytes for SFB_K_BUILD, FLOPs otherwise), and resets the counters.  `n` = capacity of out in doubles.
  */
-enum sfb_kernel_class { SFB_K_BUILD = 0, SFB_K_POTRF_DIAG = 1, SFB_K_TRSM = 2, SFB_K_SYRK = 3, SFB_K_NCLASS = 4 };
+enum sfb_kernel_class { SFB_K_BUILD = 0, SFB_K_POTRF_DIAG = 1, SFB_K_TRSM = 2, SFB_K_SYRK = 3, SFB_K_UPSTREAM = 4,
+                        SFB_K_NCLASS = 5 };
 int sfb_profile_enable(sfb_t* h, int on);
 int sfb_profile_read(sfb_t* h, double* out, int n);
 

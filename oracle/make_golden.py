@@ -152,5 +152,59 @@ def main():
         print(f"n{n}", r["lnL"], "ref s", r["ref_seconds"])
 
 
+UPSTREAM_VARIANTS = {
+    # name: (n_pix, wave window, walker, overrides; None removes the parameter from the model)
+    "a": (256, (5092.0, 5108.0), 2, dict(vsini=12.5, vz=-37.0, log_scale=None, cheb=[0.02, -0.01, 0.005])),
+    "b": (256, (5092.0, 5108.0), 4, dict(vsini=None, vz=None, log_scale=-0.2, cheb=None)),
+    "c": (256, (5092.0, 5108.0), 6, dict(vsini=None, vz=55.0, cheb=[0.03])),
+    "d": (300, (5400.0, 5690.0), 7, dict(vsini=31.0, vz=120.0)),                 # coarse pixels up to the grid edge
+    "e": (2048, (5000.0, 5070.0), 8, dict(vsini=2.5, vz=-8.0, log_scale=None)),  # 2 km/s pixels -> nf = 32768
+}
+
+
+def upstream_variant_params(name):
+    n_pix, window, walker, over = UPSTREAM_VARIANTS[name]
+    grid, p = synth.walker_params(walker)
+    mid = 0.5 * (window[0] + window[1])
+    half = 0.5 * (window[1] - window[0])
+    for k, kern in enumerate(p["local_cov"]):
+        kern["mu"] = float(mid + (0.4 * k - 0.2) * half)
+    for key, val in over.items():
+        if val is None:
+            p.pop(key, None)
+        else:
+            p[key] = val
+    return n_pix, synth.log_uniform_wave(n_pix, *window), grid, p
+
+
+def main_upstream():
+    """Stage inputs recorded inside the reference's __call__ for parameter sets that exercise every
+    upstream transform (rows f1/f2): Doppler shift, strong/weak/no rotation, renormalisation, Chebyshev
+    orders, and a fine-pixel case whose internal grid has 32768 points."""
+    os.makedirs(OUT, exist_ok=True)
+    ref_loader.load_reference()
+    import Starfish.models.spectrum_model as sm
+
+    for name in UPSTREAM_VARIANTS:
+        n_pix, wave, grid, p = upstream_variant_params(name)
+        w, f, s = synth.make_data(n_pix, wave=wave)
+        model = ref_loader.build_reference_model(synth.make_emulator_arrays(), w, f, s, grid, p)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            with _Recorder(sm) as rec:
+                flux, cov = model()
+            weights, wcov = model.emulator(model.grid_params)
+            lnl = model.log_likelihood()
+        np.savez_compressed(
+            os.path.join(OUT, f"upstream_{name}.npz"), wave=w, data_flux=f, sigma=s, X=rec.X,
+            weights=weights, weights_cov=rec.weights_cov, model_flux=flux, lnL=np.float64(lnl),
+            log_scale=np.float64(model._log_scale), n_fine=np.int64(len(model.min_dv_wave)),
+            cov_diag=cov.diagonal().copy(), labels=np.array(model.labels), param_vector=model.get_param_vector())
+        print("upstream", name, n_pix, len(model.min_dv_wave), float(lnl), float(model._log_scale))
+
+
 if __name__ == "__main__":
-    main()
+    if "upstream" in sys.argv[1:]:
+        main_upstream()
+    else:
+        main()

@@ -14,9 +14,16 @@ EXPORTS = [
     "sfb_build_cov", "sfb_potrf", "sfb_solve_lower", "sfb_loglike", "sfb_loglike_host", "sfb_sync",
     "sfb_profile_enable", "sfb_profile_read", "sfb_workspace_walkers", "sfb_padded_n",
     "sfb_launch_count", "sfb_last_error",
+    "sfb_set_model_host", "sfb_upstream", "sfb_loglike_params", "sfb_loglike_params_host",
+    "sfb_host_rfft", "sfb_host_spline_inverse_band", "sfb_host_cholesky_lower", "sfb_spline_halfwidth",
 ]
 
-KERNEL_CLASSES = ("build", "potrf_diag", "trsm", "syrk")
+ABI_VERSION = 2
+
+# sfb_model_flags of include/sfb200.h
+MODEL_VSINI, MODEL_VZ, MODEL_LOG_SCALE, MODEL_NORM, MODEL_PAPER_TERM = 1, 2, 4, 8, 16
+
+KERNEL_CLASSES = ("build", "potrf_diag", "trsm", "syrk", "upstream")
 
 _p = C.c_void_p
 _i = C.c_int
@@ -44,6 +51,14 @@ def load():
     lib.sfb_solve_lower.argtypes = [_p, _i, _p, _p, _p, _p]
     lib.sfb_loglike.argtypes = [_p, _i, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p]
     lib.sfb_loglike_host.argtypes = [_p, _i, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p]
+    lib.sfb_set_model_host.argtypes = [_p, _i, _p, _p, _i, _i, _p, _p, _p, _p, _p, _i, _i]
+    lib.sfb_upstream.argtypes = [_p, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p]
+    lib.sfb_loglike_params.argtypes = [_p, _i, _p, _i, _p, _p, _p, _i, _p, _p, _p, _p, _p]
+    lib.sfb_loglike_params_host.argtypes = [_p, _i, _p, _i, _p, _p, _p, _i, _p, _p, _p, _p]
+    lib.sfb_host_rfft.argtypes = [_i, _p, _p]
+    lib.sfb_host_spline_inverse_band.argtypes = [_i, _p, _i, _p]
+    lib.sfb_host_cholesky_lower.argtypes = [_i, _p]
+    lib.sfb_spline_halfwidth.argtypes = []
     lib.sfb_sync.argtypes = [_p]
     lib.sfb_profile_enable.argtypes = [_p, _i]
     lib.sfb_profile_read.argtypes = [_p, _p, _i]

@@ -49,6 +49,8 @@ struct sfb_ctx {
   std::vector<ProfEvent> prof;
   std::vector<cudaEvent_t> ev_pool;
   long long launches = 0;
+  ModelState model;       // upstream of the covariance (rows f1/f2); empty until sfb_set_model_host
+  bool have_model = false;
   std::string err;
 };
 
@@ -327,7 +329,7 @@ int loglike_device(sfb_ctx* h, int B, const double* X, const double* A, const do
 
 extern "C" {
 
-int sfb_abi_version(void) { return 1; }
+int sfb_abi_version(void) { return 2; }
 
 int sfb_create(int device, int N, int M, int Kmax, int Bmax, int workspace_walkers, sfb_t** out) {
   if (!out) return SFB_ERR_ARG;
@@ -389,6 +391,7 @@ int sfb_create(int device, int N, int M, int Kmax, int Bmax, int workspace_walke
   }
   ok = ok && cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess;
   ok = ok && kernels_init() == cudaSuccess;
+  ok = ok && upstream_init() == cudaSuccess;
   ok = ok && make_gemm_maps(&h->maps, h->W, h->Np, h->Minv, h->slots) == cudaSuccess;
   if (!ok) {
     sfb_destroy(h);
@@ -416,6 +419,7 @@ int sfb_destroy(sfb_t* h) {
   }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   free_gemm_maps(&h->maps);
+  model_free(&h->model);
   for (auto& pe : h->prof) {
     cudaEventDestroy(pe.a);
     cudaEventDestroy(pe.b);
@@ -582,6 +586,175 @@ int sfb_loglike_host(sfb_t* h, int B, const double* X_h, const double* A_h, cons
   for (int i = 0; i < nstreams; ++i) SFB_CUDA(h, cudaStreamSynchronize(h->streams[i]));
   return SFB_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// upstream of the covariance (rows f1/f2/f3)
+// ---------------------------------------------------------------------------------------------------
+int sfb_set_model_host(sfb_t* h, int nf, const double* fine_wave_h, const double* bulk_h, int G, int D,
+                       const double* grid_points_h, const double* variances_h, const double* lengthscales_h,
+                       const double* v11_h, const double* w_hat_h, int ncheb_max, int flags) {
+  if (!h) return SFB_ERR_ARG;
+  if (!fine_wave_h || !bulk_h || !grid_points_h || !variances_h || !lengthscales_h || !v11_h || !w_hat_h)
+    return fail(h, SFB_ERR_ARG, "sfb_set_model_host: NULL argument");
+  if (nf < 16 || (nf & (nf - 1)) != 0) return fail(h, SFB_ERR_ARG, "sfb_set_model_host: nf must be a power of two >= 16");
+  if (h->M < 1 || G < 1 || D < 1 || D > 16 || ncheb_max < 0 || ncheb_max > 32)
+    return fail(h, SFB_ERR_ARG, "sfb_set_model_host: sizes out of range (needs M >= 1)");
+  DeviceGuard guard(h->device);
+  for (int i = 0; i < 2; ++i) SFB_CUDA(h, cudaStreamSynchronize(h->streams[i]));
+  h->have_model = false;
+  std::string why;
+  cudaError_t e = model_setup(&h->model, h->N, h->M, h->Bmax, nf, fine_wave_h, bulk_h, G, D, grid_points_h,
+                              variances_h, lengthscales_h, v11_h, w_hat_h, ncheb_max, flags, &why);
+  if (e != cudaSuccess) {
+    model_free(&h->model);
+    return fail(h, e == cudaErrorInvalidValue ? SFB_ERR_ARG : (e == cudaErrorMemoryAllocation ? SFB_ERR_NOMEM : SFB_ERR_CUDA),
+                why.c_str(), e == cudaErrorInvalidValue ? cudaSuccess : e);
+  }
+  h->have_model = true;
+  return SFB_OK;
+}
+
+namespace {
+int check_upstream(sfb_ctx* h, int B, int ncheb, const char* who) {
+  int rc = check_batch(h, B);
+  if (rc != SFB_OK) return rc;
+  if (!h->have_model) return fail(h, SFB_ERR_STATE, "call sfb_set_model_host first");
+  if (!h->have_static) return fail(h, SFB_ERR_STATE, "call sfb_set_static first");
+  if (ncheb < 0 || ncheb > h->model.ncheb_max) return fail(h, SFB_ERR_ARG, "ncheb exceeds ncheb_max of sfb_set_model_host");
+  (void)who;
+  return SFB_OK;
+}
+
+int run_upstream(sfb_ctx* h, int B, const double* theta, int ncheb, double* X, double* A, double* flux,
+                 double* log_scale_out, int* status, cudaStream_t st) {
+  UpstreamArgs a;
+  a.B = B;
+  a.ncheb = ncheb;
+  a.ntheta = h->model.D + 4 + ncheb;
+  a.theta = theta;
+  a.wave = h->wave;
+  a.data_flux = h->data_flux;
+  a.X = X;
+  a.A = A;
+  a.flux = flux;
+  a.log_scale_out = log_scale_out;
+  a.status = status;
+  const double bytes = (double)B * 8.0 * ((double)h->model.R * h->model.nf * 2.0 + (double)h->model.R * h->N * 2.0 +
+                                          (double)(h->M + 1) * h->N);
+  ProfScope ps(h, st, SFB_K_UPSTREAM, bytes);
+  SFB_CUDA(h, launch_upstream(h->model, a, st, &h->launches));
+  return SFB_OK;
+}
+}  // namespace
+
+int sfb_upstream(sfb_t* h, int B, const double* theta, int ncheb, double* X, double* A, double* model_flux,
+                 double* log_scale_out, int* status, double* weights, double* weights_cov, void* stream) {
+  int rc = check_upstream(h, B, ncheb, "sfb_upstream");
+  if (rc != SFB_OK) return rc;
+  if (!theta || !X || !A || !model_flux || !log_scale_out || !status)
+    return fail(h, SFB_ERR_ARG, "sfb_upstream: NULL argument");
+  if (B == 0) return SFB_OK;
+  DeviceGuard guard(h->device);
+  cudaStream_t caller = (cudaStream_t)stream, st = h->streams[0];
+  if ((rc = fork_streams(h, caller, 1)) != SFB_OK) return rc;
+  if ((rc = run_upstream(h, B, theta, ncheb, X, A, model_flux, log_scale_out, status, st)) != SFB_OK) return rc;
+  if (weights)
+    SFB_CUDA(h, cudaMemcpyAsync(weights, h->model.mu, sizeof(double) * (size_t)B * h->M, cudaMemcpyDeviceToDevice, st));
+  if (weights_cov)
+    SFB_CUDA(h, cudaMemcpyAsync(weights_cov, h->model.wcov, sizeof(double) * (size_t)B * h->M * h->M,
+                                cudaMemcpyDeviceToDevice, st));
+  return join_streams(h, caller, 1);
+}
+
+int sfb_loglike_params(sfb_t* h, int B, const double* theta, int ncheb, const double* glob, const int* nloc,
+                       const double* loc, int shared_hyper, double* lnL, int* info, double* resid,
+                       double* log_scale_out, void* stream) {
+  int rc = check_upstream(h, B, ncheb, "sfb_loglike_params");
+  if (rc != SFB_OK) return rc;
+  if (!theta || !glob || !nloc || !loc || !lnL || !info) return fail(h, SFB_ERR_ARG, "sfb_loglike_params: NULL argument");
+  if (B == 0) return SFB_OK;
+  DeviceGuard guard(h->device);
+  cudaStream_t caller = (cudaStream_t)stream;
+  const int nstreams = (h->profile || h->slots < 2 || (h->debug_mode & 2)) ? 1 : 2;
+  ModelState& ms = h->model;
+  // the upstream stage runs once for the whole batch on stream 0; the other lane waits for it
+  SFB_CUDA(h, cudaEventRecord(h->ev_fork, caller));
+  SFB_CUDA(h, cudaStreamWaitEvent(h->streams[0], h->ev_fork, 0));
+  if ((rc = run_upstream(h, B, theta, ncheb, ms.X, ms.A, ms.flux, log_scale_out ? log_scale_out : ms.log_scale,
+                         ms.status, h->streams[0])) != SFB_OK)
+    return rc;
+  SFB_CUDA(h, cudaEventRecord(h->ev_fork, h->streams[0]));
+  for (int i = 1; i < nstreams; ++i) SFB_CUDA(h, cudaStreamWaitEvent(h->streams[i], h->ev_fork, 0));
+  rc = loglike_device(h, B, ms.X, ms.A, ms.flux, glob, nloc, loc, shared_hyper, lnL, info, resid, nstreams, nullptr,
+                      nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+  if (rc != SFB_OK) return rc;
+  if ((rc = join_streams(h, caller, nstreams)) != SFB_OK) return rc;
+  SFB_CUDA(h, launch_merge_status(ms.status, info, lnL, B, caller));
+  h->launches++;
+  return SFB_OK;
+}
+
+int sfb_loglike_params_host(sfb_t* h, int B, const double* theta_h, int ncheb, const double* glob_h,
+                            const int* nloc_h, const double* loc_h, int shared_hyper, double* lnL_h, int* info_h,
+                            double* resid_h, double* log_scale_h) {
+  int rc = check_upstream(h, B, ncheb, "sfb_loglike_params_host");
+  if (rc != SFB_OK) return rc;
+  if (!theta_h || !glob_h || !nloc_h || !loc_h || !lnL_h || !info_h)
+    return fail(h, SFB_ERR_ARG, "sfb_loglike_params_host: NULL argument");
+  if (B == 0) return SFB_OK;
+  DeviceGuard guard(h->device);
+  const int N = h->N, K = h->Kmax, Bm = h->Bmax;
+  auto lazy = [&](void** p, size_t bytes) {
+    if (*p) return true;
+    return cudaMalloc(p, std::max<size_t>(bytes, 16)) == cudaSuccess;
+  };
+  bool ok = true;
+  ok &= lazy((void**)&h->dglob, sizeof(double) * 2 * Bm);
+  ok &= lazy((void**)&h->dloc, sizeof(double) * 3 * (size_t)K * Bm);
+  ok &= lazy((void**)&h->dnloc, sizeof(int) * Bm);
+  ok &= lazy((void**)&h->dlnL, sizeof(double) * Bm);
+  ok &= lazy((void**)&h->dinfo, sizeof(int) * Bm);
+  if (resid_h) ok &= lazy((void**)&h->dresid, sizeof(double) * (size_t)Bm * N);
+  if (!ok) return fail(h, SFB_ERR_NOMEM, "sfb_loglike_params_host: staging allocation failed");
+  ModelState& ms = h->model;
+  cudaStream_t st = h->streams[0];
+  const int Bh = shared_hyper ? 1 : B;
+  const int ntheta = ms.D + 4 + ncheb;
+  SFB_CUDA(h, cudaStreamSynchronize(h->streams[1]));  // staging buffers may still be read by the other lane
+  SFB_CUDA(h, cudaMemcpyAsync(ms.theta, theta_h, sizeof(double) * (size_t)B * ntheta, cudaMemcpyHostToDevice, st));
+  SFB_CUDA(h, cudaMemcpyAsync(h->dglob, glob_h, sizeof(double) * 2 * Bh, cudaMemcpyHostToDevice, st));
+  SFB_CUDA(h, cudaMemcpyAsync(h->dnloc, nloc_h, sizeof(int) * Bh, cudaMemcpyHostToDevice, st));
+  SFB_CUDA(h, cudaMemcpyAsync(h->dloc, loc_h, sizeof(double) * 3 * (size_t)K * Bh, cudaMemcpyHostToDevice, st));
+  rc = sfb_loglike_params(h, B, ms.theta, ncheb, h->dglob, h->dnloc, h->dloc, shared_hyper, h->dlnL, h->dinfo,
+                          resid_h ? h->dresid : nullptr, ms.log_scale, (void*)st);
+  if (rc != SFB_OK) return rc;
+  SFB_CUDA(h, cudaMemcpyAsync(lnL_h, h->dlnL, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
+  SFB_CUDA(h, cudaMemcpyAsync(info_h, h->dinfo, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+  if (log_scale_h)
+    SFB_CUDA(h, cudaMemcpyAsync(log_scale_h, ms.log_scale, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
+  if (resid_h)
+    SFB_CUDA(h, cudaMemcpyAsync(resid_h, h->dresid, sizeof(double) * (size_t)B * N, cudaMemcpyDeviceToHost, st));
+  SFB_CUDA(h, cudaStreamSynchronize(st));
+  return SFB_OK;
+}
+
+int sfb_host_rfft(int n, const double* x_h, double* out_complex_h) {
+  if (n < 2 || (n & (n - 1)) != 0 || !x_h || !out_complex_h) return SFB_ERR_ARG;
+  host_rfft(n, x_h, out_complex_h);
+  return SFB_OK;
+}
+
+int sfb_host_spline_inverse_band(int nf, const double* fine_wave_h, int W, double* out_h) {
+  if (!fine_wave_h || !out_h || W < 1) return SFB_ERR_ARG;
+  return host_spline_inverse_band(nf, fine_wave_h, W, out_h) == 0 ? SFB_OK : SFB_ERR_ARG;
+}
+
+int sfb_host_cholesky_lower(int n, double* a_h) {
+  if (n < 1 || !a_h) return SFB_ERR_ARG;
+  return host_cholesky_lower(n, a_h, n);
+}
+
+int sfb_spline_halfwidth(void) { return kSplineW; }
 
 int sfb_sync(sfb_t* h) {
   if (!h) return SFB_ERR_ARG;

@@ -90,3 +90,74 @@ cudaError_t launch_solve_lower(const double* L, long long strideL, int ldl, cons
 cudaError_t kernels_init();  // sets max dynamic shared memory attributes
 
 }  // namespace sfb
+
+// ---------------------------------------------------------------------------------------------
+// upstream of the covariance: emulator GP predictive + spectral transforms
+// ---------------------------------------------------------------------------------------------
+namespace sfb {
+
+constexpr int kSplineW = 48;        // half-width of the banded inverse of the quintic collocation matrix
+                                    // (entries decay by 0.4306 per knot: 0.43^48 = 2.7e-18)
+constexpr int kFftMaxPoints = 8192; // complex points of one in-shared-memory transform (128 KB)
+
+struct ModelState {
+  // sizes
+  int nf = 0, R = 0, M = 0, G = 0, D = 0, n = 0, ld = 0, N = 0, Bmax = 0, ncheb_max = 0;
+  int flags = 0;
+  double dv_fine = 0.0, freq_val = 0.0;
+  // static tables (device)
+  double* fw = nullptr;       // nf          fine log-λ grid
+  double* bulk = nullptr;     // R×nf        bulk fluxes on the fine grid (used when there is no vsini)
+  double* F = nullptr;        // R×(nf/2+1)  complex spectrum of the bulk fluxes
+  double* T = nullptr;        // nf/2        complex twiddles exp(+2πi j/nf)
+  double* GinvT = nullptr;    // (2W+1)×nf   banded inverse of the collocation matrix, tap-major
+  double* gp_grid = nullptr;  // G×D
+  double* gp_var = nullptr;   // M
+  double* gp_ls = nullptr;    // M×D
+  double* L = nullptr;        // ld×ld lower Cholesky factor of v11 (row-major, identity padding)
+  double* zw = nullptr;       // ld  L⁻¹·ŵ
+  // per-call scratch (device), sized for Bmax walkers
+  double* theta = nullptr;    // Bmax×ntheta staging for the host-buffer entry
+  double* sb = nullptr;       // Bmax×(nf/2+1) rotational transfer function
+  double* y = nullptr;        // Bmax×R×nf   broadened bulk fluxes on the fine grid
+  double* Y = nullptr;        // Bmax×R×N    resampled onto the data pixels
+  double* mu = nullptr;       // Bmax×M      emulator weights
+  double* wcov = nullptr;     // Bmax×M×M    emulator weight covariance Σ_w
+  double* X = nullptr;        // Bmax×M×N
+  double* A = nullptr;        // Bmax×M×M
+  double* flux = nullptr;     // Bmax×N
+  double* log_scale = nullptr;  // Bmax
+  int* status = nullptr;      // Bmax
+  double* wave_max = nullptr; // device scalar: max of the data wavelengths
+};
+
+struct UpstreamArgs {
+  int B = 0;
+  int ntheta = 0;             // row length of theta
+  int ncheb = 0;              // Chebyshev coefficients c1..c_ncheb per walker (c0 is pinned to 1)
+  const double* theta = nullptr;      // B×ntheta: [grid params (D) | vsini | vz | log_scale | norm | cheb...]
+  const double* wave = nullptr;       // N  data wavelengths
+  const double* data_flux = nullptr;  // N
+  double* X = nullptr;        // outputs
+  double* A = nullptr;
+  double* flux = nullptr;
+  double* log_scale_out = nullptr;
+  int* status = nullptr;
+};
+
+// pure host helpers (also exported through the C ABI for CPU tests)
+void host_rfft(int n, const double* x, double* out_complex);                      // n power of two
+int host_spline_inverse_band(int nf, const double* fw, int W, double* out_tapmajor);
+int host_cholesky_lower(int n, double* a, int lda);                                 // in place, returns LAPACK info
+
+cudaError_t model_setup(ModelState* ms, int N, int M, int Bmax, int nf, const double* fine_wave_h,
+                        const double* bulk_h, int G, int D, const double* grid_h, const double* var_h,
+                        const double* ls_h, const double* v11_h, const double* what_h, int ncheb_max,
+                        int flags, std::string* err);
+void model_free(ModelState* ms);
+cudaError_t launch_wave_max(const double* wave, int N, double* out, cudaStream_t st);
+cudaError_t launch_upstream(const ModelState& ms, const UpstreamArgs& a, cudaStream_t st, long long* launches);
+cudaError_t launch_merge_status(const int* status, int* info, double* lnL, int B, cudaStream_t st);
+cudaError_t upstream_init();
+
+}  // namespace sfb

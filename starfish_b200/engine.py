@@ -219,6 +219,84 @@ class LikelihoodEngine:
                                                hp(resid_out, np.float64)), "sfb_loglike_host")
         return lnL_out, info_out
 
+    # -- upstream of the covariance (rows f1/f2/f3): parameters in, log-likelihood out --------------
+    def set_model(self, fine_wave, bulk_fluxes, grid_points, variances, lengthscales, v11, w_hat,
+                  ncheb_max: int = 0, flags: int = 0):
+        """Upload the static model data (SpectrumModel.min_dv_wave / bulk_fluxes and the emulator's GP
+        tables).  The library derives what it needs from them once: the spectrum of the bulk fluxes, the
+        banded inverse of the spline collocation matrix, chol(v11) and L⁻¹ŵ."""
+        def h(a, shape):
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            if a.shape != tuple(shape):
+                raise ValueError(f"expected shape {tuple(shape)}, got {a.shape}")
+            return a
+
+        fine_wave = np.ascontiguousarray(fine_wave, dtype=np.float64)
+        nf = fine_wave.shape[0]
+        grid_points = np.ascontiguousarray(grid_points, dtype=np.float64)
+        G, D = grid_points.shape
+        bulk = h(bulk_fluxes, (self.M + 2, nf))
+        var = h(variances, (self.M,))
+        ls = h(lengthscales, (self.M, D))
+        v11 = h(v11, (self.M * G, self.M * G))
+        what = h(w_hat, (self.M * G,))
+        self._check(self._lib.sfb_set_model_host(
+            self._h, nf, fine_wave.ctypes.data, bulk.ctypes.data, G, D, grid_points.ctypes.data, var.ctypes.data,
+            ls.ctypes.data, v11.ctypes.data, what.ctypes.data, int(ncheb_max), int(flags)), "sfb_set_model_host")
+        self.D, self.model_flags, self.ncheb_max = D, int(flags), int(ncheb_max)
+
+    def theta_width(self, ncheb):
+        return self.D + 4 + int(ncheb)
+
+    def upstream(self, theta, ncheb: int):
+        """Device tensors of everything SpectrumModel.__call__ computes before the rank-M term:
+        dict(X[B,M,N], A[B,M,M], flux[B,N], log_scale[B], status[B], weights[B,M], weights_cov[B,M,M])."""
+        torch = _torch()
+        th = self._dev(theta)
+        B = th.shape[0]
+        if th.dim() != 2 or th.shape[1] != self.theta_width(ncheb):
+            raise ValueError(f"theta must be [B,{self.theta_width(ncheb)}]")
+        f64 = dict(dtype=torch.float64, device=self.device)
+        out = dict(X=torch.empty((B, self.M, self.N), **f64), A=torch.empty((B, self.M, self.M), **f64),
+                   flux=torch.empty((B, self.N), **f64), log_scale=torch.empty((B,), **f64),
+                   status=torch.empty((B,), dtype=torch.int32, device=self.device),
+                   weights=torch.empty((B, self.M), **f64), weights_cov=torch.empty((B, self.M, self.M), **f64))
+        if B:
+            self._check(self._lib.sfb_upstream(self._h, B, self._ptr(th), int(ncheb), self._ptr(out["X"]),
+                                               self._ptr(out["A"]), self._ptr(out["flux"]),
+                                               self._ptr(out["log_scale"]), self._ptr(out["status"]),
+                                               self._ptr(out["weights"]), self._ptr(out["weights_cov"]),
+                                               self._stream()), "sfb_upstream")
+        self._keep = (th,)
+        return out
+
+    def log_likelihood_params_resident(self, B, theta, ncheb, g, n, l, lnL, info, shared_hyper=False):
+        """Benchmark variant: every argument is a packed device tensor."""
+        self._check(self._lib.sfb_loglike_params(self._h, B, self._ptr(theta), int(ncheb), self._ptr(g),
+                                                 self._ptr(n), self._ptr(l), int(shared_hyper), self._ptr(lnL),
+                                                 self._ptr(info), C.c_void_p(0), C.c_void_p(0), self._stream()),
+                    "sfb_loglike_params")
+
+    def log_likelihood_params_host(self, theta, ncheb, glob, nloc, loc, lnL_out, info_out, shared_hyper=False,
+                                   resid_out=None, log_scale_out=None):
+        """The ensemble step on HOST buffers: B×ntheta parameter values and the kernel hyper-parameters go
+        up, lnL/info (and optionally the fitted log_scale and the residuals) come back."""
+        def hp(a, dt):
+            if a is None:
+                return C.c_void_p(0)
+            if not (isinstance(a, np.ndarray) and a.dtype == dt and a.flags["C_CONTIGUOUS"]):
+                raise ValueError("host buffers must be C-contiguous numpy arrays of the documented dtype")
+            return C.c_void_p(a.ctypes.data)
+
+        B = theta.shape[0]
+        if theta.ndim != 2 or theta.shape[1] != self.theta_width(ncheb):
+            raise ValueError(f"theta must be [B,{self.theta_width(ncheb)}]")
+        self._check(self._lib.sfb_loglike_params_host(
+            self._h, B, hp(theta, np.float64), int(ncheb), hp(glob, np.float64), hp(nloc, np.int32),
+            hp(loc, np.float64), int(shared_hyper), hp(lnL_out, np.float64), hp(info_out, np.int32),
+            hp(resid_out, np.float64), hp(log_scale_out, np.float64)), "sfb_loglike_params_host")
+        return lnL_out, info_out
+
     def cho_factor(self, Cmat, return_logdet=False):
         """Batched in-place lower Cholesky of device tensor [B,N,N] (row-major; lower triangle read and
         overwritten with L; strict upper untouched).  Returns (Cmat, info[, logdet])."""

@@ -12,7 +12,9 @@ What differs is where the work happens.  Everything from the rank-M emulator ter
 (:334-363, :399-405) is one call into libsfb200 (``LikelihoodEngine``); the dense N×N covariance only
 comes back to the host when ``model()`` is asked for it.  ``log_likelihood_batch(P)`` is new: it evaluates
 a whole ensemble of parameter vectors in one GPU pass and plugs into ``emcee.EnsembleSampler(...,
-vectorize=True)``.  The spectral transforms upstream of the path stay on the host.
+vectorize=True)``.  The spectral transforms and the emulator's GP predictive upstream of the path
+(:287-332) run on the device as well (csrc/upstream.cu); ``upstream="host"`` selects
+the numpy mirrors of ``transforms.py`` instead (an explicit option for cross-checks, never a fallback).
 """
 from __future__ import annotations
 
@@ -67,13 +69,17 @@ class SpectrumModel:
     _LOCAL_PARAMS = list(_LOCAL_KEYS)
 
     def __init__(self, emulator, data, grid_params: Sequence[float], max_deque_len: int = 100, norm=False,
-                 name: str = "SpectrumModel", device: int = 0, emulator_term: str = "reference", **params):
+                 name: str = "SpectrumModel", device: int = 0, emulator_term: str = "reference",
+                 upstream: str = "device", **params):
         if isinstance(emulator, str) or isinstance(data, str):
             raise NotImplementedError("loading from HDF5 paths needs h5py; pass in-memory Emulator/Spectrum")
         if len(data) > 1:
             raise ValueError("Multiple orders detected in data, please use EchelleModel")
         if emulator_term not in ("reference", "paper"):
             raise ValueError("emulator_term must be 'reference' (XᵀΣ_w⁻¹X, as coded) or 'paper' (XᵀΣ_wX)")
+        if upstream not in ("device", "host"):
+            raise ValueError("upstream must be 'device' (CUDA transforms + emulator) or 'host' (numpy mirrors)")
+        self.upstream = upstream
         self.emulator = emulator
         self.data_name = data.name
         self.data = data[0]
@@ -104,6 +110,7 @@ class SpectrumModel:
         self._log_scale = params.get("log_scale", None)
         self._engine = None
         self._static_sig = None
+        self._model_sig = None
         self.log = logging.getLogger(self.__class__.__name__)
 
     # ------------------------------------------------------------------------------------------------
@@ -304,13 +311,34 @@ class SpectrumModel:
     # ------------------------------------------------------------------------------------------------
     # GPU plumbing
     # ------------------------------------------------------------------------------------------------
+    def _n_local(self):
+        return len(self.params.as_dict()["local_cov"]) if "local_cov" in self.params else 0
+
+    def _n_cheb(self):
+        return len(self.params["cheb"].keys()) if "cheb" in self.params else 0
+
+    def _model_flags(self):
+        from . import _lib
+
+        flags = 0
+        if "vsini" in self.params:
+            flags |= _lib.MODEL_VSINI
+        if "vz" in self.params:
+            flags |= _lib.MODEL_VZ
+        if "log_scale" in self.params:
+            flags |= _lib.MODEL_LOG_SCALE
+        if self.norm:
+            flags |= _lib.MODEL_NORM
+        if self.emulator_term == "paper":
+            flags |= _lib.MODEL_PAPER_TERM
+        return flags
+
     def _get_engine(self, n_walkers, n_local=None):
         from .engine import LikelihoodEngine
 
         n = len(self.data.wave)
         m = self.emulator.ncomps
-        k = max(1, n_local if n_local is not None else
-                (len(self.params.as_dict()["local_cov"]) if "local_cov" in self.params else 0))
+        k = max(1, n_local if n_local is not None else self._n_local())
         eng = self._engine
         if eng is None or eng.N != n or eng.M != m or eng.K < k or eng.B < n_walkers:
             if eng is not None:
@@ -319,6 +347,7 @@ class SpectrumModel:
                 eng.close()
             self._engine = eng = LikelihoodEngine(n, m, k, n_walkers, device=self.device)
             self._static_sig = None
+            self._model_sig = None
         return eng
 
     def _sync_static(self, eng):
@@ -330,25 +359,146 @@ class SpectrumModel:
             eng.set_data(*cur)
             self._static_sig = cur
 
+    def _sync_model(self, eng):
+        """Upload the static model tables (fine-grid bulk fluxes, emulator GP) when they changed: new
+        engine, re-trained emulator hyper-parameters, a parameter group added or removed."""
+        emu = self.emulator
+        sig = (id(eng), id(self.bulk_fluxes), id(emu.v11), id(emu.w_hat), emu.get_param_vector().tobytes(),
+               self._model_flags(), self._n_cheb())
+        if getattr(self, "_model_sig", None) != sig:
+            eng.set_model(self.min_dv_wave, self.bulk_fluxes, emu.grid_points, emu.variances, emu.lengthscales,
+                          emu.v11, emu.w_hat, ncheb_max=self._n_cheb(), flags=self._model_flags())
+            self._model_sig = sig
+
     @staticmethod
     def _check_finite(*arrays):
         for a in arrays:
             if not np.all(np.isfinite(a)):
                 raise ValueError("array must not contain infs or NaNs")
 
+    def _columns(self, P=None):
+        """{flat parameter key: value array [B]} — thawed parameters from the columns of ``P`` (in
+        ``labels`` order), frozen ones from the model; ``P=None`` means the model's current state (B=1)."""
+        if P is None:
+            return 1, {k: np.array([v], dtype=np.float64) for k, v in self.params.items()}
+        labels = self.labels
+        B = P.shape[0]
+        cols = {k: np.full(B, v, dtype=np.float64) for k, v in self.params.items()}
+        for j, key in enumerate(labels):
+            cols[key] = np.ascontiguousarray(P[:, j])
+        return B, cols
+
+    def _theta(self, B, cols):
+        """Pack the per-walker parameters the device upstream stage reads (include/sfb200.h, sfb_upstream):
+        [grid params | vsini | vz | log_scale | norm | c1..c_ncheb]."""
+        D, nc = len(self.emulator.param_names), self._n_cheb()
+        th = np.zeros((B, D + 4 + nc))
+        for d, name in enumerate(self.emulator.param_names):
+            th[:, d] = cols[name]
+        if "vsini" in self.params:
+            th[:, D] = cols["vsini"]
+        if "vz" in self.params:
+            th[:, D + 1] = cols["vz"]
+        if "log_scale" in self.params:
+            th[:, D + 2] = cols["log_scale"]
+        th[:, D + 3] = self.emulator.norm_factor(th[:, :D]) if self.norm else 1.0
+        for i, key in enumerate(self.params["cheb"].keys() if nc else []):
+            th[:, D + 4 + i] = cols[f"cheb:{key}"]
+        return th
+
+    def _hyper_rows(self, B, cols):
+        """-> (glob [Bh,2], nloc [Bh] int32, loc [Bh,K,3], shared) with the frozen-group cache semantics of
+        spectrum_model.py:341-363: a frozen group keeps the values it was first evaluated with."""
+        g_cached, l_cached = self._kernel_hyper()
+        K = max(1, self._n_local())
+        g_thawed = "global_cov" in self.params and "global_cov" not in self.frozen
+        l_thawed = "local_cov" in self.params and "local_cov" not in self.frozen
+        shared = not (g_thawed or l_thawed)
+        Bh = 1 if shared else B
+        glob = np.zeros((Bh, 2))
+        glob[:, 1] = 1.0
+        if g_thawed and not shared:
+            glob[:, 0] = np.exp(cols["global_cov:log_amp"])
+            glob[:, 1] = np.exp(cols["global_cov:log_ls"])
+        elif g_cached is not None:
+            glob[:] = g_cached
+        loc = np.zeros((Bh, K, 3))
+        nloc = np.zeros(Bh, dtype=np.int32)
+        if l_thawed and not shared:
+            nk = self._n_local()
+            for k in range(nk):
+                loc[:, k, 0] = np.exp(cols[f"local_cov:{k}:log_amp"])
+                loc[:, k, 1] = cols[f"local_cov:{k}:mu"]
+                loc[:, k, 2] = np.exp(cols[f"local_cov:{k}:log_sigma"])
+            nloc[:] = nk
+        elif l_cached is not None and len(l_cached):
+            loc[:, :len(l_cached)] = l_cached
+            nloc[:] = len(l_cached)
+        return glob, nloc, loc, shared
+
+    @staticmethod
+    def _pad_loc(eng, loc):
+        if loc.shape[1] == eng.K:
+            return loc
+        pad = np.zeros((loc.shape[0], eng.K, 3))
+        pad[:, :loc.shape[1]] = loc
+        return pad
+
+    def _check_transforms(self, cols):
+        if "Av" in self.params and np.any(cols["Av"] != 0):
+            raise NotImplementedError("extinction needs the `extinction` package, absent from this image")
+        if "vsini" in self.params and np.any(cols["vsini"] <= 0):
+            raise ValueError("vsini must be positive")
+
     # ------------------------------------------------------------------------------------------------
     # evaluation
     # ------------------------------------------------------------------------------------------------
     def __call__(self):
-        """-> (flux[N], cov[N,N]) like the reference; the covariance is assembled on the GPU."""
-        flux, X, weights_cov = self._upstream()
+        """-> (flux[N], cov[N,N]) like the reference; transforms, emulator and covariance all run on the GPU."""
+        if self.upstream == "host":
+            flux, X, weights_cov = self._upstream()
+            A = self._emulator_matrix(weights_cov)[None]
+            X = X[None]
         glob, loc = self._kernel_hyper()
         eng = self._get_engine(1)
         self._sync_static(eng)
-        A = self._emulator_matrix(weights_cov)
-        C = eng.build_covariance(X[None], A[None], glob=None if glob is None else np.array([glob]),
+        if self.upstream != "host":
+            B, cols = self._columns()
+            self._check_transforms(cols)
+            gp = self.grid_params
+            if np.any(gp < self.emulator.min_params) or np.any(gp > self.emulator.max_params):
+                raise ValueError("Querying emulator outside of original parameter range.")
+            self._sync_model(eng)
+            up = eng.upstream(self._theta(B, cols), self._n_cheb())
+            if int(up["status"].cpu().numpy()[0]) != 0:
+                raise np.linalg.LinAlgError("emulator weights covariance is not positive definite")
+            X, A = up["X"], up["A"]
+            flux = up["flux"][0].cpu().numpy()
+            self._log_scale = float(up["log_scale"].cpu().numpy()[0])
+        C = eng.build_covariance(X, A, glob=None if glob is None else np.array([glob]),
                                  loc=None if loc is None or len(loc) == 0 else loc[None], n_walkers=1)
         return flux, C[0].cpu().numpy()
+
+    def _prior_rows(self, B, cols, priors):
+        """Σ prior.logpdf per row (spectrum_model.py:387-395); priors on 'cheb' see the coefficient list."""
+        lp = np.zeros(B)
+        if priors is None:
+            return lp
+        for key, prior in priors.items():
+            if key not in self.params:
+                continue
+            if key == "cheb":
+                vals = np.stack([cols[f"cheb:{k}"] for k in self.params["cheb"].keys()], axis=1)
+                lp += np.array([np.sum(prior.logpdf(list(v))) for v in vals])
+                continue
+            try:
+                term = np.asarray(prior.logpdf(cols[key]), dtype=np.float64)
+                if term.shape != (B,):
+                    raise ValueError
+            except Exception:
+                term = np.array([prior.logpdf(v) for v in cols[key]], dtype=np.float64)
+            lp += term
+        return lp
 
     def log_likelihood(self, priors: Optional[dict] = None) -> float:
         prior_lp = 0
@@ -358,6 +508,35 @@ class SpectrumModel:
                     prior_lp += prior.logpdf(self[key])
         if not np.isfinite(prior_lp):
             return -np.inf
+        if self.upstream == "host":
+            return self._log_likelihood_host_upstream() + prior_lp
+        B, cols = self._columns()
+        self._check_transforms(cols)
+        gp = self.grid_params
+        if np.any(gp < self.emulator.min_params) or np.any(gp > self.emulator.max_params):
+            raise ValueError("Querying emulator outside of original parameter range.")
+        theta = self._theta(B, cols)
+        glob, nloc, loc, shared = self._hyper_rows(B, cols)
+        self._check_finite(theta, glob, loc)
+        eng = self._get_engine(1)
+        self._sync_static(eng)
+        self._sync_model(eng)
+        loc = self._pad_loc(eng, loc)
+        lnL, info = np.empty(1), np.empty(1, dtype=np.int32)
+        resid, lsc = np.empty((1, eng.N)), np.empty(1)
+        eng.log_likelihood_params_host(theta, self._n_cheb(), glob, nloc, loc, lnL, info, shared_hyper=shared,
+                                       resid_out=resid, log_scale_out=lsc)
+        self._log_scale = float(lsc[0])
+        self.residuals.append(resid[0])
+        if info[0] < 0:
+            raise np.linalg.LinAlgError("emulator weights covariance is not positive definite")
+        if info[0] > 0:
+            raise np.linalg.LinAlgError(f"{int(info[0])}-th leading minor of the array is not positive definite")
+        self._lnprob = float(lnL[0])
+        return self._lnprob + prior_lp
+
+    def _log_likelihood_host_upstream(self):
+        """``upstream='host'``: transforms and emulator through the numpy mirrors, covariance path on the GPU."""
         flux, X, weights_cov = self._upstream()
         glob, loc = self._kernel_hyper()
         self._check_finite(flux, X, weights_cov)
@@ -372,20 +551,70 @@ class SpectrumModel:
         if code > 0:
             raise np.linalg.LinAlgError(f"{code}-th leading minor of the array is not positive definite")
         self._lnprob = float(lnL.cpu().numpy()[0])
-        return self._lnprob + prior_lp
+        return self._lnprob
 
-    def log_likelihood_batch(self, P, priors: Optional[dict] = None, on_not_pd: str = "-inf"):
-        """Log-probability of B parameter vectors (rows of ``P``, columns in ``self.labels`` order).
+    def log_likelihood_batch(self, P, priors: Optional[dict] = None, on_not_pd: str = "-inf",
+                             store_residual: bool = False):
+        """Log-probability of B parameter vectors (rows of ``P``, columns in ``self.labels`` order) in ONE
+        GPU pass: B×ndim numbers go up, B log-likelihoods come back; transforms, emulator, covariance,
+        Cholesky and solve all run on the device.  Plugs into ``emcee.EnsembleSampler(..., vectorize=True)``.
 
-        Rows whose priors are non-finite or whose grid parameters fall outside the emulator grid get
-        ``-inf`` without any GPU work (mirrors spectrum_model.py:394-395 and the priors' usual role);
-        rows whose covariance is not positive definite get ``-inf`` (``on_not_pd='-inf'``) or raise
-        ``LinAlgError`` (``on_not_pd='raise'``).  The model's own parameters are left unchanged.
+        Rows whose priors are non-finite, whose parameters are non-finite or whose grid parameters fall
+        outside the emulator grid get ``-inf`` without any GPU work (mirrors spectrum_model.py:394-395 and
+        the priors' usual role); rows whose covariance is not positive definite get ``-inf``
+        (``on_not_pd='-inf'``) or raise ``LinAlgError`` (``on_not_pd='raise'``).  The model's own parameters
+        are left unchanged; ``store_residual`` appends the residual of the last evaluated row to
+        ``self.residuals``.
         """
         P = np.atleast_2d(np.asarray(P, dtype=np.float64))
-        labels = self.labels
-        if P.shape[1] != len(labels):
+        if P.shape[1] != len(self.labels):
             raise ValueError("Param Vector does not match length of thawed parameters")
+        if self.upstream == "host":
+            return self._log_likelihood_batch_host_upstream(P, priors, on_not_pd)
+        B, cols = self._columns(P)
+        out = np.full(B, -np.inf)
+        if B == 0:
+            return out
+        lp = self._prior_rows(B, cols, priors)
+        theta = self._theta(B, cols)
+        D = len(self.emulator.param_names)
+        ok = np.isfinite(lp) & np.all(np.isfinite(theta), axis=1)
+        ok &= ~(np.any(theta[:, :D] < self.emulator.min_params, axis=1) |
+                np.any(theta[:, :D] > self.emulator.max_params, axis=1))
+        saved_cache = (self._glob_cov, self._loc_cov)
+        try:
+            glob, nloc, loc, shared = self._hyper_rows(B, cols)
+        finally:
+            self._glob_cov, self._loc_cov = saved_cache
+        if not shared:
+            ok &= np.all(np.isfinite(glob), axis=1) & np.all(np.isfinite(loc.reshape(B, -1)), axis=1)
+        rows = np.flatnonzero(ok)
+        if rows.size == 0:
+            return out
+        self._check_transforms({k: v[rows] for k, v in cols.items()})
+        theta = np.ascontiguousarray(theta[rows])
+        if not shared:
+            glob, nloc, loc = (np.ascontiguousarray(a[rows]) for a in (glob, nloc, loc))
+        nb = rows.size
+        eng = self._get_engine(nb)
+        self._sync_static(eng)
+        self._sync_model(eng)
+        loc = self._pad_loc(eng, loc)
+        lnL, info = np.empty(nb), np.empty(nb, dtype=np.int32)
+        resid = np.empty((nb, eng.N)) if store_residual else None
+        eng.log_likelihood_params_host(theta, self._n_cheb(), glob, nloc, loc, lnL, info, shared_hyper=shared,
+                                       resid_out=resid)
+        if store_residual:
+            self.residuals.append(resid[-1])
+        if on_not_pd == "raise" and (info != 0).any():
+            bad = int(np.flatnonzero(info != 0)[0])
+            raise np.linalg.LinAlgError(f"walker {rows[bad]}: covariance not positive definite (info={int(info[bad])})")
+        good = info == 0
+        out[rows[good]] = lnL[good] + lp[rows][good]
+        return out
+
+    def _log_likelihood_batch_host_upstream(self, P, priors, on_not_pd):
+        """``upstream='host'`` variant of ``log_likelihood_batch``: per-row numpy transforms, one GPU pass."""
         B = P.shape[0]
         out = np.full(B, -np.inf)
         saved = self.get_param_vector()
@@ -426,11 +655,9 @@ class SpectrumModel:
             nloc[i] = len(l)
         eng = self._get_engine(nb, n_local=kmax)
         self._sync_static(eng)
-        lnL, info, resid = eng.log_likelihood(np.array(Xs), np.array(As), np.array(fluxes),
-                                              glob=np.array(globs), nloc=nloc, loc=loc_arr,
-                                              return_residuals=True)
+        lnL, info = eng.log_likelihood(np.array(Xs), np.array(As), np.array(fluxes),
+                                       glob=np.array(globs), nloc=nloc, loc=loc_arr)
         lnL, info = lnL.cpu().numpy(), info.cpu().numpy()
-        self.residuals.append(resid[-1].cpu().numpy())
         if on_not_pd == "raise" and (info > 0).any():
             bad = int(np.flatnonzero(info > 0)[0])
             raise np.linalg.LinAlgError(f"walker {rows[bad]}: {int(info[bad])}-th leading minor of the array "

@@ -21,3 +21,18 @@ def make_model(n_pix=256, walker=0, wave=None, mus=None, **over):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         return SpectrumModel(emu, Spectrum(w, f, sigmas=s, name="synthetic"), grid_params=grid, **p)
+
+
+def make_model_params(wave, grid, params, **kw):
+    """Our SpectrumModel for an explicit (wave, grid params, parameter dict) — the upstream variants."""
+    from starfish_b200.emulator import Emulator
+    from starfish_b200.spectrum import Spectrum
+    from starfish_b200.spectrum_model import SpectrumModel
+
+    emu = Emulator(**copy.deepcopy(synth.make_emulator_arrays()))
+    emu._trained = True
+    w, f, s = synth.make_data(len(wave), wave=wave)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return SpectrumModel(emu, Spectrum(w, f, sigmas=s, name="synthetic"), grid_params=grid,
+                             **copy.deepcopy(params), **kw)

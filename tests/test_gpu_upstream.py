@@ -1,0 +1,217 @@
+"""GPU: the device upstream stage (csrc/upstream.cu — emulator GP predictive, rotational broadening, Doppler
+shift, quintic-spline resampling, Chebyshev correction, reconstruction, scaling) against stage inputs
+recorded inside the unmodified reference's ``SpectrumModel.__call__`` and against the CPU oracle.
+
+Tolerances.  Everything here is fp64, but two steps of the reference are ill-conditioned *as coded* and
+ulp-level differences between glibc/cephes and the CUDA math library are amplified by them:
+  * Gray's transfer function  j1(u)/u − 3cos(u)/(2u²) + 3sin(u)/(2u³)  cancels catastrophically for small u
+    (error ≈ 1.5e-16/u²; u ≈ 3e-4·k for the smallest vsini used here → ~1e-9/k² on the lowest Fourier modes);
+  * the emulator's Σ_w = v22 − v21·v11⁻¹·v12 cancels 1e4 down to O(1) (noise floor 3e-12 relative even for
+    LAPACK's own LU, measured against 50-digit arithmetic).
+Hence: X and model flux to 2e-9·max|·|, Σ_w and weights to 1e-10, lnL to 1e-8·|lnL| (the whole-model
+tolerance already used by test_gpu_model.py).  Variants without rotation agree to 1e-12.
+"""
+import copy
+import os
+
+import numpy as np
+import pytest
+
+from oracle import starfish_oracle as O
+from oracle import upstream_oracle as U
+from oracle.make_golden import UPSTREAM_VARIANTS, upstream_variant_params
+from starfish_b200 import synth
+
+from _helpers import make_model, make_model_params
+
+pytestmark = pytest.mark.gpu
+
+
+def _load(golden_dir, name):
+    return dict(np.load(os.path.join(golden_dir, name), allow_pickle=False))
+
+
+def _device_upstream(m):
+    """Run sfb_upstream for the model's current parameters -> dict of numpy arrays."""
+    eng = m._get_engine(1)
+    m._sync_static(eng)
+    m._sync_model(eng)
+    B, cols = m._columns()
+    up = eng.upstream(m._theta(B, cols), m._n_cheb())
+    return {k: v.cpu().numpy()[0] for k, v in up.items()}
+
+
+@pytest.mark.parametrize("name", sorted(UPSTREAM_VARIANTS))
+def test_upstream_variants_against_reference_fixture(golden_dir, name):
+    g = _load(golden_dir, f"upstream_{name}.npz")
+    n_pix, wave, grid, p = upstream_variant_params(name)
+    m = make_model_params(wave, grid, p)
+    assert len(m.min_dv_wave) == int(g["n_fine"])
+    up = _device_upstream(m)
+    assert up["status"] == 0
+    tol = 2e-9 if "vsini" in p else 1e-12
+    ex = np.abs(up["X"] - g["X"]).max() / np.abs(g["X"]).max()
+    ef = np.abs(up["flux"] - g["model_flux"]).max() / np.abs(g["model_flux"]).max()
+    print(f"variant {name}: X rel err {ex:.2e}, flux rel err {ef:.2e}")
+    assert ex <= tol and ef <= tol
+    assert np.abs(up["weights"] - g["weights"]).max() <= 1e-10 * np.abs(g["weights"]).max()
+    assert np.abs(up["weights_cov"] - g["weights_cov"]).max() <= 1e-10 * np.abs(g["weights_cov"]).max()
+    A_ref = np.linalg.inv(g["weights_cov"])
+    assert np.abs(up["A"] - A_ref).max() <= 1e-9 * np.abs(A_ref).max()
+    assert abs(up["log_scale"] - g["log_scale"]) <= 1e-9
+    # the whole model call and the log-likelihood through the drop-in object
+    flux, cov = m()
+    assert np.abs(cov.diagonal() - g["cov_diag"]).max() <= 1e-8 * g["cov_diag"].max()
+    lnl = m.log_likelihood()
+    assert abs(lnl - g["lnL"]) <= 1e-8 * abs(g["lnL"])
+    assert abs(m._log_scale - g["log_scale"]) <= 1e-9
+
+
+@pytest.mark.parametrize("fixture,n_pix,walker", [("model_n2048_w0.npz", 2048, 0), ("model_n2048_w3.npz", 2048, 3),
+                                                  ("model_n4096_w5.npz", 4096, 5)])
+def test_upstream_config_fixtures(golden_dir, fixture, n_pix, walker):
+    g = _load(golden_dir, fixture)
+    m = make_model(n_pix, walker)
+    up = _device_upstream(m)
+    assert np.abs(up["X"] - g["X"]).max() <= 2e-9 * np.abs(g["X"]).max()
+    assert np.abs(up["flux"] - g["model_flux"]).max() <= 2e-9 * np.abs(g["model_flux"]).max()
+    assert np.abs(up["weights_cov"] - g["weights_cov"]).max() <= 1e-10 * np.abs(g["weights_cov"]).max()
+    assert abs(m.log_likelihood() - g["lnL"]) <= 1e-8 * abs(g["lnL"])
+
+
+def _oracle_lnl(m, P_row):
+    """CPU oracle for one parameter vector: upstream oracle + covariance/Cholesky oracle."""
+    mm = copy.copy(m)
+    mm.params = copy.deepcopy(m.params)
+    mm.set_param_vector(P_row)
+    p = mm.params
+    emu = m.emulator
+    mu, wcov = U.emulator_predict(emu.grid_points, emu.variances, emu.lengthscales, emu.v11, emu.w_hat,
+                                  mm.grid_params)
+    cheb = [p[f"cheb:{k}"] for k in p["cheb"].keys()] if "cheb" in p else None
+    flux, X, _ = U.model_call(m.min_dv_wave, m.bulk_fluxes, m.data.wave, m.data.flux, mu,
+                              vsini=p.get("vsini"), vz=p.get("vz"), cheb=cheb, log_scale=p.get("log_scale"))
+    glob = (np.exp(p["global_cov:log_amp"]), np.exp(p["global_cov:log_ls"])) if "global_cov" in p else None
+    loc = [(np.exp(k["log_amp"]), k["mu"], np.exp(k["log_sigma"])) for k in p.as_dict().get("local_cov", [])]
+    cov = O.assemble_covariance(m.data.wave, m.data.sigma, X, wcov, glob, np.array(loc).reshape(-1, 3))
+    return O.log_likelihood(cov, flux, m.data.flux)[0]
+
+
+def test_batch_parameters_in_loglike_out(golden_dir):
+    """log_likelihood_batch: every thawed parameter varied per row, checked row by row against the oracle."""
+    g = _load(golden_dir, "model_n256_w0.npz")
+    m = make_model(256, 0, wave=g["wave"], mus=(5098.0, 5103.0), vz=12.0)
+    labels = list(m.labels)
+    P0 = m.get_param_vector()
+    rng = np.random.default_rng(11)
+    B = 7
+    P = np.tile(P0, (B, 1))
+    step = {"T": 40.0, "logg": 0.2, "Z": 0.2, "vsini": 3.0, "vz": 60.0, "log_scale": 0.1, "cheb:1": 0.02,
+            "cheb:2": 0.02, "global_cov:log_amp": 0.5, "global_cov:log_ls": 0.2}
+    for j, key in enumerate(labels):
+        s = step.get(key, 0.3 if "log_" in key else 0.5)
+        P[1:, j] += s * rng.uniform(-1, 1, B - 1)
+    P[:, labels.index("T")] = np.clip(P[:, labels.index("T")], 6000, 6200)
+    P[:, labels.index("logg")] = np.clip(P[:, labels.index("logg")], 4.0, 5.0)
+    P[:, labels.index("Z")] = np.clip(P[:, labels.index("Z")], -0.5, 0.5)
+    P[:, labels.index("vsini")] = np.abs(P[:, labels.index("vsini")]) + 0.5
+    out = m.log_likelihood_batch(P)
+    assert np.array_equal(m.get_param_vector(), P0)
+    for b in range(B):
+        ref = _oracle_lnl(m, P[b])
+        assert abs(out[b] - ref) <= 1e-8 * abs(ref), (b, out[b], ref)
+    # scalar path agrees with the batch path bit for bit on the same row
+    m.set_param_vector(P[3])
+    assert m.log_likelihood() == out[3]
+    m.set_param_vector(P0)
+    # the numpy-mirror upstream gives the same numbers to the whole-model tolerance
+    mh = make_model(256, 0, wave=g["wave"], mus=(5098.0, 5103.0), vz=12.0, upstream="host")
+    outh = mh.log_likelihood_batch(P)
+    assert np.abs(out - outh).max() <= 1e-8 * np.abs(outh).max()
+
+
+def test_batch_masks_priors_and_errors(golden_dir):
+    import scipy.stats as st
+
+    g = _load(golden_dir, "model_n256_w0.npz")
+    m = make_model(256, 0, wave=g["wave"], mus=(5098.0, 5103.0))
+    labels = list(m.labels)
+    P0 = m.get_param_vector()
+    P = np.tile(P0, (6, 1))
+    P[1, labels.index("T")] = 9000.0                      # outside the emulator grid
+    P[2, labels.index("vsini")] = np.nan                  # non-finite parameter
+    P[3, labels.index("logg")] = 4.9
+    P[4, labels.index("vsini")] = 30.0                    # prior support excludes it
+    priors = {"vsini": st.uniform(0, 20), "T": st.norm(6100, 200)}
+    launches = m._get_engine(6).launch_count
+    out = m.log_likelihood_batch(P, priors)
+    assert out[1] == -np.inf and out[2] == -np.inf and out[4] == -np.inf
+    assert np.isfinite(out[[0, 3, 5]]).all() and out[0] == out[5]
+    m.set_param_vector(P[3])
+    assert abs(m.log_likelihood(priors) - out[3]) <= 1e-12 * abs(out[3])
+    m.set_param_vector(P0)
+    # all rows masked -> no GPU work at all
+    before = m._engine.launch_count
+    assert np.all(m.log_likelihood_batch(P[[1, 2, 4]], priors) == -np.inf)
+    assert m._engine.launch_count == before
+    # vsini <= 0 raises like transforms.py:118-119
+    P[3, labels.index("vsini")] = -1.0
+    with pytest.raises(ValueError):
+        m.log_likelihood_batch(P)
+    m["vsini"] = 0.0
+    with pytest.raises(ValueError):
+        m.log_likelihood()
+    # out-of-grid scalar call raises like emulator.py:377-378
+    m["vsini"] = 5.0
+    m["T"] = 9000.0
+    with pytest.raises(ValueError):
+        m.log_likelihood()
+
+
+def test_frozen_groups_share_hyper_rows_in_batch(golden_dir):
+    g = _load(golden_dir, "model_n256_w0.npz")
+    m = make_model(256, 0, wave=g["wave"], mus=(5098.0, 5103.0))
+    ref = m.log_likelihood()
+    m.freeze(["global_cov", "local_cov"])
+    P = np.tile(m.get_param_vector(), (3, 1))
+    out = m.log_likelihood_batch(P)
+    assert np.abs(out - ref).max() <= 1e-12 * abs(ref)
+    m.thaw("global_cov")
+    P = np.tile(m.get_param_vector(), (3, 1))
+    P[1, list(m.labels).index("global_cov:log_amp")] += 1.0
+    out = m.log_likelihood_batch(P)
+    assert out[0] == out[2] and abs(out[0] - ref) <= 1e-12 * abs(ref) and out[1] != out[0]
+    m.set_param_vector(P[1])
+    assert abs(m.log_likelihood() - out[1]) <= 1e-12 * abs(out[1])
+
+
+def test_fullsize_batch_n8192_against_structured_oracle():
+    """Config 3 shape through the parameter-level entry: N=8192, model built from the synthetic emulator."""
+    from oracle import structured_oracle as S
+
+    m = make_model(8192, 0)
+    labels = list(m.labels)
+    rows = []
+    for b in range(4):
+        grid, p = synth.walker_params(b)
+        mm = make_model(8192, b)
+        rows.append(mm.get_param_vector())
+        assert list(mm.labels) == labels
+    P = np.array(rows)
+    P[:, labels.index("vz")] = [0.0, 15.0, -40.0, 3.0]
+    out = m.log_likelihood_batch(P)
+    emu = m.emulator
+    for b in range(4):
+        mm = copy.copy(m)
+        mm.params = copy.deepcopy(m.params)
+        mm.set_param_vector(P[b])
+        p = mm.params
+        mu, wcov = U.emulator_predict(emu.grid_points, emu.variances, emu.lengthscales, emu.v11, emu.w_hat,
+                                      mm.grid_params)
+        flux, X, _ = U.model_call(m.min_dv_wave, m.bulk_fluxes, m.data.wave, m.data.flux, mu, vsini=p["vsini"],
+                                  vz=p["vz"], cheb=[p["cheb:1"], p["cheb:2"]], log_scale=p["log_scale"])
+        glob = (np.exp(p["global_cov:log_amp"]), np.exp(p["global_cov:log_ls"]))
+        loc = np.array([(np.exp(k["log_amp"]), k["mu"], np.exp(k["log_sigma"])) for k in p.as_dict()["local_cov"]])
+        ref = S.stage_log_likelihood(m.data.wave, m.data.sigma, m.data.flux, X, np.linalg.inv(wcov), flux,
+                                     glob=glob, loc=loc)
+        assert abs(out[b] - ref) <= 1e-8 * abs(ref), (b, out[b], ref)

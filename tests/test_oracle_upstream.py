@@ -1,0 +1,168 @@
+"""CPU: the upstream oracle (transforms + emulator GP) against stage inputs recorded inside the unmodified
+reference's ``SpectrumModel.__call__``; the library's pure-host set-up helpers against numpy/scipy; and the
+device algorithm's index algebra (banded-inverse spline filter, de Boor evaluation, packed inverse FFT)
+restated in numpy against the oracle."""
+import copy
+import ctypes as C
+import os
+import sys
+import warnings
+
+import numpy as np
+import pytest
+
+from oracle import upstream_oracle as U
+from oracle.make_golden import UPSTREAM_VARIANTS, upstream_variant_params
+from oracle import ref_loader
+from starfish_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+
+def _load(golden_dir, name):
+    return dict(np.load(os.path.join(golden_dir, name), allow_pickle=False))
+
+
+def _oracle_variant(name):
+    n_pix, wave, grid, p = upstream_variant_params(name)
+    emu = synth.make_emulator_arrays()
+    w, f, s = synth.make_data(n_pix, wave=wave)
+    bulk = np.vstack([emu["eigenspectra"], emu["flux_mean"], emu["flux_std"]])
+    fine, bulk_f = U.model_setup(emu["wavelength"], bulk, w)
+    from starfish_b200.emulator import Emulator
+
+    e = Emulator(**copy.deepcopy(emu))  # only for v11 / default hyper-parameters (host set-up mirror)
+    mu, cov = U.emulator_predict(e.grid_points, e.variances, e.lengthscales, e.v11, e.w_hat, grid)
+    flux, X, ls = U.model_call(fine, bulk_f, w, f, mu, vsini=p.get("vsini"), vz=p.get("vz"), cheb=p.get("cheb"),
+                               log_scale=p.get("log_scale"))
+    return dict(fine=fine, flux=flux, X=X, log_scale=ls, weights=mu, weights_cov=cov)
+
+
+@pytest.mark.parametrize("name", sorted(UPSTREAM_VARIANTS))
+def test_oracle_matches_reference_fixture(golden_dir, name):
+    g = _load(golden_dir, f"upstream_{name}.npz")
+    o = _oracle_variant(name)
+    assert len(o["fine"]) == int(g["n_fine"])
+    # same third-party routines, same order: agreement to a few ulp
+    assert np.abs(o["X"] - g["X"]).max() <= 1e-15 * np.abs(g["X"]).max()
+    assert np.abs(o["flux"] - g["model_flux"]).max() <= 5e-15 * np.abs(g["model_flux"]).max()
+    assert abs(o["log_scale"] - g["log_scale"]) <= 1e-14
+    assert np.abs(o["weights"] - g["weights"]).max() <= 1e-12 * np.abs(g["weights"]).max()
+    assert np.abs(o["weights_cov"] - g["weights_cov"]).max() <= 1e-11 * np.abs(g["weights_cov"]).max()
+
+
+@pytest.mark.skipif(not ref_loader.have_reference(), reason="reference tree not mounted")
+def test_oracle_matches_live_reference():
+    ref_loader.load_reference()
+    name = "a"
+    n_pix, wave, grid, p = upstream_variant_params(name)
+    w, f, s = synth.make_data(n_pix, wave=wave)
+    model = ref_loader.build_reference_model(synth.make_emulator_arrays(), w, f, s, grid, p)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        flux, _ = model()
+    o = _oracle_variant(name)
+    assert np.abs(o["flux"] - flux).max() <= 5e-15 * np.abs(flux).max()
+    assert abs(o["log_scale"] - model._log_scale) <= 1e-14
+
+
+# ---- pure-host set-up helpers of libsfb200 (no GPU needed) -----------------------------------------
+def _lib():
+    from starfish_b200 import _lib as L
+
+    return L.lib()
+
+
+def test_host_rfft_matches_numpy():
+    lib = _lib()
+    rng = np.random.default_rng(3)
+    for n in (16, 1024, 16384):
+        x = rng.standard_normal(n)
+        out = np.zeros(2 * (n // 2 + 1))
+        assert lib.sfb_host_rfft(n, x.ctypes.data, out.ctypes.data) == 0
+        F = out[0::2] + 1j * out[1::2]
+        ref = np.fft.rfft(x)
+        assert np.abs(F - ref).max() <= 2e-15 * np.abs(ref).max()
+    assert lib.sfb_host_rfft(12, x.ctypes.data, out.ctypes.data) != 0  # not a power of two
+
+
+def test_host_cholesky_matches_lapack():
+    lib = _lib()
+    rng = np.random.default_rng(4)
+    a = rng.standard_normal((200, 200))
+    a = a @ a.T + 200 * np.eye(200)
+    L = a.copy()
+    assert lib.sfb_host_cholesky_lower(200, L.ctypes.data) == 0
+    assert np.abs(np.tril(L) - np.linalg.cholesky(a)).max() <= 1e-12
+    bad = -np.eye(5)
+    assert lib.sfb_host_cholesky_lower(5, bad.ctypes.data) == 1  # LAPACK-style info
+
+
+def _spline_band(fw):
+    lib = _lib()
+    W = lib.sfb_spline_halfwidth()
+    G = np.zeros((2 * W + 1, len(fw)))
+    assert lib.sfb_host_spline_inverse_band(len(fw), fw.ctypes.data, W, G.ctypes.data) == 0
+    return W, G
+
+
+def _fir(G, W, y):
+    ypad = np.concatenate([np.zeros(W), y, np.zeros(W)])
+    c = np.zeros(len(y))
+    for d in range(2 * W + 1):
+        c += G[d] * ypad[d:d + len(y)]
+    return c
+
+
+def test_spline_inverse_band_reproduces_fitpack_coefficients():
+    from scipy.interpolate import InterpolatedUnivariateSpline
+
+    rng = np.random.default_rng(5)
+    for nf in (64, 1024, 16384):
+        fw = 4900.0 * (5700.0 / 4900.0) ** (np.arange(nf) / (nf - 1))
+        W, G = _spline_band(fw)
+        y = 1 + 0.1 * np.sin(fw / 7) + 0.01 * rng.standard_normal(nf)
+        s = InterpolatedUnivariateSpline(fw, y, k=5)
+        assert np.abs(_fir(G, W, y) - s.get_coeffs()).max() <= 2e-14
+    # taps at the edge of the kept band are below double-precision resolution (1e-16 of the centre tap)
+    assert np.abs(G[0]).max() <= 1e-16 * np.abs(G[W]).max() and np.abs(G[-1]).max() <= 1e-16 * np.abs(G[W]).max()
+    # an irregular (not log-uniform) fine grid works as well
+    fw = np.cumsum(rng.uniform(0.5, 1.5, 512)) + 5000.0
+    W, G = _spline_band(fw)
+    y = rng.standard_normal(512)
+    assert np.abs(_fir(G, W, y) - InterpolatedUnivariateSpline(fw, y, k=5).get_coeffs()).max() <= 1e-12
+
+
+def test_device_algorithm_restated_in_numpy_matches_oracle():
+    """The kernels' algorithm (static spectrum · transfer function → packed half-length inverse FFT with
+    S-way decimation → banded-inverse filter → de Boor with Doppler-scaled knots), in numpy."""
+    import upstream_proto as P
+    from scipy.special import j1
+
+    rng = np.random.default_rng(6)
+    nf = 1024
+    fw = U.create_log_lam_grid(30.0, 5000.0, 5000.0 * (1 + 30.0 / U.C_KMS) ** 1000)
+    assert len(fw) == nf
+    bulk = 1 + 0.1 * np.sin(fw / 7)[None] + 0.01 * rng.standard_normal((2, nf))
+    vsini, vz = 45.0, -80.0
+    new_wave = np.sort(rng.uniform(fw[10], fw[-10], 40))
+    ref = U.resample(U.doppler_shift(fw, vz), U.rotational_broaden(fw, bulk, vsini), new_wave)
+    # device algorithm
+    F = np.fft.rfft(bulk)
+    k = np.arange(nf // 2 + 1)
+    ub = 2.0 * np.pi * vsini * (k * (1.0 / (nf * U.calculate_dv(fw))))
+    sb = np.ones(nf // 2 + 1)
+    sb[1:] = j1(ub[1:]) / ub[1:] - 3 * np.cos(ub[1:]) / (2 * ub[1:] ** 2) + 3.0 * np.sin(ub[1:]) / (2 * ub[1:] ** 3)
+    W, G = _spline_band(fw)
+    scale = np.sqrt((U.C_KMS + vz) / (U.C_KMS - vz))
+    for r in range(2):
+        for n_sub in (8192, 128):  # single transform / 4-way decimated
+            y = P.irfft_device(F[r] * sb, nf, n_sub)
+            assert np.abs(y - U.rotational_broaden(fw, bulk, vsini)[r]).max() <= 1e-14
+        c = _fir(G, W, y)
+        out = np.empty(len(new_wave))
+        for i, x in enumerate(new_wave):
+            l = P.interval(fw, x, scale)
+            out[i] = P.bspl(fw, x, l, scale) @ c[l - 5:l + 1]
+        assert np.abs(out - ref[r]).max() <= 1e-13
