@@ -8,8 +8,13 @@ ulp-level differences between glibc/cephes and the CUDA math library are amplifi
     (error ≈ 1.5e-16/u²; u ≈ 3e-4·k for the smallest vsini used here → ~1e-9/k² on the lowest Fourier modes);
   * the emulator's Σ_w = v22 − v21·v11⁻¹·v12 cancels 1e4 down to O(1) (noise floor 3e-12 relative even for
     LAPACK's own LU, measured against 50-digit arithmetic).
-Hence: X and model flux to 2e-9·max|·|, Σ_w and weights to 1e-10, lnL to 1e-8·|lnL| (the whole-model
-tolerance already used by test_gpu_model.py).  Variants without rotation agree to 1e-12.
+A third floor is set by the synthetic eigenspectra themselves: they are white noise on the 2 km/s grid, so
+the quintic interpolant moves by ~1e-11 (relative to max|X|) when the Doppler-scaled knots fl(λ·s) are
+perturbed by one ulp (knot spacing 0.045 Å against ulp(5000 Å) = 9e-13 Å → 2e-11 relative; shown on the CPU
+by tests/test_oracle_upstream.py::test_doppler_knot_rounding_floor).  The device fits the spline once in the
+unshifted frame — exact in real arithmetic — so it sits inside that floor, not on the reference's rounding.
+Hence: X and model flux to 2e-9·max|·| with rotation, 1e-10 with a Doppler shift only, 1e-12 with neither;
+Σ_w and weights to 1e-10, lnL to 1e-8·|lnL| (the whole-model tolerance already used by test_gpu_model.py).
 """
 import copy
 import os
@@ -49,7 +54,7 @@ def test_upstream_variants_against_reference_fixture(golden_dir, name):
     assert len(m.min_dv_wave) == int(g["n_fine"])
     up = _device_upstream(m)
     assert up["status"] == 0
-    tol = 2e-9 if "vsini" in p else 1e-12
+    tol = 2e-9 if "vsini" in p else (1e-10 if "vz" in p else 1e-12)
     ex = np.abs(up["X"] - g["X"]).max() / np.abs(g["X"]).max()
     ef = np.abs(up["flux"] - g["model_flux"]).max() / np.abs(g["model_flux"]).max()
     print(f"variant {name}: X rel err {ex:.2e}, flux rel err {ef:.2e}")

@@ -166,3 +166,22 @@ def test_device_algorithm_restated_in_numpy_matches_oracle():
             l = P.interval(fw, x, scale)
             out[i] = P.bspl(fw, x, l, scale) @ c[l - 5:l + 1]
         assert np.abs(out - ref[r]).max() <= 1e-13
+
+
+def test_doppler_knot_rounding_floor(golden_dir):
+    """The reference's own sensitivity to ONE ulp in its Doppler-scaled knots: the quintic interpolant of the
+    (white-noise) synthetic eigenspectra moves by ~1e-11 of max|X| — the agreement floor for any
+    implementation that does not reproduce fl(λ·s) knot by knot (see tests/test_gpu_upstream.py)."""
+    n_pix, wave, grid, p = upstream_variant_params("c")
+    emu = synth.make_emulator_arrays()
+    bulk = np.vstack([emu["eigenspectra"], emu["flux_mean"], emu["flux_std"]])
+    fine, bulk_f = U.model_setup(emu["wavelength"], bulk, wave)
+    shifted = U.doppler_shift(fine, p["vz"])
+    rng = np.random.default_rng(9)
+    jig = np.where(rng.random(len(fine)) < 0.5, np.nextafter(shifted, np.inf), shifted)
+    a = U.resample(shifted, bulk_f[:1], wave)
+    b = U.resample(jig, bulk_f[:1], wave)
+    rel = np.abs(a - b).max() / np.abs(a).max()
+    assert 1e-13 < rel < 1e-10
+    smooth = np.abs(U.resample(shifted, bulk_f[6:7], wave) - U.resample(jig, bulk_f[6:7], wave)).max()
+    assert smooth < 1e-13  # the smooth rows (flux mean) are insensitive
