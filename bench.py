@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-model", action="store_true", help="skip the parameter-level (drop-in model) legs")
+    ap.add_argument("--no-structured", action="store_true", help="skip the structured-solver (row f4) legs")
     ap.add_argument("--cpu-sample", type=int, default=0, help="walkers in the CPU sample (0 = auto)")
     return ap.parse_args()
 
@@ -316,7 +317,6 @@ def run_b200(args, rank, world, local_rank):
             eng.profile(False)
             model_leg["upstream_ms_per_step"] = up["ms"]
             model_leg["upstream_gbs"] = up["work"] / (up["ms"] * 1e-3) / 1e9 if up["ms"] > 0 else None
-        model._engine = None
 
     # ---- roofline of the dominant kernel: one extra profiled step (single stream, events per launch)
     roof = None
@@ -350,12 +350,51 @@ def run_b200(args, rank, world, local_rank):
                                       "achieved": (v["work"] / (v["ms"] * 1e-3) / (1e9 if k == "build" else 1e12))
                                       if v["ms"] > 0 else None,
                                       "unit": "GB/s" if k == "build" else "TFLOP/s"}
-                                  for k, v in prof.items() if k not in ("syrk", "upstream")}}
+                                  for k, v in prof.items() if k in ("build", "potrf_diag", "trsm")}}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
             roof["other_kernels"]["build"]["peak_hbm_gbs"] = peaks.get("hbm_gbs")
         except Exception:
             pass
+
+    # ---- the structure-exploiting solver (row f4): same stage boundary, banded Cholesky + capacitance ------
+    structured = None
+    if not args.no_structured:
+        lnl_dense = lnL.clone()
+        eng.set_solver("structured")
+        s_steps = max(10, 4 * args.steps)
+        ms_s, launches_s, _ = timed(step_device, s_steps, args.warmup)
+        diff = float(((lnL - lnl_dense).abs() / lnl_dense.abs().clamp(min=1.0)).max().item())
+        structured = {"value": B / (ms_s / s_steps * 1e-3), "unit": "evals/s", "steps": s_steps,
+                      "ms_per_step": ms_s / s_steps, "gpu_launches": int(launches_s),
+                      "max_rel_diff_vs_dense_lnL": diff, "not_positive_definite": int((info != 0).sum().item()),
+                      "window_classes": {str(k): v for k, v in eng.band_classes().items()},
+                      "api": "sfb_set_solver(SFB_SOLVER_STRUCTURED) + sfb_loglike (inputs resident)"}
+        if not args.no_model:
+            model.solver = "structured"
+            ms_m, launches_m, _ = timed(step_model, s_steps, 2)
+            structured["e2e_model"] = {"value": B / (ms_m / s_steps * 1e-3), "unit": "evals/s",
+                                       "ms_per_step": ms_m / s_steps, "gpu_launches": int(launches_m),
+                                       "api": "SpectrumModel(solver='structured').log_likelihood_batch(P)"}
+            model.solver = "dense"
+        if rank == 0:
+            eng.profile(True)
+            eng.log_likelihood_resident(nb, X, A, F, g, n, l, lnL, info)
+            pr = eng.profile_read()
+            eng.profile(False)
+            bc, bb = pr["band_chol"], pr["band_build"]
+            ach = bc["work"] / (bc["ms"] * 1e-3) / 1e12 if bc["ms"] > 0 else 0.0
+            structured["roofline"] = {
+                "kernel": "band_chol_kernel (register-resident sliding-window banded Cholesky + forward solves)",
+                "bound": "fp64 FMA issue", "achieved": ach, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
+                "frac": ach / FP64_DMMA_PEAK_TFLOPS,
+                "work": "algorithmic N*(b^2 + 2b(M+1)) FLOP per walker, b = its exact half-bandwidth",
+                "launches": bc["launches"], "ms": bc["ms"],
+                "band_build": {"launches": bb["launches"], "ms": bb["ms"],
+                               "achieved_gbs": bb["work"] / (bb["ms"] * 1e-3) / 1e9 if bb["ms"] > 0 else None}}
+        eng.set_solver("dense")
+    if not args.no_model:
+        model._engine = None
 
     # whole-path fp64 FLOPs per evaluation: N^3/3 + 2MN^2 + 2N^2
     flops_eval = N ** 3 / 3 + 2 * M * N ** 2 + 2 * N ** 2
@@ -366,7 +405,8 @@ def run_b200(args, rank, world, local_rank):
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(args, world),
-            "clocks": clocks, "e2e": e2e, "e2e_model": model_leg, "gpu_launches": int(launches),
+            "clocks": clocks, "e2e": e2e, "e2e_model": model_leg, "structured": structured,
+            "gpu_launches": int(launches),
             "roofline": roof,
             "path_tflops": value * flops_eval / 1e12,
             "path_frac_of_fp64_peak": value * flops_eval / 1e12 / (FP64_DMMA_PEAK_TFLOPS * world),

@@ -165,6 +165,24 @@ int sfb_host_spline_inverse_band(int nf, const double* fine_wave_h, int W, doubl
 int sfb_host_cholesky_lower(int n, double* a_h /* n×n row-major, in place */);
 int sfb_spline_halfwidth(void);
 
+/*
+ * ---- Structure-exploiting solver (scope-table row f4) ----
+ * Same contract and results as the dense path (the lines of spectrum_model.py:334-363 + :399-405), computed
+ * from C = S + XᵀAX with S = diag + K_global + ΣK_local banded on a strictly increasing wavelength grid:
+ * banded Cholesky of S (N·b² FLOP instead of N³/3) + the M×M capacitance system (determinant lemma,
+ * Woodbury).  SFB_SOLVER_STRUCTURED makes sfb_loglike / sfb_loglike_host / sfb_loglike_params(_host) use it;
+ * walkers whose band does not fit the widest register window (160 pixels), or an unsorted grid, silently
+ * take the dense path inside the same call, so results never depend on the choice beyond rounding
+ * (|ΔlnL| <= 1e-10·|lnL|, tests/test_gpu_structured.py).  The default is SFB_SOLVER_DENSE.
+ * In structured mode the call synchronises with the host once (B ints: each walker's half-bandwidth).
+ */
+enum sfb_solver { SFB_SOLVER_DENSE = 0, SFB_SOLVER_STRUCTURED = 1 };
+int sfb_set_solver(sfb_t* h, int solver);
+int sfb_get_solver(const sfb_t* h);
+/* Walkers routed to each register-window width since creation; the last entry (width 0) is the dense
+ * fallback.  Returns the number of entries written (n must be >= 5). */
+int sfb_band_classes(const sfb_t* h, int* widths, long long* walkers, int n);
+
 /* Block the host until all work queued on the handle has finished. */
 int sfb_sync(sfb_t* h);
 
@@ -175,7 +193,7 @@ int sfb_sync(sfb_t* h);
  * (bytes for SFB_K_BUILD, FLOPs otherwise), and resets the counters.  `n` = capacity of out in doubles.
  */
 enum sfb_kernel_class { SFB_K_BUILD = 0, SFB_K_POTRF_DIAG = 1, SFB_K_TRSM = 2, SFB_K_SYRK = 3, SFB_K_UPSTREAM = 4,
-                        SFB_K_NCLASS = 5 };
+                        SFB_K_BAND_BUILD = 5, SFB_K_BAND_CHOL = 6, SFB_K_NCLASS = 7 };
 int sfb_profile_enable(sfb_t* h, int on);
 int sfb_profile_read(sfb_t* h, double* out, int n);
 

@@ -16,14 +16,17 @@ EXPORTS = [
     "sfb_launch_count", "sfb_last_error",
     "sfb_set_model_host", "sfb_upstream", "sfb_loglike_params", "sfb_loglike_params_host",
     "sfb_host_rfft", "sfb_host_spline_inverse_band", "sfb_host_cholesky_lower", "sfb_spline_halfwidth",
+    "sfb_set_solver", "sfb_get_solver", "sfb_band_classes",
 ]
+
+SOLVER_DENSE, SOLVER_STRUCTURED = 0, 1
 
 ABI_VERSION = 2
 
 # sfb_model_flags of include/sfb200.h
 MODEL_VSINI, MODEL_VZ, MODEL_LOG_SCALE, MODEL_NORM, MODEL_PAPER_TERM = 1, 2, 4, 8, 16
 
-KERNEL_CLASSES = ("build", "potrf_diag", "trsm", "syrk", "upstream")
+KERNEL_CLASSES = ("build", "potrf_diag", "trsm", "syrk", "upstream", "band_build", "band_chol")
 
 _p = C.c_void_p
 _i = C.c_int
@@ -59,6 +62,9 @@ def load():
     lib.sfb_host_spline_inverse_band.argtypes = [_i, _p, _i, _p]
     lib.sfb_host_cholesky_lower.argtypes = [_i, _p]
     lib.sfb_spline_halfwidth.argtypes = []
+    lib.sfb_set_solver.argtypes = [_p, _i]
+    lib.sfb_get_solver.argtypes = [_p]
+    lib.sfb_band_classes.argtypes = [_p, _p, _p, _i]
     lib.sfb_sync.argtypes = [_p]
     lib.sfb_profile_enable.argtypes = [_p, _i]
     lib.sfb_profile_read.argtypes = [_p, _p, _i]

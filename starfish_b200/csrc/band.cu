@@ -1,0 +1,462 @@
+// Structure-exploiting solver: the same log-likelihood as the dense path, computed from
+//     C = S + XᵀAX,   S = diag(σ² + jitter) + K_global + Σ K_local
+// On a strictly increasing wavelength grid S is banded (half-width b ≈ 24ℓ/dv pixels; the local blocks lie
+// inside the band), so
+//     log det C = log det S + log det(I + A·G),          G = X S⁻¹ Xᵀ  (M×M)
+//     RᵀC⁻¹R   = RᵀS⁻¹R − uᵀ (I + A·G)⁻¹ A u,            u = X S⁻¹ R
+// needs one banded Cholesky S = LLᵀ (N·b² FLOP instead of N³/3) and the forward solves Z = L⁻¹[R | Xᵀ]:
+// everything above is a Gram matrix of Z.  It replaces Starfish/models/spectrum_model.py:334-363 + :399-405
+// exactly like the dense path; it is a separate mode with its own roofline (fp64 FMA issue of the window
+// update), reported separately by bench.py.
+//
+//   band_build_kernel   S in band storage Sb[i][d] = S[i, i−d], d < WD — same element arithmetic (operation
+//                       order, support masks) as cov_build_kernel, 8·N·WD bytes per walker instead of 8·N²
+//   band_chol_kernel    ONE persistent CTA per walker.  The active window of the factorisation (rows/columns
+//                       j..j+WD−1) lives in REGISTERS, addressed circularly (index mod WD), 8×(WD/32) elements
+//                       per thread; per pivot: the owners publish column j through a double-buffered
+//                       shared-memory column, one __syncthreads, every thread applies the rank-1 update to
+//                       its registers, and the row that enters the window replaces the one that retires.  The
+//                       M+1 right-hand sides ride along in registers, the Gram matrix ZᵀZ is accumulated on
+//                       the fly, so L is never written anywhere: HBM traffic is one read of Sb and of X.
+//                       Entering rows are staged 16 pivots ahead into a shared-memory ring with cp.async.
+#include <cmath>
+#include <cstdint>
+
+#include "sfb_internal.cuh"
+
+namespace sfb {
+
+namespace {
+
+constexpr double kPi = 3.141592653589793;  // == numpy.pi
+constexpr int NRP = kMaxM + 2;             // padded right-hand-side columns per ring row (even)
+constexpr int BATCH = 16;                  // pivots per staging batch
+
+// ------------------------------------------------------------------------------------------------
+// band build
+// ------------------------------------------------------------------------------------------------
+constexpr int BB_ROWS = 8;  // rows per CTA (one per warp)
+
+__global__ void __launch_bounds__(BB_ROWS * 32)
+band_build_kernel(BandBuildParams p) {
+  __shared__ double l_amp[kMaxK], l_mu[kMaxK], l_sig[kMaxK];
+  const int b = p.rowmap ? p.rowmap[blockIdx.y] : blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int hb = b * p.hyper_stride;
+  const double g_amp = p.glob[2 * hb], g_ls = p.glob[2 * hb + 1];
+  const int nloc = min(p.nloc[hb], p.Kmax);
+  if (threadIdx.x < nloc) {
+    const double* l = p.loc + ((long long)hb * p.Kmax + threadIdx.x) * 3;
+    l_amp[threadIdx.x] = l[0];
+    l_mu[threadIdx.x] = l[1];
+    l_sig[threadIdx.x] = l[2];
+  }
+  __syncthreads();
+  const int i = blockIdx.x * BB_ROWS + warp;
+  if (i >= p.N) return;
+  const int WD = p.WD;
+  const double wi = p.wave[i];
+  const double r0g = 6 * g_ls, sqrt3 = sqrt(3.0);
+  double* out = p.Sb + (long long)b * p.strideSb + (long long)i * WD;
+  int over = 0;
+  // local kernels: this row's metric per kernel, and the overflow test (block wider than the window)
+  for (int d = lane; d <= WD; d += 32) {  // d == WD is only the "does the band fit" probe
+    const int k = i - d;
+    double v = 0.0;
+    bool nz = false;
+    if (k >= 0) {
+      const double wk = p.wave[k];
+      if (d == 0) {
+        const double s = p.sigma[i];
+        v = s * s;
+      }
+      if (g_amp > 0.0) {
+        const double rv = kC_KMS / 2 * fabs((wk - wi) / (wk + wi));
+        if (rv <= r0g) {
+          const double taper = 0.5 + 0.5 * cos(kPi * rv / r0g);
+          v += taper * g_amp * (1 + sqrt3 * rv / g_ls) * exp(-sqrt3 * rv / g_ls);
+          nz = true;
+        }
+      }
+      double lsum = 0.0;
+      bool any = false;
+      for (int q = 0; q < nloc; ++q) {
+        const double mu = l_mu[q], r0 = 4 * l_sig[q], f = kC_KMS / mu;
+        const double mi = f * fabs(wi - mu), mj = f * fabs(wk - mu);
+        if (mi <= r0 && mj <= r0) {
+          const double rt = fmax(mi, mj);
+          const double taper = 0.5 + 0.5 * cos(kPi * rt / r0);
+          lsum += taper * l_amp[q] * exp(-0.5 * (mi * mi + mj * mj) / (l_sig[q] * l_sig[q]));
+          any = true;
+        }
+      }
+      if (any) {
+        v += lsum;
+        nz = true;
+      }
+      if (d == 0) v += p.jitter;
+    }
+    if (d < WD)
+      out[d] = v;
+    else if (nz)
+      over = 1;
+  }
+  if (over) atomicOr(p.overflow + b, 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// exact half-bandwidth of S per walker (strictly increasing grid): the largest i − k with S[i,k] != 0.
+// Global kernel: its support test is monotone in k, so row i's first in-support column is found by bisection
+// with the very same r <= r0 expression the build uses; local kernel: its support is the contiguous pixel
+// block with m <= 4σ, whose width is a count.  One CTA per walker.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+band_width_kernel(int N, int Kmax, int hyper_stride, const double* __restrict__ wave,
+                  const double* __restrict__ glob, const int* __restrict__ nloc, const double* __restrict__ loc,
+                  int* __restrict__ bw) {
+  __shared__ int s_max;
+  __shared__ int s_cnt[kMaxK];
+  const int b = blockIdx.x, hb = b * hyper_stride, tid = threadIdx.x;
+  const double g_amp = glob[2 * hb], g_ls = glob[2 * hb + 1];
+  const int nl = min(nloc[hb], Kmax);
+  if (tid == 0) s_max = 0;
+  if (tid < kMaxK) s_cnt[tid] = 0;
+  __syncthreads();
+  const double r0g = 6 * g_ls;
+  int mx = 0;
+  if (g_amp > 0.0) {
+    for (int i = tid; i < N; i += blockDim.x) {
+      const double wi = wave[i];
+      int lo = 0, hi = i;  // smallest k in [0, i] with r(i,k) <= r0g (k = i always qualifies: r = 0)
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const double wk = wave[mid];
+        if (kC_KMS / 2 * fabs((wk - wi) / (wk + wi)) <= r0g) hi = mid; else lo = mid + 1;
+      }
+      mx = max(mx, i - lo);
+    }
+  }
+  for (int q = 0; q < nl; ++q) {
+    const double* l = loc + ((long long)hb * Kmax + q) * 3;
+    const double mu = l[1], r0 = 4 * l[2], f = kC_KMS / mu;
+    int c = 0;
+    for (int i = tid; i < N; i += blockDim.x) c += (f * fabs(wave[i] - mu) <= r0) ? 1 : 0;
+    if (c) atomicAdd(&s_cnt[q], c);
+  }
+  atomicMax(&s_max, mx);
+  __syncthreads();
+  if (tid == 0) {
+    int m = s_max;
+    for (int q = 0; q < nl; ++q) m = max(m, s_cnt[q] - 1);
+    bw[b] = m;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// banded Cholesky + forward solves + Gram matrix + capacitance epilogue
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_src) {
+  const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// MAXNR = right-hand sides the instantiation can carry (M + 1 <= MAXNR)
+template <int WD, int MAXNR>
+__global__ void __launch_bounds__(WD * 4)
+band_chol_kernel(BandCholParams p) {
+  constexpr int ER = 8, EC = WD / 32, NT = WD * 4, ROWLEN = WD + NRP;
+  constexpr int NE = (WD * MAXNR + NT - 1) / NT;          // right-hand-side registers per thread
+  __shared__ double colbuf[2][WD];
+  __shared__ double zbuf[2][NRP];
+  __shared__ double gram[(kMaxM + 1) * (kMaxM + 1)];
+  extern __shared__ double ring[];  // [2][BATCH][ROWLEN]
+
+  const int b = p.rowmap ? p.rowmap[blockIdx.x] : blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, tr = tid >> 5;
+  const int N = p.N, M = p.M, NR = M + 1;
+  if (p.overflow[b] != 0 || *p.sorted == 0) {  // band wider than the window / grid not increasing: not ours
+    if (tid == 0) {
+      p.info[b] = p.overflow[b] != 0 ? -2 : -3;
+      p.lnL[b] = nan("");
+    }
+    return;
+  }
+  const double* Sb = p.Sb + (long long)b * p.strideSb;
+  const double* Xb = (M > 0) ? p.X + (long long)b * M * N : nullptr;
+  const double* Fb = p.model_flux + (long long)b * N;
+
+  auto rhs_at = [&](int i, int q) -> double {
+    if (i >= N) return 0.0;
+    return q == 0 ? Fb[i] - p.data_flux[i] : Xb[(long long)(q - 1) * N + i];
+  };
+  // fill one half of the ring with the rows that enter during the batch whose first pivot is j0 (rows
+  // j0+WD ...): band rows and X columns by 8-byte cp.async (fire and forget), the residual column and the
+  // identity padding past the end of the matrix by plain stores
+  auto stage_issue = [&](int j0, double* dst) {
+    for (int sidx = tid; sidx < BATCH * ROWLEN; sidx += NT) {
+      const int rb = sidx / ROWLEN, col = sidx - rb * ROWLEN;
+      const int i = j0 + WD + rb;
+      if (col < WD) {
+        if (i < N) cp_async8(dst + sidx, Sb + (long long)i * WD + col);
+        else dst[sidx] = (col == 0) ? 1.0 : 0.0;
+      } else {
+        const int q = col - WD;
+        if (q >= 1 && q < NR && i < N) cp_async8(dst + sidx, Xb + (long long)(q - 1) * N + i);
+        else dst[sidx] = (q == 0) ? rhs_at(i, 0) : 0.0;
+      }
+    }
+    cp_async_commit();
+  };
+
+  // ---- initial window: slot (r, c) = element (i = r, k = c), symmetric fill is not needed (k <= i only)
+  double a[ER][EC];
+#pragma unroll
+  for (int er = 0; er < ER; ++er) {
+    const int i = tr * ER + er;
+#pragma unroll
+    for (int ec = 0; ec < EC; ++ec) {
+      const int k = lane * EC + ec;
+      double v = 0.0;
+      if (k <= i) v = (i < N) ? Sb[(long long)i * WD + (i - k)] : (k == i ? 1.0 : 0.0);
+      a[er][ec] = v;
+    }
+  }
+  double rv[NE];
+  int rres[NE], rq[NE];
+#pragma unroll
+  for (int e = 0; e < NE; ++e) {
+    const int idx = tid + NT * e;
+    const bool ok = idx < WD * NR;
+    rres[e] = ok ? idx / NR : -1;
+    rq[e] = ok ? idx - (idx / NR) * NR : 0;
+    rv[e] = ok ? rhs_at(rres[e], rq[e]) : 0.0;
+  }
+  stage_issue(0, ring);
+
+  double logdet = 0.0, gacc = 0.0;
+  int info = 0;
+  const int gp_ = tid / NR, gq_ = tid - (tid / NR) * NR;  // Gram element of this thread (tid < NR²)
+  const bool gram_on = tid < NR * NR;
+
+  int jr = 0;
+  for (int j = 0; j < N; ++j) {
+    const int buf = j & 1, jb = j & (BATCH - 1), half = (j / BATCH) & 1;
+    // staging boundary: this batch's rows (issued one boundary ago) must have landed before the barrier below
+    if (jb == 0) cp_async_wait_all();
+    // ---- phase A: owners publish column j of the window and the pivot row of the right-hand sides
+    if (lane == jr / EC) {
+      const int e0 = jr - (jr / EC) * EC;
+#pragma unroll
+      for (int er = 0; er < ER; ++er) {
+        double x = a[er][0];
+#pragma unroll
+        for (int ec = 1; ec < EC; ++ec) x = (e0 == ec) ? a[er][ec] : x;
+        colbuf[buf][tr * ER + er] = x;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < NE; ++e)
+      if (rres[e] == jr) zbuf[buf][rq[e]] = rv[e];
+    __syncthreads();
+    // past the barrier nobody reads the other ring half any more (its last reader was the previous pivot):
+    // start filling it with the next batch
+    if (jb == 0) stage_issue(j + BATCH, ring + (half ^ 1) * (BATCH * ROWLEN));
+    // ---- phase C: rank-1 update of the window, right-hand sides, Gram matrix
+    const double pj = colbuf[buf][jr];
+    const double inv = 1.0 / pj;
+    if (tid == 0) {
+      if (!(pj > 0.0) && info == 0) info = j + 1;
+      logdet += log(pj);
+    }
+    double ai[ER], ak[EC];
+#pragma unroll
+    for (int er = 0; er < ER; ++er) ai[er] = colbuf[buf][tr * ER + er];
+#pragma unroll
+    for (int ec = 0; ec < EC; ++ec) ak[ec] = colbuf[buf][lane * EC + ec] * inv;
+#pragma unroll
+    for (int er = 0; er < ER; ++er)
+#pragma unroll
+      for (int ec = 0; ec < EC; ++ec) a[er][ec] = fma(-ai[er], ak[ec], a[er][ec]);
+#pragma unroll
+    for (int e = 0; e < NE; ++e)
+      if (rres[e] >= 0) rv[e] = fma(-colbuf[buf][rres[e]], zbuf[buf][rq[e]] * inv, rv[e]);
+    if (gram_on) gacc = fma(zbuf[buf][gp_] * inv, zbuf[buf][gq_], gacc);
+    // ---- the row that enters the window (index j + WD) takes the slots of the retiring index j
+    const double* row = ring + half * (BATCH * ROWLEN) + jb * ROWLEN;
+    if (tr == jr / ER) {
+      const int er0 = jr - (jr / ER) * ER;
+      double val[EC];
+#pragma unroll
+      for (int ec = 0; ec < EC; ++ec) {
+        int t = lane * EC + ec - jr - 1;
+        if (t < 0) t += WD;
+        val[ec] = row[WD - 1 - t];
+      }
+#pragma unroll
+      for (int er = 0; er < ER; ++er)
+        if (er == er0) {
+#pragma unroll
+          for (int ec = 0; ec < EC; ++ec) a[er][ec] = val[ec];
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < NE; ++e)
+      if (rres[e] == jr) rv[e] = row[WD + rq[e]];
+    jr = (jr + 1 == WD) ? 0 : jr + 1;
+  }
+
+  // ---- epilogue: lnL = −½ (log det S + log det(I + A·G) + RᵀS⁻¹R − uᵀ(I + A·G)⁻¹A u)
+  if (gram_on) gram[tid] = gacc;
+  __syncthreads();
+  if (tid == 0) {
+    double quad = gram[0], ld = logdet;
+    if (M > 0 && info == 0) {
+      double Kc[kMaxM][kMaxM], v[kMaxM], u[kMaxM];
+      const double* A = p.A + (long long)b * M * M;
+      for (int i = 0; i < M; ++i) {
+        u[i] = gram[(i + 1) * NR];
+        for (int k = 0; k < M; ++k) {
+          double s = (i == k) ? 1.0 : 0.0;
+          for (int q = 0; q < M; ++q) s = fma(A[i * M + q], gram[(q + 1) * NR + (k + 1)], s);
+          Kc[i][k] = s;
+        }
+      }
+      for (int i = 0; i < M; ++i) {
+        double s = 0.0;
+        for (int q = 0; q < M; ++q) s = fma(A[i * M + q], u[q], s);
+        v[i] = s;
+      }
+      // LU with partial pivoting on the M×M capacitance matrix, solving K y = v alongside
+      double sign = 1.0, ldk = 0.0;
+      for (int c = 0; c < M; ++c) {
+        int piv = c;
+        for (int r = c + 1; r < M; ++r)
+          if (fabs(Kc[r][c]) > fabs(Kc[piv][c])) piv = r;
+        if (piv != c) {
+          for (int q = 0; q < M; ++q) { const double t = Kc[c][q]; Kc[c][q] = Kc[piv][q]; Kc[piv][q] = t; }
+          const double t = v[c]; v[c] = v[piv]; v[piv] = t;
+          sign = -sign;
+        }
+        const double d = Kc[c][c];
+        if (d < 0.0) sign = -sign;
+        ldk += log(fabs(d));
+        for (int r = c + 1; r < M; ++r) {
+          const double f = Kc[r][c] / d;
+          for (int q = c + 1; q < M; ++q) Kc[r][q] = fma(-f, Kc[c][q], Kc[r][q]);
+          v[r] = fma(-f, v[c], v[r]);
+        }
+      }
+      for (int c = M - 1; c >= 0; --c) {
+        double s = v[c];
+        for (int q = c + 1; q < M; ++q) s = fma(-Kc[c][q], v[q], s);
+        v[c] = s / Kc[c][c];
+      }
+      // Positive definiteness of C.  With S = LLᵀ positive definite, C is PD iff every eigenvalue of I + A·G is
+      // positive (they are real: A·G is similar to the symmetric GcᵀA·Gc with G = Gc·Gcᵀ); the sign of the
+      // determinant alone would miss an even number of negative ones.  Gc: semi-definite Cholesky of the Gram
+      // matrix (a numerically zero pivot zeroes its column), then a plain Cholesky of T = I + GcᵀA·Gc decides.
+      {
+        double Gc[kMaxM][kMaxM], T[kMaxM][kMaxM];
+        double gmax = 0.0;
+        for (int i = 0; i < M; ++i) gmax = fmax(gmax, gram[(i + 1) * NR + (i + 1)]);
+        for (int c = 0; c < M; ++c) {
+          double dd = gram[(c + 1) * NR + (c + 1)];
+          for (int q = 0; q < c; ++q) dd -= Gc[c][q] * Gc[c][q];
+          const bool zero = !(dd > 1e-14 * gmax);
+          const double piv = zero ? 0.0 : sqrt(dd);
+          for (int r = 0; r < M; ++r) {
+            if (r < c) { Gc[r][c] = 0.0; continue; }
+            if (r == c) { Gc[r][c] = piv; continue; }
+            double sacc = gram[(r + 1) * NR + (c + 1)];
+            for (int q = 0; q < c; ++q) sacc -= Gc[r][q] * Gc[c][q];
+            Gc[r][c] = zero ? 0.0 : sacc / piv;
+          }
+        }
+        for (int i = 0; i < M; ++i)
+          for (int k = 0; k < M; ++k) {  // T = I + GcᵀA·Gc
+            double sacc = (i == k) ? 1.0 : 0.0;
+            for (int r = 0; r < M; ++r) {
+              double t = 0.0;
+              for (int q = 0; q < M; ++q) t = fma(A[r * M + q], Gc[q][k], t);
+              sacc = fma(Gc[r][i], t, sacc);
+            }
+            T[i][k] = sacc;
+          }
+        bool pd = true;
+        for (int c = 0; c < M && pd; ++c) {
+          double dd = 0.5 * (T[c][c] + T[c][c]);
+          for (int q = 0; q < c; ++q) dd -= T[c][q] * T[c][q];
+          if (!(dd > 0.0)) { pd = false; break; }
+          dd = sqrt(dd);
+          T[c][c] = dd;
+          for (int r = c + 1; r < M; ++r) {
+            double sacc = 0.5 * (T[r][c] + T[c][r]);
+            for (int q = 0; q < c; ++q) sacc -= T[r][q] * T[c][q];
+            T[r][c] = sacc / dd;
+          }
+        }
+        if (!pd || !(sign > 0.0) || !(ldk == ldk)) info = N;  // C is not positive definite
+      }
+      ld += ldk;
+      for (int i = 0; i < M; ++i) quad = fma(-u[i], v[i], quad);
+    }
+    p.info[b] = info;
+    p.lnL[b] = info == 0 ? -(ld + quad) / 2 : nan("");
+  }
+}
+
+template <int WD>
+cudaError_t launch_band_t(const BandCholParams& p, int B, cudaStream_t st) {
+  const size_t smem = sizeof(double) * 2 * BATCH * (WD + NRP);
+  if (p.M + 1 <= 8)
+    band_chol_kernel<WD, 8><<<B, WD * 4, smem, st>>>(p);
+  else
+    band_chol_kernel<WD, kMaxM + 1><<<B, WD * 4, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+const int kBandWidths[] = {64, 96, 128, 160};
+const int kNumBandWidths = 4;
+
+__global__ void residual_only_kernel(const double* __restrict__ F, const double* __restrict__ data, int N,
+                                     double* __restrict__ resid) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (i < N) resid[(long long)b * N + i] = F[(long long)b * N + i] - data[i];
+}
+
+cudaError_t launch_residual_only(const double* model_flux, const double* data_flux, int N, int B, double* resid,
+                                 cudaStream_t st) {
+  if (B <= 0) return cudaSuccess;
+  residual_only_kernel<<<dim3((N + 255) / 256, B), 256, 0, st>>>(model_flux, data_flux, N, resid);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_band_width(int N, int Kmax, int hyper_stride, const double* wave, const double* glob,
+                              const int* nloc, const double* loc, int* bw, int B, cudaStream_t st) {
+  if (B <= 0) return cudaSuccess;
+  band_width_kernel<<<B, 256, 0, st>>>(N, Kmax, hyper_stride, wave, glob, nloc, loc, bw);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_band_build(const BandBuildParams& p, int B, cudaStream_t st) {
+  if (B <= 0) return cudaSuccess;
+  band_build_kernel<<<dim3((p.N + BB_ROWS - 1) / BB_ROWS, B), BB_ROWS * 32, 0, st>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_band_chol(const BandCholParams& p, int WD, int B, cudaStream_t st) {
+  if (B <= 0) return cudaSuccess;
+  switch (WD) {
+    case 64: return launch_band_t<64>(p, B, st);
+    case 96: return launch_band_t<96>(p, B, st);
+    case 128: return launch_band_t<128>(p, B, st);
+    case 160: return launch_band_t<160>(p, B, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace sfb

@@ -49,6 +49,13 @@ struct sfb_ctx {
   std::vector<ProfEvent> prof;
   std::vector<cudaEvent_t> ev_pool;
   long long launches = 0;
+  // structure-exploiting solver (row f4): band storage of S and the per-walker window classes
+  int solver = SFB_SOLVER_DENSE;
+  double* Sb = nullptr;
+  int *bw_d = nullptr, *overflow = nullptr, *rowmap_d = nullptr;
+  int *bw_h = nullptr, *rowmap_h = nullptr;  // pinned
+  cudaEvent_t ev_band = nullptr;
+  long long band_rows[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // walkers per window class (last = dense fallback) since creation
   ModelState model;       // upstream of the covariance (rows f1/f2); empty until sfb_set_model_host
   bool have_model = false;
   std::string err;
@@ -325,6 +332,112 @@ int loglike_device(sfb_ctx* h, int B, const double* X, const double* A, const do
   return SFB_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// structure-exploiting solver (row f4).  One host round trip of B ints (the exact half-bandwidth of every
+// walker's S) decides each walker's window class; every class is one band_build + one band_chol launch
+// over a row map; walkers whose band exceeds the widest window, or an unsorted grid, take the dense path.
+// ---------------------------------------------------------------------------------------------------
+int structured_device(sfb_ctx* h, int B, const double* X, const double* A, const double* model_flux,
+                      const double* glob, const int* nloc, const double* loc, int shared_hyper, double* lnL,
+                      int* info, double* resid, cudaStream_t caller) {
+  const int N = h->N, K = h->Kmax, Bm = h->Bmax;
+  const int WDmax = kBandWidths[kNumBandWidths - 1];
+  if (!h->Sb) {
+    bool ok = cudaMalloc((void**)&h->Sb, sizeof(double) * (size_t)Bm * N * WDmax) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&h->bw_d, sizeof(int) * (Bm + 1)) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&h->overflow, sizeof(int) * Bm) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&h->rowmap_d, sizeof(int) * Bm) == cudaSuccess;
+    ok = ok && cudaMallocHost((void**)&h->bw_h, sizeof(int) * (Bm + 1)) == cudaSuccess;
+    ok = ok && cudaMallocHost((void**)&h->rowmap_h, sizeof(int) * Bm) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->ev_band, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) return fail(h, SFB_ERR_NOMEM, "structured solver: band storage allocation failed");
+  }
+  cudaStream_t s0 = h->streams[0], s1 = h->streams[1];
+  int rc = fork_streams(h, caller, 2);
+  if (rc != SFB_OK) return rc;
+  const int hs = shared_hyper ? 0 : 1;
+  // 1. exact half-bandwidths + the sortedness flag, one small D2H
+  SFB_CUDA(h, launch_band_width(N, K, hs, h->wave, glob, nloc, loc, h->bw_d, B, s0));
+  h->launches++;
+  SFB_CUDA(h, cudaMemcpyAsync(h->bw_h, h->bw_d, sizeof(int) * B, cudaMemcpyDeviceToHost, s0));
+  SFB_CUDA(h, cudaMemcpyAsync(h->bw_h + Bm, h->sorted, sizeof(int), cudaMemcpyDeviceToHost, s0));
+  if (resid) SFB_CUDA(h, launch_residual_only(model_flux, h->data_flux, N, B, resid, s1));
+  SFB_CUDA(h, cudaStreamSynchronize(s0));
+  const bool sorted = h->bw_h[Bm] != 0;
+  // 2. classes -> row map
+  int count[8] = {0}, start[8] = {0};
+  const int nclass = kNumBandWidths;  // class nclass = dense
+  auto cls = [&](int b) {
+    if (!sorted) return nclass;
+    for (int c = 0; c < nclass; ++c)
+      if (h->bw_h[b] + 1 <= kBandWidths[c]) return c;
+    return nclass;
+  };
+  for (int b = 0; b < B; ++b) count[cls(b)]++;
+  for (int c = 1; c <= nclass; ++c) start[c] = start[c - 1] + count[c - 1];
+  {
+    int pos[8];
+    for (int c = 0; c <= nclass; ++c) pos[c] = start[c];
+    for (int b = 0; b < B; ++b) h->rowmap_h[pos[cls(b)]++] = b;
+  }
+  SFB_CUDA(h, cudaMemcpyAsync(h->rowmap_d, h->rowmap_h, sizeof(int) * B, cudaMemcpyHostToDevice, s0));
+  SFB_CUDA(h, cudaMemsetAsync(h->overflow, 0, sizeof(int) * B, s0));
+  SFB_CUDA(h, cudaEventRecord(h->ev_band, s0));
+  SFB_CUDA(h, cudaStreamWaitEvent(s1, h->ev_band, 0));
+  // 3. one build + one factorisation launch per class, classes alternating between the two lanes
+  int lane = 0;
+  for (int c = 0; c < nclass; ++c) {
+    if (!count[c]) continue;
+    h->band_rows[c] += count[c];
+    cudaStream_t st = h->profile ? s0 : (lane++ & 1 ? s1 : s0);
+    const int WD = kBandWidths[c];
+    BandBuildParams bp;
+    bp.N = N; bp.WD = WD; bp.Kmax = K; bp.hyper_stride = hs; bp.jitter = 1e-10;
+    bp.wave = h->wave; bp.sigma = h->sigma; bp.glob = glob; bp.nloc = nloc; bp.loc = loc;
+    bp.Sb = h->Sb; bp.strideSb = (long long)N * WDmax; bp.overflow = h->overflow;
+    bp.rowmap = h->rowmap_d + start[c];
+    {
+      ProfScope ps(h, st, SFB_K_BAND_BUILD, (double)count[c] * 8.0 * N * WD);
+      SFB_CUDA(h, launch_band_build(bp, count[c], st));
+    }
+    BandCholParams cp;
+    cp.N = N; cp.M = X ? h->M : 0; cp.Sb = h->Sb; cp.strideSb = bp.strideSb; cp.rowmap = bp.rowmap;
+    cp.X = X; cp.A = A; cp.model_flux = model_flux; cp.data_flux = h->data_flux; cp.overflow = h->overflow;
+    cp.sorted = h->sorted; cp.lnL = lnL; cp.info = info;
+    double flops = 0.0;
+    for (int q = 0; q < count[c]; ++q) {
+      const double bwq = h->bw_h[h->rowmap_h[start[c] + q]];
+      flops += (double)N * (bwq * bwq + 2.0 * bwq * (cp.M + 1));
+    }
+    {
+      ProfScope ps(h, st, SFB_K_BAND_CHOL, flops);
+      SFB_CUDA(h, launch_band_chol(cp, WD, count[c], st));
+    }
+    h->launches += 2;
+  }
+  // 4. dense path for what does not fit a window (contiguous runs of the original order)
+  if (count[nclass]) {
+    h->band_rows[nclass] += count[nclass];
+    const int nstreams = (h->profile || h->slots < 2 || (h->debug_mode & 2)) ? 1 : 2;
+    const int M = h->M;
+    int q = 0;
+    while (q < count[nclass]) {
+      const int b0 = h->rowmap_h[start[nclass] + q];
+      int len = 1;
+      while (q + len < count[nclass] && h->rowmap_h[start[nclass] + q + len] == b0 + len) ++len;
+      const int hb = shared_hyper ? 0 : b0;
+      rc = loglike_device(h, len, X ? X + (long long)b0 * M * N : nullptr, A ? A + (long long)b0 * M * M : nullptr,
+                          model_flux + (long long)b0 * N, glob + 2LL * hb, nloc + hb, loc + 3LL * K * hb,
+                          shared_hyper, lnL + b0, info + b0, nullptr, nstreams, nullptr, nullptr, nullptr, nullptr,
+                          nullptr, nullptr, nullptr, nullptr, nullptr);
+      if (rc != SFB_OK) return rc;
+      q += len;
+    }
+  }
+  return join_streams(h, caller, 2);
+}
+
 }  // namespace
 
 extern "C" {
@@ -420,6 +533,13 @@ int sfb_destroy(sfb_t* h) {
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   free_gemm_maps(&h->maps);
   model_free(&h->model);
+  if (h->Sb) cudaFree(h->Sb);
+  if (h->bw_d) cudaFree(h->bw_d);
+  if (h->overflow) cudaFree(h->overflow);
+  if (h->rowmap_d) cudaFree(h->rowmap_d);
+  if (h->bw_h) cudaFreeHost(h->bw_h);
+  if (h->rowmap_h) cudaFreeHost(h->rowmap_h);
+  if (h->ev_band) cudaEventDestroy(h->ev_band);
   for (auto& pe : h->prof) {
     cudaEventDestroy(pe.a);
     cudaEventDestroy(pe.b);
@@ -544,6 +664,8 @@ int sfb_loglike(sfb_t* h, int B, const double* X, const double* A, const double*
   if (B == 0) return SFB_OK;
   DeviceGuard guard(h->device);
   cudaStream_t caller = (cudaStream_t)stream;
+  if (h->solver == SFB_SOLVER_STRUCTURED)
+    return structured_device(h, B, X, A, model_flux, glob, nloc, loc, shared_hyper, lnL, info, resid, caller);
   const int nstreams = (h->profile || h->slots < 2 || (h->debug_mode & 2)) ? 1 : 2;
   if ((rc = fork_streams(h, caller, nstreams)) != SFB_OK) return rc;
   rc = loglike_device(h, B, X, A, model_flux, glob, nloc, loc, shared_hyper, lnL, info, resid, nstreams, nullptr,
@@ -578,6 +700,28 @@ int sfb_loglike_host(sfb_t* h, int B, const double* X_h, const double* A_h, cons
   ok &= lazy((void**)&h->dinfo, sizeof(int) * Bm);
   if (resid_h) ok &= lazy((void**)&h->dresid, sizeof(double) * (size_t)Bm * N);
   if (!ok) return fail(h, SFB_ERR_NOMEM, "sfb_loglike_host: staging allocation failed");
+  if (h->solver == SFB_SOLVER_STRUCTURED) {  // inputs up on lane 0, structured solve, results down
+    cudaStream_t st = h->streams[0];
+    const int Bh = shared_hyper ? 1 : B;
+    SFB_CUDA(h, cudaStreamSynchronize(h->streams[1]));
+    if (X_h) {
+      SFB_CUDA(h, cudaMemcpyAsync(h->dX, X_h, sizeof(double) * (size_t)B * M * N, cudaMemcpyHostToDevice, st));
+      SFB_CUDA(h, cudaMemcpyAsync(h->dA, A_h, sizeof(double) * (size_t)B * M * M, cudaMemcpyHostToDevice, st));
+    }
+    SFB_CUDA(h, cudaMemcpyAsync(h->dflux, model_flux_h, sizeof(double) * (size_t)B * N, cudaMemcpyHostToDevice, st));
+    SFB_CUDA(h, cudaMemcpyAsync(h->dglob, glob_h, sizeof(double) * 2 * Bh, cudaMemcpyHostToDevice, st));
+    SFB_CUDA(h, cudaMemcpyAsync(h->dnloc, nloc_h, sizeof(int) * Bh, cudaMemcpyHostToDevice, st));
+    SFB_CUDA(h, cudaMemcpyAsync(h->dloc, loc_h, sizeof(double) * 3 * (size_t)K * Bh, cudaMemcpyHostToDevice, st));
+    rc = structured_device(h, B, X_h ? h->dX : nullptr, X_h ? h->dA : nullptr, h->dflux, h->dglob, h->dnloc, h->dloc,
+                           shared_hyper, h->dlnL, h->dinfo, resid_h ? h->dresid : nullptr, st);
+    if (rc != SFB_OK) return rc;
+    SFB_CUDA(h, cudaMemcpyAsync(lnL_h, h->dlnL, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
+    SFB_CUDA(h, cudaMemcpyAsync(info_h, h->dinfo, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+    if (resid_h)
+      SFB_CUDA(h, cudaMemcpyAsync(resid_h, h->dresid, sizeof(double) * (size_t)B * N, cudaMemcpyDeviceToHost, st));
+    SFB_CUDA(h, cudaStreamSynchronize(st));
+    return SFB_OK;
+  }
   const int nstreams = (h->profile || h->slots < 2 || (h->debug_mode & 2)) ? 1 : 2;
   rc = loglike_device(h, B, X_h ? h->dX : nullptr, X_h ? h->dA : nullptr, h->dflux, h->dglob, h->dnloc, h->dloc,
                       shared_hyper, h->dlnL, h->dinfo, resid_h ? h->dresid : nullptr, nstreams, X_h, A_h,
@@ -683,6 +827,16 @@ int sfb_loglike_params(sfb_t* h, int B, const double* theta, int ncheb, const do
   if ((rc = run_upstream(h, B, theta, ncheb, ms.X, ms.A, ms.flux, log_scale_out ? log_scale_out : ms.log_scale,
                          ms.status, h->streams[0])) != SFB_OK)
     return rc;
+  if (h->solver == SFB_SOLVER_STRUCTURED) {
+    if ((rc = structured_device(h, B, ms.X, ms.A, ms.flux, glob, nloc, loc, shared_hyper, lnL, info, resid,
+                                h->streams[0])) != SFB_OK)
+      return rc;
+    SFB_CUDA(h, cudaEventRecord(h->ev_join[0], h->streams[0]));
+    SFB_CUDA(h, cudaStreamWaitEvent(caller, h->ev_join[0], 0));
+    SFB_CUDA(h, launch_merge_status(ms.status, info, lnL, B, caller));
+    h->launches++;
+    return SFB_OK;
+  }
   SFB_CUDA(h, cudaEventRecord(h->ev_fork, h->streams[0]));
   for (int i = 1; i < nstreams; ++i) SFB_CUDA(h, cudaStreamWaitEvent(h->streams[i], h->ev_fork, 0));
   rc = loglike_device(h, B, ms.X, ms.A, ms.flux, glob, nloc, loc, shared_hyper, lnL, info, resid, nstreams, nullptr,
@@ -755,6 +909,23 @@ int sfb_host_cholesky_lower(int n, double* a_h) {
 }
 
 int sfb_spline_halfwidth(void) { return kSplineW; }
+
+int sfb_set_solver(sfb_t* h, int solver) {
+  if (!h) return SFB_ERR_ARG;
+  if (solver != SFB_SOLVER_DENSE && solver != SFB_SOLVER_STRUCTURED) return fail(h, SFB_ERR_ARG, "unknown solver");
+  h->solver = solver;
+  return SFB_OK;
+}
+
+int sfb_get_solver(const sfb_t* h) { return h ? h->solver : -1; }
+
+int sfb_band_classes(const sfb_t* h, int* widths, long long* walkers, int n) {
+  if (!h || !widths || !walkers || n < kNumBandWidths + 1) return SFB_ERR_ARG;
+  for (int c = 0; c < kNumBandWidths; ++c) { widths[c] = kBandWidths[c]; walkers[c] = h->band_rows[c]; }
+  widths[kNumBandWidths] = 0;  // dense fallback
+  walkers[kNumBandWidths] = h->band_rows[kNumBandWidths];
+  return kNumBandWidths + 1;
+}
 
 int sfb_sync(sfb_t* h) {
   if (!h) return SFB_ERR_ARG;

@@ -161,3 +161,48 @@ cudaError_t launch_merge_status(const int* status, int* info, double* lnL, int B
 cudaError_t upstream_init();
 
 }  // namespace sfb
+
+// ---------------------------------------------------------------------------------------------
+// structure-exploiting solver: banded Cholesky of S + rank-M capacitance
+// ---------------------------------------------------------------------------------------------
+namespace sfb {
+
+struct BandBuildParams {
+  int N, WD, Kmax, hyper_stride;
+  double jitter;
+  const double* wave;
+  const double* sigma;
+  const double* glob;
+  const int* nloc;
+  const double* loc;
+  double* Sb;            // walker b at Sb + b*strideSb, N×WD row-major
+  long long strideSb;
+  int* overflow;         // per walker: set when the band does not fit in WD (caller zeroes it)
+  const int* rowmap;     // optional: CTA y -> walker index (classes of equal window width)
+};
+
+struct BandCholParams {
+  int N, M;
+  const double* Sb;
+  long long strideSb;
+  const int* rowmap;
+  const double* X;           // B×M×N (may be null when M == 0)
+  const double* A;           // B×M×M
+  const double* model_flux;  // B×N
+  const double* data_flux;   // N
+  const int* overflow;       // B
+  const int* sorted;         // device flag from sfb_set_static
+  double* lnL;
+  int* info;
+};
+
+extern const int kBandWidths[];
+extern const int kNumBandWidths;
+cudaError_t launch_band_width(int N, int Kmax, int hyper_stride, const double* wave, const double* glob,
+                              const int* nloc, const double* loc, int* bw, int B, cudaStream_t st);
+cudaError_t launch_band_build(const BandBuildParams& p, int B, cudaStream_t st);
+cudaError_t launch_band_chol(const BandCholParams& p, int WD, int B, cudaStream_t st);
+cudaError_t launch_residual_only(const double* model_flux, const double* data_flux, int N, int B, double* resid,
+                                 cudaStream_t st);
+
+}  // namespace sfb

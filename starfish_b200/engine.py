@@ -219,6 +219,28 @@ class LikelihoodEngine:
                                                hp(resid_out, np.float64)), "sfb_loglike_host")
         return lnL_out, info_out
 
+    # -- solver choice (row f4) -----------------------------------------------------------------------
+    def set_solver(self, solver: str):
+        """'dense' (default: blocked fp64 Cholesky of the N×N covariance) or 'structured' (banded Cholesky of
+        diag + kernels, rank-M capacitance system; walkers whose band does not fit take the dense path)."""
+        code = {"dense": _lib.SOLVER_DENSE, "structured": _lib.SOLVER_STRUCTURED}.get(solver)
+        if code is None:
+            raise ValueError("solver must be 'dense' or 'structured'")
+        self._check(self._lib.sfb_set_solver(self._h, code), "sfb_set_solver")
+
+    @property
+    def solver(self) -> str:
+        return "structured" if self._lib.sfb_get_solver(self._h) == _lib.SOLVER_STRUCTURED else "dense"
+
+    def band_classes(self):
+        """{window width: walkers routed to it since creation}; key 0 is the dense fallback."""
+        w = (C.c_int * 8)()
+        n = (C.c_longlong * 8)()
+        k = self._lib.sfb_band_classes(self._h, w, n, 8)
+        if k < 0:
+            self._check(k, "sfb_band_classes")
+        return {int(w[i]): int(n[i]) for i in range(k)}
+
     # -- upstream of the covariance (rows f1/f2/f3): parameters in, log-likelihood out --------------
     def set_model(self, fine_wave, bulk_fluxes, grid_points, variances, lengthscales, v11, w_hat,
                   ncheb_max: int = 0, flags: int = 0):

@@ -15,6 +15,8 @@ a whole ensemble of parameter vectors in one GPU pass and plugs into ``emcee.Ens
 vectorize=True)``.  The spectral transforms and the emulator's GP predictive upstream of the path
 (:287-332) run on the device as well (csrc/upstream.cu); ``upstream="host"`` selects
 the numpy mirrors of ``transforms.py`` instead (an explicit option for cross-checks, never a fallback).
+``solver="structured"`` evaluates the same likelihood through the banded-plus-low-rank structure of the
+covariance (csrc/band.cu) instead of the dense N×N Cholesky.
 """
 from __future__ import annotations
 
@@ -70,7 +72,7 @@ class SpectrumModel:
 
     def __init__(self, emulator, data, grid_params: Sequence[float], max_deque_len: int = 100, norm=False,
                  name: str = "SpectrumModel", device: int = 0, emulator_term: str = "reference",
-                 upstream: str = "device", **params):
+                 upstream: str = "device", solver: str = "dense", **params):
         if isinstance(emulator, str) or isinstance(data, str):
             raise NotImplementedError("loading from HDF5 paths needs h5py; pass in-memory Emulator/Spectrum")
         if len(data) > 1:
@@ -79,7 +81,10 @@ class SpectrumModel:
             raise ValueError("emulator_term must be 'reference' (XᵀΣ_w⁻¹X, as coded) or 'paper' (XᵀΣ_wX)")
         if upstream not in ("device", "host"):
             raise ValueError("upstream must be 'device' (CUDA transforms + emulator) or 'host' (numpy mirrors)")
+        if solver not in ("dense", "structured"):
+            raise ValueError("solver must be 'dense' or 'structured'")
         self.upstream = upstream
+        self.solver = solver
         self.emulator = emulator
         self.data_name = data.name
         self.data = data[0]
@@ -348,6 +353,8 @@ class SpectrumModel:
             self._engine = eng = LikelihoodEngine(n, m, k, n_walkers, device=self.device)
             self._static_sig = None
             self._model_sig = None
+        if eng.solver != self.solver:
+            eng.set_solver(self.solver)
         return eng
 
     def _sync_static(self, eng):
