@@ -197,7 +197,57 @@ class Emulator:
     def norm_factor(self, params):
         return self.factor_interpolator(np.asarray(params))
 
-    def log_likelihood(self) -> float:
-        L, low = cho_factor(self.v11)
-        logdet = 2 * np.sum(np.log(np.diag(L)))
-        return -(logdet + self.w_hat @ cho_solve((L, low), self.w_hat)) / 2
+    def log_likelihood(self, device: Optional[int] = None) -> float:
+        """−½(log det v11 + ŵᵀ v11⁻¹ ŵ) (Starfish/emulator/emulator.py:602-619).
+
+        ``device=None`` evaluates on the host like the reference; an integer runs the (M·G)² Cholesky and
+        the forward solve on that GPU with the same kernels as the spectrum likelihood (``sfb_potrf`` /
+        ``sfb_solve_lower``) — worthwhile for emulators with thousands of grid points × components.
+        Raises ``numpy.linalg.LinAlgError`` when v11 is not positive definite, as scipy does."""
+        if device is None:
+            L, low = cho_factor(self.v11)
+            logdet = 2 * np.sum(np.log(np.diag(L)))
+            return -(logdet + self.w_hat @ cho_solve((L, low), self.w_hat)) / 2
+        import torch
+
+        from .engine import LikelihoodEngine
+
+        n = self.v11.shape[0]
+        eng = getattr(self, "_gpu_engine", None)
+        if eng is None or eng.N != n or eng.device.index != device:
+            if eng is not None:
+                eng.close()
+            self._gpu_engine = eng = LikelihoodEngine(n, 0, 1, 1, device=device, workspace_walkers=2)
+        Cm = torch.from_numpy(np.ascontiguousarray(self.v11, dtype=np.float64)[None]).to(eng.device)
+        Cm, info, logdet = eng.cho_factor(Cm, return_logdet=True)
+        if int(info.cpu()[0]) != 0:
+            raise np.linalg.LinAlgError(f"{int(info.cpu()[0])}-th leading minor of the array is not positive definite")
+        z = eng.solve_lower(Cm, np.asarray(self.w_hat, dtype=np.float64)[None])
+        return float(-(logdet[0] + (z * z).sum()).cpu() / 2)
+
+    def train(self, device: Optional[int] = None, **opt_kwargs):
+        """Optimise the GP hyper-parameters with ``scipy.optimize.minimize`` (Nelder-Mead, maxiter 10000 by
+        default), mirroring Starfish/emulator/emulator.py:484-524; ``device`` is passed to ``log_likelihood``."""
+        from scipy.optimize import minimize
+
+        def nll(P):
+            if np.any(~np.isfinite(P)):
+                return np.inf
+            self.set_param_vector(P)
+            if np.any(self.lengthscales < 2 * self._grid_sep):
+                return np.inf
+            try:
+                return -self.log_likelihood(device=device)
+            except np.linalg.LinAlgError:
+                return np.inf
+
+        kwargs = {"method": "Nelder-Mead", "options": {"maxiter": 10000}}
+        kwargs.update(opt_kwargs)
+        P0 = self.get_param_vector()
+        soln = minimize(nll, P0, **kwargs)
+        if soln.success:
+            self.set_param_vector(soln.x)
+            self._trained = True
+        else:
+            self.set_param_vector(P0)
+        return soln

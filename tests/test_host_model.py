@@ -180,3 +180,21 @@ def test_emulator_call_contract():
     P = emu.get_param_vector()
     emu.set_param_vector(P)
     assert np.allclose(emu.get_param_vector(), P)
+
+
+def test_emulator_train_improves_likelihood_and_respects_bounds():
+    """Emulator.train mirrors emulator.py:484-524: Nelder-Mead on the hyper-parameters, lengthscales kept
+    above twice the grid separation, state restored when the optimiser does not converge."""
+    import copy
+
+    from starfish_b200 import synth
+    from starfish_b200.emulator import Emulator
+
+    emu = Emulator(**copy.deepcopy(synth.make_emulator_arrays(n_comp=2)))
+    before = emu.log_likelihood()
+    soln = emu.train(options={"maxiter": 60})
+    if soln.success:
+        assert emu._trained and emu.log_likelihood() >= before
+    else:
+        assert abs(emu.log_likelihood() - before) <= 1e-9 * abs(before)
+    assert np.all(emu.lengthscales >= 2 * emu._grid_sep - 1e-12)
