@@ -30,7 +30,6 @@ namespace {
 
 constexpr double kPi = 3.141592653589793;  // == numpy.pi
 constexpr int NRP = kMaxM + 2;             // padded right-hand-side columns per ring row (even)
-constexpr int BATCH = 16;                  // pivots per staging batch
 
 // ------------------------------------------------------------------------------------------------
 // band build
@@ -162,11 +161,19 @@ __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_s
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// MAXNR = right-hand sides the instantiation can carry (M + 1 <= MAXNR)
-template <int WD, int MAXNR>
-__global__ void __launch_bounds__(WD * 4)
+__host__ __device__ constexpr int band_lcm(int WD, int ER) { return (ER % (WD / 32) == 0) ? ER : ER * (WD / 32); }
+__host__ __device__ constexpr int band_batch(int WD, int ER) {
+  const int l = band_lcm(WD, ER);
+  return (l <= 24 && WD % l == 0) ? (l < 16 ? 2 * l : l) : 16;
+}
+
+// ER = window rows per thread (8 → WD·4 threads; the 160-pixel window uses 10 → 512 threads so that its
+// 10×5 register tile fits a 128-register budget), MAXNR = right-hand sides the instantiation can carry (M + 1 <= MAXNR)
+template <int WD, int ER, int MAXNR>
+__global__ void __launch_bounds__(WD * 32 / ER, 1)
 band_chol_kernel(BandCholParams p) {
-  constexpr int ER = 8, EC = WD / 32, NT = WD * 4, ROWLEN = WD + NRP;
+  constexpr int EC = WD / 32, NT = WD * 32 / ER, ROWLEN = WD + NRP;
+  constexpr int BATCH = band_batch(WD, ER);  // pivots per staging batch (a multiple of the unroll length)
   constexpr int NE = (WD * MAXNR + NT - 1) / NT;          // right-hand-side registers per thread
   __shared__ double colbuf[2][WD];
   __shared__ double zbuf[2][NRP];
@@ -240,72 +247,117 @@ band_chol_kernel(BandCholParams p) {
   const int gp_ = tid / NR, gq_ = tid - (tid / NR) * NR;  // Gram element of this thread (tid < NR²)
   const bool gram_on = tid < NR * NR;
 
-  int jr = 0;
-  for (int j = 0; j < N; ++j) {
-    const int buf = j & 1, jb = j & (BATCH - 1), half = (j / BATCH) & 1;
-    // staging boundary: this batch's rows (issued one boundary ago) must have landed before the barrier below
-    if (jb == 0) cp_async_wait_all();
-    // ---- phase A: owners publish column j of the window and the pivot row of the right-hand sides
-    if (lane == jr / EC) {
-      const int e0 = jr - (jr / EC) * EC;
+  // log det S = Σ log(pivot): the pivots are multiplied up as mantissa × 2^exponent by warp 0 (a handful of
+  // integer/DMUL instructions per pivot instead of a log() on the critical path) and logged once at the end.
+  double mant = 1.0;
+  long long expo = 0;
+
+  // The pivot loop is unrolled by UN = lcm(ER, EC) so that "which register holds column j / row j" is a
+  // compile-time fact inside the body (j ≡ u mod UN, UN | WD): publishing the pivot column and replacing
+  // the retiring row are plain register moves, no selects.
+  // (Windows whose lcm would be too long to unroll — WD = 160 — index their registers through selects.)
+  constexpr int LCM = band_lcm(WD, ER);               // ER, EC as used here: 8|{1,2,4}, 8·3, 10|5
+  constexpr bool STATIC = LCM <= 24 && WD % LCM == 0;
+  constexpr int UN = STATIC ? LCM : 1;
+  static_assert(WD % UN == 0 && (!STATIC || (UN % ER == 0 && UN % EC == 0)), "unroll must divide the window");
+  for (int j0 = 0, jr0 = 0; j0 < N; j0 += UN, jr0 = (jr0 + UN == WD) ? 0 : jr0 + UN) {
+    const int own_lane0 = jr0 / EC, own_warp0 = jr0 / ER;
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int j = j0 + u, jr = jr0 + u;
+      if (j >= N) break;
+      const int buf = STATIC ? (u & 1) : (j & 1);   // UN is even on the static path
+      const int jb = j % BATCH, half = (j / BATCH) & 1;
+      const bool boundary = STATIC ? (u == 0 && jb == 0) : (jb == 0);
+      // staging boundary: this batch's rows (issued one boundary ago) must have landed before the barrier
+      if (boundary) cp_async_wait_all();
+      // ---- phase A: owners publish column j of the window and the pivot row of the right-hand sides
+      if constexpr (STATIC) {
+        if (lane == own_lane0 + u / EC) {
+#pragma unroll
+          for (int er = 0; er < ER; ++er) colbuf[buf][tr * ER + er] = a[er][u % EC];
+        }
+      } else {
+        if (lane == jr / EC) {
+          const int e0 = jr - (jr / EC) * EC;
+#pragma unroll
+          for (int er = 0; er < ER; ++er) {
+            double x = a[er][0];
+#pragma unroll
+            for (int ec = 1; ec < EC; ++ec) x = (e0 == ec) ? a[er][ec] : x;
+            colbuf[buf][tr * ER + er] = x;
+          }
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < NE; ++e)
+        if (rres[e] == jr) zbuf[buf][rq[e]] = rv[e];
+      __syncthreads();
+      // past the barrier nobody reads the other ring half any more (its last reader was the previous
+      // pivot): start filling it with the next batch
+      if (boundary) stage_issue(j + BATCH, ring + (half ^ 1) * (BATCH * ROWLEN));
+      // ---- phase C: rank-1 update of the window, right-hand sides, Gram matrix
+      const double pj = colbuf[buf][jr];
+      const double inv = 1.0 / pj;
+      if (tr == 0) {  // warp-uniform bookkeeping
+        if (!(pj > 0.0) && info == 0) info = j + 1;
+        const int hi = __double2hiint(pj);
+        expo += ((hi >> 20) & 0x7ff) - 1022;
+        mant *= __hiloint2double((hi & 0x800fffff) | 0x3fe00000, __double2loint(pj));
+        if ((j & 511) == 511) {
+          const int h2 = __double2hiint(mant);
+          expo += ((h2 >> 20) & 0x7ff) - 1022;
+          mant = __hiloint2double((h2 & 0x800fffff) | 0x3fe00000, __double2loint(mant));
+        }
+      }
+      double ak[EC];
+#pragma unroll
+      for (int ec = 0; ec < EC; ++ec) ak[ec] = colbuf[buf][lane * EC + ec] * inv;
 #pragma unroll
       for (int er = 0; er < ER; ++er) {
-        double x = a[er][0];
+        const double ai = -colbuf[buf][tr * ER + er];
 #pragma unroll
-        for (int ec = 1; ec < EC; ++ec) x = (e0 == ec) ? a[er][ec] : x;
-        colbuf[buf][tr * ER + er] = x;
-      }
-    }
-#pragma unroll
-    for (int e = 0; e < NE; ++e)
-      if (rres[e] == jr) zbuf[buf][rq[e]] = rv[e];
-    __syncthreads();
-    // past the barrier nobody reads the other ring half any more (its last reader was the previous pivot):
-    // start filling it with the next batch
-    if (jb == 0) stage_issue(j + BATCH, ring + (half ^ 1) * (BATCH * ROWLEN));
-    // ---- phase C: rank-1 update of the window, right-hand sides, Gram matrix
-    const double pj = colbuf[buf][jr];
-    const double inv = 1.0 / pj;
-    if (tid == 0) {
-      if (!(pj > 0.0) && info == 0) info = j + 1;
-      logdet += log(pj);
-    }
-    double ai[ER], ak[EC];
-#pragma unroll
-    for (int er = 0; er < ER; ++er) ai[er] = colbuf[buf][tr * ER + er];
-#pragma unroll
-    for (int ec = 0; ec < EC; ++ec) ak[ec] = colbuf[buf][lane * EC + ec] * inv;
-#pragma unroll
-    for (int er = 0; er < ER; ++er)
-#pragma unroll
-      for (int ec = 0; ec < EC; ++ec) a[er][ec] = fma(-ai[er], ak[ec], a[er][ec]);
-#pragma unroll
-    for (int e = 0; e < NE; ++e)
-      if (rres[e] >= 0) rv[e] = fma(-colbuf[buf][rres[e]], zbuf[buf][rq[e]] * inv, rv[e]);
-    if (gram_on) gacc = fma(zbuf[buf][gp_] * inv, zbuf[buf][gq_], gacc);
-    // ---- the row that enters the window (index j + WD) takes the slots of the retiring index j
-    const double* row = ring + half * (BATCH * ROWLEN) + jb * ROWLEN;
-    if (tr == jr / ER) {
-      const int er0 = jr - (jr / ER) * ER;
-      double val[EC];
-#pragma unroll
-      for (int ec = 0; ec < EC; ++ec) {
-        int t = lane * EC + ec - jr - 1;
-        if (t < 0) t += WD;
-        val[ec] = row[WD - 1 - t];
+        for (int ec = 0; ec < EC; ++ec) a[er][ec] = fma(ai, ak[ec], a[er][ec]);
       }
 #pragma unroll
-      for (int er = 0; er < ER; ++er)
-        if (er == er0) {
+      for (int e = 0; e < NE; ++e)
+        if (rres[e] >= 0) rv[e] = fma(-colbuf[buf][rres[e]], zbuf[buf][rq[e]] * inv, rv[e]);
+      if (gram_on) gacc = fma(zbuf[buf][gp_] * inv, zbuf[buf][gq_], gacc);
+      // ---- the row that enters the window (index j + WD) takes the slots of the retiring index j
+      const double* row = ring + half * (BATCH * ROWLEN) + jb * ROWLEN;
+      if constexpr (STATIC) {
+        if (tr == own_warp0 + u / ER) {
 #pragma unroll
-          for (int ec = 0; ec < EC; ++ec) a[er][ec] = val[ec];
+          for (int ec = 0; ec < EC; ++ec) {
+            int t = lane * EC + ec - jr - 1;
+            if (t < 0) t += WD;
+            a[u % ER][ec] = row[WD - 1 - t];
+          }
         }
-    }
+      } else {
+        if (tr == jr / ER) {
+          const int er0 = jr - (jr / ER) * ER;
+          double val[EC];
 #pragma unroll
-    for (int e = 0; e < NE; ++e)
-      if (rres[e] == jr) rv[e] = row[WD + rq[e]];
-    jr = (jr + 1 == WD) ? 0 : jr + 1;
+          for (int ec = 0; ec < EC; ++ec) {
+            int t = lane * EC + ec - jr - 1;
+            if (t < 0) t += WD;
+            val[ec] = row[WD - 1 - t];
+          }
+#pragma unroll
+          for (int er = 0; er < ER; ++er)
+            if (er == er0) {
+#pragma unroll
+              for (int ec = 0; ec < EC; ++ec) a[er][ec] = val[ec];
+            }
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < NE; ++e)
+        if (rres[e] == jr) rv[e] = row[WD + rq[e]];
+    }
   }
+  if (tid == 0) logdet = log(mant) + (double)expo * 0.6931471805599453;
 
   // ---- epilogue: lnL = −½ (log det S + log det(I + A·G) + RᵀS⁻¹R − uᵀ(I + A·G)⁻¹A u)
   if (gram_on) gram[tid] = gacc;
@@ -407,13 +459,22 @@ band_chol_kernel(BandCholParams p) {
   }
 }
 
-template <int WD>
+template <int WD, int ER>
 cudaError_t launch_band_t(const BandCholParams& p, int B, cudaStream_t st) {
-  const size_t smem = sizeof(double) * 2 * BATCH * (WD + NRP);
+  const size_t smem = sizeof(double) * 2 * band_batch(WD, ER) * (WD + NRP);
+  static bool opted_in = false;  // static + dynamic shared memory exceeds 48 KB for the widest window
+  if (!opted_in) {
+    cudaError_t e = cudaFuncSetAttribute(band_chol_kernel<WD, ER, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(band_chol_kernel<WD, ER, kMaxM + 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               64 * 1024);
+    if (e != cudaSuccess) return e;
+    opted_in = true;
+  }
   if (p.M + 1 <= 8)
-    band_chol_kernel<WD, 8><<<B, WD * 4, smem, st>>>(p);
+    band_chol_kernel<WD, ER, 8><<<B, WD * 32 / ER, smem, st>>>(p);
   else
-    band_chol_kernel<WD, kMaxM + 1><<<B, WD * 4, smem, st>>>(p);
+    band_chol_kernel<WD, ER, kMaxM + 1><<<B, WD * 32 / ER, smem, st>>>(p);
   return cudaGetLastError();
 }
 
@@ -451,10 +512,10 @@ cudaError_t launch_band_build(const BandBuildParams& p, int B, cudaStream_t st) 
 cudaError_t launch_band_chol(const BandCholParams& p, int WD, int B, cudaStream_t st) {
   if (B <= 0) return cudaSuccess;
   switch (WD) {
-    case 64: return launch_band_t<64>(p, B, st);
-    case 96: return launch_band_t<96>(p, B, st);
-    case 128: return launch_band_t<128>(p, B, st);
-    case 160: return launch_band_t<160>(p, B, st);
+    case 64: return launch_band_t<64, 8>(p, B, st);
+    case 96: return launch_band_t<96, 8>(p, B, st);
+    case 128: return launch_band_t<128, 8>(p, B, st);
+    case 160: return launch_band_t<160, 10>(p, B, st);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -244,11 +244,11 @@ def test_ensemble_sampler_drives_the_batched_likelihood(golden_dir):
     m = make_model(256, 0, wave=g["wave"], mus=(5098.0, 5103.0))
     m.freeze(["global_cov", "local_cov", "cheb", "logg", "Z"])
     labels = list(m.labels)
-    assert labels == ["T", "vsini", "vz", "log_scale"]
+    assert labels == ["vsini", "vz", "log_scale", "T"]
     priors = {"T": st.uniform(6000, 200), "vsini": st.uniform(0.5, 30)}
     nw = 16
     rng = np.random.default_rng(0)
-    p0 = m.get_param_vector() + 1e-3 * rng.standard_normal((nw, len(labels))) * [10.0, 1.0, 1.0, 0.01]
+    p0 = m.get_param_vector() + 1e-3 * rng.standard_normal((nw, len(labels))) * [1.0, 1.0, 0.01, 10.0]
     s = EnsembleSampler(nw, len(labels), m.log_likelihood_batch, kwargs={"priors": priors}, seed=5)
     launches0 = m._get_engine(nw // 2).launch_count
     p, lnp = s.run_mcmc(p0, 5)
