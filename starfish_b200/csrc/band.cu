@@ -177,6 +177,7 @@ band_chol_kernel(BandCholParams p) {
   constexpr int NE = (WD * MAXNR + NT - 1) / NT;          // right-hand-side registers per thread
   __shared__ double colbuf[2][WD];
   __shared__ double zbuf[2][NRP];
+  __shared__ double invbuf[2];
   __shared__ double gram[(kMaxM + 1) * (kMaxM + 1)];
   extern __shared__ double ring[];  // [2][BATCH][ROWLEN]
 
@@ -255,39 +256,29 @@ band_chol_kernel(BandCholParams p) {
   // The pivot loop is unrolled by UN = lcm(ER, EC) so that "which register holds column j / row j" is a
   // compile-time fact inside the body (j ≡ u mod UN, UN | WD): publishing the pivot column and replacing
   // the retiring row are plain register moves, no selects.
-  // (Windows whose lcm would be too long to unroll — WD = 160 — index their registers through selects.)
-  constexpr int LCM = band_lcm(WD, ER);               // ER, EC as used here: 8|{1,2,4}, 8·3, 10|5
-  constexpr bool STATIC = LCM <= 24 && WD % LCM == 0;
-  constexpr int UN = STATIC ? LCM : 1;
-  static_assert(WD % UN == 0 && (!STATIC || (UN % ER == 0 && UN % EC == 0)), "unroll must divide the window");
+  constexpr int UN = band_lcm(WD, ER);                // ER, EC as used here: 8|{1,2,4}, 8·3, 10|5
+  static_assert(UN <= 24 && WD % UN == 0 && UN % ER == 0 && UN % EC == 0 && UN % 2 == 0 && BATCH % UN == 0,
+                "unroll length must divide the window and the staging batch");
+  // 1/pivot is taken off the critical path: the owner of the NEXT diagonal element updates it first thing
+  // after the barrier, starts its reciprocal and publishes it for the following pivot, so that nobody waits
+  // for a division between the barrier and the FMAs.
+  if (tid == 0) invbuf[0] = 1.0 / a[0][0];
   for (int j0 = 0, jr0 = 0; j0 < N; j0 += UN, jr0 = (jr0 + UN == WD) ? 0 : jr0 + UN) {
     const int own_lane0 = jr0 / EC, own_warp0 = jr0 / ER;
+    const int jb0 = j0 % BATCH, half = (j0 / BATCH) & 1;
+    const double* rowbase = ring + half * (BATCH * ROWLEN) + jb0 * ROWLEN;
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
       const int j = j0 + u, jr = jr0 + u;
       if (j >= N) break;
-      const int buf = STATIC ? (u & 1) : (j & 1);   // UN is even on the static path
-      const int jb = j % BATCH, half = (j / BATCH) & 1;
-      const bool boundary = STATIC ? (u == 0 && jb == 0) : (jb == 0);
+      const int buf = u & 1;
+      const bool boundary = (u == 0) && (jb0 == 0);
       // staging boundary: this batch's rows (issued one boundary ago) must have landed before the barrier
       if (boundary) cp_async_wait_all();
       // ---- phase A: owners publish column j of the window and the pivot row of the right-hand sides
-      if constexpr (STATIC) {
-        if (lane == own_lane0 + u / EC) {
+      if (lane == own_lane0 + u / EC) {
 #pragma unroll
-          for (int er = 0; er < ER; ++er) colbuf[buf][tr * ER + er] = a[er][u % EC];
-        }
-      } else {
-        if (lane == jr / EC) {
-          const int e0 = jr - (jr / EC) * EC;
-#pragma unroll
-          for (int er = 0; er < ER; ++er) {
-            double x = a[er][0];
-#pragma unroll
-            for (int ec = 1; ec < EC; ++ec) x = (e0 == ec) ? a[er][ec] : x;
-            colbuf[buf][tr * ER + er] = x;
-          }
-        }
+        for (int er = 0; er < ER; ++er) colbuf[buf][tr * ER + er] = a[er][u % EC];
       }
 #pragma unroll
       for (int e = 0; e < NE; ++e)
@@ -297,9 +288,16 @@ band_chol_kernel(BandCholParams p) {
       // pivot): start filling it with the next batch
       if (boundary) stage_issue(j + BATCH, ring + (half ^ 1) * (BATCH * ROWLEN));
       // ---- phase C: rank-1 update of the window, right-hand sides, Gram matrix
-      const double pj = colbuf[buf][jr];
-      const double inv = 1.0 / pj;
+      const double inv = invbuf[buf];
+      {
+        const int jn = (jr + 1 == WD) ? 0 : jr + 1;
+        if (tr == jn / ER && lane == jn / EC) {  // next pivot: same arithmetic as the bulk update below
+          const double aj1 = colbuf[buf][jn];
+          invbuf[buf ^ 1] = 1.0 / fma(-aj1, aj1 * inv, a[(u + 1) % ER][(u + 1) % EC]);
+        }
+      }
       if (tr == 0) {  // warp-uniform bookkeeping
+        const double pj = colbuf[buf][jr];
         if (!(pj > 0.0) && info == 0) info = j + 1;
         const int hi = __double2hiint(pj);
         expo += ((hi >> 20) & 0x7ff) - 1022;
@@ -324,32 +322,13 @@ band_chol_kernel(BandCholParams p) {
         if (rres[e] >= 0) rv[e] = fma(-colbuf[buf][rres[e]], zbuf[buf][rq[e]] * inv, rv[e]);
       if (gram_on) gacc = fma(zbuf[buf][gp_] * inv, zbuf[buf][gq_], gacc);
       // ---- the row that enters the window (index j + WD) takes the slots of the retiring index j
-      const double* row = ring + half * (BATCH * ROWLEN) + jb * ROWLEN;
-      if constexpr (STATIC) {
-        if (tr == own_warp0 + u / ER) {
+      const double* row = rowbase + u * ROWLEN;
+      if (tr == own_warp0 + u / ER) {
 #pragma unroll
-          for (int ec = 0; ec < EC; ++ec) {
-            int t = lane * EC + ec - jr - 1;
-            if (t < 0) t += WD;
-            a[u % ER][ec] = row[WD - 1 - t];
-          }
-        }
-      } else {
-        if (tr == jr / ER) {
-          const int er0 = jr - (jr / ER) * ER;
-          double val[EC];
-#pragma unroll
-          for (int ec = 0; ec < EC; ++ec) {
-            int t = lane * EC + ec - jr - 1;
-            if (t < 0) t += WD;
-            val[ec] = row[WD - 1 - t];
-          }
-#pragma unroll
-          for (int er = 0; er < ER; ++er)
-            if (er == er0) {
-#pragma unroll
-              for (int ec = 0; ec < EC; ++ec) a[er][ec] = val[ec];
-            }
+        for (int ec = 0; ec < EC; ++ec) {
+          int t = lane * EC + ec - jr - 1;
+          if (t < 0) t += WD;
+          a[u % ER][ec] = row[WD - 1 - t];
         }
       }
 #pragma unroll

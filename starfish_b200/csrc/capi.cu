@@ -384,13 +384,19 @@ int structured_device(sfb_ctx* h, int B, const double* X, const double* A, const
   SFB_CUDA(h, cudaMemcpyAsync(h->rowmap_d, h->rowmap_h, sizeof(int) * B, cudaMemcpyHostToDevice, s0));
   SFB_CUDA(h, cudaMemsetAsync(h->overflow, 0, sizeof(int) * B, s0));
   SFB_CUDA(h, cudaEventRecord(h->ev_band, s0));
-  SFB_CUDA(h, cudaStreamWaitEvent(s1, h->ev_band, 0));
-  // 3. one build + one factorisation launch per class, classes alternating between the two lanes
+  // 3. one build + one factorisation launch per class, widest window first (its CTAs run longest), each
+  //    class on its own stream so that the classes' CTAs fill the SMs together
+  cudaStream_t lanes[4] = {h->hi[0], s0, s1, h->hi[1]};
+  for (int i = 0; i < 4; ++i)
+    if (lanes[i] != s0) SFB_CUDA(h, cudaStreamWaitEvent(lanes[i], h->ev_band, 0));
   int lane = 0;
-  for (int c = 0; c < nclass; ++c) {
+  bool used[4] = {false, false, false, false};
+  for (int c = nclass - 1; c >= 0; --c) {
     if (!count[c]) continue;
     h->band_rows[c] += count[c];
-    cudaStream_t st = h->profile ? s0 : (lane++ & 1 ? s1 : s0);
+    const int li = h->profile ? 1 : (lane++ & 3);
+    cudaStream_t st = lanes[li];
+    used[li] = true;
     const int WD = kBandWidths[c];
     BandBuildParams bp;
     bp.N = N; bp.WD = WD; bp.Kmax = K; bp.hyper_stride = hs; bp.jitter = 1e-10;
@@ -416,6 +422,9 @@ int structured_device(sfb_ctx* h, int B, const double* X, const double* A, const
     }
     h->launches += 2;
   }
+  // the two high-priority streams fold back into the lanes the caller is joined with
+  if (used[0]) { SFB_CUDA(h, cudaEventRecord(h->ev_hi[0], h->hi[0])); SFB_CUDA(h, cudaStreamWaitEvent(s0, h->ev_hi[0], 0)); }
+  if (used[3]) { SFB_CUDA(h, cudaEventRecord(h->ev_hi[1], h->hi[1])); SFB_CUDA(h, cudaStreamWaitEvent(s1, h->ev_hi[1], 0)); }
   // 4. dense path for what does not fit a window (contiguous runs of the original order)
   if (count[nclass]) {
     h->band_rows[nclass] += count[nclass];

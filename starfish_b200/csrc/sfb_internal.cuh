@@ -114,7 +114,7 @@ struct ModelState {
   double* gp_grid = nullptr;  // G×D
   double* gp_var = nullptr;   // M
   double* gp_ls = nullptr;    // M×D
-  double* L = nullptr;        // ld×ld lower Cholesky factor of v11 (row-major, identity padding)
+  double* L = nullptr;        // ld×ld INVERSE of the lower Cholesky factor of v11 (row-major, identity padding)
   double* zw = nullptr;       // ld  L⁻¹·ŵ
   // per-call scratch (device), sized for Bmax walkers
   double* theta = nullptr;    // Bmax×ntheta staging for the host-buffer entry

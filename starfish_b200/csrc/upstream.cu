@@ -106,10 +106,11 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // ------------------------------------------------------------------------------------------------
 // (1) emulator GP predictive, one CTA per walker.
-//     v12 (block diagonal: column m lives in rows [mG,(m+1)G)) → u = L⁻¹v12 by a 32-row blocked
-//     forward substitution in shared memory → mu = uᵀ(L⁻¹ŵ), Σ_w = diag(var) − uᵀu → A = Σ_w⁻¹.
+//     v12 (block diagonal: column m lives in rows [mG,(m+1)G)) → u = L⁻¹v12 as a matrix-vector product
+//     with the explicit inverse of the Cholesky factor → mu = uᵀ(L⁻¹ŵ), Σ_w = diag(var) − uᵀu → A = Σ_w⁻¹.
 //     The u-form (rather than an explicit v11⁻¹) keeps the cancellation 1e4 → O(1) as accurate as the
-//     reference's LU solves (measured against 50-digit arithmetic: 2.7e-12 vs 2.9e-12 relative).
+//     reference's LU solves (measured against 50-digit arithmetic: 2.7e-12 vs 2.9e-12 relative; an
+//     explicit v11⁻¹ gives 2e-8).
 // ------------------------------------------------------------------------------------------------
 constexpr int GP_THREADS = 256;
 
@@ -142,49 +143,26 @@ gp_predict_kernel(int M, int G, int D, int n, int ld, const double* __restrict__
   }
   __syncthreads();
 
-  for (int k0 = 0; k0 < ld; k0 += 32) {
-    if (k0 > 0) {  // rows k0..k0+31 minus the contribution of the already solved rows
-      for (int rr = warp; rr < 32; rr += NW) {
-        const int r = k0 + rr;
-        double acc[kMaxM];
-#pragma unroll
-        for (int m = 0; m < kMaxM; ++m) acc[m] = 0.0;
-        const double* Lr = L + (long long)r * ld;
-        for (int j = lane; j < k0; j += 32) {
-          const double lv = Lr[j];
-#pragma unroll
-          for (int m = 0; m < kMaxM; ++m)
-            if (m < M) acc[m] = fma(lv, u[j * M + m], acc[m]);
-        }
-#pragma unroll
-        for (int m = 0; m < kMaxM; ++m) {
-          if (m < M) {
-            const double s = warp_sum(acc[m]);
-            if (lane == 0) u[r * M + m] -= s;
-          }
-        }
-      }
-      __syncthreads();
+  // u = L⁻¹·v12 with the explicit inverse of the Cholesky factor (set-up): column m of v12 is non-zero only
+  // in rows [mG,(m+1)G), so u[r][m] = Σ_g Linv[r][mG+g]·k_m[g] — one warp per row, lanes over g, no
+  // sequential dependency.  (Inverting the triangular factor is benign — its condition number is the
+  // square root of v11's; it is the explicit v11⁻¹ that loses the 1e4 → O(1) cancellation.)
+  {
+    double* kk = u + (size_t)ld * M;  // [n] kernel values, block m at offset mG
+    for (int idx = tid; idx < n; idx += GP_THREADS) {
+      const int m = idx / G;
+      kk[idx] = u[idx * M + m];
     }
-    if (warp == 0) {  // 32×32 triangular diagonal block, lane = row
-      const int r = k0 + lane;
-      double v[kMaxM];
-#pragma unroll
-      for (int m = 0; m < kMaxM; ++m) v[m] = (m < M) ? u[r * M + m] : 0.0;
-      for (int c = 0; c < 32; ++c) {
-        const double lrc = L[(long long)r * ld + k0 + c];  // row r, column k0+c (diagonal when lane == c)
-#pragma unroll
-        for (int m = 0; m < kMaxM; ++m) {
-          if (m < M) {
-            if (lane == c) v[m] = v[m] / lrc;
-            const double xc = __shfl_sync(0xffffffffu, v[m], c);
-            if (lane > c) v[m] = fma(-lrc, xc, v[m]);
-          }
-        }
+    __syncthreads();
+    for (int r = warp; r < n; r += NW) {
+      const double* Lr = L + (long long)r * ld;
+      for (int m = 0; m < M; ++m) {
+        double acc = 0.0;
+        const int c1 = min((m + 1) * G, r + 1);
+        for (int c = m * G + lane; c < c1; c += 32) acc = fma(Lr[c], kk[c], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) u[r * M + m] = acc;
       }
-#pragma unroll
-      for (int m = 0; m < kMaxM; ++m)
-        if (m < M) u[r * M + m] = v[m];
     }
     __syncthreads();
   }
@@ -339,7 +317,8 @@ broaden_kernel(int nf, int S, int log2np, int R, const double2* __restrict__ F, 
 //     evaluates de Boor's recurrence with the knots scaled by the walker's Doppler factor.
 // ------------------------------------------------------------------------------------------------
 constexpr int RS_THREADS = 256;
-constexpr int RS_SPAN = 1024;  // coefficients a tile may stage; wider tiles (masked gaps) go pixel by pixel
+constexpr int RS_SPAN = 512;   // coefficients a tile may stage; wider tiles (masked gaps) go pixel by pixel
+constexpr int RS_ROWS = 4;     // bulk-flux rows handled together: one read of the filter taps serves all of them
 
 __device__ __forceinline__ double spline_coef_direct(const double* __restrict__ GinvT, const double* __restrict__ yb,
                                                      int nf, int j) {
@@ -355,11 +334,12 @@ __global__ void __launch_bounds__(RS_THREADS)
 resample_kernel(int nf, int R, int N, const double* __restrict__ fw, const double* __restrict__ GinvT,
                 const double* __restrict__ wave, const double* __restrict__ theta, int ntheta, int col_vz,
                 const double* __restrict__ ysrc, long long y_stride_b, double* __restrict__ Y) {
-  __shared__ double ys[RS_SPAN + 2 * kSplineW];
-  __shared__ double cs[RS_SPAN];
+  __shared__ double ys[RS_ROWS][RS_SPAN + 2 * kSplineW];
+  __shared__ double cs[RS_ROWS][RS_SPAN];
   __shared__ int s_min[RS_THREADS / 32], s_max[RS_THREADS / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int p = blockIdx.x * RS_THREADS + tid, r = blockIdx.y, b = blockIdx.z;
+  const int p = blockIdx.x * RS_THREADS + tid, r0 = blockIdx.y * RS_ROWS, b = blockIdx.z;
+  const int nr = min(RS_ROWS, R - r0);
   double scale = 1.0;
   if (col_vz >= 0) {
     const double vz = theta[(long long)b * ntheta + col_vz];
@@ -380,34 +360,49 @@ resample_kernel(int nf, int R, int N, const double* __restrict__ fw, const doubl
 #pragma unroll
   for (int w = 1; w < RS_THREADS / 32; ++w) { lmin = min(lmin, s_min[w]); lmax = max(lmax, s_max[w]); }
   const int jlo = lmin - kDeg, span = lmax - jlo + 1;
-  const double* yb = ysrc + (long long)b * y_stride_b + (long long)r * nf;
-  double out = 0.0;
+  const double* yb = ysrc + (long long)b * y_stride_b + (long long)r0 * nf;
+  double hb[kDeg + 1];
+  if (act) bspl6(fw, nf, x, l, scale, hb);
+  double out[RS_ROWS];
+#pragma unroll
+  for (int q = 0; q < RS_ROWS; ++q) out[q] = 0.0;
   if (span <= RS_SPAN) {
-    for (int i = tid; i < span + 2 * kSplineW; i += RS_THREADS) {
-      const int gi = jlo - kSplineW + i;
-      ys[i] = (gi >= 0 && gi < nf) ? yb[gi] : 0.0;
-    }
+    for (int q = 0; q < nr; ++q)
+      for (int i = tid; i < span + 2 * kSplineW; i += RS_THREADS) {
+        const int gi = jlo - kSplineW + i;
+        ys[q][i] = (gi >= 0 && gi < nf) ? yb[(long long)q * nf + gi] : 0.0;
+      }
+    for (int q = nr; q < RS_ROWS; ++q)
+      for (int i = tid; i < span + 2 * kSplineW; i += RS_THREADS) ys[q][i] = 0.0;
     __syncthreads();
     for (int jj = tid; jj < span; jj += RS_THREADS) {
       const double* g = GinvT + (jlo + jj);
-      double acc = 0.0;
+      double acc[RS_ROWS];
+#pragma unroll
+      for (int q = 0; q < RS_ROWS; ++q) acc[q] = 0.0;
 #pragma unroll 4
-      for (int d = 0; d <= 2 * kSplineW; ++d) acc = fma(g[(long long)d * nf], ys[jj + d], acc);
-      cs[jj] = acc;
+      for (int d = 0; d <= 2 * kSplineW; ++d) {
+        const double gv = g[(long long)d * nf];
+#pragma unroll
+        for (int q = 0; q < RS_ROWS; ++q) acc[q] = fma(gv, ys[q][jj + d], acc[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < RS_ROWS; ++q) cs[q][jj] = acc[q];
     }
     __syncthreads();
     if (act) {
-      double hb[kDeg + 1];
-      bspl6(fw, nf, x, l, scale, hb);
 #pragma unroll
-      for (int m = 0; m <= kDeg; ++m) out = fma(hb[m], cs[l - kDeg - jlo + m], out);
+      for (int q = 0; q < RS_ROWS; ++q)
+#pragma unroll
+        for (int m = 0; m <= kDeg; ++m) out[q] = fma(hb[m], cs[q][l - kDeg - jlo + m], out[q]);
     }
   } else if (act) {
-    double hb[kDeg + 1];
-    bspl6(fw, nf, x, l, scale, hb);
-    for (int m = 0; m <= kDeg; ++m) out = fma(hb[m], spline_coef_direct(GinvT, yb, nf, l - kDeg + m), out);
+    for (int q = 0; q < nr; ++q)
+      for (int m = 0; m <= kDeg; ++m)
+        out[q] = fma(hb[m], spline_coef_direct(GinvT, yb + (long long)q * nf, nf, l - kDeg + m), out[q]);
   }
-  if (act) Y[((long long)b * R + r) * N + p] = out;
+  if (act)
+    for (int q = 0; q < nr; ++q) Y[((long long)b * R + r0 + q) * N + p] = out[q];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -683,7 +678,7 @@ cudaError_t model_setup(ModelState* ms, int N, int M, int Bmax, int nf, const do
                         int flags, std::string* err) {
   model_free(ms);
   const int R = M + 2, n = M * G, ld = ((n + 31) / 32) * 32, n2 = nf / 2;
-  if ((size_t)ld * M * sizeof(double) > 200 * 1024) {
+  if ((size_t)ld * (M + 1) * sizeof(double) > 200 * 1024) {
     *err = "emulator too large for the shared-memory GP solve (M·G·M·8 B > 200 KB)";
     return cudaErrorInvalidValue;
   }
@@ -727,6 +722,23 @@ cudaError_t model_setup(ModelState* ms, int N, int M, int Bmax, int nf, const do
     for (int k = 0; k < i; ++k) s -= L[(size_t)i * ld + k] * zw[k];
     zw[i] = s / L[(size_t)i * ld + i];
   }
+  // explicit inverse of the triangular factor, row by row: Linv[i][:] = (e_i − Σ_{k<i} L[i][k]·Linv[k][:]) / L[i][i]
+  std::vector<double> Linv((size_t)ld * ld, 0.0);
+  for (int i = 0; i < ld; ++i) {
+    double* out = &Linv[(size_t)i * ld];
+    if (i >= n) { out[i] = 1.0; continue; }
+    const double* Li = &L[(size_t)i * ld];
+    for (int k = 0; k < i; ++k) {
+      const double lik = Li[k];
+      if (lik == 0.0) continue;
+      const double* rk = &Linv[(size_t)k * ld];
+      for (int c = 0; c <= k; ++c) out[c] -= lik * rk[c];
+    }
+    out[i] += 1.0;
+    const double d = 1.0 / Li[i];
+    for (int c = 0; c <= i; ++c) out[c] *= d;
+  }
+  L.swap(Linv);
   cudaError_t e;
 #define UP(call) if ((e = (call)) != cudaSuccess) { *err = #call; return e; }
   UP(upload(&ms->fw, fine_wave_h, (size_t)nf));
@@ -775,7 +787,7 @@ cudaError_t launch_upstream(const ModelState& ms, const UpstreamArgs& a, cudaStr
   wave_max_kernel<<<1, 1024, 0, st>>>(a.wave, N, ms.wave_max);
   ++*launches;
   // (1) emulator
-  gp_predict_kernel<<<B, GP_THREADS, sizeof(double) * (size_t)ms.ld * M, st>>>(
+  gp_predict_kernel<<<B, GP_THREADS, sizeof(double) * ((size_t)ms.ld * M + ms.ld), st>>>(
       M, ms.G, D, ms.n, ms.ld, ms.gp_grid, ms.gp_var, ms.gp_ls, ms.L, ms.zw, a.theta, a.ntheta,
       (ms.flags & SFB_MODEL_PAPER_TERM) ? 1 : 0, ms.mu, ms.wcov, a.A, a.status);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
@@ -801,7 +813,7 @@ cudaError_t launch_upstream(const ModelState& ms, const UpstreamArgs& a, cudaStr
     ystride = (long long)R * nf;
   }
   // (3) Doppler shift + spline resampling onto the data pixels
-  resample_kernel<<<dim3((N + RS_THREADS - 1) / RS_THREADS, R, B), RS_THREADS, 0, st>>>(
+  resample_kernel<<<dim3((N + RS_THREADS - 1) / RS_THREADS, (R + RS_ROWS - 1) / RS_ROWS, B), RS_THREADS, 0, st>>>(
       nf, R, N, ms.fw, ms.GinvT, a.wave, a.theta, a.ntheta, (ms.flags & SFB_MODEL_VZ) ? D + 1 : -1, ysrc, ystride,
       ms.Y);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
