@@ -59,7 +59,7 @@ band_build_kernel(BandBuildParams p) {
   double* out = p.Sb + (long long)b * p.strideSb + (long long)i * WD;
   int over = 0;
   // local kernels: this row's metric per kernel, and the overflow test (block wider than the window)
-  for (int d = lane; d <= WD; d += 32) {  // d == WD is only the "does the band fit" probe
+  for (int d = lane; d <= WD; d += 32) {  // d == WD is only a probe; the factorisation needs a band <= WD−2
     const int k = i - d;
     double v = 0.0;
     bool nz = false;
@@ -95,10 +95,8 @@ band_build_kernel(BandBuildParams p) {
       }
       if (d == 0) v += p.jitter;
     }
-    if (d < WD)
-      out[d] = v;
-    else if (nz)
-      over = 1;
+    if (d < WD) out[d] = v;
+    if (d >= WD - 1 && nz) over = 1;
   }
   if (over) atomicOr(p.overflow + b, 1);
 }
@@ -175,8 +173,8 @@ band_chol_kernel(BandCholParams p) {
   constexpr int EC = WD / 32, NT = WD * 32 / ER, ROWLEN = WD + NRP;
   constexpr int BATCH = band_batch(WD, ER);  // pivots per staging batch (a multiple of the unroll length)
   constexpr int NE = (WD * MAXNR + NT - 1) / NT;          // right-hand-side registers per thread
-  __shared__ double colbuf[2][WD];
-  __shared__ double zbuf[2][NRP];
+  __shared__ double colbuf[2][2][WD];
+  __shared__ double zbuf[2][2][NRP];
   __shared__ double invbuf[2];
   __shared__ double gram[(kMaxM + 1) * (kMaxM + 1)];
   extern __shared__ double ring[];  // [2][BATCH][ROWLEN]
@@ -259,81 +257,128 @@ band_chol_kernel(BandCholParams p) {
   constexpr int UN = band_lcm(WD, ER);                // ER, EC as used here: 8|{1,2,4}, 8·3, 10|5
   static_assert(UN <= 24 && WD % UN == 0 && UN % ER == 0 && UN % EC == 0 && UN % 2 == 0 && BATCH % UN == 0,
                 "unroll length must divide the window and the staging batch");
-  // 1/pivot is taken off the critical path: the owner of the NEXT diagonal element updates it first thing
-  // after the barrier, starts its reciprocal and publishes it for the following pivot, so that nobody waits
-  // for a division between the barrier and the FMAs.
+  // Two pivots per barrier.  The owners publish the raw columns j and j+1 (both as left by the pivots before
+  // j); every thread corrects the entries of column j+1 it needs with pivot j itself (one FMA each) and then
+  // applies the rank-2 update to its registers.  1/pivot_j is taken off the critical path: the owner of the
+  // diagonal element of the NEXT pair updates it first thing after the barrier (same arithmetic as the bulk
+  // update) and publishes its reciprocal for the following step.  Rows j+WD and j+1+WD enter afterwards;
+  // row j+WD misses pivot j+1's update, which is exactly zero because the band is at most WD−2 wide.
+  auto track_pivot = [&](double pj, int j) {  // warp 0: LAPACK-style info, log det as mantissa × 2^exponent
+    if (!(pj > 0.0) && info == 0) info = j + 1;
+    const int hi = __double2hiint(pj);
+    expo += ((hi >> 20) & 0x7ff) - 1022;
+    mant *= __hiloint2double((hi & 0x800fffff) | 0x3fe00000, __double2loint(pj));
+  };
   if (tid == 0) invbuf[0] = 1.0 / a[0][0];
   for (int j0 = 0, jr0 = 0; j0 < N; j0 += UN, jr0 = (jr0 + UN == WD) ? 0 : jr0 + UN) {
     const int own_lane0 = jr0 / EC, own_warp0 = jr0 / ER;
     const int jb0 = j0 % BATCH, half = (j0 / BATCH) & 1;
     const double* rowbase = ring + half * (BATCH * ROWLEN) + jb0 * ROWLEN;
 #pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      const int j = j0 + u, jr = jr0 + u;
+    for (int u = 0; u < UN; u += 2) {
+      const int j = j0 + u, jr = jr0 + u, jr1 = jr + 1;  // UN is even and divides WD: no wrap inside a pair
       if (j >= N) break;
-      const int buf = u & 1;
+      // double buffer by pair parity (static when a block holds an even number of pairs)
+      const int buf = ((UN / 2) % 2 == 0) ? ((u >> 1) & 1) : ((j >> 1) & 1);
       const bool boundary = (u == 0) && (jb0 == 0);
       // staging boundary: this batch's rows (issued one boundary ago) must have landed before the barrier
       if (boundary) cp_async_wait_all();
-      // ---- phase A: owners publish column j of the window and the pivot row of the right-hand sides
+      // ---- phase A: owners publish columns j, j+1 of the window and rows j, j+1 of the right-hand sides
       if (lane == own_lane0 + u / EC) {
 #pragma unroll
-        for (int er = 0; er < ER; ++er) colbuf[buf][tr * ER + er] = a[er][u % EC];
+        for (int er = 0; er < ER; ++er) colbuf[buf][0][tr * ER + er] = a[er][u % EC];
+      }
+      if (lane == own_lane0 + (u + 1) / EC) {
+#pragma unroll
+        for (int er = 0; er < ER; ++er) colbuf[buf][1][tr * ER + er] = a[er][(u + 1) % EC];
       }
 #pragma unroll
-      for (int e = 0; e < NE; ++e)
-        if (rres[e] == jr) zbuf[buf][rq[e]] = rv[e];
+      for (int e = 0; e < NE; ++e) {
+        if (rres[e] == jr) zbuf[buf][0][rq[e]] = rv[e];
+        if (rres[e] == jr1) zbuf[buf][1][rq[e]] = rv[e];
+      }
       __syncthreads();
       // past the barrier nobody reads the other ring half any more (its last reader was the previous
-      // pivot): start filling it with the next batch
+      // pair): start filling it with the next batch
       if (boundary) stage_issue(j + BATCH, ring + (half ^ 1) * (BATCH * ROWLEN));
-      // ---- phase C: rank-1 update of the window, right-hand sides, Gram matrix
-      const double inv = invbuf[buf];
+      // ---- phase C
+      const double* cb0 = colbuf[buf][0];
+      const double* cb1 = colbuf[buf][1];
+      const double inv0 = invbuf[buf];
+      const double m = cb0[jr1] * inv0;                 // a(j+1,j)/pivot_j
+      const double p1 = fma(-cb0[jr1], m, cb1[jr1]);    // pivot j+1 after pivot j's update
+      const double inv1 = 1.0 / p1;
       {
-        const int jn = (jr + 1 == WD) ? 0 : jr + 1;
-        if (tr == jn / ER && lane == jn / EC) {  // next pivot: same arithmetic as the bulk update below
-          const double aj1 = colbuf[buf][jn];
-          invbuf[buf ^ 1] = 1.0 / fma(-aj1, aj1 * inv, a[(u + 1) % ER][(u + 1) % EC]);
+        const int jn = (jr + 2 == WD) ? 0 : jr + 2;
+        if (tr == jn / ER && lane == jn / EC) {  // first pivot of the next pair
+          const double x0 = cb0[jn], x1 = fma(-x0, m, cb1[jn]);
+          double d = fma(-x0, x0 * inv0, a[(u + 2) % ER][(u + 2) % EC]);
+          d = fma(-x1, x1 * inv1, d);
+          invbuf[buf ^ 1] = 1.0 / d;
         }
       }
       if (tr == 0) {  // warp-uniform bookkeeping
-        const double pj = colbuf[buf][jr];
-        if (!(pj > 0.0) && info == 0) info = j + 1;
-        const int hi = __double2hiint(pj);
-        expo += ((hi >> 20) & 0x7ff) - 1022;
-        mant *= __hiloint2double((hi & 0x800fffff) | 0x3fe00000, __double2loint(pj));
-        if ((j & 511) == 511) {
+        track_pivot(cb0[jr], j);
+        if (j + 1 < N) track_pivot(p1, j + 1);
+        if ((j & 510) == 510) {
           const int h2 = __double2hiint(mant);
           expo += ((h2 >> 20) & 0x7ff) - 1022;
           mant = __hiloint2double((h2 & 0x800fffff) | 0x3fe00000, __double2loint(mant));
         }
       }
-      double ak[EC];
+      double ak0[EC], ak1[EC];
 #pragma unroll
-      for (int ec = 0; ec < EC; ++ec) ak[ec] = colbuf[buf][lane * EC + ec] * inv;
-#pragma unroll
-      for (int er = 0; er < ER; ++er) {
-        const double ai = -colbuf[buf][tr * ER + er];
-#pragma unroll
-        for (int ec = 0; ec < EC; ++ec) a[er][ec] = fma(ai, ak[ec], a[er][ec]);
+      for (int ec = 0; ec < EC; ++ec) {
+        const double c0 = cb0[lane * EC + ec];
+        ak0[ec] = c0 * inv0;
+        ak1[ec] = fma(-c0, m, cb1[lane * EC + ec]) * inv1;
       }
 #pragma unroll
-      for (int e = 0; e < NE; ++e)
-        if (rres[e] >= 0) rv[e] = fma(-colbuf[buf][rres[e]], zbuf[buf][rq[e]] * inv, rv[e]);
-      if (gram_on) gacc = fma(zbuf[buf][gp_] * inv, zbuf[buf][gq_], gacc);
-      // ---- the row that enters the window (index j + WD) takes the slots of the retiring index j
-      const double* row = rowbase + u * ROWLEN;
+      for (int er = 0; er < ER; ++er) {
+        const double c0 = cb0[tr * ER + er];
+        const double ai0 = -c0, ai1 = -fma(-c0, m, cb1[tr * ER + er]);
+#pragma unroll
+        for (int ec = 0; ec < EC; ++ec) a[er][ec] = fma(ai1, ak1[ec], fma(ai0, ak0[ec], a[er][ec]));
+      }
+      const double* zb0 = zbuf[buf][0];
+      const double* zb1 = zbuf[buf][1];
+#pragma unroll
+      for (int e = 0; e < NE; ++e) {
+        if (rres[e] >= 0) {
+          const double c0 = cb0[rres[e]], c1 = fma(-c0, m, cb1[rres[e]]);
+          const double z0 = zb0[rq[e]], z1 = fma(-m, z0, zb1[rq[e]]);
+          rv[e] = fma(-c1, z1 * inv1, fma(-c0, z0 * inv0, rv[e]));
+        }
+      }
+      if (gram_on) {
+        const double z0p = zb0[gp_], z0q = zb0[gq_];
+        gacc = fma(z0p * inv0, z0q, gacc);
+        gacc = fma(fma(-m, z0p, zb1[gp_]) * inv1, fma(-m, z0q, zb1[gq_]), gacc);
+      }
+      // ---- rows j+WD and j+1+WD enter the window in the slots of the retiring indices j and j+1
+      const double* row0 = rowbase + u * ROWLEN;
+      const double* row1 = row0 + ROWLEN;
       if (tr == own_warp0 + u / ER) {
 #pragma unroll
         for (int ec = 0; ec < EC; ++ec) {
           int t = lane * EC + ec - jr - 1;
           if (t < 0) t += WD;
-          a[u % ER][ec] = row[WD - 1 - t];
+          a[u % ER][ec] = row0[WD - 1 - t];
+        }
+      }
+      if (tr == own_warp0 + (u + 1) / ER) {
+#pragma unroll
+        for (int ec = 0; ec < EC; ++ec) {
+          int t = lane * EC + ec - jr1 - 1;
+          if (t < 0) t += WD;
+          a[(u + 1) % ER][ec] = row1[WD - 1 - t];
         }
       }
 #pragma unroll
-      for (int e = 0; e < NE; ++e)
-        if (rres[e] == jr) rv[e] = row[WD + rq[e]];
+      for (int e = 0; e < NE; ++e) {
+        if (rres[e] == jr) rv[e] = row0[WD + rq[e]];
+        if (rres[e] == jr1) rv[e] = row1[WD + rq[e]];
+      }
     }
   }
   if (tid == 0) logdet = log(mant) + (double)expo * 0.6931471805599453;
