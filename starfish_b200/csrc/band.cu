@@ -59,7 +59,7 @@ band_build_kernel(BandBuildParams p) {
   double* out = p.Sb + (long long)b * p.strideSb + (long long)i * WD;
   int over = 0;
   // local kernels: this row's metric per kernel, and the overflow test (block wider than the window)
-  for (int d = lane; d <= WD; d += 32) {  // d == WD is only a probe; the factorisation needs a band <= WD−2
+  for (int d = lane; d <= WD; d += 32) {  // d == WD is only the "does the band fit" probe
     const int k = i - d;
     double v = 0.0;
     bool nz = false;
@@ -95,8 +95,10 @@ band_build_kernel(BandBuildParams p) {
       }
       if (d == 0) v += p.jitter;
     }
-    if (d < WD) out[d] = v;
-    if (d >= WD - 1 && nz) over = 1;
+    if (d < WD)
+      out[d] = v;
+    else if (nz)
+      over = 1;
   }
   if (over) atomicOr(p.overflow + b, 1);
 }
@@ -159,26 +161,22 @@ __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_s
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-__host__ __device__ constexpr int band_batch(int ER) { return ER < 16 ? 2 * ER : ER; }
+__host__ __device__ constexpr int band_lcm(int WD, int ER) { return (ER % (WD / 32) == 0) ? ER : ER * (WD / 32); }
+__host__ __device__ constexpr int band_batch(int WD, int ER) {
+  const int l = band_lcm(WD, ER);
+  return (l <= 24 && WD % l == 0) ? (l < 16 ? 2 * l : l) : 16;
+}
 
-// One CTA per walker; thread (warp tr, lane) keeps the window slots of rows [tr·ER, tr·ER+ER) × columns
-// {lane + 32·ec} in registers.  ER = rows per thread: 16 → WD·2 threads (8 warps for the 128-pixel window);
-// the 160-pixel window uses 10 → 512 threads so that its 10×5 tile fits a 128-register budget.
-// MAXNR = right-hand sides the instantiation can carry (M + 1 <= MAXNR).
-//
-// What bounds this kernel is the shared-memory pipe (every warp re-reads the pivot columns), then the fp64
-// pipe; hence: few, fat warps (a warp reads a column once for ER rows), column ownership strided by 32 so
-// that a warp's read of a whole column is conflict-free, and two pivots per barrier.
+// ER = window rows per thread (8 → WD·4 threads; the 160-pixel window uses 10 → 512 threads so that its
+// 10×5 register tile fits a 128-register budget), MAXNR = right-hand sides the instantiation can carry (M + 1 <= MAXNR)
 template <int WD, int ER, int MAXNR>
 __global__ void __launch_bounds__(WD * 32 / ER, 1)
 band_chol_kernel(BandCholParams p) {
   constexpr int EC = WD / 32, NT = WD * 32 / ER, ROWLEN = WD + NRP;
-  constexpr int BATCH = band_batch(ER);                   // pivots per staging batch (a multiple of ER)
+  constexpr int BATCH = band_batch(WD, ER);  // pivots per staging batch (a multiple of the unroll length)
   constexpr int NE = (WD * MAXNR + NT - 1) / NT;          // right-hand-side registers per thread
-  constexpr int NG = (MAXNR * MAXNR + NT - 1) / NT;       // Gram-matrix accumulators per thread
-  static_assert(WD % 32 == 0 && WD % ER == 0 && ER % 2 == 0 && BATCH % ER == 0, "window tiling");
-  __shared__ double colbuf[2][2][WD];
-  __shared__ double zbuf[2][2][NRP];
+  __shared__ double colbuf[2][WD];
+  __shared__ double zbuf[2][NRP];
   __shared__ double invbuf[2];
   __shared__ double gram[(kMaxM + 1) * (kMaxM + 1)];
   extern __shared__ double ring[];  // [2][BATCH][ROWLEN]
@@ -220,14 +218,14 @@ band_chol_kernel(BandCholParams p) {
     cp_async_commit();
   };
 
-  // ---- initial window: slot (r, c) = element (i = r, k = c), k <= i (the other half is not live yet)
+  // ---- initial window: slot (r, c) = element (i = r, k = c), symmetric fill is not needed (k <= i only)
   double a[ER][EC];
 #pragma unroll
   for (int er = 0; er < ER; ++er) {
     const int i = tr * ER + er;
 #pragma unroll
     for (int ec = 0; ec < EC; ++ec) {
-      const int k = lane + 32 * ec;
+      const int k = lane * EC + ec;
       double v = 0.0;
       if (k <= i) v = (i < N) ? Sb[(long long)i * WD + (i - k)] : (k == i ? 1.0 : 0.0);
       a[er][ec] = v;
@@ -243,168 +241,105 @@ band_chol_kernel(BandCholParams p) {
     rq[e] = ok ? idx - (idx / NR) * NR : 0;
     rv[e] = ok ? rhs_at(rres[e], rq[e]) : 0.0;
   }
-  double gacc[NG];
-  int gp_[NG], gq_[NG];
-#pragma unroll
-  for (int g = 0; g < NG; ++g) {
-    const int idx = tid + NT * g;
-    const bool ok = idx < NR * NR;
-    gp_[g] = ok ? idx / NR : -1;
-    gq_[g] = ok ? idx - (idx / NR) * NR : 0;
-    gacc[g] = 0.0;
-  }
   stage_issue(0, ring);
 
-  double logdet = 0.0;
+  double logdet = 0.0, gacc = 0.0;
   int info = 0;
+  const int gp_ = tid / NR, gq_ = tid - (tid / NR) * NR;  // Gram element of this thread (tid < NR²)
+  const bool gram_on = tid < NR * NR;
+
   // log det S = Σ log(pivot): the pivots are multiplied up as mantissa × 2^exponent by warp 0 (a handful of
   // integer/DMUL instructions per pivot instead of a log() on the critical path) and logged once at the end.
   double mant = 1.0;
   long long expo = 0;
-  auto track_pivot = [&](double pj, int j) {  // LAPACK-style info, log det as mantissa × 2^exponent
-    if (!(pj > 0.0) && info == 0) info = j + 1;
-    const int hi = __double2hiint(pj);
-    expo += ((hi >> 20) & 0x7ff) - 1022;
-    mant *= __hiloint2double((hi & 0x800fffff) | 0x3fe00000, __double2loint(pj));
-  };
-  // register of this thread that holds column-slot c of its row er (c / 32 is uniform over the CTA, so the
-  // branch is uniform and the register index compile-time inside each arm)
-  auto col_reg = [&](int er_static_row, int ecj, const double (&row)[EC]) -> double {
-    (void)er_static_row;
-    double x = row[0];
-#pragma unroll
-    for (int ec = 1; ec < EC; ++ec)
-      if (ecj == ec) x = row[ec];
-    return x;
-  };
 
-  // The pivot loop is unrolled by ER so that "which register row holds index j" is a compile-time fact inside
-  // the body (j ≡ u mod ER, ER | WD).  Two pivots per barrier: the owners publish the raw columns j and j+1
-  // (both as left by the pivots before j); every thread corrects the entries of column j+1 it needs with
-  // pivot j itself (one FMA each) and then applies the rank-2 update to its registers.  1/pivot_j is taken off
-  // the critical path: the owner of the diagonal element of the NEXT pair updates it first thing after the
-  // barrier (same arithmetic as the bulk update) and publishes its reciprocal for the following step.  Rows
-  // j+WD and j+1+WD enter afterwards; row j+WD misses pivot j+1's update, which is exactly zero because the
-  // band is at most WD−2 wide.
+  // The pivot loop is unrolled by UN = lcm(ER, EC) so that "which register holds column j / row j" is a
+  // compile-time fact inside the body (j ≡ u mod UN, UN | WD): publishing the pivot column and replacing
+  // the retiring row are plain register moves, no selects.
+  constexpr int UN = band_lcm(WD, ER);                // ER, EC as used here: 8|{1,2,4}, 8·3, 10|5
+  static_assert(UN <= 24 && WD % UN == 0 && UN % ER == 0 && UN % EC == 0 && UN % 2 == 0 && BATCH % UN == 0,
+                "unroll length must divide the window and the staging batch");
+  // 1/pivot is taken off the critical path: the owner of the NEXT diagonal element updates it first thing
+  // after the barrier, starts its reciprocal and publishes it for the following pivot, so that nobody waits
+  // for a division between the barrier and the FMAs.
   if (tid == 0) invbuf[0] = 1.0 / a[0][0];
-  for (int j0 = 0, jr0 = 0; j0 < N; j0 += ER, jr0 = (jr0 + ER == WD) ? 0 : jr0 + ER) {
-    const int own_warp = jr0 / ER;
+  for (int j0 = 0, jr0 = 0; j0 < N; j0 += UN, jr0 = (jr0 + UN == WD) ? 0 : jr0 + UN) {
+    const int own_lane0 = jr0 / EC, own_warp0 = jr0 / ER;
     const int jb0 = j0 % BATCH, half = (j0 / BATCH) & 1;
     const double* rowbase = ring + half * (BATCH * ROWLEN) + jb0 * ROWLEN;
 #pragma unroll
-    for (int u = 0; u < ER; u += 2) {
-      const int j = j0 + u, jr = jr0 + u, jr1 = jr + 1;  // ER is even and divides WD: no wrap inside a pair
+    for (int u = 0; u < UN; ++u) {
+      const int j = j0 + u, jr = jr0 + u;
       if (j >= N) break;
-      // double buffer by pair parity (static when a block holds an even number of pairs)
-      const int buf = ((ER / 2) % 2 == 0) ? ((u >> 1) & 1) : ((j >> 1) & 1);
+      const int buf = u & 1;
       const bool boundary = (u == 0) && (jb0 == 0);
       // staging boundary: this batch's rows (issued one boundary ago) must have landed before the barrier
       if (boundary) cp_async_wait_all();
-      // ---- phase A: owners publish columns j, j+1 of the window and rows j, j+1 of the right-hand sides
-      {
-        const int ec0 = jr >> 5, ec1 = jr1 >> 5;
-        if (lane == (jr & 31)) {
+      // ---- phase A: owners publish column j of the window and the pivot row of the right-hand sides
+      if (lane == own_lane0 + u / EC) {
 #pragma unroll
-          for (int er = 0; er < ER; ++er) colbuf[buf][0][tr * ER + er] = col_reg(er, ec0, a[er]);
-        }
-        if (lane == (jr1 & 31)) {
-#pragma unroll
-          for (int er = 0; er < ER; ++er) colbuf[buf][1][tr * ER + er] = col_reg(er, ec1, a[er]);
-        }
+        for (int er = 0; er < ER; ++er) colbuf[buf][tr * ER + er] = a[er][u % EC];
       }
 #pragma unroll
-      for (int e = 0; e < NE; ++e) {
-        if (rres[e] == jr) zbuf[buf][0][rq[e]] = rv[e];
-        if (rres[e] == jr1) zbuf[buf][1][rq[e]] = rv[e];
-      }
+      for (int e = 0; e < NE; ++e)
+        if (rres[e] == jr) zbuf[buf][rq[e]] = rv[e];
       __syncthreads();
       // past the barrier nobody reads the other ring half any more (its last reader was the previous
-      // pair): start filling it with the next batch
+      // pivot): start filling it with the next batch
       if (boundary) stage_issue(j + BATCH, ring + (half ^ 1) * (BATCH * ROWLEN));
-      // ---- phase C
-      const double* cb0 = colbuf[buf][0];
-      const double* cb1 = colbuf[buf][1];
-      const double inv0 = invbuf[buf];
-      const double m = cb0[jr1] * inv0;                 // a(j+1,j)/pivot_j
-      const double p1 = fma(-cb0[jr1], m, cb1[jr1]);    // pivot j+1 after pivot j's update
-      const double inv1 = 1.0 / p1;
+      // ---- phase C: rank-1 update of the window, right-hand sides, Gram matrix
+      const double inv = invbuf[buf];
       {
-        const int jn = (jr + 2 == WD) ? 0 : jr + 2;
-        if (tr == jn / ER && lane == (jn & 31)) {  // first pivot of the next pair
-          const double x0 = cb0[jn], x1 = fma(-x0, m, cb1[jn]);
-          double d = fma(-x0, x0 * inv0, col_reg(0, jn >> 5, a[(u + 2) % ER]));
-          d = fma(-x1, x1 * inv1, d);
-          invbuf[buf ^ 1] = 1.0 / d;
+        const int jn = (jr + 1 == WD) ? 0 : jr + 1;
+        if (tr == jn / ER && lane == jn / EC) {  // next pivot: same arithmetic as the bulk update below
+          const double aj1 = colbuf[buf][jn];
+          invbuf[buf ^ 1] = 1.0 / fma(-aj1, aj1 * inv, a[(u + 1) % ER][(u + 1) % EC]);
         }
       }
       if (tr == 0) {  // warp-uniform bookkeeping
-        track_pivot(cb0[jr], j);
-        if (j + 1 < N) track_pivot(p1, j + 1);
-        if ((j & 510) == 510) {
+        const double pj = colbuf[buf][jr];
+        if (!(pj > 0.0) && info == 0) info = j + 1;
+        const int hi = __double2hiint(pj);
+        expo += ((hi >> 20) & 0x7ff) - 1022;
+        mant *= __hiloint2double((hi & 0x800fffff) | 0x3fe00000, __double2loint(pj));
+        if ((j & 511) == 511) {
           const int h2 = __double2hiint(mant);
           expo += ((h2 >> 20) & 0x7ff) - 1022;
           mant = __hiloint2double((h2 & 0x800fffff) | 0x3fe00000, __double2loint(mant));
         }
       }
-      double ak0[EC], ak1[EC];
+      double ak[EC];
 #pragma unroll
-      for (int ec = 0; ec < EC; ++ec) {
-        const double c0 = cb0[lane + 32 * ec];
-        ak0[ec] = c0 * inv0;
-        ak1[ec] = fma(-c0, m, cb1[lane + 32 * ec]) * inv1;
-      }
+      for (int ec = 0; ec < EC; ++ec) ak[ec] = colbuf[buf][lane * EC + ec] * inv;
 #pragma unroll
       for (int er = 0; er < ER; ++er) {
-        const double c0 = cb0[tr * ER + er];
-        const double ai0 = -c0, ai1 = -fma(-c0, m, cb1[tr * ER + er]);
+        const double ai = -colbuf[buf][tr * ER + er];
 #pragma unroll
-        for (int ec = 0; ec < EC; ++ec) a[er][ec] = fma(ai1, ak1[ec], fma(ai0, ak0[ec], a[er][ec]));
-      }
-      const double* zb0 = zbuf[buf][0];
-      const double* zb1 = zbuf[buf][1];
-#pragma unroll
-      for (int e = 0; e < NE; ++e) {
-        if (rres[e] >= 0) {
-          const double c0 = cb0[rres[e]], c1 = fma(-c0, m, cb1[rres[e]]);
-          const double z0 = zb0[rq[e]], z1 = fma(-m, z0, zb1[rq[e]]);
-          rv[e] = fma(-c1, z1 * inv1, fma(-c0, z0 * inv0, rv[e]));
-        }
+        for (int ec = 0; ec < EC; ++ec) a[er][ec] = fma(ai, ak[ec], a[er][ec]);
       }
 #pragma unroll
-      for (int g = 0; g < NG; ++g) {
-        if (gp_[g] >= 0) {
-          const double z0p = zb0[gp_[g]], z0q = zb0[gq_[g]];
-          gacc[g] = fma(z0p * inv0, z0q, gacc[g]);
-          gacc[g] = fma(fma(-m, z0p, zb1[gp_[g]]) * inv1, fma(-m, z0q, zb1[gq_[g]]), gacc[g]);
-        }
-      }
-      // ---- rows j+WD and j+1+WD enter the window in the slots of the retiring indices j and j+1
-      if (tr == own_warp) {
-        const double* row0 = rowbase + u * ROWLEN;
-        const double* row1 = row0 + ROWLEN;
+      for (int e = 0; e < NE; ++e)
+        if (rres[e] >= 0) rv[e] = fma(-colbuf[buf][rres[e]], zbuf[buf][rq[e]] * inv, rv[e]);
+      if (gram_on) gacc = fma(zbuf[buf][gp_] * inv, zbuf[buf][gq_], gacc);
+      // ---- the row that enters the window (index j + WD) takes the slots of the retiring index j
+      const double* row = rowbase + u * ROWLEN;
+      if (tr == own_warp0 + u / ER) {
 #pragma unroll
         for (int ec = 0; ec < EC; ++ec) {
-          int t0 = lane + 32 * ec - jr - 1;
-          if (t0 < 0) t0 += WD;
-          a[u][ec] = row0[WD - 1 - t0];
-          int t1 = lane + 32 * ec - jr1 - 1;
-          if (t1 < 0) t1 += WD;
-          a[u + 1][ec] = row1[WD - 1 - t1];
+          int t = lane * EC + ec - jr - 1;
+          if (t < 0) t += WD;
+          a[u % ER][ec] = row[WD - 1 - t];
         }
       }
 #pragma unroll
-      for (int e = 0; e < NE; ++e) {
-        if (rres[e] == jr) rv[e] = (rowbase + u * ROWLEN)[WD + rq[e]];
-        if (rres[e] == jr1) rv[e] = (rowbase + (u + 1) * ROWLEN)[WD + rq[e]];
-      }
+      for (int e = 0; e < NE; ++e)
+        if (rres[e] == jr) rv[e] = row[WD + rq[e]];
     }
   }
   if (tid == 0) logdet = log(mant) + (double)expo * 0.6931471805599453;
 
   // ---- epilogue: lnL = −½ (log det S + log det(I + A·G) + RᵀS⁻¹R − uᵀ(I + A·G)⁻¹A u)
-#pragma unroll
-  for (int g = 0; g < NG; ++g)
-    if (gp_[g] >= 0) gram[tid + NT * g] = gacc[g];
+  if (gram_on) gram[tid] = gacc;
   __syncthreads();
   if (tid == 0) {
     double quad = gram[0], ld = logdet;
@@ -505,7 +440,7 @@ band_chol_kernel(BandCholParams p) {
 
 template <int WD, int ER>
 cudaError_t launch_band_t(const BandCholParams& p, int B, cudaStream_t st) {
-  const size_t smem = sizeof(double) * 2 * band_batch(ER) * (WD + NRP);
+  const size_t smem = sizeof(double) * 2 * band_batch(WD, ER) * (WD + NRP);
   static bool opted_in = false;  // static + dynamic shared memory exceeds 48 KB for the widest window
   if (!opted_in) {
     cudaError_t e = cudaFuncSetAttribute(band_chol_kernel<WD, ER, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
@@ -556,9 +491,9 @@ cudaError_t launch_band_build(const BandBuildParams& p, int B, cudaStream_t st) 
 cudaError_t launch_band_chol(const BandCholParams& p, int WD, int B, cudaStream_t st) {
   if (B <= 0) return cudaSuccess;
   switch (WD) {
-    case 64: return launch_band_t<64, 16>(p, B, st);
-    case 96: return launch_band_t<96, 16>(p, B, st);
-    case 128: return launch_band_t<128, 16>(p, B, st);
+    case 64: return launch_band_t<64, 8>(p, B, st);
+    case 96: return launch_band_t<96, 8>(p, B, st);
+    case 128: return launch_band_t<128, 8>(p, B, st);
     case 160: return launch_band_t<160, 10>(p, B, st);
     default: return cudaErrorInvalidValue;
   }

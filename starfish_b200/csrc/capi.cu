@@ -371,7 +371,7 @@ int structured_device(sfb_ctx* h, int B, const double* X, const double* A, const
   auto cls = [&](int b) {
     if (!sorted) return nclass;
     for (int c = 0; c < nclass; ++c)
-      if (h->bw_h[b] + 2 <= kBandWidths[c]) return c;  // the two-pivot kernel needs a band <= WD−2
+      if (h->bw_h[b] + 1 <= kBandWidths[c]) return c;
     return nclass;
   };
   for (int b = 0; b < B; ++b) count[cls(b)]++;
