@@ -21,6 +21,7 @@
 //                       Entering rows are staged 16 pivots ahead into a shared-memory ring with cp.async.
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 
 #include "sfb_internal.cuh"
 
@@ -160,6 +161,108 @@ __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_s
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Thread-0 epilogue shared by the band kernels: the M×M capacitance system on the Gram matrix of
+// Z = L⁻¹[R | Xᵀ] (gram[p·NR+q], NR = M+1), lnL = −½ (log det S + log det(I + A·G) + RᵀS⁻¹R − uᵀ(I + A·G)⁻¹A u).
+__device__ __noinline__ void band_epilogue(const BandCholParams& p, int b, int M, const double* gram, double logdet,
+                                           int info) {
+  const int N = p.N, NR = M + 1;
+  {
+    double quad = gram[0], ld = logdet;
+    if (M > 0 && info == 0) {
+      double Kc[kMaxM][kMaxM], v[kMaxM], u[kMaxM];
+      const double* A = p.A + (long long)b * M * M;
+      for (int i = 0; i < M; ++i) {
+        u[i] = gram[(i + 1) * NR];
+        for (int k = 0; k < M; ++k) {
+          double s = (i == k) ? 1.0 : 0.0;
+          for (int q = 0; q < M; ++q) s = fma(A[i * M + q], gram[(q + 1) * NR + (k + 1)], s);
+          Kc[i][k] = s;
+        }
+      }
+      for (int i = 0; i < M; ++i) {
+        double s = 0.0;
+        for (int q = 0; q < M; ++q) s = fma(A[i * M + q], u[q], s);
+        v[i] = s;
+      }
+      // LU with partial pivoting on the M×M capacitance matrix, solving K y = v alongside
+      double sign = 1.0, ldk = 0.0;
+      for (int c = 0; c < M; ++c) {
+        int piv = c;
+        for (int r = c + 1; r < M; ++r)
+          if (fabs(Kc[r][c]) > fabs(Kc[piv][c])) piv = r;
+        if (piv != c) {
+          for (int q = 0; q < M; ++q) { const double t = Kc[c][q]; Kc[c][q] = Kc[piv][q]; Kc[piv][q] = t; }
+          const double t = v[c]; v[c] = v[piv]; v[piv] = t;
+          sign = -sign;
+        }
+        const double d = Kc[c][c];
+        if (d < 0.0) sign = -sign;
+        ldk += log(fabs(d));
+        for (int r = c + 1; r < M; ++r) {
+          const double f = Kc[r][c] / d;
+          for (int q = c + 1; q < M; ++q) Kc[r][q] = fma(-f, Kc[c][q], Kc[r][q]);
+          v[r] = fma(-f, v[c], v[r]);
+        }
+      }
+      for (int c = M - 1; c >= 0; --c) {
+        double s = v[c];
+        for (int q = c + 1; q < M; ++q) s = fma(-Kc[c][q], v[q], s);
+        v[c] = s / Kc[c][c];
+      }
+      // Positive definiteness of C.  With S = LLᵀ positive definite, C is PD iff every eigenvalue of I + A·G is
+      // positive (they are real: A·G is similar to the symmetric GcᵀA·Gc with G = Gc·Gcᵀ); the sign of the
+      // determinant alone would miss an even number of negative ones.  Gc: semi-definite Cholesky of the Gram
+      // matrix (a numerically zero pivot zeroes its column), then a plain Cholesky of T = I + GcᵀA·Gc decides.
+      {
+        double Gc[kMaxM][kMaxM], T[kMaxM][kMaxM];
+        double gmax = 0.0;
+        for (int i = 0; i < M; ++i) gmax = fmax(gmax, gram[(i + 1) * NR + (i + 1)]);
+        for (int c = 0; c < M; ++c) {
+          double dd = gram[(c + 1) * NR + (c + 1)];
+          for (int q = 0; q < c; ++q) dd -= Gc[c][q] * Gc[c][q];
+          const bool zero = !(dd > 1e-14 * gmax);
+          const double piv = zero ? 0.0 : sqrt(dd);
+          for (int r = 0; r < M; ++r) {
+            if (r < c) { Gc[r][c] = 0.0; continue; }
+            if (r == c) { Gc[r][c] = piv; continue; }
+            double sacc = gram[(r + 1) * NR + (c + 1)];
+            for (int q = 0; q < c; ++q) sacc -= Gc[r][q] * Gc[c][q];
+            Gc[r][c] = zero ? 0.0 : sacc / piv;
+          }
+        }
+        for (int i = 0; i < M; ++i)
+          for (int k = 0; k < M; ++k) {  // T = I + GcᵀA·Gc
+            double sacc = (i == k) ? 1.0 : 0.0;
+            for (int r = 0; r < M; ++r) {
+              double t = 0.0;
+              for (int q = 0; q < M; ++q) t = fma(A[r * M + q], Gc[q][k], t);
+              sacc = fma(Gc[r][i], t, sacc);
+            }
+            T[i][k] = sacc;
+          }
+        bool pd = true;
+        for (int c = 0; c < M && pd; ++c) {
+          double dd = 0.5 * (T[c][c] + T[c][c]);
+          for (int q = 0; q < c; ++q) dd -= T[c][q] * T[c][q];
+          if (!(dd > 0.0)) { pd = false; break; }
+          dd = sqrt(dd);
+          T[c][c] = dd;
+          for (int r = c + 1; r < M; ++r) {
+            double sacc = 0.5 * (T[r][c] + T[c][r]);
+            for (int q = 0; q < c; ++q) sacc -= T[r][q] * T[c][q];
+            T[r][c] = sacc / dd;
+          }
+        }
+        if (!pd || !(sign > 0.0) || !(ldk == ldk)) info = N;  // C is not positive definite
+      }
+      ld += ldk;
+      for (int i = 0; i < M; ++i) quad = fma(-u[i], v[i], quad);
+    }
+    p.info[b] = info;
+    p.lnL[b] = info == 0 ? -(ld + quad) / 2 : nan("");
+  }
+}
 
 __host__ __device__ constexpr int band_lcm(int WD, int ER) { return (ER % (WD / 32) == 0) ? ER : ER * (WD / 32); }
 __host__ __device__ constexpr int band_batch(int WD, int ER) {
@@ -341,101 +444,200 @@ band_chol_kernel(BandCholParams p) {
   // ---- epilogue: lnL = −½ (log det S + log det(I + A·G) + RᵀS⁻¹R − uᵀ(I + A·G)⁻¹A u)
   if (gram_on) gram[tid] = gacc;
   __syncthreads();
-  if (tid == 0) {
-    double quad = gram[0], ld = logdet;
-    if (M > 0 && info == 0) {
-      double Kc[kMaxM][kMaxM], v[kMaxM], u[kMaxM];
-      const double* A = p.A + (long long)b * M * M;
-      for (int i = 0; i < M; ++i) {
-        u[i] = gram[(i + 1) * NR];
-        for (int k = 0; k < M; ++k) {
-          double s = (i == k) ? 1.0 : 0.0;
-          for (int q = 0; q < M; ++q) s = fma(A[i * M + q], gram[(q + 1) * NR + (k + 1)], s);
-          Kc[i][k] = s;
-        }
-      }
-      for (int i = 0; i < M; ++i) {
-        double s = 0.0;
-        for (int q = 0; q < M; ++q) s = fma(A[i * M + q], u[q], s);
-        v[i] = s;
-      }
-      // LU with partial pivoting on the M×M capacitance matrix, solving K y = v alongside
-      double sign = 1.0, ldk = 0.0;
-      for (int c = 0; c < M; ++c) {
-        int piv = c;
-        for (int r = c + 1; r < M; ++r)
-          if (fabs(Kc[r][c]) > fabs(Kc[piv][c])) piv = r;
-        if (piv != c) {
-          for (int q = 0; q < M; ++q) { const double t = Kc[c][q]; Kc[c][q] = Kc[piv][q]; Kc[piv][q] = t; }
-          const double t = v[c]; v[c] = v[piv]; v[piv] = t;
-          sign = -sign;
-        }
-        const double d = Kc[c][c];
-        if (d < 0.0) sign = -sign;
-        ldk += log(fabs(d));
-        for (int r = c + 1; r < M; ++r) {
-          const double f = Kc[r][c] / d;
-          for (int q = c + 1; q < M; ++q) Kc[r][q] = fma(-f, Kc[c][q], Kc[r][q]);
-          v[r] = fma(-f, v[c], v[r]);
-        }
-      }
-      for (int c = M - 1; c >= 0; --c) {
-        double s = v[c];
-        for (int q = c + 1; q < M; ++q) s = fma(-Kc[c][q], v[q], s);
-        v[c] = s / Kc[c][c];
-      }
-      // Positive definiteness of C.  With S = LLᵀ positive definite, C is PD iff every eigenvalue of I + A·G is
-      // positive (they are real: A·G is similar to the symmetric GcᵀA·Gc with G = Gc·Gcᵀ); the sign of the
-      // determinant alone would miss an even number of negative ones.  Gc: semi-definite Cholesky of the Gram
-      // matrix (a numerically zero pivot zeroes its column), then a plain Cholesky of T = I + GcᵀA·Gc decides.
-      {
-        double Gc[kMaxM][kMaxM], T[kMaxM][kMaxM];
-        double gmax = 0.0;
-        for (int i = 0; i < M; ++i) gmax = fmax(gmax, gram[(i + 1) * NR + (i + 1)]);
-        for (int c = 0; c < M; ++c) {
-          double dd = gram[(c + 1) * NR + (c + 1)];
-          for (int q = 0; q < c; ++q) dd -= Gc[c][q] * Gc[c][q];
-          const bool zero = !(dd > 1e-14 * gmax);
-          const double piv = zero ? 0.0 : sqrt(dd);
-          for (int r = 0; r < M; ++r) {
-            if (r < c) { Gc[r][c] = 0.0; continue; }
-            if (r == c) { Gc[r][c] = piv; continue; }
-            double sacc = gram[(r + 1) * NR + (c + 1)];
-            for (int q = 0; q < c; ++q) sacc -= Gc[r][q] * Gc[c][q];
-            Gc[r][c] = zero ? 0.0 : sacc / piv;
-          }
-        }
-        for (int i = 0; i < M; ++i)
-          for (int k = 0; k < M; ++k) {  // T = I + GcᵀA·Gc
-            double sacc = (i == k) ? 1.0 : 0.0;
-            for (int r = 0; r < M; ++r) {
-              double t = 0.0;
-              for (int q = 0; q < M; ++q) t = fma(A[r * M + q], Gc[q][k], t);
-              sacc = fma(Gc[r][i], t, sacc);
-            }
-            T[i][k] = sacc;
-          }
-        bool pd = true;
-        for (int c = 0; c < M && pd; ++c) {
-          double dd = 0.5 * (T[c][c] + T[c][c]);
-          for (int q = 0; q < c; ++q) dd -= T[c][q] * T[c][q];
-          if (!(dd > 0.0)) { pd = false; break; }
-          dd = sqrt(dd);
-          T[c][c] = dd;
-          for (int r = c + 1; r < M; ++r) {
-            double sacc = 0.5 * (T[r][c] + T[c][r]);
-            for (int q = 0; q < c; ++q) sacc -= T[r][q] * T[c][q];
-            T[r][c] = sacc / dd;
-          }
-        }
-        if (!pd || !(sign > 0.0) || !(ldk == ldk)) info = N;  // C is not positive definite
-      }
-      ld += ldk;
-      for (int i = 0; i < M; ++i) quad = fma(-u[i], v[i], quad);
+  if (tid == 0) band_epilogue(p, b, M, gram, logdet, info);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Symmetric window.  The active window W[r][c] = S(index(r), index(c)) (residues mod WD) is a symmetric
+// matrix and the rank-1 update W −= v·vᵀ/pivot is symmetric as well, so only one of every pair of T×T tiles
+// {(I,J), (J,I)} needs to exist: tile (I, J) is kept iff (J − I) mod 32 ≤ 16.  Warp δ ∈ [0,16], lane I owns
+// tile (I, (I+δ) mod 32): 17 warps, T² registers per thread (WD = 32·T) — half the FMAs and half the
+// registers of the full square, which lets two walkers share an SM for T ≤ 4, and windows up to 256 pixels.
+// The pivot column v (all pairs {r, jr}) is scattered over the tiles that touch residue jr: in warp δ the
+// lane (Jp − δ) mod 32 holds a column piece of it and — for δ ≥ 1 — lane Jp a row piece (Jp = jr / T); the same
+// threads take the entering row's values when index j + WD replaces j.  The pivot loop is unrolled by T, so
+// jr mod T is a compile-time register index.
+// ------------------------------------------------------------------------------------------------
+template <int T, int MAXNR>
+__global__ void __launch_bounds__(17 * 32, (T <= 4) ? 2 : 1)
+band_sym_kernel(BandCholParams p) {
+  constexpr int WD = 32 * T, NT = 17 * 32, ROWLEN = WD + NRP;
+  constexpr int BATCH = ((16 + T - 1) / T) * T;             // pivots per staging batch (a multiple of T)
+  constexpr int NE = (WD * MAXNR + NT - 1) / NT;            // right-hand-side registers per thread
+  __shared__ double colbuf[2][WD];
+  __shared__ double zbuf[2][NRP];
+  __shared__ double invbuf[2];
+  __shared__ double gram[(kMaxM + 1) * (kMaxM + 1)];
+  extern __shared__ double ring[];  // [2][BATCH][ROWLEN]
+
+  const int b = p.rowmap ? p.rowmap[blockIdx.x] : blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, dl = tid >> 5;  // dl = tile offset δ of this warp
+  const int N = p.N, M = p.M, NR = M + 1;
+  if (p.overflow[b] != 0 || *p.sorted == 0) {
+    if (tid == 0) {
+      p.info[b] = p.overflow[b] != 0 ? -2 : -3;
+      p.lnL[b] = nan("");
     }
-    p.info[b] = info;
-    p.lnL[b] = info == 0 ? -(ld + quad) / 2 : nan("");
+    return;
   }
+  const double* Sb = p.Sb + (long long)b * p.strideSb;
+  const double* Xb = (M > 0) ? p.X + (long long)b * M * N : nullptr;
+  const double* Fb = p.model_flux + (long long)b * N;
+  const int r0 = T * lane, c0 = T * ((lane + dl) & 31);     // first row / column residue of this thread's tile
+
+  auto rhs_at = [&](int i, int q) -> double {
+    if (i >= N) return 0.0;
+    return q == 0 ? Fb[i] - p.data_flux[i] : Xb[(long long)(q - 1) * N + i];
+  };
+  auto stage_issue = [&](int j0, double* dst) {
+    for (int sidx = tid; sidx < BATCH * ROWLEN; sidx += NT) {
+      const int rb = sidx / ROWLEN, col = sidx - rb * ROWLEN;
+      const int i = j0 + WD + rb;
+      if (col < WD) {
+        if (i < N) cp_async8(dst + sidx, Sb + (long long)i * WD + col);
+        else dst[sidx] = (col == 0) ? 1.0 : 0.0;
+      } else {
+        const int q = col - WD;
+        if (q >= 1 && q < NR && i < N) cp_async8(dst + sidx, Xb + (long long)(q - 1) * N + i);
+        else dst[sidx] = (q == 0) ? rhs_at(i, 0) : 0.0;
+      }
+    }
+    cp_async_commit();
+  };
+
+  // ---- initial window: residue = index for the first WD indices
+  double a[T][T];
+#pragma unroll
+  for (int rr = 0; rr < T; ++rr)
+#pragma unroll
+    for (int cc = 0; cc < T; ++cc) {
+      const int i = max(r0 + rr, c0 + cc), k = min(r0 + rr, c0 + cc);
+      a[rr][cc] = (i < N) ? Sb[(long long)i * WD + (i - k)] : (i == k ? 1.0 : 0.0);
+    }
+  double rv[NE];
+  int rres[NE], rq[NE];
+#pragma unroll
+  for (int e = 0; e < NE; ++e) {
+    const int idx = tid + NT * e;
+    const bool ok = idx < WD * NR;
+    rres[e] = ok ? idx / NR : -1;
+    rq[e] = ok ? idx - (idx / NR) * NR : 0;
+    rv[e] = ok ? rhs_at(rres[e], rq[e]) : 0.0;
+  }
+  stage_issue(0, ring);
+
+  double logdet = 0.0, gacc = 0.0, mant = 1.0;
+  long long expo = 0;
+  int info = 0;
+  const int gp_ = tid / NR, gq_ = tid - (tid / NR) * NR;
+  const bool gram_on = tid < NR * NR;
+
+  if (tid == 0) invbuf[0] = 1.0 / a[0][0];
+  for (int j0 = 0, jr0 = 0; j0 < N; j0 += T, jr0 = (jr0 + T == WD) ? 0 : jr0 + T) {
+    const int Jp = jr0 / T;                                   // tile index of the pivots of this block
+    const bool colpiece = lane == ((Jp - dl) & 31);           // holds W[r0..r0+T)[jr]   (its column jr mod T)
+    const bool rowpiece = (dl >= 1) && (lane == Jp);          // holds W[jr][c0..c0+T)   (its row jr mod T)
+    const bool diagtile = (dl == 0) && (lane == Jp);
+    const int jb0 = j0 % BATCH, half = (j0 / BATCH) & 1;
+    const double* rowbase = ring + half * (BATCH * ROWLEN) + jb0 * ROWLEN;
+#pragma unroll
+    for (int u = 0; u < T; ++u) {
+      const int j = j0 + u, jr = jr0 + u;
+      if (j >= N) break;
+      const int buf = ((T % 2) == 0) ? (u & 1) : (j & 1);
+      const bool boundary = (u == 0) && (jb0 == 0);
+      if (boundary) cp_async_wait_all();
+      // ---- phase A: publish column jr of the symmetric window and the pivot row of the right-hand sides
+      if (colpiece) {
+#pragma unroll
+        for (int rr = 0; rr < T; ++rr) colbuf[buf][r0 + rr] = a[rr][u];
+      }
+      if (rowpiece && dl <= 15) {
+#pragma unroll
+        for (int cc = 0; cc < T; ++cc) colbuf[buf][c0 + cc] = a[u][cc];
+      }
+#pragma unroll
+      for (int e = 0; e < NE; ++e)
+        if (rres[e] == jr) zbuf[buf][rq[e]] = rv[e];
+      __syncthreads();
+      if (boundary) stage_issue(j + BATCH, ring + (half ^ 1) * (BATCH * ROWLEN));
+      // ---- phase C: symmetric rank-1 update, right-hand sides, Gram matrix
+      const double inv = invbuf[buf];
+      if (diagtile || (dl == 0 && u == T - 1)) {  // reciprocal of the next pivot, one step ahead
+        const int jn = (jr + 1 == WD) ? 0 : jr + 1;
+        if (lane == jn / T) {
+          const double x = colbuf[buf][jn];
+          invbuf[buf ^ 1] = 1.0 / fma(-x, x * inv, a[(u + 1) % T][(u + 1) % T]);
+        }
+      }
+      if (dl == 0) {  // warp-uniform bookkeeping
+        const double pj = colbuf[buf][jr];
+        if (!(pj > 0.0) && info == 0) info = j + 1;
+        const int hi = __double2hiint(pj);
+        expo += ((hi >> 20) & 0x7ff) - 1022;
+        mant *= __hiloint2double((hi & 0x800fffff) | 0x3fe00000, __double2loint(pj));
+        if ((j & 511) == 511) {
+          const int h2 = __double2hiint(mant);
+          expo += ((h2 >> 20) & 0x7ff) - 1022;
+          mant = __hiloint2double((h2 & 0x800fffff) | 0x3fe00000, __double2loint(mant));
+        }
+      }
+      double vc[T];
+#pragma unroll
+      for (int cc = 0; cc < T; ++cc) vc[cc] = colbuf[buf][c0 + cc] * inv;
+#pragma unroll
+      for (int rr = 0; rr < T; ++rr) {
+        const double vr = -colbuf[buf][r0 + rr];
+#pragma unroll
+        for (int cc = 0; cc < T; ++cc) a[rr][cc] = fma(vr, vc[cc], a[rr][cc]);
+      }
+#pragma unroll
+      for (int e = 0; e < NE; ++e)
+        if (rres[e] >= 0) rv[e] = fma(-colbuf[buf][rres[e]], zbuf[buf][rq[e]] * inv, rv[e]);
+      if (gram_on) gacc = fma(zbuf[buf][gp_] * inv, zbuf[buf][gq_], gacc);
+      // ---- index j + WD takes over residue jr: its row of S replaces every pair {·, jr}
+      const double* row = rowbase + u * ROWLEN;
+      auto entering = [&](int c) -> double {  // S(j+WD, index of residue c in the new window)
+        int t = c - jr - 1;
+        if (t < 0) t += WD;
+        return row[WD - 1 - t];
+      };
+      if (colpiece) {
+#pragma unroll
+        for (int rr = 0; rr < T; ++rr) a[rr][u] = entering(r0 + rr);
+      }
+      if (rowpiece || diagtile) {
+#pragma unroll
+        for (int cc = 0; cc < T; ++cc) a[u][cc] = entering(c0 + cc);
+      }
+#pragma unroll
+      for (int e = 0; e < NE; ++e)
+        if (rres[e] == jr) rv[e] = row[WD + rq[e]];
+    }
+  }
+  if (tid == 0) logdet = log(mant) + (double)expo * 0.6931471805599453;
+  if (gram_on) gram[tid] = gacc;
+  __syncthreads();
+  if (tid == 0) band_epilogue(p, b, M, gram, logdet, info);
+}
+
+template <int T>
+cudaError_t launch_band_sym_t(const BandCholParams& p, int B, cudaStream_t st) {
+  constexpr int WD = 32 * T, BATCH = ((16 + T - 1) / T) * T;
+  const size_t smem = sizeof(double) * 2 * BATCH * (WD + NRP);
+  static bool opted_in = false;
+  if (!opted_in) {
+    cudaError_t e = cudaFuncSetAttribute(band_sym_kernel<T, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(band_sym_kernel<T, kMaxM + 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    if (e != cudaSuccess) return e;
+    opted_in = true;
+  }
+  if (p.M + 1 <= 8)
+    band_sym_kernel<T, 8><<<B, 17 * 32, smem, st>>>(p);
+  else
+    band_sym_kernel<T, kMaxM + 1><<<B, 17 * 32, smem, st>>>(p);
+  return cudaGetLastError();
 }
 
 template <int WD, int ER>
@@ -459,8 +661,8 @@ cudaError_t launch_band_t(const BandCholParams& p, int B, cudaStream_t st) {
 
 }  // namespace
 
-const int kBandWidths[] = {64, 96, 128, 160};
-const int kNumBandWidths = 4;
+const int kBandWidths[] = {64, 96, 128, 160, 192, 256};
+const int kNumBandWidths = 6;
 
 __global__ void residual_only_kernel(const double* __restrict__ F, const double* __restrict__ data, int N,
                                      double* __restrict__ resid) {
@@ -490,6 +692,18 @@ cudaError_t launch_band_build(const BandBuildParams& p, int B, cudaStream_t st) 
 
 cudaError_t launch_band_chol(const BandCholParams& p, int WD, int B, cudaStream_t st) {
   if (B <= 0) return cudaSuccess;
+  static const bool rect = getenv("SFB_BAND_RECT") != nullptr;  // A/B switch: the full-square register window
+  if (!rect || WD > 160) {
+    switch (WD) {
+      case 64: return launch_band_sym_t<2>(p, B, st);
+      case 96: return launch_band_sym_t<3>(p, B, st);
+      case 128: return launch_band_sym_t<4>(p, B, st);
+      case 160: return launch_band_sym_t<5>(p, B, st);
+      case 192: return launch_band_sym_t<6>(p, B, st);
+      case 256: return launch_band_sym_t<8>(p, B, st);
+      default: return cudaErrorInvalidValue;
+    }
+  }
   switch (WD) {
     case 64: return launch_band_t<64, 8>(p, B, st);
     case 96: return launch_band_t<96, 8>(p, B, st);

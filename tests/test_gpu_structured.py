@@ -37,17 +37,18 @@ def _run(eng, d, **kw):
 
 
 def test_every_window_class_and_dense_fallback_n2048():
-    """ℓ chosen so that the band needs the 64/96/128/160-pixel windows and, for the last walker, more than
-    any window (dense path inside the same call)."""
-    N, B = 2048, 6
+    """ℓ chosen so that the band (half-widths 30, 85, 117, 152, 182, 218, 247 and 291 pixels) needs each of the
+    64/96/128/160/192/256-pixel windows and, for the last walker, more than any window (dense path inside
+    the same call)."""
+    N, B = 2048, 9
     d = synth.stage_inputs_direct(N, B, n_comp=6, n_local=2)
-    d["glob"][:, 1] = [20.0, 58.0, 80.0, 104.0, 135.0, 20.0]
-    d["glob"][:, 0] = [1e-4, 2e-4, 1e-4, 3e-4, 1e-4, 5e-3]
+    d["glob"][:, 1] = [20.0, 58.0, 80.0, 104.0, 125.0, 150.0, 170.0, 200.0, 20.0]
+    d["glob"][:, 0] = [1e-4, 2e-4, 1e-4, 3e-4, 1e-4, 2e-4, 1e-4, 1e-4, 5e-3]
     eng = _engine(N, 6, 2, B)
     eng.set_data(d["wave"], d["sigma"], d["data_flux"])
     lnL, info = _run(eng, d)
     classes = eng.band_classes()
-    assert classes == {64: 2, 96: 1, 128: 1, 160: 1, 0: 1}, classes
+    assert classes == {64: 2, 96: 1, 128: 1, 160: 1, 192: 1, 256: 2, 0: 1}, classes
     assert (info == 0).all()
     for b in range(B):
         ref = _dense_ref(d, b)
@@ -87,6 +88,7 @@ def test_config3_shape_n8192_against_cpu_checker_and_dense_cuda():
     assert (info == 0).all()
     classes = eng.band_classes()
     assert classes[0] == 0 and sum(classes.values()) == B and classes[128] > 0 and classes[160] > 0, classes
+    assert classes[192] == 0 and classes[256] == 0
     for b in range(B):
         ref = S.stage_log_likelihood(d["wave"], d["sigma"], d["data_flux"], d["X"][b], d["A"][b], d["model_flux"][b],
                                      glob=d["glob"][b], loc=d["loc"][b])
@@ -187,3 +189,19 @@ def test_model_level_structured_solver(golden_dir):
     P[2, list(m.labels).index("global_cov:log_ls")] += 1.2
     a, b = m.log_likelihood_batch(P), md.log_likelihood_batch(P)
     assert np.abs(a - b).max() <= 1e-9 * np.abs(b).max()
+
+
+def test_config5_shape_n16384_multi_order_takes_the_256_window():
+    """configs[4]: 8 concatenated orders (16384 px, 2 km/s pixels → half-bandwidth ≈ 236), 16 local kernels."""
+    B = 3
+    d = synth.stage_inputs_orders(B)
+    eng = _engine(16384, 6, 16, B, workspace_walkers=2)
+    eng.set_data(d["wave"], d["sigma"], d["data_flux"])
+    lnL, info = _run(eng, d)
+    classes = eng.band_classes()
+    assert (info == 0).all() and classes[0] == 0 and classes[256] == B, classes
+    for b in range(B):
+        ref = S.stage_log_likelihood(d["wave"], d["sigma"], d["data_flux"], d["X"][b], d["A"][b], d["model_flux"][b],
+                                     glob=d["glob"][b], loc=d["loc"][b])
+        assert abs(lnL[b] - ref) <= TOL * max(1.0, abs(ref)), (b, lnL[b], ref)
+    eng.close()
