@@ -259,3 +259,44 @@ def test_ensemble_sampler_drives_the_batched_likelihood(golden_dir):
         m.set_param_vector(p[b])
         assert abs(m.log_likelihood(priors) - lnp[b]) <= 1e-9 * abs(lnp[b])
     assert m._engine.launch_count > launches0
+
+
+def test_parameter_level_entry_error_behaviour():
+    """C-ABI contract of the new entry points: call order and sizes are checked, nothing crashes."""
+    from starfish_b200 import _lib
+    from starfish_b200.engine import LikelihoodEngine
+
+    eng = LikelihoodEngine(256, 6, 2, 4)
+    wave = synth.log_uniform_wave(256, 5092.0, 5108.0)
+    w, f, s = synth.make_data(256, wave=wave)
+    theta = np.zeros((2, 3 + 4 + 2))
+    with pytest.raises(_lib.SfbError):                       # no model yet
+        eng.D = 3
+        eng.upstream(theta, 2)
+    emu = synth.make_emulator_arrays()
+    from starfish_b200.emulator import Emulator
+
+    e = Emulator(**copy.deepcopy(emu))
+    fine = U.create_log_lam_grid(U.calculate_dv(w), emu["wavelength"].min(), emu["wavelength"].max())
+    bulk = U.resample(emu["wavelength"], np.vstack([emu["eigenspectra"], emu["flux_mean"], emu["flux_std"]]), fine)
+    with pytest.raises(ValueError):                          # wrong bulk shape
+        eng.set_model(fine, bulk[:-1], e.grid_points, e.variances, e.lengthscales, e.v11, e.w_hat)
+    with pytest.raises(_lib.SfbError):                       # nf not a power of two
+        eng.set_model(fine[:-3], bulk[:, :-3], e.grid_points, e.variances, e.lengthscales, e.v11, e.w_hat)
+    bad = -np.eye(e.v11.shape[0])
+    with pytest.raises(_lib.SfbError):                       # v11 not positive definite
+        eng.set_model(fine, bulk, e.grid_points, e.variances, e.lengthscales, bad, e.w_hat)
+    eng.set_model(fine, bulk, e.grid_points, e.variances, e.lengthscales, e.v11, e.w_hat, ncheb_max=2,
+                  flags=_lib.MODEL_VSINI | _lib.MODEL_VZ | _lib.MODEL_LOG_SCALE)
+    with pytest.raises(_lib.SfbError):                       # static data missing
+        eng.upstream(theta, 2)
+    eng.set_data(w, s, f)
+    with pytest.raises(_lib.SfbError):                       # more Chebyshev terms than announced
+        eng.upstream(np.zeros((2, 3 + 4 + 3)), 3)
+    with pytest.raises(_lib.SfbError):                       # batch larger than the handle
+        eng.upstream(np.zeros((5, 3 + 4 + 2)), 2)
+    theta[:, :3] = [6100.0, 4.5, 0.0]
+    theta[:, 3] = 5.0
+    out = eng.upstream(theta, 2)
+    assert out["status"].cpu().numpy().tolist() == [0, 0] and np.isfinite(out["X"].cpu().numpy()).all()
+    eng.close()
