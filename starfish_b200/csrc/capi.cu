@@ -370,8 +370,11 @@ int structured_device(sfb_ctx* h, int B, const double* X, const double* A, const
   const int nclass = kNumBandWidths;  // class nclass = dense
   auto cls = [&](int b) {
     if (!sorted) return nclass;
-    for (int c = 0; c < nclass; ++c)
-      if (h->bw_h[b] + 1 <= kBandWidths[c]) return c;
+    const int nr = (X ? h->M : 0) + 1;
+    for (int c = 0; c < nclass; ++c) {
+      if (kBandWidths[c] == 64 && nr * nr > 256) continue;  // the 64-pixel window's 256 threads hold the Gram matrix
+      if (h->bw_h[b] + band_slack(kBandWidths[c]) <= kBandWidths[c]) return c;
+    }
     return nclass;
   };
   for (int b = 0; b < B; ++b) count[cls(b)]++;

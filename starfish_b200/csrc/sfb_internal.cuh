@@ -202,6 +202,7 @@ cudaError_t launch_band_width(int N, int Kmax, int hyper_stride, const double* w
                               const int* nloc, const double* loc, int* bw, int B, cudaStream_t st);
 cudaError_t launch_band_build(const BandBuildParams& p, int B, cudaStream_t st);
 cudaError_t launch_band_chol(const BandCholParams& p, int WD, int B, cudaStream_t st);
+int band_slack(int WD);  // b + band_slack(WD) <= WD must hold for a walker to use window WD
 cudaError_t launch_residual_only(const double* model_flux, const double* data_flux, int N, int B, double* resid,
                                  cudaStream_t st);
 

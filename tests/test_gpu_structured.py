@@ -37,12 +37,12 @@ def _run(eng, d, **kw):
 
 
 def test_every_window_class_and_dense_fallback_n2048():
-    """ℓ chosen so that the band (half-widths 30, 85, 117, 152, 182, 218, 247 and 291 pixels) needs each of the
+    """ℓ chosen so that the band (half-widths 30, 85, 117, 140, 182, 218, 247 and 291 pixels) needs each of the
     64/96/128/160/192/256-pixel windows and, for the last walker, more than any window (dense path inside
     the same call)."""
     N, B = 2048, 9
     d = synth.stage_inputs_direct(N, B, n_comp=6, n_local=2)
-    d["glob"][:, 1] = [20.0, 58.0, 80.0, 104.0, 125.0, 150.0, 170.0, 200.0, 20.0]
+    d["glob"][:, 1] = [20.0, 58.0, 80.0, 96.0, 125.0, 150.0, 170.0, 200.0, 20.0]
     d["glob"][:, 0] = [1e-4, 2e-4, 1e-4, 3e-4, 1e-4, 2e-4, 1e-4, 1e-4, 5e-3]
     eng = _engine(N, 6, 2, B)
     eng.set_data(d["wave"], d["sigma"], d["data_flux"])
