@@ -749,27 +749,53 @@ band_blk_kernel(BandCholParams p) {
 #pragma unroll
         for (int ec = 0; ec < EC; ++ec) Dblk[er * (NBK + 1) + (lane - Lb) * EC + ec] = a[er][ec];
     }
-    for (int c = 0; c < NBK; ++c) {
-      __syncwarp();
-      const double dc = Dblk[c * (NBK + 1) + c];
-      const double di = 1.0 / dc;
-      if (lane == 0) { dv[c] = dc; dinvv[c] = di; }
-      for (int e = lane; e < NBK * NBK; e += 32) {
-        const int rr = e / NBK, cc = e - rr * NBK;
-        if (cc > c && rr >= cc)
-          Dblk[rr * (NBK + 1) + cc] -= Dblk[rr * (NBK + 1) + c] * Dblk[cc * (NBK + 1) + c] * di;
-      }
-      __syncwarp();
-      if (lane > c && lane < NBK) Dblk[lane * (NBK + 1) + c] *= di;
-    }
     __syncwarp();
-    if (lane < NBK) {  // column `lane` of M = Lu⁻¹ (unit lower)
-      const int q0 = lane;
-      for (int r = 0; r < NBK; ++r) Minv[r * NBK + q0] = (r == q0) ? 1.0 : 0.0;
-      for (int r = q0 + 1; r < NBK; ++r) {
-        double sacc = 0.0;
-        for (int q = q0; q < r; ++q) sacc = fma(Dblk[r * (NBK + 1) + q], Minv[q * NBK + q0], sacc);
-        Minv[r * NBK + q0] = -sacc;
+    if (lane == 0) {  // NBK×NBK LDLᵀ and the inverse of its unit factor, entirely in registers (static indices)
+      double Dm[NBK][NBK], Mi[NBK][NBK], dd[NBK], di[NBK];
+#pragma unroll
+      for (int rr = 0; rr < NBK; ++rr)
+#pragma unroll
+        for (int cc = 0; cc < NBK; ++cc)
+          if (cc <= rr) Dm[rr][cc] = Dblk[rr * (NBK + 1) + cc];
+#pragma unroll
+      for (int c = 0; c < NBK; ++c) {
+        dd[c] = Dm[c][c];
+        di[c] = 1.0 / dd[c];
+#pragma unroll
+        for (int rr = 0; rr < NBK; ++rr) {
+          if (rr > c) {
+            const double lrc = Dm[rr][c] * di[c];  // Lu[rr][c]
+#pragma unroll
+            for (int cc = 0; cc < NBK; ++cc)
+              if (cc > c && cc <= rr) Dm[rr][cc] = fma(-lrc, Dm[cc][c], Dm[rr][cc]);
+          }
+        }
+#pragma unroll
+        for (int rr = 0; rr < NBK; ++rr)
+          if (rr > c) Dm[rr][c] *= di[c];
+      }
+      // M = Lu⁻¹ (unit lower), column by column
+#pragma unroll
+      for (int q0 = 0; q0 < NBK; ++q0) {
+#pragma unroll
+        for (int r = 0; r < NBK; ++r) {
+          if (r < q0) Mi[r][q0] = 0.0;
+          if (r == q0) Mi[r][q0] = 1.0;
+          if (r > q0) {
+            double sacc = 0.0;
+#pragma unroll
+            for (int q = 0; q < NBK; ++q)
+              if (q >= q0 && q < r) sacc = fma(Dm[r][q], Mi[q][q0], sacc);
+            Mi[r][q0] = -sacc;
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < NBK; ++c) {
+        dv[c] = dd[c];
+        dinvv[c] = di[c];
+#pragma unroll
+        for (int q = 0; q < NBK; ++q) Minv[c * NBK + q] = Mi[c][q];
       }
     }
     __syncwarp();
