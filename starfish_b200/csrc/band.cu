@@ -641,302 +641,6 @@ cudaError_t launch_band_sym_t(const BandCholParams& p, int B, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-// ------------------------------------------------------------------------------------------------
-// Block (delayed-update) variant of the full-square register window.  Pivots are taken NBK = ER at a time:
-//   S1  the owners publish the raw panel P (all WD rows × the block's NBK columns) and the block's rhs rows
-//   S2  everybody computes a slice of Y = P·Lu⁻ᵀ (D = Lu·diag(d)·Luᵀ is the block's diagonal part) with the
-//       inverse factor M = Lu⁻¹ that was prepared one block ahead, and of the transformed right-hand sides
-//   S3  rank-NBK update of the registers, W −= Y·diag(1/d)·Yᵀ, straight from shared memory — no barrier and
-//       no dependence on other threads inside the loop over the block's columns
-//   S3b the warp that owns the NEXT diagonal block factors it (LDLᵀ, warp-cooperative) and inverts its unit
-//       factor while the other warps are still in S3: the serial chain of NBK reciprocals is off the
-//       critical path
-//   S4  NBK rows enter the window
-// Two barriers per NBK pivots instead of one per pivot.  A row that enters misses the updates of the later
-// pivots of its own block, which are exactly zero when the band is at most WD − NBK wide.
-// ------------------------------------------------------------------------------------------------
-template <int WD, int ER, int MAXNR>
-__global__ void __launch_bounds__(WD * 32 / ER, 1)
-band_blk_kernel(BandCholParams p) {
-  constexpr int EC = WD / 32, NT = WD * 32 / ER, NBK = ER, NL = ER / EC, ROWLEN = WD + NRP;
-  constexpr int BATCH = 2 * NBK;
-  constexpr int NE = (WD * MAXNR + NT - 1) / NT;
-  static_assert(ER % EC == 0 && WD % ER == 0 && NL >= 1, "block columns must be whole lanes");
-  extern __shared__ double sm[];
-  double* Pn = sm;                              // [WD][NBK]  raw panel
-  double* YT = Pn + WD * NBK;                   // [NBK][WD]  Y, column-major (row reads)
-  double* YsE = YT + NBK * WD;                  // [NBK][EC][32]  Y/d arranged for the lanes' column reads
-  double* Minv = YsE + NBK * WD;                // [NBK][NBK] Lu⁻¹ of the current block
-  double* dv = Minv + NBK * NBK;                // [NBK] pivots d
-  double* dinvv = dv + NBK;                     // [NBK] 1/d
-  double* Dblk = dinvv + NBK;                   // [NBK][NBK+1] scratch of the look-ahead warp
-  double* Rb = Dblk + NBK * (NBK + 1);          // [NBK][NRP] raw rhs rows of the block
-  double* Zz = Rb + NBK * NRP;                  // [NBK][NRP] Lu⁻¹·Rb
-  double* Zs = Zz + NBK * NRP;                  // [NBK][NRP] … / d
-  double* gram = Zs + NBK * NRP;                // [(kMaxM+1)²]
-  double* ring = gram + (kMaxM + 1) * (kMaxM + 1);  // [2][BATCH][ROWLEN]
-
-  const int b = p.rowmap ? p.rowmap[blockIdx.x] : blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31, tr = tid >> 5;
-  const int N = p.N, M = p.M, NR = M + 1;
-  if (p.overflow[b] != 0 || *p.sorted == 0) {
-    if (tid == 0) {
-      p.info[b] = p.overflow[b] != 0 ? -2 : -3;
-      p.lnL[b] = nan("");
-    }
-    return;
-  }
-  const double* Sb = p.Sb + (long long)b * p.strideSb;
-  const double* Xb = (M > 0) ? p.X + (long long)b * M * N : nullptr;
-  const double* Fb = p.model_flux + (long long)b * N;
-
-  auto rhs_at = [&](int i, int q) -> double {
-    if (i >= N) return 0.0;
-    return q == 0 ? Fb[i] - p.data_flux[i] : Xb[(long long)(q - 1) * N + i];
-  };
-  auto stage_issue = [&](int j0, double* dst) {
-    for (int sidx = tid; sidx < BATCH * ROWLEN; sidx += NT) {
-      const int rb = sidx / ROWLEN, col = sidx - rb * ROWLEN;
-      const int i = j0 + WD + rb;
-      if (col < WD) {
-        if (i < N) cp_async8(dst + sidx, Sb + (long long)i * WD + col);
-        else dst[sidx] = (col == 0) ? 1.0 : 0.0;
-      } else {
-        const int q = col - WD;
-        if (q >= 1 && q < NR && i < N) cp_async8(dst + sidx, Xb + (long long)(q - 1) * N + i);
-        else dst[sidx] = (q == 0) ? rhs_at(i, 0) : 0.0;
-      }
-    }
-    cp_async_commit();
-  };
-
-  double a[ER][EC];
-#pragma unroll
-  for (int er = 0; er < ER; ++er) {
-    const int i = tr * ER + er;
-#pragma unroll
-    for (int ec = 0; ec < EC; ++ec) {
-      const int k = lane * EC + ec;
-      double v = 0.0;
-      if (k <= i) v = (i < N) ? Sb[(long long)i * WD + (i - k)] : (k == i ? 1.0 : 0.0);
-      a[er][ec] = v;
-    }
-  }
-  double rv[NE];
-  int rres[NE], rq[NE];
-#pragma unroll
-  for (int e = 0; e < NE; ++e) {
-    const int idx = tid + NT * e;
-    const bool ok = idx < WD * NR;
-    rres[e] = ok ? idx / NR : -1;
-    rq[e] = ok ? idx - (idx / NR) * NR : 0;
-    rv[e] = ok ? rhs_at(rres[e], rq[e]) : 0.0;
-  }
-  stage_issue(0, ring);
-
-  double logdet = 0.0, mant = 1.0;
-  long long expo = 0;
-  int info = 0;
-  double gacc = 0.0;
-  const bool gram_on = tid < NR * NR;
-  const int gp_ = gram_on ? tid / NR : 0, gq_ = gram_on ? tid - (tid / NR) * NR : 0;
-
-  // LDLᵀ of the diagonal block held by this warp's lanes [Lb, Lb+NL) and the inverse of its unit factor
-  auto factor_block = [&](int Lb) {
-    if (lane >= Lb && lane < Lb + NL) {
-#pragma unroll
-      for (int er = 0; er < ER; ++er)
-#pragma unroll
-        for (int ec = 0; ec < EC; ++ec) Dblk[er * (NBK + 1) + (lane - Lb) * EC + ec] = a[er][ec];
-    }
-    __syncwarp();
-    if (lane == 0) {  // NBK×NBK LDLᵀ and the inverse of its unit factor, entirely in registers (static indices)
-      double Dm[NBK][NBK], Mi[NBK][NBK], dd[NBK], di[NBK];
-#pragma unroll
-      for (int rr = 0; rr < NBK; ++rr)
-#pragma unroll
-        for (int cc = 0; cc < NBK; ++cc)
-          if (cc <= rr) Dm[rr][cc] = Dblk[rr * (NBK + 1) + cc];
-#pragma unroll
-      for (int c = 0; c < NBK; ++c) {
-        dd[c] = Dm[c][c];
-        di[c] = 1.0 / dd[c];
-#pragma unroll
-        for (int rr = 0; rr < NBK; ++rr) {
-          if (rr > c) {
-            const double lrc = Dm[rr][c] * di[c];  // Lu[rr][c]
-#pragma unroll
-            for (int cc = 0; cc < NBK; ++cc)
-              if (cc > c && cc <= rr) Dm[rr][cc] = fma(-lrc, Dm[cc][c], Dm[rr][cc]);
-          }
-        }
-#pragma unroll
-        for (int rr = 0; rr < NBK; ++rr)
-          if (rr > c) Dm[rr][c] *= di[c];
-      }
-      // M = Lu⁻¹ (unit lower), column by column
-#pragma unroll
-      for (int q0 = 0; q0 < NBK; ++q0) {
-#pragma unroll
-        for (int r = 0; r < NBK; ++r) {
-          if (r < q0) Mi[r][q0] = 0.0;
-          if (r == q0) Mi[r][q0] = 1.0;
-          if (r > q0) {
-            double sacc = 0.0;
-#pragma unroll
-            for (int q = 0; q < NBK; ++q)
-              if (q >= q0 && q < r) sacc = fma(Dm[r][q], Mi[q][q0], sacc);
-            Mi[r][q0] = -sacc;
-          }
-        }
-      }
-#pragma unroll
-      for (int c = 0; c < NBK; ++c) {
-        dv[c] = dd[c];
-        dinvv[c] = di[c];
-#pragma unroll
-        for (int q = 0; q < NBK; ++q) Minv[c * NBK + q] = Mi[c][q];
-      }
-    }
-    __syncwarp();
-  };
-  if (tr == 0) factor_block(0);
-
-  for (int j0 = 0, jr0 = 0; j0 < N; j0 += NBK, jr0 = (jr0 + NBK == WD) ? 0 : jr0 + NBK) {
-    const int tr0 = jr0 / ER, L0 = jr0 / EC;
-    const int jb0 = j0 % BATCH, half = (j0 / BATCH) & 1;
-    const bool boundary = jb0 == 0;
-    const double* rowbase = ring + half * (BATCH * ROWLEN) + jb0 * ROWLEN;
-    if (boundary) cp_async_wait_all();
-    // ---- S1: raw panel and the block's right-hand-side rows
-    if (lane >= L0 && lane < L0 + NL) {
-#pragma unroll
-      for (int er = 0; er < ER; ++er)
-#pragma unroll
-        for (int ec = 0; ec < EC; ++ec) Pn[(tr * ER + er) * NBK + (lane - L0) * EC + ec] = a[er][ec];
-    }
-#pragma unroll
-    for (int e = 0; e < NE; ++e) {
-      const int dd = rres[e] - jr0;
-      if (rres[e] >= 0 && dd >= 0 && dd < NBK) Rb[dd * NRP + rq[e]] = rv[e];
-    }
-    __syncthreads();
-    if (boundary) stage_issue(j0 + BATCH, ring + (half ^ 1) * (BATCH * ROWLEN));
-    // ---- S2: Y = P·Lu⁻ᵀ, transformed right-hand sides, pivots
-    for (int o = tid; o < WD * NBK; o += NT) {
-      const int r = o / NBK, c = o - r * NBK;
-      double y = Pn[r * NBK + c];
-      for (int q = 0; q < c; ++q) y = fma(Pn[r * NBK + q], Minv[c * NBK + q], y);
-      YT[c * WD + r] = y;
-      YsE[(c * EC + (r % EC)) * 32 + r / EC] = y * dinvv[c];
-    }
-    for (int o = tid; o < NBK * NR; o += NT) {
-      const int c = o / NR, q = o - c * NR;
-      double z = Rb[c * NRP + q];
-      for (int a2 = 0; a2 < c; ++a2) z = fma(Minv[c * NBK + a2], Rb[a2 * NRP + q], z);
-      Zz[c * NRP + q] = z;
-      Zs[c * NRP + q] = z * dinvv[c];
-    }
-    if (tr == 0) {  // warp-uniform bookkeeping: LAPACK-style info, log det as mantissa × 2^exponent
-      for (int c = 0; c < NBK; ++c) {
-        if (j0 + c >= N) break;
-        const double pj = dv[c];
-        if (!(pj > 0.0) && info == 0) info = j0 + c + 1;
-        const int hi = __double2hiint(pj);
-        expo += ((hi >> 20) & 0x7ff) - 1022;
-        mant *= __hiloint2double((hi & 0x800fffff) | 0x3fe00000, __double2loint(pj));
-      }
-      if (((j0 / NBK) & 31) == 31) {
-        const int h2 = __double2hiint(mant);
-        expo += ((h2 >> 20) & 0x7ff) - 1022;
-        mant = __hiloint2double((h2 & 0x800fffff) | 0x3fe00000, __double2loint(mant));
-      }
-    }
-    __syncthreads();
-    // ---- S3: rank-NBK update of the registers, right-hand sides, Gram matrix
-#pragma unroll
-    for (int c = 0; c < NBK; ++c) {
-      double yk[EC];
-#pragma unroll
-      for (int ec = 0; ec < EC; ++ec) yk[ec] = YsE[(c * EC + ec) * 32 + lane];
-#pragma unroll
-      for (int er = 0; er < ER; ++er) {
-        const double yi = -YT[c * WD + tr * ER + er];
-#pragma unroll
-        for (int ec = 0; ec < EC; ++ec) a[er][ec] = fma(yi, yk[ec], a[er][ec]);
-      }
-    }
-#pragma unroll
-    for (int e = 0; e < NE; ++e) {
-      if (rres[e] >= 0) {
-        double acc = rv[e];
-#pragma unroll
-        for (int c = 0; c < NBK; ++c) acc = fma(-YT[c * WD + rres[e]], Zs[c * NRP + rq[e]], acc);
-        rv[e] = acc;
-      }
-    }
-    if (gram_on) {
-#pragma unroll
-      for (int c = 0; c < NBK; ++c) gacc = fma(Zz[c * NRP + gp_], Zs[c * NRP + gq_], gacc);
-    }
-    // ---- S3b: the owner warp of the next diagonal block factors it one block ahead
-    {
-      const int jrn = (jr0 + NBK == WD) ? 0 : jr0 + NBK;
-      if (tr == jrn / ER) factor_block(jrn / EC);
-    }
-    // ---- S4: rows j0+WD … j0+WD+NBK−1 enter in the slots of the retiring block
-    if (tr == tr0) {
-#pragma unroll
-      for (int a2 = 0; a2 < NBK; ++a2) {
-        const double* row = rowbase + a2 * ROWLEN;
-#pragma unroll
-        for (int ec = 0; ec < EC; ++ec) {
-          int t = lane * EC + ec - jr0 - NBK;
-          if (t < 0) t += WD;
-          double v;
-          if (t < WD - NBK) {
-            v = row[a2 + WD - NBK - t];
-          } else {
-            const int ap = t - (WD - NBK);
-            v = (ap <= a2) ? row[a2 - ap] : 0.0;
-          }
-          a[a2][ec] = v;
-        }
-      }
-    }
-#pragma unroll
-    for (int e = 0; e < NE; ++e) {
-      const int dd = rres[e] - jr0;
-      if (rres[e] >= 0 && dd >= 0 && dd < NBK) rv[e] = (rowbase + dd * ROWLEN)[WD + rq[e]];
-    }
-  }
-  if (tid == 0) logdet = log(mant) + (double)expo * 0.6931471805599453;
-  if (gram_on) gram[tid] = gacc;
-  __syncthreads();
-  if (tid == 0) band_epilogue(p, b, M, gram, logdet, info);
-}
-
-template <int WD, int ER>
-cudaError_t launch_band_blk_t(const BandCholParams& p, int B, cudaStream_t st) {
-  constexpr int NBK = ER;
-  const size_t smem = sizeof(double) * ((size_t)3 * WD * NBK + NBK * NBK + 2 * NBK + NBK * (NBK + 1) + 3 * NBK * NRP +
-                                        (kMaxM + 1) * (kMaxM + 1) + (size_t)2 * 2 * NBK * (WD + NRP));
-  static bool opted_in = false;
-  if (!opted_in) {
-    cudaError_t e = cudaFuncSetAttribute(band_blk_kernel<WD, ER, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(band_blk_kernel<WD, ER, kMaxM + 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               160 * 1024);
-    if (e != cudaSuccess) return e;
-    opted_in = true;
-  }
-  if (p.M + 1 <= 8)
-    band_blk_kernel<WD, ER, 8><<<B, WD * 32 / ER, smem, st>>>(p);
-  else
-    band_blk_kernel<WD, ER, kMaxM + 1><<<B, WD * 32 / ER, smem, st>>>(p);
-  return cudaGetLastError();
-}
-
 template <int WD, int ER>
 cudaError_t launch_band_t(const BandCholParams& p, int B, cudaStream_t st) {
   const size_t smem = sizeof(double) * 2 * band_batch(WD, ER) * (WD + NRP);
@@ -987,38 +691,23 @@ cudaError_t launch_band_build(const BandBuildParams& p, int B, cudaStream_t st) 
   return cudaGetLastError();
 }
 
-// which kernel serves a window class: 0 = one pivot per barrier (full square), 1 = block/delayed update,
-// 2 = symmetric window.  SFB_BAND_KERNEL=rect|blk|sym overrides for A/B measurements.
-static int band_kernel_choice(int WD) {
-  static const char* env = getenv("SFB_BAND_KERNEL");
-  if (WD > 160) return 2;
-  if (env && !strcmp(env, "sym")) return 2;
-  if (env && !strcmp(env, "rect")) return 0;
-  return 1;
+// Windows up to 160 pixels use the full-square register window (measured fastest); the
+// symmetric window serves the 192- and 256-pixel classes, which do not fit the register file as a square.
+// SFB_BAND_SYM=1 forces the symmetric kernel for every class (A/B measurements).
+static bool band_use_sym(int WD) {
+  static const bool force = getenv("SFB_BAND_SYM") != nullptr;
+  return force || WD > 160;
 }
 
 // pixels of slack a window needs beyond the half-bandwidth: b + slack <= WD
 int band_slack(int WD) {
-  if (band_kernel_choice(WD) != 1) return 1;
-  return WD == 96 ? 6 : (WD == 160 ? 10 : 8);
+  (void)WD;
+  return 1;
 }
 
 cudaError_t launch_band_chol(const BandCholParams& p, int WD, int B, cudaStream_t st) {
   if (B <= 0) return cudaSuccess;
-  if (band_kernel_choice(WD) == 1) {
-    switch (WD) {
-      case 64: return launch_band_blk_t<64, 8>(p, B, st);
-      case 96: return launch_band_blk_t<96, 6>(p, B, st);
-      case 128: return launch_band_blk_t<128, 8>(p, B, st);
-      case 160: return launch_band_blk_t<160, 10>(p, B, st);
-      default: return cudaErrorInvalidValue;
-    }
-  }
-  // Windows up to 160 pixels use the full-square register window (measured faster: 15.9 vs 22.8 ms per
-  // 256-walker step — the per-pivot publish/barrier/load chain, not the FMA count, is what limits both); the
-  // symmetric window serves the 192- and 256-pixel classes, which do not fit the register file as a square.
-  // SFB_BAND_SYM=1 forces the symmetric kernel everywhere (A/B measurements).
-  if (band_kernel_choice(WD) == 2) {
+  if (band_use_sym(WD)) {
     switch (WD) {
       case 64: return launch_band_sym_t<2>(p, B, st);
       case 96: return launch_band_sym_t<3>(p, B, st);
