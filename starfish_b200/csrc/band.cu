@@ -9,8 +9,8 @@
 // exactly like the dense path; it is a separate mode with its own roofline (fp64 FMA issue of the window
 // update), reported separately by bench.py.
 //
-//   band_build_kernel   S in band storage Sb[i][d] = S[i, i−d], d < WD — same element arithmetic (operation
-//                       order, support masks) as cov_build_kernel, 8·N·WD bytes per walker instead of 8·N²
+//   band_build_kernel   S in band storage Sb[i][d] = S[i, i−d], d < WD — the support masks of cov_build_kernel
+//                       bit for bit, values within 2 ulp, 8·N·WD bytes per walker instead of 8·N²
 //   band_chol_kernel    ONE persistent CTA per walker.  The active window of the factorisation (rows/columns
 //                       j..j+WD−1) lives in REGISTERS, addressed circularly (index mod WD), 8×(WD/32) elements
 //                       per thread; per pivot: the owners publish column j through a double-buffered
@@ -40,7 +40,7 @@ constexpr int BB_ROWS = 8;  // rows per CTA (one per warp)
 
 __global__ void __launch_bounds__(BB_ROWS * 32)
 band_build_kernel(BandBuildParams p) {
-  __shared__ double l_amp[kMaxK], l_mu[kMaxK], l_sig[kMaxK];
+  __shared__ double l_amp[kMaxK], l_mu[kMaxK], l_sig[kMaxK], l_ir0[kMaxK], l_mh[kMaxK];
   const int b = p.rowmap ? p.rowmap[blockIdx.y] : blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int hb = b * p.hyper_stride;
@@ -51,6 +51,8 @@ band_build_kernel(BandBuildParams p) {
     l_amp[threadIdx.x] = l[0];
     l_mu[threadIdx.x] = l[1];
     l_sig[threadIdx.x] = l[2];
+    l_ir0[threadIdx.x] = 1.0 / (4 * l[2]);     // 1/r0
+    l_mh[threadIdx.x] = -0.5 / (l[2] * l[2]);   // −1/(2σ²)
   }
   __syncthreads();
   const int i = blockIdx.x * BB_ROWS + warp;
@@ -58,9 +60,13 @@ band_build_kernel(BandBuildParams p) {
   const int WD = p.WD;
   const double wi = p.wave[i];
   const double r0g = 6 * g_ls, sqrt3 = sqrt(3.0);
+  // The support tests (r <= r0) use exactly the expressions of cov_build_kernel, so both solvers agree on
+  // which entries exist; inside the support the divisions by per-walker constants become multiplications by
+  // their reciprocals and cos(π·x) is evaluated as cospi(x) — values within 2 ulp of the dense build's, at
+  // half the instruction count (this kernel is issue-bound on fp64 division / cos / exp sequences).
+  const double inv_r0g = 1.0 / r0g, s3_ls = sqrt3 / g_ls;
   double* out = p.Sb + (long long)b * p.strideSb + (long long)i * WD;
   int over = 0;
-  // local kernels: this row's metric per kernel, and the overflow test (block wider than the window)
   for (int d = lane; d <= WD; d += 32) {  // d == WD is only the "does the band fit" probe
     const int k = i - d;
     double v = 0.0;
@@ -74,8 +80,9 @@ band_build_kernel(BandBuildParams p) {
       if (g_amp > 0.0) {
         const double rv = kC_KMS / 2 * fabs((wk - wi) / (wk + wi));
         if (rv <= r0g) {
-          const double taper = 0.5 + 0.5 * cos(kPi * rv / r0g);
-          v += taper * g_amp * (1 + sqrt3 * rv / g_ls) * exp(-sqrt3 * rv / g_ls);
+          const double taper = 0.5 + 0.5 * cospi(rv * inv_r0g);
+          const double y = s3_ls * rv;
+          v += taper * g_amp * (1 + y) * exp(-y);
           nz = true;
         }
       }
@@ -86,8 +93,8 @@ band_build_kernel(BandBuildParams p) {
         const double mi = f * fabs(wi - mu), mj = f * fabs(wk - mu);
         if (mi <= r0 && mj <= r0) {
           const double rt = fmax(mi, mj);
-          const double taper = 0.5 + 0.5 * cos(kPi * rt / r0);
-          lsum += taper * l_amp[q] * exp(-0.5 * (mi * mi + mj * mj) / (l_sig[q] * l_sig[q]));
+          const double taper = 0.5 + 0.5 * cospi(rt * l_ir0[q]);
+          lsum += taper * l_amp[q] * exp((mi * mi + mj * mj) * l_mh[q]);
           any = true;
         }
       }

@@ -206,3 +206,30 @@ def test_config5_shape_n16384_multi_order_takes_the_256_window():
                                      glob=d["glob"][b], loc=d["loc"][b])
         assert abs(lnL[b] - ref) <= TOL * max(1.0, abs(ref)), (b, lnL[b], ref)
     eng.close()
+
+
+def test_randomised_hyper_parameters_dense_vs_structured():
+    """24 walkers with hyper-parameters drawn over two decades of amplitude, ℓ ∈ [5, 90] km/s, 0–3 local kernels of
+    random position/width (some overlapping, some outside the grid): both solvers, same numbers."""
+    N, B, K, M = 1536, 24, 3, 5
+    rng = np.random.default_rng(21)
+    wave = synth.log_uniform_wave(N, 5050.0, 5250.0)
+    d = synth.stage_inputs_direct(N, B, n_comp=M, n_local=K, wave=wave)
+    d["glob"][:, 0] = 10.0 ** rng.uniform(-5.0, -3.0, B)
+    d["glob"][:, 1] = rng.uniform(5.0, 90.0, B)
+    d["glob"][rng.integers(0, B, 3), 0] = 0.0                  # a few walkers without a global kernel
+    d["nloc"] = rng.integers(0, K + 1, B).astype(np.int32)
+    d["loc"][:, :, 0] = 10.0 ** rng.uniform(-5.0, -3.5, (B, K))
+    d["loc"][:, :, 1] = rng.uniform(5040.0, 5260.0, (B, K))    # some centres fall off the grid
+    d["loc"][:, :, 2] = rng.uniform(8.0, 60.0, (B, K))
+    eng = _engine(N, M, K, B)
+    eng.set_data(d["wave"], d["sigma"], d["data_flux"])
+    lnL_s, info_s = _run(eng, d)
+    eng.set_solver("dense")
+    lnL_d, info_d = _run(eng, d)
+    assert (info_s == 0).all() and (info_d == 0).all()
+    assert np.abs(lnL_s - lnL_d).max() <= TOL * np.abs(lnL_d).max()
+    for b in (0, 7, 19):
+        ref = _dense_ref(d, b)
+        assert abs(lnL_s[b] - ref) <= TOL * max(1.0, abs(ref))
+    eng.close()
