@@ -54,7 +54,7 @@ struct sfb_ctx {
   double* Sb = nullptr;
   int *bw_d = nullptr, *overflow = nullptr, *rowmap_d = nullptr;
   int *bw_h = nullptr, *rowmap_h = nullptr;  // pinned
-  cudaEvent_t ev_band = nullptr;
+  cudaEvent_t ev_band = nullptr, ev_up = nullptr;
   long long band_rows[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // walkers per window class (last = dense fallback) since creation
   ModelState model;       // upstream of the covariance (rows f1/f2); empty until sfb_set_model_host
   bool have_model = false;
@@ -338,9 +338,17 @@ int loglike_device(sfb_ctx* h, int B, const double* X, const double* A, const do
 // walker's S) decides each walker's window class; every class is one band_build + one band_chol launch
 // over a row map; walkers whose band exceeds the widest window, or an unsorted grid, take the dense path.
 // ---------------------------------------------------------------------------------------------------
+struct UpstreamJob {  // parameters whose upstream stage should run concurrently with the band set-up
+  const double* theta;
+  int ncheb;
+  double* log_scale_out;
+};
+int run_upstream(sfb_ctx* h, int B, const double* theta, int ncheb, double* X, double* A, double* flux,
+                 double* log_scale_out, int* status, cudaStream_t st);
+
 int structured_device(sfb_ctx* h, int B, const double* X, const double* A, const double* model_flux,
                       const double* glob, const int* nloc, const double* loc, int shared_hyper, double* lnL,
-                      int* info, double* resid, cudaStream_t caller) {
+                      int* info, double* resid, cudaStream_t caller, const UpstreamJob* up = nullptr) {
   const int N = h->N, K = h->Kmax, Bm = h->Bmax;
   const int WDmax = kBandWidths[kNumBandWidths - 1];
   if (!h->Sb) {
@@ -351,12 +359,21 @@ int structured_device(sfb_ctx* h, int B, const double* X, const double* A, const
     ok = ok && cudaMallocHost((void**)&h->bw_h, sizeof(int) * (Bm + 1)) == cudaSuccess;
     ok = ok && cudaMallocHost((void**)&h->rowmap_h, sizeof(int) * Bm) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h->ev_band, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->ev_up, cudaEventDisableTiming) == cudaSuccess;
     if (!ok) return fail(h, SFB_ERR_NOMEM, "structured solver: band storage allocation failed");
   }
   cudaStream_t s0 = h->streams[0], s1 = h->streams[1];
   int rc = fork_streams(h, caller, 2);
   if (rc != SFB_OK) return rc;
   const int hs = shared_hyper ? 0 : 1;
+  // 0. the transforms and the emulator (when asked for) run on lane 1 while lane 0 and the host size up the
+  //    bands: band widths and band builds need only the kernel hyper-parameters, not X or the model flux
+  if (up) {
+    rc = run_upstream(h, B, up->theta, up->ncheb, (double*)X, (double*)A, (double*)model_flux, up->log_scale_out,
+                      h->model.status, s1);
+    if (rc != SFB_OK) return rc;
+    SFB_CUDA(h, cudaEventRecord(h->ev_up, s1));
+  }
   // 1. exact half-bandwidths + the sortedness flag, one small D2H
   SFB_CUDA(h, launch_band_width(N, K, hs, h->wave, glob, nloc, loc, h->bw_d, B, s0));
   h->launches++;
@@ -419,6 +436,7 @@ int structured_device(sfb_ctx* h, int B, const double* X, const double* A, const
       const double bwq = h->bw_h[h->rowmap_h[start[c] + q]];
       flops += (double)N * (bwq * bwq + 2.0 * bwq * (cp.M + 1));
     }
+    if (up && st != s1) SFB_CUDA(h, cudaStreamWaitEvent(st, h->ev_up, 0));  // X, A, model flux ready
     {
       ProfScope ps(h, st, SFB_K_BAND_CHOL, flops);
       SFB_CUDA(h, launch_band_chol(cp, WD, count[c], st));
@@ -429,6 +447,7 @@ int structured_device(sfb_ctx* h, int B, const double* X, const double* A, const
   if (used[0]) { SFB_CUDA(h, cudaEventRecord(h->ev_hi[0], h->hi[0])); SFB_CUDA(h, cudaStreamWaitEvent(s0, h->ev_hi[0], 0)); }
   if (used[3]) { SFB_CUDA(h, cudaEventRecord(h->ev_hi[1], h->hi[1])); SFB_CUDA(h, cudaStreamWaitEvent(s1, h->ev_hi[1], 0)); }
   // 4. dense path for what does not fit a window (contiguous runs of the original order)
+  if (count[nclass] && up) SFB_CUDA(h, cudaStreamWaitEvent(s0, h->ev_up, 0));
   if (count[nclass]) {
     h->band_rows[nclass] += count[nclass];
     const int nstreams = (h->profile || h->slots < 2 || (h->debug_mode & 2)) ? 1 : 2;
@@ -552,6 +571,7 @@ int sfb_destroy(sfb_t* h) {
   if (h->bw_h) cudaFreeHost(h->bw_h);
   if (h->rowmap_h) cudaFreeHost(h->rowmap_h);
   if (h->ev_band) cudaEventDestroy(h->ev_band);
+  if (h->ev_up) cudaEventDestroy(h->ev_up);
   for (auto& pe : h->prof) {
     cudaEventDestroy(pe.a);
     cudaEventDestroy(pe.b);
@@ -770,6 +790,7 @@ int sfb_set_model_host(sfb_t* h, int nf, const double* fine_wave_h, const double
   return SFB_OK;
 }
 
+extern "C++" {
 namespace {
 int check_upstream(sfb_ctx* h, int B, int ncheb, const char* who) {
   int rc = check_batch(h, B);
@@ -802,6 +823,7 @@ int run_upstream(sfb_ctx* h, int B, const double* theta, int ncheb, double* X, d
   return SFB_OK;
 }
 }  // namespace
+}  // extern "C++"
 
 int sfb_upstream(sfb_t* h, int B, const double* theta, int ncheb, double* X, double* A, double* model_flux,
                  double* log_scale_out, int* status, double* weights, double* weights_cov, void* stream) {
@@ -833,22 +855,21 @@ int sfb_loglike_params(sfb_t* h, int B, const double* theta, int ncheb, const do
   cudaStream_t caller = (cudaStream_t)stream;
   const int nstreams = (h->profile || h->slots < 2 || (h->debug_mode & 2)) ? 1 : 2;
   ModelState& ms = h->model;
+  if (h->solver == SFB_SOLVER_STRUCTURED) {  // upstream on lane 1, overlapped with the band set-up on lane 0
+    UpstreamJob job{theta, ncheb, log_scale_out ? log_scale_out : ms.log_scale};
+    if ((rc = structured_device(h, B, ms.X, ms.A, ms.flux, glob, nloc, loc, shared_hyper, lnL, info, resid, caller,
+                                &job)) != SFB_OK)
+      return rc;
+    SFB_CUDA(h, launch_merge_status(ms.status, info, lnL, B, caller));
+    h->launches++;
+    return SFB_OK;
+  }
   // the upstream stage runs once for the whole batch on stream 0; the other lane waits for it
   SFB_CUDA(h, cudaEventRecord(h->ev_fork, caller));
   SFB_CUDA(h, cudaStreamWaitEvent(h->streams[0], h->ev_fork, 0));
   if ((rc = run_upstream(h, B, theta, ncheb, ms.X, ms.A, ms.flux, log_scale_out ? log_scale_out : ms.log_scale,
                          ms.status, h->streams[0])) != SFB_OK)
     return rc;
-  if (h->solver == SFB_SOLVER_STRUCTURED) {
-    if ((rc = structured_device(h, B, ms.X, ms.A, ms.flux, glob, nloc, loc, shared_hyper, lnL, info, resid,
-                                h->streams[0])) != SFB_OK)
-      return rc;
-    SFB_CUDA(h, cudaEventRecord(h->ev_join[0], h->streams[0]));
-    SFB_CUDA(h, cudaStreamWaitEvent(caller, h->ev_join[0], 0));
-    SFB_CUDA(h, launch_merge_status(ms.status, info, lnL, B, caller));
-    h->launches++;
-    return SFB_OK;
-  }
   SFB_CUDA(h, cudaEventRecord(h->ev_fork, h->streams[0]));
   for (int i = 1; i < nstreams; ++i) SFB_CUDA(h, cudaStreamWaitEvent(h->streams[i], h->ev_fork, 0));
   rc = loglike_device(h, B, ms.X, ms.A, ms.flux, glob, nloc, loc, shared_hyper, lnL, info, resid, nstreams, nullptr,
