@@ -198,3 +198,56 @@ def test_emulator_train_improves_likelihood_and_respects_bounds():
     else:
         assert abs(emu.log_likelihood() - before) <= 1e-9 * abs(before)
     assert np.all(emu.lengthscales >= 2 * emu._grid_sep - 1e-12)
+
+
+def test_batch_parameter_packing_is_pure_host_logic():
+    """theta / hyper-parameter packing of log_likelihood_batch (no GPU involved): column order, frozen values,
+    frozen-group sharing, vectorised priors."""
+    import scipy.stats as st
+
+    from _helpers import make_model
+
+    m = make_model(256, 0, wave=np.linspace(5092.0, 5108.0, 256), mus=(5098.0, 5103.0), vz=3.0)
+    labels = list(m.labels)
+    P0 = m.get_param_vector()
+    P = np.tile(P0, (3, 1))
+    P[1, labels.index("vsini")] = 7.5
+    P[2, labels.index("cheb:2")] = 0.03
+    P[2, labels.index("local_cov:1:log_sigma")] += 0.25
+    B, cols = m._columns(P)
+    th = m._theta(B, cols)
+    D = 3
+    assert th.shape == (3, D + 4 + 2)
+    assert np.array_equal(th[:, :D], np.tile(m.grid_params, (3, 1)))
+    assert th[:, D].tolist() == [5.0, 7.5, 5.0] and np.all(th[:, D + 1] == 3.0) and np.all(th[:, D + 3] == 1.0)
+    assert th[:, D + 4].tolist() == [0.01] * 3 and th[:, D + 5].tolist() == [-0.01, -0.01, 0.03]
+    glob, nloc, loc, shared = m._hyper_rows(B, cols)
+    assert not shared and glob.shape == (3, 2) and nloc.tolist() == [2, 2, 2]
+    assert np.allclose(loc[2, 1, 2], np.exp(cols["local_cov:1:log_sigma"][2])) and loc[0, 1, 2] != loc[2, 1, 2]
+    assert np.allclose(glob[:, 0], np.exp(m["global_cov:log_amp"]))
+    # frozen parameters keep the model's value whatever P holds for the thawed ones
+    m.freeze("vz")
+    labels2 = list(m.labels)
+    assert "vz" not in labels2
+    B2, cols2 = m._columns(np.tile(m.get_param_vector(), (2, 1)))
+    assert np.all(cols2["vz"] == 3.0)
+    # frozen kernel groups: one shared hyper-parameter row
+    m.freeze(["global_cov", "local_cov"])
+    B3, cols3 = m._columns(np.tile(m.get_param_vector(), (4, 1)))
+    g3, n3, l3, shared3 = m._hyper_rows(B3, cols3)
+    assert shared3 and g3.shape == (1, 2) and l3.shape[0] == 1 and n3.tolist() == [2]
+    # priors are evaluated on whole columns; scalar-only prior objects fall back to per-row calls
+    class ScalarOnly:
+        def logpdf(self, v):
+            if np.ndim(v):
+                raise TypeError("scalar only")
+            return -0.5 * (v - 5.0) ** 2
+
+    m.thaw("all")
+    B4, cols4 = m._columns(P)
+    lp = m._prior_rows(B4, cols4, {"vsini": ScalarOnly(), "T": st.uniform(6000, 200), "nope": st.norm()})
+    assert np.allclose(lp, [-0.5 * 0.0 + st.uniform(6000, 200).logpdf(m["T"]),
+                            -0.5 * 2.5 ** 2 + st.uniform(6000, 200).logpdf(m["T"]),
+                            st.uniform(6000, 200).logpdf(m["T"])])
+    with np.testing.assert_raises(ValueError):
+        m._check_transforms({"vsini": np.array([5.0, 0.0]), **{k: v for k, v in cols4.items() if k != "vsini"}})
