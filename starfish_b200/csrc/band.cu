@@ -23,7 +23,6 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
-#include <type_traits>
 
 #include "sfb_internal.cuh"
 
@@ -273,9 +272,10 @@ __device__ __noinline__ void band_epilogue(const BandCholParams& p, int b, int M
   }
 }
 
+__host__ __device__ constexpr int band_lcm(int WD, int ER) { return (ER % (WD / 32) == 0) ? ER : ER * (WD / 32); }
 __host__ __device__ constexpr int band_batch(int WD, int ER) {
-  (void)WD;
-  return 2 * ER;  // pivots per staging batch: a multiple of the unroll length
+  const int l = band_lcm(WD, ER);
+  return (l <= 24 && WD % l == 0) ? (l < 16 ? 2 * l : l) : 16;
 }
 
 // ER = window rows per thread (8 → WD·4 threads; the 160-pixel window uses 10 → 512 threads so that its
@@ -336,7 +336,7 @@ band_chol_kernel(BandCholParams p) {
     const int i = tr * ER + er;
 #pragma unroll
     for (int ec = 0; ec < EC; ++ec) {
-      const int k = lane + 32 * ec;
+      const int k = lane * EC + ec;
       double v = 0.0;
       if (k <= i) v = (i < N) ? Sb[(long long)i * WD + (i - k)] : (k == i ? 1.0 : 0.0);
       a[er][ec] = v;
@@ -364,29 +364,18 @@ band_chol_kernel(BandCholParams p) {
   double mant = 1.0;
   long long expo = 0;
 
-  // The pivot loop is unrolled by ER so that "which register row holds index j" is a compile-time fact inside
-  // the body (j ≡ u mod ER, ER | WD): replacing the retiring row is a plain register move.
-  constexpr int UN = ER;
-  static_assert(WD % UN == 0 && UN % 2 == 0 && BATCH % UN == 0, "unroll length must divide the window and the batch");
-  // Column slots are owned with stride 32 (column c lives in lane c & 31, register c >> 5), so a warp reads a
-  // whole pivot column from shared memory without bank conflicts; c >> 5 is uniform over the CTA, hence the
-  // register that holds the pivot column is picked by a uniform switch with compile-time arms.
-  auto with_col = [&](int ecj, auto&& f) {
-    switch (ecj) {
-      case 0: f(std::integral_constant<int, 0>{}); break;
-      case 1: if constexpr (EC > 1) f(std::integral_constant<int, 1>{}); break;
-      case 2: if constexpr (EC > 2) f(std::integral_constant<int, 2>{}); break;
-      case 3: if constexpr (EC > 3) f(std::integral_constant<int, 3>{}); break;
-      case 4: if constexpr (EC > 4) f(std::integral_constant<int, 4>{}); break;
-      default: break;
-    }
-  };
+  // The pivot loop is unrolled by UN = lcm(ER, EC) so that "which register holds column j / row j" is a
+  // compile-time fact inside the body (j ≡ u mod UN, UN | WD): publishing the pivot column and replacing
+  // the retiring row are plain register moves, no selects.
+  constexpr int UN = band_lcm(WD, ER);                // ER, EC as used here: 8|{1,2,4}, 8·3, 10|5
+  static_assert(UN <= 24 && WD % UN == 0 && UN % ER == 0 && UN % EC == 0 && UN % 2 == 0 && BATCH % UN == 0,
+                "unroll length must divide the window and the staging batch");
   // 1/pivot is taken off the critical path: the owner of the NEXT diagonal element updates it first thing
   // after the barrier, starts its reciprocal and publishes it for the following pivot, so that nobody waits
   // for a division between the barrier and the FMAs.
   if (tid == 0) invbuf[0] = 1.0 / a[0][0];
   for (int j0 = 0, jr0 = 0; j0 < N; j0 += UN, jr0 = (jr0 + UN == WD) ? 0 : jr0 + UN) {
-    const int own_warp0 = jr0 / ER;
+    const int own_lane0 = jr0 / EC, own_warp0 = jr0 / ER;
     const int jb0 = j0 % BATCH, half = (j0 / BATCH) & 1;
     const double* rowbase = ring + half * (BATCH * ROWLEN) + jb0 * ROWLEN;
 #pragma unroll
@@ -398,11 +387,9 @@ band_chol_kernel(BandCholParams p) {
       // staging boundary: this batch's rows (issued one boundary ago) must have landed before the barrier
       if (boundary) cp_async_wait_all();
       // ---- phase A: owners publish column j of the window and the pivot row of the right-hand sides
-      if (lane == (jr & 31)) {
-        with_col(jr >> 5, [&](auto ecj) {
+      if (lane == own_lane0 + u / EC) {
 #pragma unroll
-          for (int er = 0; er < ER; ++er) colbuf[buf][tr * ER + er] = a[er][decltype(ecj)::value];
-        });
+        for (int er = 0; er < ER; ++er) colbuf[buf][tr * ER + er] = a[er][u % EC];
       }
 #pragma unroll
       for (int e = 0; e < NE; ++e)
@@ -415,11 +402,9 @@ band_chol_kernel(BandCholParams p) {
       const double inv = invbuf[buf];
       {
         const int jn = (jr + 1 == WD) ? 0 : jr + 1;
-        if (tr == jn / ER && lane == (jn & 31)) {  // next pivot: same arithmetic as the bulk update below
+        if (tr == jn / ER && lane == jn / EC) {  // next pivot: same arithmetic as the bulk update below
           const double aj1 = colbuf[buf][jn];
-          with_col(jn >> 5, [&](auto ecj) {
-            invbuf[buf ^ 1] = 1.0 / fma(-aj1, aj1 * inv, a[(u + 1) % ER][decltype(ecj)::value]);
-          });
+          invbuf[buf ^ 1] = 1.0 / fma(-aj1, aj1 * inv, a[(u + 1) % ER][(u + 1) % EC]);
         }
       }
       if (tr == 0) {  // warp-uniform bookkeeping
@@ -436,7 +421,7 @@ band_chol_kernel(BandCholParams p) {
       }
       double ak[EC];
 #pragma unroll
-      for (int ec = 0; ec < EC; ++ec) ak[ec] = colbuf[buf][lane + 32 * ec] * inv;
+      for (int ec = 0; ec < EC; ++ec) ak[ec] = colbuf[buf][lane * EC + ec] * inv;
 #pragma unroll
       for (int er = 0; er < ER; ++er) {
         const double ai = -colbuf[buf][tr * ER + er];
@@ -452,7 +437,7 @@ band_chol_kernel(BandCholParams p) {
       if (tr == own_warp0 + u / ER) {
 #pragma unroll
         for (int ec = 0; ec < EC; ++ec) {
-          int t = lane + 32 * ec - jr - 1;
+          int t = lane * EC + ec - jr - 1;
           if (t < 0) t += WD;
           a[u % ER][ec] = row[WD - 1 - t];
         }
