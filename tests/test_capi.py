@@ -76,3 +76,16 @@ def test_sass_uses_dmma_and_tma(built_lib):
     sass = subprocess.run([cuobjdump, "-sass", built_lib], capture_output=True, text=True).stdout
     for mnemonic in ("DMMA.8x8x4", "UTMALDG.3D", "UBLKCP", "SYNCS.ARRIVE.TRANS64", "LDS.128"):
         assert mnemonic in sass, mnemonic
+
+
+def test_header_is_plain_c():
+    """include/sfb200.h must be consumable from C (cgo / JNI / FFI generators read it): C99, no warnings."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    res = subprocess.run([gcc, "-fsyntax-only", "-x", "c", "-std=c99", "-Wall", "-Werror",
+                          os.path.join(ROOT, "include", "sfb200.h")], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
