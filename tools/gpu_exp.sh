@@ -1,7 +1,7 @@
 #!/bin/bash
-# A/B on the GPU box: the committed band.cu, then tools/exp/<name>.cu.txt swapped in and rebuilt there.
+# A/B on the GPU box: the committed band.cu first, then every tools/exp/*.cu.txt swapped in and rebuilt there.
 set -u
-TAG=${1:-exp}; VARIANT=${2:-band_strided}
+TAG=${1:-exp}
 mkdir -p gpurun_out
 run() {
   local tag=$1
@@ -14,7 +14,12 @@ print("$tag: structured", s["value"], "ms", s["ms_per_step"], "model", s["e2e_mo
 PY
 }
 run ${TAG}_base
-cp tools/exp/${VARIANT}.cu.txt starfish_b200/csrc/band.cu && python -m starfish_b200.build --force > gpurun_out/${TAG}_build.log 2>&1; echo "rebuild rc=$?"
-run ${TAG}_${VARIANT}
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'band_chol_kernel' -c 3 \
-  -o gpurun_out/${TAG}_${VARIANT} python bench.py --walkers 64 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-model > gpurun_out/${TAG}_ncu.log 2>&1; echo "ncu rc=$?"
+cp starfish_b200/csrc/band.cu /tmp/band_committed.cu
+for f in tools/exp/*.cu.txt; do
+  v=$(basename $f .cu.txt)
+  cp $f starfish_b200/csrc/band.cu && python -m starfish_b200.build --force > gpurun_out/${TAG}_${v}_build.log 2>&1; echo "$v rebuild rc=$?"
+  run ${TAG}_${v}
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:'band_chol_kernel<\(int\)128' -c 1 \
+    -o gpurun_out/${TAG}_${v} python bench.py --walkers 64 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-model > gpurun_out/${TAG}_${v}_ncu.log 2>&1; echo "$v ncu rc=$?"
+done
+cp /tmp/band_committed.cu starfish_b200/csrc/band.cu
