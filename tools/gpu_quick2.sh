@@ -3,9 +3,9 @@
 set -u
 TAG=${1:-q}
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_structured.py -q -x > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?"; tail -6 gpurun_out/${TAG}_pytest.log
-for mode in blk rect; do
-  export SFB_BAND_KERNEL=$mode
+SFB_BAND_LOOKAHEAD=1 timeout 900 python -m pytest tests/test_gpu_structured.py -q -x > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest (look-ahead) rc=$?"; tail -6 gpurun_out/${TAG}_pytest.log
+for mode in base la; do
+  if [ $mode = la ]; then export SFB_BAND_LOOKAHEAD=1; else unset SFB_BAND_LOOKAHEAD; fi
   timeout 600 python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_bench_$mode.json 2> gpurun_out/${TAG}_bench_$mode.err; echo "bench $mode rc=$?"
   python - <<PY
 import json
@@ -15,6 +15,6 @@ print("$mode: structured", s["value"], "ms", s["ms_per_step"], "model", s["e2e_m
 PY
   tail -2 gpurun_out/${TAG}_bench_$mode.err
 done
-unset SFB_BAND_KERNEL
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'band_blk_kernel' -c 3 \
+export SFB_BAND_LOOKAHEAD=1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'band_chol_kernel' -c 3 \
   -o gpurun_out/${TAG}_band python bench.py --walkers 64 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-model > gpurun_out/${TAG}_ncu_band.log 2>&1; echo "ncu band rc=$?"
