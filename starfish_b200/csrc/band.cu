@@ -404,11 +404,12 @@ band_chol_kernel(BandCholParams p) {
         const bool boundary = (u == 0) && (jb0 == 0);
         if (j > 0) {  // column j published by every warp?  (phase j−1 of the mbarrier)
           const uint32_t parity = (uint32_t)((j - 1) & 1);
-          uint32_t ok = 0;
+          uint32_t ok = 0, spins = 0;
           while (!ok) {
             asm volatile(
                 "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+            if (++spins > (1u << 22)) __trap();  // a protocol error must fail loudly, never hang the device
           }
         }
         if (boundary) {  // once per staging batch: the ring half of this batch must be complete and visible

@@ -3,7 +3,7 @@
 set -u
 TAG=${1:-q}
 mkdir -p gpurun_out
-SFB_BAND_LOOKAHEAD=1 timeout 900 python -m pytest tests/test_gpu_structured.py -q -x > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest (look-ahead) rc=$?"; tail -6 gpurun_out/${TAG}_pytest.log
+SFB_BAND_LOOKAHEAD=1 timeout 300 python -m pytest tests/test_gpu_structured.py -q -x > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest (look-ahead) rc=$?"; tail -6 gpurun_out/${TAG}_pytest.log
 for mode in base la; do
   if [ $mode = la ]; then export SFB_BAND_LOOKAHEAD=1; else unset SFB_BAND_LOOKAHEAD; fi
   timeout 600 python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_bench_$mode.json 2> gpurun_out/${TAG}_bench_$mode.err; echo "bench $mode rc=$?"
