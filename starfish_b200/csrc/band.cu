@@ -280,20 +280,16 @@ __host__ __device__ constexpr int band_batch(int WD, int ER) {
 
 // ER = window rows per thread (8 → WD·4 threads; the 160-pixel window uses 10 → 512 threads so that its
 // 10×5 register tile fits a 128-register budget), MAXNR = right-hand sides the instantiation can carry (M + 1 <= MAXNR)
-// LA = look-ahead by one column: the next pivot column is updated and published FIRST, the warps signal an
-// mbarrier and only then apply the bulk rank-1 update, so that the publish → barrier → load chain of pivot
-// j+1 runs underneath the FMAs of pivot j instead of between them.
-template <int WD, int ER, int MAXNR, bool LA>
+template <int WD, int ER, int MAXNR>
 __global__ void __launch_bounds__(WD * 32 / ER, 1)
 band_chol_kernel(BandCholParams p) {
   constexpr int EC = WD / 32, NT = WD * 32 / ER, ROWLEN = WD + NRP;
   constexpr int BATCH = band_batch(WD, ER);  // pivots per staging batch (a multiple of the unroll length)
   constexpr int NE = (WD * MAXNR + NT - 1) / NT;          // right-hand-side registers per thread
-  __shared__ double colbuf[3][WD];   // 2 buffers in use without look-ahead, 3 with
-  __shared__ double zbuf[3][NRP];
-  __shared__ double invbuf[3];
+  __shared__ double colbuf[2][WD];
+  __shared__ double zbuf[2][NRP];
+  __shared__ double invbuf[2];
   __shared__ double gram[(kMaxM + 1) * (kMaxM + 1)];
-  __shared__ __align__(8) unsigned long long la_bar;
   extern __shared__ double ring[];  // [2][BATCH][ROWLEN]
 
   const int b = p.rowmap ? p.rowmap[blockIdx.x] : blockIdx.x;
@@ -374,114 +370,6 @@ band_chol_kernel(BandCholParams p) {
   constexpr int UN = band_lcm(WD, ER);                // ER, EC as used here: 8|{1,2,4}, 8·3, 10|5
   static_assert(UN <= 24 && WD % UN == 0 && UN % ER == 0 && UN % EC == 0 && UN % 2 == 0 && BATCH % UN == 0,
                 "unroll length must divide the window and the staging batch");
-  if constexpr (LA) {
-    // ---- look-ahead loop.  Buffers are indexed j mod 3: column j+1 is written while column j is still being
-    // read, and column j+2 may be written (by a warp that is already one pivot ahead) only after every warp has
-    // signalled pivot j+1 — which it does after finishing the bulk update of pivot j.
-    const uint32_t bar = static_cast<uint32_t>(__cvta_generic_to_shared(&la_bar));
-    if (tid == 0) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(NT / 32) : "memory");
-      invbuf[0] = 1.0 / a[0][0];
-    }
-    if (lane == 0) {
-#pragma unroll
-      for (int er = 0; er < ER; ++er) colbuf[0][tr * ER + er] = a[er][0];
-    }
-#pragma unroll
-    for (int e = 0; e < NE; ++e)
-      if (rres[e] == 0) zbuf[0][rq[e]] = rv[e];
-    __syncthreads();
-    int b0 = 0;  // j mod 3
-    for (int j0 = 0, jr0 = 0; j0 < N; j0 += UN, jr0 = (jr0 + UN == WD) ? 0 : jr0 + UN) {
-      const int own_warp0 = jr0 / ER;
-      const int jb0 = j0 % BATCH, half = (j0 / BATCH) & 1;
-      const double* rowbase = ring + half * (BATCH * ROWLEN) + jb0 * ROWLEN;
-#pragma unroll
-      for (int u = 0; u < UN; ++u) {
-        const int j = j0 + u, jr = jr0 + u;
-        if (j >= N) break;
-        const int b1 = (b0 == 2) ? 0 : b0 + 1;
-        const bool boundary = (u == 0) && (jb0 == 0);
-        if (j > 0) {  // column j published by every warp?  (phase j−1 of the mbarrier)
-          const uint32_t parity = (uint32_t)((j - 1) & 1);
-          uint32_t ok = 0, spins = 0;
-          while (!ok) {
-            asm volatile(
-                "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-                : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-            if (++spins > (1u << 22)) __trap();  // a protocol error must fail loudly, never hang the device
-          }
-        }
-        if (boundary) {  // once per staging batch: the ring half of this batch must be complete and visible
-          cp_async_wait_all();
-          __syncthreads();
-          stage_issue(j + BATCH, ring + (half ^ 1) * (BATCH * ROWLEN));
-        }
-        const double* row = rowbase + u * ROWLEN;   // band row of the entering index j + WD
-        const double inv = invbuf[b0];
-        double ai[ER], ak[EC];
-#pragma unroll
-        for (int er = 0; er < ER; ++er) ai[er] = -colbuf[b0][tr * ER + er];
-#pragma unroll
-        for (int ec = 0; ec < EC; ++ec) ak[ec] = colbuf[b0][lane * EC + ec] * inv;
-        // -- early part: column j+1 as pivot j leaves it (the bulk loop below recomputes the same values in place)
-        const int jn = (jr + 1 == WD) ? 0 : jr + 1;
-        if (lane == jn / EC) {
-#pragma unroll
-          for (int er = 0; er < ER; ++er) {
-            double v = fma(ai[er], ak[(u + 1) % EC], a[er][(u + 1) % EC]);
-            // the slot of the retiring index j in this column will hold S(j+WD, j+1) = the band row's last entry
-            if (er == u % ER && tr == own_warp0 + u / ER) v = row[WD - 1];
-            colbuf[b1][tr * ER + er] = v;
-          }
-          if (tr == jn / ER)
-            invbuf[b1] = 1.0 / fma(ai[(u + 1) % ER], ak[(u + 1) % EC], a[(u + 1) % ER][(u + 1) % EC]);
-        }
-#pragma unroll
-        for (int e = 0; e < NE; ++e)
-          if (rres[e] == jn) zbuf[b1][rq[e]] = fma(-colbuf[b0][jn], zbuf[b0][rq[e]] * inv, rv[e]);
-        __syncwarp();
-        if (lane == 0) {
-          unsigned long long st_;
-          asm volatile("mbarrier.arrive.shared::cta.b64 %0, [%1];" : "=l"(st_) : "r"(bar) : "memory");
-        }
-        // -- bookkeeping, bulk update, right-hand sides, Gram matrix
-        if (tr == 0) {
-          const double pj = colbuf[b0][jr];
-          if (!(pj > 0.0) && info == 0) info = j + 1;
-          const int hi = __double2hiint(pj);
-          expo += ((hi >> 20) & 0x7ff) - 1022;
-          mant *= __hiloint2double((hi & 0x800fffff) | 0x3fe00000, __double2loint(pj));
-          if ((j & 511) == 511) {
-            const int h2 = __double2hiint(mant);
-            expo += ((h2 >> 20) & 0x7ff) - 1022;
-            mant = __hiloint2double((h2 & 0x800fffff) | 0x3fe00000, __double2loint(mant));
-          }
-        }
-#pragma unroll
-        for (int er = 0; er < ER; ++er)
-#pragma unroll
-          for (int ec = 0; ec < EC; ++ec) a[er][ec] = fma(ai[er], ak[ec], a[er][ec]);
-#pragma unroll
-        for (int e = 0; e < NE; ++e)
-          if (rres[e] >= 0) rv[e] = fma(-colbuf[b0][rres[e]], zbuf[b0][rq[e]] * inv, rv[e]);
-        if (gram_on) gacc = fma(zbuf[b0][gp_] * inv, zbuf[b0][gq_], gacc);
-        // -- the row that enters the window (index j + WD) takes the slots of the retiring index j
-        if (tr == own_warp0 + u / ER) {
-#pragma unroll
-          for (int ec = 0; ec < EC; ++ec) {
-            int t = lane * EC + ec - jr - 1;
-            if (t < 0) t += WD;
-            a[u % ER][ec] = row[WD - 1 - t];
-          }
-        }
-#pragma unroll
-        for (int e = 0; e < NE; ++e)
-          if (rres[e] == jr) rv[e] = row[WD + rq[e]];
-        b0 = b1;
-      }
-    }
-  } else {
   // 1/pivot is taken off the critical path: the owner of the NEXT diagonal element updates it first thing
   // after the barrier, starts its reciprocal and publishes it for the following pivot, so that nobody waits
   // for a division between the barrier and the FMAs.
@@ -558,7 +446,6 @@ band_chol_kernel(BandCholParams p) {
       for (int e = 0; e < NE; ++e)
         if (rres[e] == jr) rv[e] = row[WD + rq[e]];
     }
-  }
   }
   if (tid == 0) logdet = log(mant) + (double)expo * 0.6931471805599453;
 
@@ -766,24 +653,17 @@ cudaError_t launch_band_t(const BandCholParams& p, int B, cudaStream_t st) {
   const size_t smem = sizeof(double) * 2 * band_batch(WD, ER) * (WD + NRP);
   static bool opted_in = false;  // static + dynamic shared memory exceeds 48 KB for the widest window
   if (!opted_in) {
-    const void* fns[] = {(const void*)band_chol_kernel<WD, ER, 8, false>, (const void*)band_chol_kernel<WD, ER, 8, true>,
-                         (const void*)band_chol_kernel<WD, ER, kMaxM + 1, false>,
-                         (const void*)band_chol_kernel<WD, ER, kMaxM + 1, true>};
-    for (const void* fn : fns) {
-      cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-      if (e != cudaSuccess) return e;
-    }
+    cudaError_t e = cudaFuncSetAttribute(band_chol_kernel<WD, ER, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(band_chol_kernel<WD, ER, kMaxM + 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               64 * 1024);
+    if (e != cudaSuccess) return e;
     opted_in = true;
   }
-  static const bool la = getenv("SFB_BAND_LOOKAHEAD") != nullptr;  // A/B switch until verified faster
-  const bool small = p.M + 1 <= 8;
-  if (la) {
-    if (small) band_chol_kernel<WD, ER, 8, true><<<B, WD * 32 / ER, smem, st>>>(p);
-    else band_chol_kernel<WD, ER, kMaxM + 1, true><<<B, WD * 32 / ER, smem, st>>>(p);
-  } else {
-    if (small) band_chol_kernel<WD, ER, 8, false><<<B, WD * 32 / ER, smem, st>>>(p);
-    else band_chol_kernel<WD, ER, kMaxM + 1, false><<<B, WD * 32 / ER, smem, st>>>(p);
-  }
+  if (p.M + 1 <= 8)
+    band_chol_kernel<WD, ER, 8><<<B, WD * 32 / ER, smem, st>>>(p);
+  else
+    band_chol_kernel<WD, ER, kMaxM + 1><<<B, WD * 32 / ER, smem, st>>>(p);
   return cudaGetLastError();
 }
 
