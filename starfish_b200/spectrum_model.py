@@ -13,8 +13,7 @@ What differs is where the work happens.  Everything from the rank-M emulator ter
 comes back to the host when ``model()`` is asked for it.  ``log_likelihood_batch(P)`` is new: it evaluates
 a whole ensemble of parameter vectors in one GPU pass and plugs into ``emcee.EnsembleSampler(...,
 vectorize=True)``.  The spectral transforms and the emulator's GP predictive upstream of the path
-(:287-332) run on the device as well (csrc/upstream.cu); ``upstream="host"`` selects
-the numpy mirrors of ``transforms.py`` instead (an explicit option for cross-checks, never a fallback).
+(:287-332) run on the device as well (csrc/upstream.cu); there is no host path.
 ``solver="structured"`` evaluates the same likelihood through the banded-plus-low-rank structure of the
 covariance (csrc/band.cu) instead of the dense N×N Cholesky.
 """
@@ -25,13 +24,11 @@ from collections import deque
 from typing import Optional, Sequence
 
 import numpy as np
-from scipy.linalg import cho_factor, cho_solve
 from scipy.optimize import minimize
 
 from .constants import JITTER
 from .paramtree import ParamTree
-from .transforms import (_get_renorm_factor, chebyshev_correct, doppler_shift, rescale, resample,
-                         rotational_broaden)
+from .transforms import resample
 from .utils import calculate_dv, create_log_lam_grid
 
 _TRANSFORM_KEYS = ("vz", "vsini", "Av", "Rv", "log_scale", "global_cov", "local_cov", "cheb")
@@ -72,18 +69,15 @@ class SpectrumModel:
 
     def __init__(self, emulator, data, grid_params: Sequence[float], max_deque_len: int = 100, norm=False,
                  name: str = "SpectrumModel", device: int = 0, emulator_term: str = "reference",
-                 upstream: str = "device", solver: str = "dense", **params):
+                 solver: str = "dense", **params):
         if isinstance(emulator, str) or isinstance(data, str):
             raise NotImplementedError("loading from HDF5 paths needs h5py; pass in-memory Emulator/Spectrum")
         if len(data) > 1:
             raise ValueError("Multiple orders detected in data, please use EchelleModel")
         if emulator_term not in ("reference", "paper"):
             raise ValueError("emulator_term must be 'reference' (XᵀΣ_w⁻¹X, as coded) or 'paper' (XᵀΣ_wX)")
-        if upstream not in ("device", "host"):
-            raise ValueError("upstream must be 'device' (CUDA transforms + emulator) or 'host' (numpy mirrors)")
         if solver not in ("dense", "structured"):
             raise ValueError("solver must be 'dense' or 'structured'")
-        self.upstream = upstream
         self.solver = solver
         self.emulator = emulator
         self.data_name = data.name
@@ -257,45 +251,8 @@ class SpectrumModel:
                 self.frozen.remove(name)
 
     # ------------------------------------------------------------------------------------------------
-    # host side of the evaluation: everything upstream of the covariance (spectrum_model.py:287-332)
+    # kernel hyper-parameters (host bookkeeping only)
     # ------------------------------------------------------------------------------------------------
-    def _upstream(self):
-        """-> (flux[N], X[M,N], weights_cov[M,M]) for the current parameters."""
-        wave, fluxes = self.min_dv_wave, self.bulk_fluxes
-        if "vsini" in self.params:
-            fluxes = rotational_broaden(wave, fluxes, self.params["vsini"])
-        if "vz" in self.params:
-            wave = doppler_shift(wave, self.params["vz"])
-        fluxes = resample(wave, fluxes, self.data.wave)
-        if "Av" in self.params:
-            if self.params["Av"] != 0:
-                raise NotImplementedError("extinction needs the `extinction` package, absent from this image")
-        if "cheb" in self.params:
-            fluxes = chebyshev_correct(self.data.wave, fluxes, [1, *self.cheb])
-        weights, weights_cov = self.emulator(self.grid_params)
-        *eigenspectra, flux_mean, flux_std = fluxes
-        X = eigenspectra * flux_std
-        flux = weights @ X + flux_mean
-        norm = self.emulator.norm_factor(self.grid_params) if self.norm else 1
-        if "log_scale" not in self.params:
-            scale = _get_renorm_factor(self.data.wave, flux * norm, self.data.flux)
-            self._log_scale = np.log(scale)
-            scale *= norm
-            self.log.debug(f"fit scale factor using integrated flux ratio: {scale}")
-        else:
-            self._log_scale = self.params["log_scale"]
-            scale = np.exp(self.params["log_scale"]) * norm
-        return rescale(flux, scale), rescale(X, scale), weights_cov
-
-    def _emulator_matrix(self, weights_cov):
-        """The M×M matrix A of the rank-M term XᵀAX: Σ_w⁻¹ as the reference codes it (:334-335), or Σ_w
-        as the paper/docs state it (``emulator_term='paper'``)."""
-        weights_cov = np.array(weights_cov, dtype=np.float64)
-        if self.emulator_term == "paper":
-            return weights_cov
-        fac = cho_factor(weights_cov)
-        return cho_solve(fac, np.eye(weights_cov.shape[0]))
-
     def _kernel_hyper(self):
         """(glob (amp, ls) | None, loc [K,3] | None) honouring the frozen-group cache semantics of
         spectrum_model.py:341-363: a group is re-read from the parameters on every call unless it is
@@ -462,27 +419,21 @@ class SpectrumModel:
     # ------------------------------------------------------------------------------------------------
     def __call__(self):
         """-> (flux[N], cov[N,N]) like the reference; transforms, emulator and covariance all run on the GPU."""
-        if self.upstream == "host":
-            flux, X, weights_cov = self._upstream()
-            A = self._emulator_matrix(weights_cov)[None]
-            X = X[None]
         glob, loc = self._kernel_hyper()
         eng = self._get_engine(1)
         self._sync_static(eng)
-        if self.upstream != "host":
-            B, cols = self._columns()
-            self._check_transforms(cols)
-            gp = self.grid_params
-            if np.any(gp < self.emulator.min_params) or np.any(gp > self.emulator.max_params):
-                raise ValueError("Querying emulator outside of original parameter range.")
-            self._sync_model(eng)
-            up = eng.upstream(self._theta(B, cols), self._n_cheb())
-            if int(up["status"].cpu().numpy()[0]) != 0:
-                raise np.linalg.LinAlgError("emulator weights covariance is not positive definite")
-            X, A = up["X"], up["A"]
-            flux = up["flux"][0].cpu().numpy()
-            self._log_scale = float(up["log_scale"].cpu().numpy()[0])
-        C = eng.build_covariance(X, A, glob=None if glob is None else np.array([glob]),
+        B, cols = self._columns()
+        self._check_transforms(cols)
+        gp = self.grid_params
+        if np.any(gp < self.emulator.min_params) or np.any(gp > self.emulator.max_params):
+            raise ValueError("Querying emulator outside of original parameter range.")
+        self._sync_model(eng)
+        up = eng.upstream(self._theta(B, cols), self._n_cheb())
+        if int(up["status"].cpu().numpy()[0]) != 0:
+            raise np.linalg.LinAlgError("emulator weights covariance is not positive definite")
+        flux = up["flux"][0].cpu().numpy()
+        self._log_scale = float(up["log_scale"].cpu().numpy()[0])
+        C = eng.build_covariance(up["X"], up["A"], glob=None if glob is None else np.array([glob]),
                                  loc=None if loc is None or len(loc) == 0 else loc[None], n_walkers=1)
         return flux, C[0].cpu().numpy()
 
@@ -515,8 +466,6 @@ class SpectrumModel:
                     prior_lp += prior.logpdf(self[key])
         if not np.isfinite(prior_lp):
             return -np.inf
-        if self.upstream == "host":
-            return self._log_likelihood_host_upstream() + prior_lp
         B, cols = self._columns()
         self._check_transforms(cols)
         gp = self.grid_params
@@ -542,24 +491,6 @@ class SpectrumModel:
         self._lnprob = float(lnL[0])
         return self._lnprob + prior_lp
 
-    def _log_likelihood_host_upstream(self):
-        """``upstream='host'``: transforms and emulator through the numpy mirrors, covariance path on the GPU."""
-        flux, X, weights_cov = self._upstream()
-        glob, loc = self._kernel_hyper()
-        self._check_finite(flux, X, weights_cov)
-        eng = self._get_engine(1)
-        self._sync_static(eng)
-        A = self._emulator_matrix(weights_cov)
-        lnL, info, resid = eng.log_likelihood(
-            X[None], A[None], flux[None], glob=None if glob is None else np.array([glob]),
-            loc=None if loc is None or len(loc) == 0 else loc[None], return_residuals=True)
-        code = int(info.cpu().numpy()[0])
-        self.residuals.append(resid[0].cpu().numpy())
-        if code > 0:
-            raise np.linalg.LinAlgError(f"{code}-th leading minor of the array is not positive definite")
-        self._lnprob = float(lnL.cpu().numpy()[0])
-        return self._lnprob
-
     def log_likelihood_batch(self, P, priors: Optional[dict] = None, on_not_pd: str = "-inf",
                              store_residual: bool = False):
         """Log-probability of B parameter vectors (rows of ``P``, columns in ``self.labels`` order) in ONE
@@ -576,8 +507,6 @@ class SpectrumModel:
         P = np.atleast_2d(np.asarray(P, dtype=np.float64))
         if P.shape[1] != len(self.labels):
             raise ValueError("Param Vector does not match length of thawed parameters")
-        if self.upstream == "host":
-            return self._log_likelihood_batch_host_upstream(P, priors, on_not_pd)
         B, cols = self._columns(P)
         out = np.full(B, -np.inf)
         if B == 0:
@@ -618,59 +547,6 @@ class SpectrumModel:
             raise np.linalg.LinAlgError(f"walker {rows[bad]}: covariance not positive definite (info={int(info[bad])})")
         good = info == 0
         out[rows[good]] = lnL[good] + lp[rows][good]
-        return out
-
-    def _log_likelihood_batch_host_upstream(self, P, priors, on_not_pd):
-        """``upstream='host'`` variant of ``log_likelihood_batch``: per-row numpy transforms, one GPU pass."""
-        B = P.shape[0]
-        out = np.full(B, -np.inf)
-        saved = self.get_param_vector()
-        saved_cache = (self._glob_cov, self._loc_cov, self._log_scale)
-        rows, fluxes, Xs, As, globs, locs, plp = [], [], [], [], [], [], []
-        try:
-            for b in range(B):
-                self.set_param_vector(P[b])
-                lp = 0.0
-                if priors is not None:
-                    for key, prior in priors.items():
-                        if key in self.params:
-                            lp += prior.logpdf(self[key])
-                if not np.isfinite(lp):
-                    continue
-                gp = self.grid_params
-                if np.any(gp < self.emulator.min_params) or np.any(gp > self.emulator.max_params):
-                    continue
-                flux, X, wcov = self._upstream()
-                glob, loc = self._kernel_hyper()
-                if not (np.all(np.isfinite(flux)) and np.all(np.isfinite(X)) and np.all(np.isfinite(wcov))):
-                    continue
-                rows.append(b); plp.append(lp); fluxes.append(flux); Xs.append(X)
-                As.append(self._emulator_matrix(wcov))
-                globs.append((0.0, 1.0) if glob is None else glob)
-                locs.append(np.zeros((0, 3)) if loc is None else loc)
-        finally:
-            self.set_param_vector(saved)
-            self._glob_cov, self._loc_cov, self._log_scale = saved_cache
-        if not rows:
-            return out
-        nb = len(rows)
-        kmax = max(1, max(len(l) for l in locs))
-        loc_arr = np.zeros((nb, kmax, 3))
-        nloc = np.zeros(nb, dtype=np.int32)
-        for i, l in enumerate(locs):
-            loc_arr[i, :len(l)] = l
-            nloc[i] = len(l)
-        eng = self._get_engine(nb, n_local=kmax)
-        self._sync_static(eng)
-        lnL, info = eng.log_likelihood(np.array(Xs), np.array(As), np.array(fluxes),
-                                       glob=np.array(globs), nloc=nloc, loc=loc_arr)
-        lnL, info = lnL.cpu().numpy(), info.cpu().numpy()
-        if on_not_pd == "raise" and (info > 0).any():
-            bad = int(np.flatnonzero(info > 0)[0])
-            raise np.linalg.LinAlgError(f"walker {rows[bad]}: {int(info[bad])}-th leading minor of the array "
-                                        "is not positive definite")
-        good = info == 0
-        out[np.array(rows)[good]] = lnL[good] + np.array(plp)[good]
         return out
 
     # ------------------------------------------------------------------------------------------------
@@ -745,7 +621,6 @@ class SpectrumModel:
             else:
                 lines.append(f"  {key}: {value}")
         if "log_scale" not in self.params:
-            self._upstream()
             lines.append(f"  log_scale: {self._log_scale} (fit)")
         shown = [k for k in self.frozen if k not in ("global_cov", "local_cov")]
         if self.frozen:

@@ -129,10 +129,6 @@ def test_batch_parameters_in_loglike_out(golden_dir):
     m.set_param_vector(P[3])
     assert m.log_likelihood() == out[3]
     m.set_param_vector(P0)
-    # the numpy-mirror upstream gives the same numbers to the whole-model tolerance
-    mh = make_model(256, 0, wave=g["wave"], mus=(5098.0, 5103.0), vz=12.0, upstream="host")
-    outh = mh.log_likelihood_batch(P)
-    assert np.abs(out - outh).max() <= 1e-8 * np.abs(outh).max()
 
 
 def test_batch_masks_priors_and_errors(golden_dir):

@@ -145,12 +145,23 @@ def test_train_validates_priors(model):
 
 
 @pytest.mark.parametrize("walker", [0, 1])
-def test_upstream_reproduces_reference_stage_inputs(golden_dir, walker):
+def test_transform_mirrors_reproduce_reference_stage_inputs(golden_dir, walker):
+    """The public numpy mirrors of Starfish/transforms.py + Emulator.__call__, chained as spectrum_model.py:287-332
+    chains them, reproduce the stage inputs recorded inside the reference (the model itself runs these stages on
+    the device; this pins the host-side API functions)."""
+    from starfish_b200 import transforms as T
+
     g = dict(np.load(os.path.join(golden_dir, f"model_n256_w{walker}.npz")))
     m = make_model(256, walker, wave=g["wave"], mus=(5098.0, 5103.0))
     assert tuple(g["labels"]) == m.labels
     assert np.array_equal(g["param_vector"], m.get_param_vector())
-    flux, X, wcov = m._upstream()
+    fluxes = T.rotational_broaden(m.min_dv_wave, m.bulk_fluxes, m["vsini"])
+    fluxes = T.resample(T.doppler_shift(m.min_dv_wave, m["vz"]), fluxes, m.data.wave)
+    fluxes = T.chebyshev_correct(m.data.wave, fluxes, [1, *m.cheb])
+    weights, wcov = m.emulator(m.grid_params)
+    *eig, mean, std = fluxes
+    X = T.rescale(eig * std, np.exp(m["log_scale"]))
+    flux = T.rescale(weights @ (eig * std) + mean, np.exp(m["log_scale"]))
     assert np.abs(flux - g["model_flux"]).max() <= 1e-13
     assert np.abs(X - g["X"]).max() <= 1e-15
     # Σ_w = v22 − v21·v11⁻¹·v12 cancels 1e4 down to O(1): its fp64 noise floor is ~1e-11 relative and
