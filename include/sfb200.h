@@ -175,6 +175,9 @@ int sfb_spline_halfwidth(void);
  * take the dense path inside the same call, so results never depend on the choice beyond rounding
  * (|ΔlnL| <= 1e-10·|lnL|, tests/test_gpu_structured.py).  The default is SFB_SOLVER_DENSE.
  * In structured mode the call synchronises with the host once (B ints: each walker's half-bandwidth).
+ * info[b] in structured mode: 0 = ok; i in [1, N] = pivot i of the banded factor of S is not positive (S itself is
+ * not positive definite — the dense path reports the same leading minor); N = S is fine but S + XᵀAX is not
+ * positive definite (the dense path reports whichever leading minor fails first — both mean LinAlgError upstream).
  */
 enum sfb_solver { SFB_SOLVER_DENSE = 0, SFB_SOLVER_STRUCTURED = 1 };
 int sfb_set_solver(sfb_t* h, int solver);
