@@ -72,38 +72,49 @@ struct ColBuf {  // one stage of the column double buffer
 
 // MT = register/unroll width of the rank-M term; for MT <= 8 the kernel is instantiated with MT == M exactly
 // (no predication in the hot loop), wider models use MT = 12 or 16 with the tail predicated.
+//
+// Thread layout inside a 128×128 tile: a warp owns 64 consecutive columns (2 per lane, one 16-byte store per
+// lane = 512 contiguous bytes per warp store) and every fourth row, so a thread carries only 2·M column
+// factors in registers.  That keeps the kernel at <= 64 registers and 4 CTAs (32 warps) per SM: the
+// transcendental-heavy tiles on the band (two per tile row, but two thirds of the instructions) of one CTA
+// then overlap the store streams of the other three.  One __syncthreads per tile: Y = A·X of the columns and
+// the local-kernel column metrics are double-buffered like the column slices themselves.
 template <int MT>
-__global__ void __launch_bounds__(NTHREADS) cov_build_kernel(BuildParams p) {
+__global__ void __launch_bounds__(NTHREADS, (MT <= 8 ? 4 : 2)) cov_build_kernel(BuildParams p) {
+  constexpr int MA = (MT > 0) ? MT : 1;            // array extent
+  constexpr int MP = (MT > 0) ? ((MT + 1) & ~1) : 2;  // row stride of Xr: even, so rows are 16-byte aligned
   const int nt = (p.padN + BT - 1) / BT;
   const int ti = nt - 1 - (int)blockIdx.x;  // longest rows first (lower-only mode: row ti has ti+1 tiles)
   const int b = blockIdx.y;
   const int i0 = ti * BT;
   const int ntj = p.lower_only ? ti + 1 : nt;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int half = warp & 1, rph = warp >> 1;  // column half of the tile, row phase (rows rph, rph+4, ...)
+  const int c0 = 64 * half + 2 * lane;         // this thread's columns c0, c0+1
   const int N = p.N;
   const int M = (MT <= 8) ? MT : p.M;  // compile-time constant on the common path
+  const int Kmax = p.Kmax;
 
   extern __shared__ __align__(16) uint8_t smem_raw[];
   ColBuf<MT>* cbuf = reinterpret_cast<ColBuf<MT>*>(smem_raw);          // [2]
   double* wr = reinterpret_cast<double*>(cbuf + 2);                      // [BT] row wavelengths
   double* s2 = wr + BT;                                                  // [BT] σ² of rows
-  double* Xr = s2 + BT;                                                  // [MT][BT] X rows
-  double* Yc = Xr + MT * BT;                                             // [MT][BT] Y = A·X of the current columns
-  double* Am = Yc + MT * BT;                                             // [MT*MT]
-  double* rowm = Am + MT * MT;                                           // [Kmax][BT] local metric of rows
-  double* colm = rowm + p.Kmax * BT;                                     // [Kmax][BT] ... of current columns
+  double* Xr = s2 + BT;                                                  // [BT][MP] X of the rows, row-major
+  double* Yc = Xr + BT * MP;                                             // [2][MA][BT] Y = A·X of the columns
+  double* Am = Yc + 2 * MA * BT;                                         // [MA*MA]
+  double* rowm = Am + MA * MA;                                           // [Kmax][BT] local metric of rows
+  double* colm = rowm + Kmax * BT;                                       // [2][Kmax][BT] ... of the columns
   __shared__ __align__(8) unsigned long long bars[2];
   __shared__ LocalK lk[kMaxK];
   __shared__ int lk_row_any[kMaxK];
-  __shared__ int lk_active[kMaxK];
 
   const int hb = b * p.hyper_stride;
   const double g_amp = p.glob ? p.glob[2 * hb] : 0.0;
   const double g_ls = p.glob ? p.glob[2 * hb + 1] : 1.0;
-  const int nloc = p.nloc ? min(p.nloc[hb], p.Kmax) : 0;
+  const int nloc = p.nloc ? min(p.nloc[hb], Kmax) : 0;
   const double* Xb = (MT > 0) ? p.X + (long long)b * M * N : nullptr;
   // bulk copies need 16-byte aligned sources: every row offset (m·N + j0)·8 is, iff N is even and the
-  // base pointers are 16-byte aligned (checked on the host and passed in p.vec2-like flag bulk_ok)
+  // base pointers are 16-byte aligned (checked on the host and passed in p.bulk_ok)
   const bool bulk_ok = p.bulk_ok != 0;
   const uint32_t bar0 = smem_u32(&bars[0]);
 
@@ -145,14 +156,14 @@ __global__ void __launch_bounds__(NTHREADS) cov_build_kernel(BuildParams p) {
     s2[t] = s * s;
   }
   if (MT > 0) {
-    for (int t = tid; t < M * BT; t += NTHREADS) {
-      const int m = t / BT, r = t % BT;
-      Xr[m * BT + r] = (i0 + r < N) ? Xb[(long long)m * N + i0 + r] : 0.0;
+    for (int t = tid; t < MP * BT; t += NTHREADS) {
+      const int m = t / BT, r = t % BT;  // coalesced reads along the row of X, transposed into [r][m]
+      Xr[r * MP + m] = (m < M && i0 + r < N) ? Xb[(long long)m * N + i0 + r] : 0.0;
     }
     for (int t = tid; t < M * M; t += NTHREADS) Am[t] = p.A[(long long)b * M * M + t];
   }
   if (tid < nloc) {
-    const double* l = p.loc + ((long long)hb * p.Kmax + tid) * 3;
+    const double* l = p.loc + ((long long)hb * Kmax + tid) * 3;
     lk[tid].amp = l[0];
     lk[tid].mu = l[1];
     lk[tid].sigma = l[2];
@@ -176,10 +187,9 @@ __global__ void __launch_bounds__(NTHREADS) cov_build_kernel(BuildParams p) {
   const double r0g = 6 * g_ls;
   const double sqrt3 = sqrt(3.0);
   const bool sorted = (*p.sorted != 0);
-  const int cA = 2 * lane, cB = 64 + 2 * lane;  // this thread's column pairs (cA, cA+1) and (cB, cB+1)
-  auto col_of = [&](int q) { return (q < 2 ? cA : cB) + (q & 1); };
   double* Cb = p.C + (long long)b * p.strideC;
   const int padN = p.padN;
+  const int nrow = min(BT, N - i0);  // rows of this tile row inside the N×N block (may be <= 0)
 
   // ---- sweep over the column tiles ---------------------------------------------------------------
   for (int tj = 0; tj < ntj; ++tj) {
@@ -187,14 +197,15 @@ __global__ void __launch_bounds__(NTHREADS) cov_build_kernel(BuildParams p) {
     const int j0 = tj * BT;
     const int ncol = min(BT, N - j0);
     ColBuf<MT>& cb = cbuf[st];
-    if (tj + 1 < ntj) prefetch(tj + 1, st ^ 1);  // stage st^1 was released by the barrier ending tile tj-1
+    double* Ycs = Yc + st * MA * BT;
+    double* colms = colm + st * Kmax * BT;
     if (ncol > 0 && bulk_ok) mbar_wait(bar0 + 8 * st, (tj >> 1) & 1);
-    if (!bulk_ok) __syncthreads();               // plain-load fallback: make the stage visible
+    if (!bulk_ok) __syncthreads();  // plain-load fallback: make the stage visible
 
     // Y = A·Xc for this tile's columns, local-kernel column metrics
     if (MT > 0) {
       for (int c = tid; c < BT; c += NTHREADS) {
-        double xc[MT > 0 ? MT : 1];
+        double xc[MA];
 #pragma unroll
         for (int m = 0; m < MT; ++m) xc[m] = (m < M && c < ncol) ? cb.Xc[m * BT + c] : 0.0;
 #pragma unroll
@@ -203,163 +214,161 @@ __global__ void __launch_bounds__(NTHREADS) cov_build_kernel(BuildParams p) {
 #pragma unroll
           for (int q = 0; q < MT; ++q)
             if (m < M && q < M) acc = fma(Am[m * M + q], xc[q], acc);
-          if (m < M) Yc[m * BT + c] = acc;
+          if (m < M) Ycs[m * BT + c] = acc;
         }
       }
     }
-    int n_active = 0;
+    unsigned active = 0;  // bit k: local kernel k intersects this tile (uniform across the CTA)
     for (int k = 0; k < nloc; ++k) {
-      int any_c = 0;
       if (lk_row_any[k]) {  // uniform
+        int any_c = 0;
         const double mu = lk[k].mu, r0 = 4 * lk[k].sigma, f = kC_KMS / mu;
         for (int t = tid; t < BT; t += NTHREADS) {
           const double mc = (t < ncol) ? f * fabs(cb.wc[t] - mu) : 0.0;
           const bool in_c = (t < ncol) && (mc <= r0);
-          colm[k * BT + t] = in_c ? mc : -1.0;
+          colms[k * BT + t] = in_c ? mc : -1.0;
           any_c |= in_c;
         }
-        any_c = __syncthreads_or(any_c);
+        if (__syncthreads_or(any_c)) active |= 1u << k;
       }
-      if (tid == 0) lk_active[k] = any_c;
-      n_active += any_c;  // uniform: __syncthreads_or returns the same value to every thread
     }
-    __syncthreads();  // Yc, colm, lk_active visible
+    // Ycs / colms of this tile visible; every thread has left the row loop of tile tj-1, so the other stage of
+    // the column buffer is free: the next tile's slices are fetched while this one is computed and stored
+    __syncthreads();
+    if (tj + 1 < ntj) prefetch(tj + 1, st ^ 1);
 
     // does the tile intersect the Matérn band?
     bool band = g_amp > 0.0;
-    if (band && sorted && i0 != j0) {
+    if (band && sorted && i0 != j0 && nrow > 0 && ncol > 0) {
       // sorted ascending: the closest pair is (last row, first col) for tiles right of the diagonal and
-      // (first row, last col) for tiles below it
-      int ilo, jhi;
-      if (j0 > i0) { ilo = min(i0 + BT, N) - 1; jhi = j0; } else { ilo = i0; jhi = min(j0 + BT, N) - 1; }
-      if (ilo < N && jhi < N && ilo >= 0 && jhi >= 0) {
-        const double a = p.wave[ilo], c = p.wave[jhi];
-        band = (kC_KMS / 2 * fabs((c - a) / (c + a))) <= r0g;
-      }
+      // (first row, last col) for tiles below it — both already staged in shared memory
+      const double a = (j0 > i0) ? wr[nrow - 1] : wr[0];
+      const double c = (j0 > i0) ? cb.wc[0] : cb.wc[ncol - 1];
+      band = (kC_KMS / 2 * fabs((c - a) / (c + a))) <= r0g;
     }
     const bool diag_tile = (i0 == j0);
     const bool interior = p.vec2 && (i0 + BT <= N) && (j0 + BT <= N);
 
-    double wj[4];
-    double yj[MT > 0 ? MT : 1][4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      wj[q] = (col_of(q) < ncol) ? cb.wc[col_of(q)] : 0.0;
-#pragma unroll
-      for (int m = 0; m < MT; ++m) yj[m][q] = (m < M) ? Yc[m * BT + col_of(q)] : 0.0;
-    }
-
     // Fast path — the overwhelming majority of tiles: fully inside the N×N block, away from the diagonal,
-    // outside the Matérn band and every local block.  Only the rank-M term is left: M shared loads, 4·M
-    // DFMA and two 16-byte stores per row, with the row pointer carried as an induction variable.
-    const bool fast = interior && !band && !n_active && !diag_tile;
+    // outside the Matérn band and every local block.  Only the rank-M term is left: M/2 broadcast 16-byte
+    // shared loads, 2·M DFMA and one 16-byte store per row, with the row pointer carried as an induction variable.
+    const bool fast = interior && !band && !active && !diag_tile;
     if (fast) {
-      double* rowp = Cb + (long long)(i0 + warp) * p.ldc + j0;
-      const long long step = 8 * p.ldc;
+      double y0[MA], y1[MA];
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        const double2 y = *reinterpret_cast<const double2*>(Ycs + m * BT + c0);
+        y0[m] = (m < M) ? y.x : 0.0;
+        y1[m] = (m < M) ? y.y : 0.0;
+      }
+      double* rowp = Cb + (long long)(i0 + rph) * p.ldc + j0 + c0;
+      const long long step = 4 * p.ldc;
+      const double* xr = Xr + rph * MP;
 #pragma unroll 4
-      for (int rr = 0; rr < BT / 8; ++rr) {
-        const int r = warp + 8 * rr;
-        double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+      for (int rr = 0; rr < BT / 4; ++rr) {
+        double v0 = 0.0, v1 = 0.0;
 #pragma unroll
-        for (int m = 0; m < MT; ++m) {
-          if (m < M) {
-            const double x = Xr[m * BT + r];
-            v0 = fma(x, yj[m][0], v0);
-            v1 = fma(x, yj[m][1], v1);
-            v2 = fma(x, yj[m][2], v2);
-            v3 = fma(x, yj[m][3], v3);
-          }
-        }
-        *reinterpret_cast<double2*>(rowp + cA) = make_double2(v0, v1);
-        *reinterpret_cast<double2*>(rowp + cB) = make_double2(v2, v3);
-        rowp += step;
-      }
-    } else
-#pragma unroll 2
-    for (int rr = 0; rr < BT / 8; ++rr) {
-      const int r = warp + 8 * rr;
-      const int i = i0 + r;
-      if (i >= padN) break;
-      const double wi = wr[r];
-      double v[4] = {0.0, 0.0, 0.0, 0.0};
-      if (MT > 0) {
-#pragma unroll
-        for (int m = 0; m < MT; ++m) {
-          if (m < M) {
-            const double x = Xr[m * BT + r];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) v[q] = fma(x, yj[m][q], v[q]);
-          }
-        }
-      }
-      if (diag_tile) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          if (col_of(q) == r) v[q] += s2[r];
-      }
-      if (band) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const double rv = kC_KMS / 2 * fabs((wj[q] - wi) / (wj[q] + wi));
-          if (rv <= r0g) {
-            const double taper = 0.5 + 0.5 * cos(kPi * rv / r0g);
-            v[q] += taper * g_amp * (1 + sqrt3 * rv / g_ls) * exp(-sqrt3 * rv / g_ls);
-          }
-        }
-      }
-      if (n_active) {
-        double lsum[4] = {0.0, 0.0, 0.0, 0.0};
-        for (int k = 0; k < nloc; ++k) {
-          if (!lk_active[k]) continue;
-          const double mi = rowm[k * BT + r];
-          if (mi < 0.0) continue;
-          const double r0 = 4 * lk[k].sigma, sg2 = lk[k].sigma * lk[k].sigma, amp = lk[k].amp;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const double mj = colm[k * BT + col_of(q)];
-            if (mj >= 0.0) {
-              const double rt = fmax(mi, mj);
-              const double taper = 0.5 + 0.5 * cos(kPi * rt / r0);
-              lsum[q] += taper * amp * exp(-0.5 * (mi * mi + mj * mj) / sg2);
+        for (int m2 = 0; m2 < MP / 2; ++m2) {
+          if (MT > 0 && 2 * m2 < M) {
+            const double2 x = *reinterpret_cast<const double2*>(xr + 2 * m2);
+            v0 = fma(x.x, y0[2 * m2], v0);
+            v1 = fma(x.x, y1[2 * m2], v1);
+            if (2 * m2 + 1 < MT && 2 * m2 + 1 < M) {
+              v0 = fma(x.y, y0[2 * m2 + 1], v0);
+              v1 = fma(x.y, y1[2 * m2 + 1], v1);
             }
           }
         }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) v[q] += lsum[q];
+        *reinterpret_cast<double2*>(rowp) = make_double2(v0, v1);
+        rowp += step;
+        xr += 4 * MP;
       }
-      if (diag_tile) {
+    } else {
+      const double wj0 = (c0 < ncol) ? cb.wc[c0] : 0.0;
+      const double wj1 = (c0 + 1 < ncol) ? cb.wc[c0 + 1] : 0.0;
+#pragma unroll 1
+      for (int rr = 0; rr < BT / 4; ++rr) {
+        const int r = rph + 4 * rr;
+        const int i = i0 + r;
+        if (i >= padN) break;
+        const double wi = wr[r];
+        double v[2] = {0.0, 0.0};
+        if (MT > 0) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          if (col_of(q) == r) v[q] += p.jitter;
-      }
-      if (i >= N) {  // identity padding of the factorisation workspace
+          for (int m = 0; m < MT; ++m) {
+            if (m < M) {
+              const double x = Xr[r * MP + m];
+              const double2 y = *reinterpret_cast<const double2*>(Ycs + m * BT + c0);
+              v[0] = fma(x, y.x, v[0]);
+              v[1] = fma(x, y.y, v[1]);
+            }
+          }
+        }
+        if (diag_tile) {
+          if (c0 == r) v[0] += s2[r];
+          if (c0 + 1 == r) v[1] += s2[r];
+        }
+        // Lower-only workspace: nothing reads the strict upper triangle of a diagonal tile (potrf_diag_kernel
+        // loads c <= r only), so a warp whose 64 columns all lie right of row r skips the kernel functions
+        const bool kernels_on = !(p.lower_only && diag_tile && 64 * half > r);  // warp-uniform
+        if (band && kernels_on) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) v[q] = (j0 + col_of(q) == i) ? 1.0 : 0.0;
-      }
-      double* row = Cb + (long long)i * p.ldc + j0;
-      if (interior) {  // whole tile inside the N×N block and 16-byte aligned rows: two unconditional 16 B stores
-        *reinterpret_cast<double2*>(row + cA) = make_double2(v[0], v[1]);
-        *reinterpret_cast<double2*>(row + cB) = make_double2(v[2], v[3]);
-      } else {
+          for (int q = 0; q < 2; ++q) {
+            const double wj = q ? wj1 : wj0;
+            const double rv = kC_KMS / 2 * fabs((wj - wi) / (wj + wi));
+            if (rv <= r0g) {
+              const double taper = 0.5 + 0.5 * cos(kPi * rv / r0g);
+              v[q] += taper * g_amp * (1 + sqrt3 * rv / g_ls) * exp(-sqrt3 * rv / g_ls);
+            }
+          }
+        }
+        if (active && kernels_on) {
+          double lsum[2] = {0.0, 0.0};
+          for (int k = 0; k < nloc; ++k) {
+            if (!((active >> k) & 1u)) continue;
+            const double mi = rowm[k * BT + r];
+            if (mi < 0.0) continue;
+            const double r0 = 4 * lk[k].sigma, sg2 = lk[k].sigma * lk[k].sigma, amp = lk[k].amp;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int c = h ? cB : cA;
-          const int j = j0 + c;
-          double a = v[2 * h], c1 = v[2 * h + 1];
+            for (int q = 0; q < 2; ++q) {
+              const double mj = colms[k * BT + c0 + q];
+              if (mj >= 0.0) {
+                const double rt = fmax(mi, mj);
+                const double taper = 0.5 + 0.5 * cos(kPi * rt / r0);
+                lsum[q] += taper * amp * exp(-0.5 * (mi * mi + mj * mj) / sg2);
+              }
+            }
+          }
+          v[0] += lsum[0];
+          v[1] += lsum[1];
+        }
+        if (diag_tile) {
+          if (c0 == r) v[0] += p.jitter;
+          if (c0 + 1 == r) v[1] += p.jitter;
+        }
+        if (i >= N) {  // identity padding of the factorisation workspace
+          v[0] = (j0 + c0 == i) ? 1.0 : 0.0;
+          v[1] = (j0 + c0 + 1 == i) ? 1.0 : 0.0;
+        }
+        double* row = Cb + (long long)i * p.ldc + j0;
+        if (interior) {  // whole tile inside the N×N block and 16-byte aligned rows: one unconditional 16 B store
+          *reinterpret_cast<double2*>(row + c0) = make_double2(v[0], v[1]);
+        } else {
+          const int j = j0 + c0;
+          double a = v[0], c1 = v[1];
           if (i < N) {  // columns beyond N inside a padded workspace are zero
             if (j >= N) a = 0.0;
             if (j + 1 >= N) c1 = 0.0;
           }
           if (j + 1 < padN && p.vec2) {
-            *reinterpret_cast<double2*>(row + c) = make_double2(a, c1);
+            *reinterpret_cast<double2*>(row + c0) = make_double2(a, c1);
           } else {
-            if (j < padN) row[c] = a;
-            if (j + 1 < padN) row[c + 1] = c1;
+            if (j < padN) row[c0] = a;
+            if (j + 1 < padN) row[c0 + 1] = c1;
           }
         }
       }
     }
-    __syncthreads();  // everyone is done with stage st, Yc and colm before they are overwritten
   }
 }
 
@@ -374,10 +383,15 @@ __global__ void set_flag_kernel(int* flag, int v) { *flag = v; }
 
 template <int MT>
 cudaError_t launch_build_t(const BuildParams& p, int B, cudaStream_t st) {
+  constexpr int MA = (MT > 0) ? MT : 1, MP = (MT > 0) ? ((MT + 1) & ~1) : 2;
   const size_t smem = 2 * sizeof(ColBuf<MT>) +
-                      sizeof(double) * (2 * BT + 2 * MT * BT + MT * MT + 2 * (size_t)p.Kmax * BT);
+                      sizeof(double) * (2 * BT + MP * BT + 2 * MA * BT + MA * MA + 3 * (size_t)p.Kmax * BT);
   cudaError_t e =
       cudaFuncSetAttribute(cov_build_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e != cudaSuccess) return e;
+  // 4 CTAs of ~40 KB per SM: ask for the shared-memory-heavy L1 split (the kernel's global traffic is stores)
+  e = cudaFuncSetAttribute(cov_build_kernel<MT>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                           cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return e;
   const int nt = (p.padN + BT - 1) / BT;
   dim3 grid(nt, B);
