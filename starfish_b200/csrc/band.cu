@@ -40,7 +40,7 @@ constexpr int BB_ROWS = 8;  // rows per CTA (one per warp)
 
 __global__ void __launch_bounds__(BB_ROWS * 32)
 band_build_kernel(BandBuildParams p) {
-  __shared__ double l_amp[kMaxK], l_mu[kMaxK], l_sig[kMaxK], l_ir0[kMaxK], l_mh[kMaxK];
+  __shared__ double l_amp[kMaxK], l_mu[kMaxK], l_sig[kMaxK], l_ir0[kMaxK], l_mh[kMaxK], l_f[kMaxK];
   const int b = p.rowmap ? p.rowmap[blockIdx.y] : blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int hb = b * p.hyper_stride;
@@ -53,6 +53,7 @@ band_build_kernel(BandBuildParams p) {
     l_sig[threadIdx.x] = l[2];
     l_ir0[threadIdx.x] = 1.0 / (4 * l[2]);     // 1/r0
     l_mh[threadIdx.x] = -0.5 / (l[2] * l[2]);   // −1/(2σ²)
+    l_f[threadIdx.x] = kC_KMS / l[1];            // c/μ, the factor of the metric m = (c/μ)|λ − μ|
   }
   __syncthreads();
   const int i = blockIdx.x * BB_ROWS + warp;
@@ -66,6 +67,11 @@ band_build_kernel(BandBuildParams p) {
   // half the instruction count (this kernel is issue-bound on fp64 division / cos / exp sequences).
   const double inv_r0g = 1.0 / r0g, s3_ls = sqrt3 / g_ls;
   double* out = p.Sb + (long long)b * p.strideSb + (long long)i * WD;
+  // local kernels whose block contains THIS row (m_i <= 4σ): almost always none, so the per-element loop over
+  // the kernels (a metric and two compares each) runs only for the few rows inside a local block
+  unsigned rowmask = 0;
+  for (int q = 0; q < nloc; ++q)
+    if (l_f[q] * fabs(wi - l_mu[q]) <= 4 * l_sig[q]) rowmask |= 1u << q;
   int over = 0;
   for (int d = lane; d <= WD; d += 32) {  // d == WD is only the "does the band fit" probe
     const int k = i - d;
@@ -88,8 +94,9 @@ band_build_kernel(BandBuildParams p) {
       }
       double lsum = 0.0;
       bool any = false;
-      for (int q = 0; q < nloc; ++q) {
-        const double mu = l_mu[q], r0 = 4 * l_sig[q], f = kC_KMS / mu;
+      for (unsigned rem = rowmask; rem; rem &= rem - 1) {
+        const int q = __ffs(rem) - 1;
+        const double mu = l_mu[q], r0 = 4 * l_sig[q], f = l_f[q];
         const double mi = f * fabs(wi - mu), mj = f * fabs(wk - mu);
         if (mi <= r0 && mj <= r0) {
           const double rt = fmax(mi, mj);
@@ -633,37 +640,35 @@ template <int T>
 cudaError_t launch_band_sym_t(const BandCholParams& p, int B, cudaStream_t st) {
   constexpr int WD = 32 * T, BATCH = ((16 + T - 1) / T) * T;
   const size_t smem = sizeof(double) * 2 * BATCH * (WD + NRP);
-  static bool opted_in = false;
-  if (!opted_in) {
+  // the opt-in is a per-device function attribute: set it on every launch (a handle may live on any device)
+  if (p.M + 1 <= 8) {
     cudaError_t e = cudaFuncSetAttribute(band_sym_kernel<T, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(band_sym_kernel<T, kMaxM + 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     if (e != cudaSuccess) return e;
-    opted_in = true;
-  }
-  if (p.M + 1 <= 8)
     band_sym_kernel<T, 8><<<B, 17 * 32, smem, st>>>(p);
-  else
+  } else {
+    cudaError_t e =
+        cudaFuncSetAttribute(band_sym_kernel<T, kMaxM + 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    if (e != cudaSuccess) return e;
     band_sym_kernel<T, kMaxM + 1><<<B, 17 * 32, smem, st>>>(p);
+  }
   return cudaGetLastError();
 }
 
 template <int WD, int ER>
 cudaError_t launch_band_t(const BandCholParams& p, int B, cudaStream_t st) {
   const size_t smem = sizeof(double) * 2 * band_batch(WD, ER) * (WD + NRP);
-  static bool opted_in = false;  // static + dynamic shared memory exceeds 48 KB for the widest window
-  if (!opted_in) {
+  // static + dynamic shared memory exceeds 48 KB for the widest window; the opt-in is a per-device function
+  // attribute, so it is set on every launch (a handle may live on any device)
+  if (p.M + 1 <= 8) {
     cudaError_t e = cudaFuncSetAttribute(band_chol_kernel<WD, ER, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(band_chol_kernel<WD, ER, kMaxM + 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               64 * 1024);
     if (e != cudaSuccess) return e;
-    opted_in = true;
-  }
-  if (p.M + 1 <= 8)
     band_chol_kernel<WD, ER, 8><<<B, WD * 32 / ER, smem, st>>>(p);
-  else
+  } else {
+    cudaError_t e = cudaFuncSetAttribute(band_chol_kernel<WD, ER, kMaxM + 1>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (e != cudaSuccess) return e;
     band_chol_kernel<WD, ER, kMaxM + 1><<<B, WD * 32 / ER, smem, st>>>(p);
+  }
   return cudaGetLastError();
 }
 
