@@ -174,6 +174,10 @@ __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_s
   const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gmem_src) {
+  const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
@@ -463,6 +467,336 @@ band_chol_kernel(BandCholParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Rank-4 window update on the fp64 tensor path (mma.sync m8n8k4, SASS DMMA).  Same circular band window in
+// registers as band_chol_kernel, but laid out as DMMA accumulator fragments — 16 warps as a 4×4 grid, a warp
+// owns (WD/4)×(WD/4) slots as TW×TW tiles of 8×8, lane (g = lane/4, t = lane%4) holds C[g][2t], C[g][2t+1] of
+// every tile — and FOUR pivots are eliminated per step:
+//   1. the owners publish the raw columns of the four pivots (Praw[row][0..3]) and the four pivot rows of the
+//      right-hand sides;                                                                      __syncthreads
+//   2. panel: every thread below WD + NR factors the 4×4 diagonal block (LDLᵀ, redundantly — no communication),
+//      thread x then solves its row, W[x][t] = P[x][t] − Σ_{k<t} W[x][k]·L[j+t][k], L = W/d, and the threads
+//      WD.. do the same for the right-hand-side columns; −W, L, z go to shared memory            __syncthreads
+//   3. every warp loads 2·TW fragment values per lane and issues TW² DMMAs: C[r][c] −= Σ_t W[r][t]·L[c][t];
+//      the right-hand sides and the Gram matrix take their four rank-1 terms with DFMA;
+//   4. the four rows j+WD … j+WD+3 enter together; a row that reaches pivots of the block just eliminated (only
+//      when b > WD − 4) receives their updates as it enters, so b <= WD − 1 suffices like for the rank-1 kernel.
+// Per pivot this moves 2·TW/4 doubles per thread through shared memory instead of 12 and needs half a barrier
+// instead of one; the arithmetic order of every slot equals the rank-1 kernel's, so results agree to rounding.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void band_dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+__host__ __device__ constexpr int band_gcd(int x, int y) { return y == 0 ? x : band_gcd(y, x % y); }
+
+// WRG × WCG = warp grid over the window (rows × columns); a warp owns TR × TC tiles of 8×8.  The 160-pixel
+// window (200 KB) leaves a 512-thread CTA no registers to work with, so it runs as 4×2 warps of 5×10 tiles
+// (200 accumulator registers per thread, 256 threads); the narrower ones as 4×4 warps.
+// 1/x for a positive normal x: MUFU.RCP64H seed (>= 20 bits) and two Newton steps — within 1 ulp, no special-case
+// branches; four of these are chained in every panel, so their latency is on the critical path
+__device__ __forceinline__ double band_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+
+template <int WD, int WRG, int WCG, int MAXNR>
+__global__ void __launch_bounds__(32 * WRG * WCG, 1)
+band_mma_kernel(BandCholParams p) {
+  constexpr int NT = 32 * WRG * WCG, TR = WD / 8 / WRG, TC = WD / 8 / WCG, ROWLEN = WD + NRP, BATCH = 16;
+  constexpr int TL = TR * TC / band_gcd(TR, TC);  // tiles per unrolled sweep: lcm(TR, TC)
+  constexpr int NE = (WD * MAXNR + NT - 1) / NT;  // right-hand-side registers per thread
+  static_assert(TR <= TC && WD % (8 * WRG) == 0 && WD % (8 * WCG) == 0 && (WD / 8) % TL == 0 && WD + MAXNR <= NT &&
+                    MAXNR * MAXNR <= NT && BATCH % (NT / 32) == 0,
+                "warp grid must tile the window; panel rows, Gram elements and ring rows need enough threads");
+  __shared__ __align__(16) double Praw[WD * 4];  // raw columns of the four pivots, [row residue][pivot]
+  __shared__ __align__(16) double Wn[WD * 4];    // −W (unscaled panel): the DMMA A operand
+  __shared__ __align__(16) double Lp[WD * 4];    // L = W/d: the DMMA B operand
+  __shared__ double zraw[4][NRP], zW[4][NRP], zL[4][NRP];
+  __shared__ double facL[4];  // L21, L31, L32 of the current block (late-row correction)
+  __shared__ double gram[(kMaxM + 1) * (kMaxM + 1)];
+  extern __shared__ __align__(16) double ring[];  // [2][BATCH][ROWLEN]
+
+  const int b = p.rowmap ? p.rowmap[blockIdx.x] : blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wr = warp / WCG, wc = warp % WCG, g = lane >> 2, t = lane & 3;
+  const int N = p.N, M = p.M, NR = M + 1;
+  if (p.overflow[b] != 0 || *p.sorted == 0) {  // band wider than the window / grid not increasing: not ours
+    if (tid == 0) {
+      p.info[b] = p.overflow[b] != 0 ? -2 : -3;
+      p.lnL[b] = nan("");
+    }
+    return;
+  }
+  const double* Sb = p.Sb + (long long)b * p.strideSb;
+  const double* Xb = (M > 0) ? p.X + (long long)b * M * N : nullptr;
+  const double* Fb = p.model_flux + (long long)b * N;
+
+  auto rhs_at = [&](int i, int q) -> double {
+    if (i >= N) return 0.0;
+    return q == 0 ? Fb[i] - p.data_flux[i] : Xb[(long long)(q - 1) * N + i];
+  };
+  // Entering rows j0+WD … j0+WD+BATCH−1, one warp per ring row (BATCH == 16 warps): the band by 16-byte
+  // cp.async, X by 8-byte cp.async; the residual column is staged as its two terms (model flux in column WD,
+  // data flux in the spare column WD+NRP−1) and subtracted when the row is consumed, so nothing here waits for
+  // a global load; rows past the end of the matrix are the identity padding.
+  auto stage_issue = [&](int j0, double* dst) {
+   for (int rb = warp; rb < BATCH; rb += NT / 32) {
+    const int i = j0 + WD + rb;
+    double* drow = dst + rb * ROWLEN;
+    if (i < N) {
+      const double* srow = Sb + (long long)i * WD;
+      for (int c2 = lane; c2 < WD / 2; c2 += 32) cp_async16(drow + 2 * c2, srow + 2 * c2);
+      if (lane == 0) cp_async8(drow + WD, Fb + i);
+      else if (lane < NR) cp_async8(drow + WD + lane, Xb + (long long)(lane - 1) * N + i);
+      else if (lane == NRP - 1) cp_async8(drow + WD + NRP - 1, p.data_flux + i);
+    } else {
+      for (int c = lane; c < ROWLEN; c += 32) drow[c] = (c == 0) ? 1.0 : 0.0;
+    }
+   }
+    cp_async_commit();
+  };
+  static_assert(NRP <= 32, "one lane per right-hand-side column");
+
+  // ---- initial window: slot (r, c) = element (i = r, k = c) for k <= i
+  double a[TR][TC][2];
+#pragma unroll
+  for (int tr = 0; tr < TR; ++tr)
+#pragma unroll
+    for (int tc = 0; tc < TC; ++tc)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int i = 8 * (wr * TR + tr) + g, k = 8 * (wc * TC + tc) + 2 * t + h;
+        double v = 0.0;
+        if (k <= i) v = (i < N) ? Sb[(long long)i * WD + (i - k)] : (k == i ? 1.0 : 0.0);
+        a[tr][tc][h] = v;
+      }
+  double rv[NE];
+  int rcode[NE];  // residue·32 + column of the right-hand-side element held in rv[e]; negative: none
+#pragma unroll
+  for (int e = 0; e < NE; ++e) {
+    const int idx = tid + NT * e;
+    const bool ok = idx < WD * NR;
+    const int res = idx / NR, q = idx - res * NR;
+    rcode[e] = ok ? res * 32 + q : -32;
+    rv[e] = ok ? rhs_at(res, q) : 0.0;
+  }
+  stage_issue(0, ring);
+
+  // Four rows enter together.  If the band comes within three pixels of the window width (b > WD − 4), an entering
+  // row j+WD+s reaches pivots j+s+1 … j+3 of the block that has just been eliminated without it; those updates are
+  // then applied as the row enters (below).  Whether this walker needs that is a CTA-uniform fact of its band.
+  int late_any = 0;
+  for (int idx = tid; idx < 3 * N; idx += NT) {
+    const int i = idx / 3, d = WD - 1 - (idx - 3 * i);
+    late_any |= (Sb[(long long)i * WD + d] != 0.0) ? 1 : 0;
+  }
+  const bool late = __syncthreads_or(late_any) != 0;
+
+  double logdet = 0.0, gacc = 0.0, mant = 1.0;
+  long long expo = 0;
+  int info = 0;
+  const int gp_ = tid / NR, gq_ = tid - (tid / NR) * NR;  // Gram element of this thread (tid < NR²)
+  const bool gram_on = tid < NR * NR;
+
+  // The block loop is unrolled over lcm(TR, TC) tiles (two blocks of four pivots each), so that the tile-in-warp
+  // index of the pivots' columns / of the retiring rows is a compile-time register index.
+  for (int J = 0, jrJ = 0; J < N; J += 8 * TL, jrJ = (jrJ + 8 * TL == WD) ? 0 : jrJ + 8 * TL) {
+#pragma unroll
+    for (int ub = 0; ub < 2 * TL; ++ub) {
+      const int j = J + 4 * ub, jr = jrJ + 4 * ub;
+      if (j >= N) break;
+      const int tci = (ub >> 1) % TC, tri = (ub >> 1) % TR, pp = ub & 1;  // tile inside the warp, half of the tile
+      const int ownc = (jrJ >> 3) / TC + (ub >> 1) / TC;  // warp column holding these pivot columns
+      const int ownr = (jrJ >> 3) / TR + (ub >> 1) / TR;  // warp row holding the retiring rows
+      const bool boundary = (j & (BATCH - 1)) == 0;
+      if (boundary) cp_async_wait_all();  // this batch's entering rows have landed (visible after the barrier)
+      // ---- 1. publish the raw pivot columns and the pivot rows of the right-hand sides
+      if (wc == ownc && (t >> 1) == pp) {
+#pragma unroll
+        for (int tr = 0; tr < TR; ++tr)
+          *reinterpret_cast<double2*>(&Praw[(8 * (wr * TR + tr) + g) * 4 + 2 * (t & 1)]) =
+              make_double2(a[tr][tci][0], a[tr][tci][1]);
+      }
+#pragma unroll
+      for (int e = 0; e < NE; ++e) {
+        const int rs = rcode[e] >> 5;
+        if (rs >= jr && rs < jr + 4) zraw[rs - jr][rcode[e] & 31] = rv[e];
+      }
+      __syncthreads();
+      // nobody reads the other ring half any more (its last readers were the previous block's entering rows)
+      if (boundary) stage_issue(j + BATCH, ring + (((j / BATCH) & 1) ^ 1) * (BATCH * ROWLEN));
+      // ---- 2. panel: 4×4 LDLᵀ of the diagonal block (redundantly), then one row / one rhs column per thread
+      if (tid < WD + NR) {
+        const double* Dp = Praw + jr * 4;
+        const double D00 = Dp[0], D10 = Dp[4], D11 = Dp[5], D20 = Dp[8], D21 = Dp[9], D22 = Dp[10];
+        const double D30 = Dp[12], D31 = Dp[13], D32 = Dp[14], D33 = Dp[15];
+        const double inv0 = band_rcp(D00);
+        const double L10 = D10 * inv0, L20 = D20 * inv0, L30 = D30 * inv0;
+        const double W11 = fma(-D10, L10, D11);
+        const double inv1 = band_rcp(W11);
+        const double W21 = fma(-D20, L10, D21), W31 = fma(-D30, L10, D31);
+        const double L21 = W21 * inv1, L31 = W31 * inv1;
+        const double W22 = fma(-W21, L21, fma(-D20, L20, D22));
+        const double inv2 = band_rcp(W22);
+        const double W32 = fma(-W31, L21, fma(-D30, L20, D32));
+        const double L32 = W32 * inv2;
+        const double W33 = fma(-W32, L32, fma(-W31, L31, fma(-D30, L30, D33)));
+        const double inv3 = band_rcp(W33);
+        if (tid < WD) {
+          const double2 p01 = *reinterpret_cast<const double2*>(&Praw[tid * 4]);
+          const double2 p23 = *reinterpret_cast<const double2*>(&Praw[tid * 4 + 2]);
+          const double w0 = p01.x;
+          const double w1 = fma(-w0, L10, p01.y);
+          const double w2 = fma(-w1, L21, fma(-w0, L20, p23.x));
+          const double w3 = fma(-w2, L32, fma(-w1, L31, fma(-w0, L30, p23.y)));
+          *reinterpret_cast<double2*>(&Wn[tid * 4]) = make_double2(-w0, -w1);
+          *reinterpret_cast<double2*>(&Wn[tid * 4 + 2]) = make_double2(-w2, -w3);
+          *reinterpret_cast<double2*>(&Lp[tid * 4]) = make_double2(w0 * inv0, w1 * inv1);
+          *reinterpret_cast<double2*>(&Lp[tid * 4 + 2]) = make_double2(w2 * inv2, w3 * inv3);
+        } else {
+          const int q = tid - WD;
+          const double z0 = zraw[0][q], zl0 = z0 * inv0;
+          const double z1 = fma(-D10, zl0, zraw[1][q]), zl1 = z1 * inv1;
+          const double z2 = fma(-W21, zl1, fma(-D20, zl0, zraw[2][q])), zl2 = z2 * inv2;
+          const double z3 = fma(-W32, zl2, fma(-W31, zl1, fma(-D30, zl0, zraw[3][q]))), zl3 = z3 * inv3;
+          zW[0][q] = z0; zW[1][q] = z1; zW[2][q] = z2; zW[3][q] = z3;
+          zL[0][q] = zl0; zL[1][q] = zl1; zL[2][q] = zl2; zL[3][q] = zl3;
+        }
+        if (tid == 0) {
+          facL[0] = L21;
+          facL[1] = L31;
+          facL[2] = L32;
+        }
+        if (tid == 0) {  // log det S = Σ log(pivot) as mantissa × 2^exponent (see band_chol_kernel), info
+          const double piv[4] = {D00, W11, W22, W33};
+#pragma unroll
+          for (int s4 = 0; s4 < 4; ++s4) {
+            const double pj = piv[s4];
+            if (!(pj > 0.0) && info == 0) info = j + s4 + 1;
+            const int hi = __double2hiint(pj);
+            expo += ((hi >> 20) & 0x7ff) - 1022;
+            mant *= __hiloint2double((hi & 0x800fffff) | 0x3fe00000, __double2loint(pj));
+          }
+          if ((j & 511) == 508) {
+            const int h2 = __double2hiint(mant);
+            expo += ((h2 >> 20) & 0x7ff) - 1022;
+            mant = __hiloint2double((h2 & 0x800fffff) | 0x3fe00000, __double2loint(mant));
+          }
+        }
+      }
+      __syncthreads();
+      // ---- 3. rank-4 update of the window (DMMA), of the right-hand sides and of the Gram matrix (DFMA)
+      {
+        double af[TR];  // TR <= TC: the shorter fragment set is held, the longer one streamed
+#pragma unroll
+        for (int tr = 0; tr < TR; ++tr) af[tr] = Wn[(8 * (wr * TR + tr) + g) * 4 + t];
+#pragma unroll
+        for (int tc = 0; tc < TC; ++tc) {
+          const double bf = Lp[(8 * (wc * TC + tc) + g) * 4 + t];
+#pragma unroll
+          for (int tr = 0; tr < TR; ++tr) band_dmma(a[tr][tc][0], a[tr][tc][1], af[tr], bf);
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < NE; ++e)
+        if (rcode[e] >= 0) {
+          const int rs = rcode[e] >> 5, q = rcode[e] & 31;
+          const double2 w01 = *reinterpret_cast<const double2*>(&Wn[rs * 4]);
+          const double2 w23 = *reinterpret_cast<const double2*>(&Wn[rs * 4 + 2]);
+          double r = rv[e];
+          r = fma(w01.x, zL[0][q], r);
+          r = fma(w01.y, zL[1][q], r);
+          r = fma(w23.x, zL[2][q], r);
+          r = fma(w23.y, zL[3][q], r);
+          rv[e] = r;
+        }
+      if (gram_on) {
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) gacc = fma(zL[s4][gp_], zW[s4][gq_], gacc);
+      }
+      // ---- 4. indices j+WD … j+WD+3 take over the residues jr … jr+3: their rows of S replace the retiring rows
+      const double* rowbase = ring + ((j / BATCH) & 1) * (BATCH * ROWLEN) + (j & (BATCH - 1)) * ROWLEN;
+      // panel values of a late row (s = its position in the block): W'[t] = S(j+WD+s, j+t) − Σ_{s<k<t} W'[k]·L[j+t][k]
+      auto late_w = [&](const double* row, int sblk, double& w1, double& w2, double& w3) {
+        const double r1 = (sblk < 1) ? row[WD + sblk - 1] : 0.0;
+        const double r2 = (sblk < 2) ? row[WD + sblk - 2] : 0.0;
+        const double r3 = (sblk < 3) ? row[WD + sblk - 3] : 0.0;
+        w1 = r1;
+        w2 = fma(-w1, facL[0], r2);
+        w3 = fma(-w2, facL[2], fma(-w1, facL[1], r3));
+      };
+      if (wr == ownr && (g >> 2) == pp) {
+        const int rres_new = jr + (g & 3);
+        const double* row = rowbase + (g & 3) * ROWLEN;
+        double w1 = 0.0, w2 = 0.0, w3 = 0.0;
+        if (late) late_w(row, g & 3, w1, w2, w3);
+#pragma unroll
+        for (int tc = 0; tc < TC; ++tc)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int c = 8 * (wc * TC + tc) + 2 * t + h;
+            int dd = rres_new - c;  // band offset of the slot's column
+            if (dd < 0) dd += WD;
+            double v = row[dd];
+            if (late && (unsigned)(c - jr) >= 4u) {  // not the block's own residues (new / dead columns)
+              const double l1 = Lp[c * 4 + 1];
+              const double2 l23 = *reinterpret_cast<const double2*>(&Lp[c * 4 + 2]);
+              v = fma(-w3, l23.y, fma(-w2, l23.x, fma(-w1, l1, v)));
+            }
+            a[tri][tc][h] = v;
+          }
+      }
+#pragma unroll
+      for (int e = 0; e < NE; ++e) {
+        const int rs = rcode[e] >> 5, q = rcode[e] & 31;
+        if (rs >= jr && rs < jr + 4) {
+          const double* row = rowbase + (rs - jr) * ROWLEN;
+          const double* rr = row + WD;
+          double v = (q == 0) ? rr[0] - rr[NRP - 1] : rr[q];  // residual = model flux − data flux
+          if (late) {
+            double w1, w2, w3;
+            late_w(row, rs - jr, w1, w2, w3);
+            v = fma(-w3, zL[3][q], fma(-w2, zL[2][q], fma(-w1, zL[1][q], v)));
+          }
+          rv[e] = v;
+        }
+      }
+    }
+  }
+  if (tid == 0) logdet = log(mant) + (double)expo * 0.6931471805599453;
+
+  if (gram_on) gram[tid] = gacc;
+  __syncthreads();
+  if (tid == 0) band_epilogue(p, b, M, gram, logdet, info);
+}
+
+template <int WD, int WRG, int WCG>
+cudaError_t launch_band_mma_t(const BandCholParams& p, int B, cudaStream_t st) {
+  const size_t smem = sizeof(double) * 2 * 16 * (WD + NRP);
+  constexpr int NT = 32 * WRG * WCG;
+  if (p.M + 1 <= 8) {
+    cudaError_t e = cudaFuncSetAttribute(band_mma_kernel<WD, WRG, WCG, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         64 * 1024);
+    if (e != cudaSuccess) return e;
+    band_mma_kernel<WD, WRG, WCG, 8><<<B, NT, smem, st>>>(p);
+  } else if constexpr (WD + kMaxM + 1 <= NT && (kMaxM + 1) * (kMaxM + 1) <= NT) {
+    cudaError_t e = cudaFuncSetAttribute(band_mma_kernel<WD, WRG, WCG, kMaxM + 1>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (e != cudaSuccess) return e;
+    band_mma_kernel<WD, WRG, WCG, kMaxM + 1><<<B, NT, smem, st>>>(p);
+  } else {
+    return cudaErrorInvalidValue;  // launch_band_chol routes these to the rank-1 kernel
+  }
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
 // Symmetric window.  The active window W[r][c] = S(index(r), index(c)) (residues mod WD) is a symmetric
 // matrix and the rank-1 update W −= v·vᵀ/pivot is symmetric as well, so only one of every pair of T×T tiles
 // {(I,J), (J,I)} needs to exist: tile (I, J) is kept iff (J − I) mod 32 ≤ 16.  Warp δ ∈ [0,16], lane I owns
@@ -711,6 +1045,12 @@ static bool band_use_sym(int WD) {
   return force || WD > 160;
 }
 
+// SFB_BAND_MMA=1 routes the classes up to 160 pixels to the rank-4 DMMA kernel (A/B measurements)
+static bool band_use_mma(int WD) {
+  static const bool on = getenv("SFB_BAND_MMA") != nullptr;
+  return on && WD <= 160 && !band_use_sym(WD);
+}
+
 // pixels of slack a window needs beyond the half-bandwidth: b + slack <= WD
 int band_slack(int WD) {
   (void)WD;
@@ -719,6 +1059,15 @@ int band_slack(int WD) {
 
 cudaError_t launch_band_chol(const BandCholParams& p, int WD, int B, cudaStream_t st) {
   if (B <= 0) return cudaSuccess;
+  if (band_use_mma(WD) && (WD < 160 || p.M + 1 <= 8)) {  // (the 256-thread 160-pixel kernel carries <= 8 right-hand sides)
+    switch (WD) {
+      case 64: return launch_band_mma_t<64, 4, 4>(p, B, st);
+      case 96: return launch_band_mma_t<96, 4, 4>(p, B, st);
+      case 128: return launch_band_mma_t<128, 4, 4>(p, B, st);
+      case 160: return launch_band_mma_t<160, 4, 2>(p, B, st);
+      default: return cudaErrorInvalidValue;
+    }
+  }
   if (band_use_sym(WD)) {
     switch (WD) {
       case 64: return launch_band_sym_t<2>(p, B, st);

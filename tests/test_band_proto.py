@@ -35,6 +35,9 @@ def test_sliding_window_restatement_matches_oracles():
         dense = O.log_likelihood(cov, d["model_flux"][b], d["data_flux"])[0]
         assert info == 0
         assert abs(lnl - ref) <= 1e-11 * abs(ref) and abs(lnl - dense) <= 1e-11 * abs(dense)
+        # the rank-4 variant (four pivots per step, rows enter four at a time: b <= WD - 4)
+        lnl4, info4 = P.window_loglike_blocked(Sb, rhs, d["A"][b])
+        assert info4 == 0 and abs(lnl4 - dense) <= 1e-11 * abs(dense)
     # M = 0 (config-2 shape) and a band that does not fit
     lnl0, info0 = P.window_loglike(Sb, rhs[:, :1])
     ref0 = S.stage_log_likelihood(d["wave"], d["sigma"], d["data_flux"], None, None, d["model_flux"][B - 1],

@@ -77,3 +77,87 @@ def window_loglike(Sb, rhs, A=None):
         logdet += ldk
         quad -= u @ np.linalg.solve(K, A @ u)
     return (-(logdet + quad) / 2 if info == 0 else np.nan), info
+
+
+def window_loglike_blocked(Sb, rhs, A=None):
+    """The rank-4 (DMMA) variant, band_mma_kernel: four pivots per step.  Publish the raw columns of the four
+    pivots; factor their 4x4 diagonal block (LDL^T); panel solve per row (W = unscaled, L = W/d); one rank-4
+    update of every slot; the four rows j+WD .. j+WD+3 enter together, each corrected for the pivots of the block
+    it reaches (b <= WD-1 like the rank-1 kernel).  Returns (lnL, info) like window_loglike."""
+    N, WD = Sb.shape
+    NR = rhs.shape[1]
+    M = NR - 1
+
+    def row_of(i):
+        if i < N:
+            return Sb[i]
+        r = np.zeros(WD)
+        r[0] = 1.0
+        return r
+
+    def rhs_of(i):
+        return rhs[i] if i < N else np.zeros(NR)
+
+    W = np.zeros((WD, WD))
+    for i in range(WD):
+        for k in range(i + 1):
+            W[i, k] = row_of(i)[i - k]
+    rw = np.array([rhs_of(i) for i in range(WD)])
+    gram = np.zeros((NR, NR))
+    logdet, info = 0.0, 0
+    for j in range(0, N, 4):
+        jr = j % WD
+        P = W[:, jr:jr + 4].copy()          # raw panel, P[x, t] = slot (x, jr+t)
+        zraw = rw[jr:jr + 4].copy()
+        D = P[jr:jr + 4]                    # rows of the four pivots
+        Lp = np.zeros((4, 4))
+        inv = np.zeros(4)
+        Wp = np.zeros((WD, 4))
+        for t in range(4):                  # panel solve, row-parallel on the device
+            Wp[:, t] = P[:, t]
+            for k in range(t):
+                Wp[:, t] -= Wp[:, k] * Lp[t, k]
+            d = Wp[jr + t, t]
+            if not d > 0 and info == 0:
+                info = j + t + 1
+            logdet += np.log(d) if d > 0 else np.nan
+            inv[t] = 1.0 / d
+            Lp[:, t] = Wp[jr:jr + 4, t] * inv[t]
+        L = Wp * inv
+        zW = np.zeros((4, NR))
+        for t in range(4):
+            zW[t] = zraw[t]
+            for k in range(t):
+                zW[t] -= Wp[jr + t, k] * (zW[k] * inv[k])
+        zL = zW * inv[:, None]
+        W -= Wp @ L.T                        # the DMMA update: C[r][c] -= sum_t W[r][t] L[c][t]
+        rw -= Wp @ zL
+        gram += zL.T @ zW
+        for s4 in range(4):                  # rows j+WD+s4 take the slots of the retiring indices j+s4
+            new = row_of(j + WD + s4)
+            # Late-row correction: row j+WD+s4 may reach the pivots j+s4+1 .. j+3 of THIS block (band offsets
+            # WD-3+s4 .. WD-1, non-zero when b > WD-4); it was not in the window when they were eliminated, so
+            # their updates are applied as it enters: W' = its panel values, then raw - sum W'[t] L[c][t].
+            Wl = np.zeros(4)
+            for t in range(s4 + 1, 4):
+                Wl[t] = new[WD + s4 - t]
+                for k in range(s4 + 1, t):
+                    Wl[t] -= Wl[k] * Lp[t, k]
+            for c in range(WD):
+                v = new[(jr + s4 - c) % WD]
+                if not (0 <= c - jr < 4):    # the block's own residues: new columns / dead columns, no update
+                    for t in range(1, 4):
+                        v -= Wl[t] * L[c, t]
+                W[jr + s4, c] = v
+            rw[jr + s4] = rhs_of(j + WD + s4) - Wl @ zL
+    quad = gram[0, 0]
+    if M > 0 and info == 0:
+        G = gram[1:, 1:]
+        u = gram[1:, 0]
+        K = np.eye(M) + A @ G
+        sign, ldk = np.linalg.slogdet(K)
+        if sign <= 0:
+            info = N
+        logdet += ldk
+        quad -= u @ np.linalg.solve(K, A @ u)
+    return (-(logdet + quad) / 2 if info == 0 else np.nan), info
