@@ -1037,18 +1037,20 @@ cudaError_t launch_band_build(const BandBuildParams& p, int B, cudaStream_t st) 
   return cudaGetLastError();
 }
 
-// Windows up to 160 pixels use the full-square register window (measured fastest); the
-// symmetric window serves the 192- and 256-pixel classes, which do not fit the register file as a square.
+// Windows up to 160 pixels use the full-square register window (rank-4 DMMA kernel, or the rank-1 kernel for
+// more than 8 right-hand sides at 160 pixels); the symmetric window serves the 192- and 256-pixel classes,
+// which do not fit the register file as a square.
 // SFB_BAND_SYM=1 forces the symmetric kernel for every class (A/B measurements).
 static bool band_use_sym(int WD) {
   static const bool force = getenv("SFB_BAND_SYM") != nullptr;
   return force || WD > 160;
 }
 
-// SFB_BAND_MMA=1 routes the classes up to 160 pixels to the rank-4 DMMA kernel (A/B measurements)
+// The classes up to 160 pixels run the rank-4 DMMA kernel (measured faster for every class);
+// SFB_BAND_RANK1=1 keeps the rank-1 kernel for A/B measurements.
 static bool band_use_mma(int WD) {
-  static const bool on = getenv("SFB_BAND_MMA") != nullptr;
-  return on && WD <= 160 && !band_use_sym(WD);
+  static const bool off = getenv("SFB_BAND_RANK1") != nullptr;
+  return !off && WD <= 160 && !band_use_sym(WD);
 }
 
 // pixels of slack a window needs beyond the half-bandwidth: b + slack <= WD
