@@ -505,7 +505,11 @@ __device__ __forceinline__ double band_rcp(double x) {
   return fma(r, e, r);
 }
 
-template <int WD, int WRG, int WCG, int MAXNR>
+// ROLLED = true (SFB_BAND_MMA_ROLLED=1, NOT YET RUN ON A GPU — prepared for the next A/B): one copy of the block body
+// instead of 2·lcm(TR,TC); the tile that holds the pivot columns / the retiring rows is then a run-time index and only
+// the publish and the entering-row code select it (a chain of TC resp. TR predicated copies).  Meant to bring the
+// 160-pixel kernel (30 k SASS instructions unrolled) back inside the instruction cache.
+template <int WD, int WRG, int WCG, int MAXNR, bool ROLLED>
 __global__ void __launch_bounds__(32 * WRG * WCG, 1)
 band_mma_kernel(BandCholParams p) {
   constexpr int NT = 32 * WRG * WCG, TR = WD / 8 / WRG, TC = WD / 8 / WCG, ROWLEN = WD + NRP, BATCH = 16;
@@ -606,22 +610,42 @@ band_mma_kernel(BandCholParams p) {
 
   // The block loop is unrolled over lcm(TR, TC) tiles (two blocks of four pivots each), so that the tile-in-warp
   // index of the pivots' columns / of the retiring rows is a compile-time register index.
-  for (int J = 0, jrJ = 0; J < N; J += 8 * TL, jrJ = (jrJ + 8 * TL == WD) ? 0 : jrJ + 8 * TL) {
+  constexpr int UBN = ROLLED ? 1 : 2 * TL;  // blocks per trip of the outer loop
+  for (int J = 0, jrJ = 0; J < N; J += 4 * UBN, jrJ = (jrJ + 4 * UBN == WD) ? 0 : jrJ + 4 * UBN) {
 #pragma unroll
-    for (int ub = 0; ub < 2 * TL; ++ub) {
+    for (int ub = 0; ub < UBN; ++ub) {
       const int j = J + 4 * ub, jr = jrJ + 4 * ub;
       if (j >= N) break;
-      const int tci = (ub >> 1) % TC, tri = (ub >> 1) % TR, pp = ub & 1;  // tile inside the warp, half of the tile
-      const int ownc = (jrJ >> 3) / TC + (ub >> 1) / TC;  // warp column holding these pivot columns
-      const int ownr = (jrJ >> 3) / TR + (ub >> 1) / TR;  // warp row holding the retiring rows
+      int tci, tri, pp;  // tile inside the warp (columns / rows), half of the tile
+      int ownc, ownr;    // warp column holding these pivot columns, warp row holding the retiring rows
+      if constexpr (ROLLED) {
+        const int ct = jr >> 3;
+        tci = ct % TC; tri = ct % TR; pp = (jr >> 2) & 1;
+        ownc = ct / TC; ownr = ct / TR;
+      } else {
+        tci = (ub >> 1) % TC; tri = (ub >> 1) % TR; pp = ub & 1;
+        ownc = (jrJ >> 3) / TC + (ub >> 1) / TC;
+        ownr = (jrJ >> 3) / TR + (ub >> 1) / TR;
+      }
       const bool boundary = (j & (BATCH - 1)) == 0;
       if (boundary) cp_async_wait_all();  // this batch's entering rows have landed (visible after the barrier)
       // ---- 1. publish the raw pivot columns and the pivot rows of the right-hand sides
       if (wc == ownc && (t >> 1) == pp) {
+        if constexpr (ROLLED) {
 #pragma unroll
-        for (int tr = 0; tr < TR; ++tr)
-          *reinterpret_cast<double2*>(&Praw[(8 * (wr * TR + tr) + g) * 4 + 2 * (t & 1)]) =
-              make_double2(a[tr][tci][0], a[tr][tci][1]);
+          for (int q = 0; q < TC; ++q)
+            if (q == tci) {
+#pragma unroll
+              for (int tr = 0; tr < TR; ++tr)
+                *reinterpret_cast<double2*>(&Praw[(8 * (wr * TR + tr) + g) * 4 + 2 * (t & 1)]) =
+                    make_double2(a[tr][q][0], a[tr][q][1]);
+            }
+        } else {
+#pragma unroll
+          for (int tr = 0; tr < TR; ++tr)
+            *reinterpret_cast<double2*>(&Praw[(8 * (wr * TR + tr) + g) * 4 + 2 * (t & 1)]) =
+                make_double2(a[tr][tci][0], a[tr][tci][1]);
+        }
       }
 #pragma unroll
       for (int e = 0; e < NE; ++e) {
@@ -749,7 +773,13 @@ band_mma_kernel(BandCholParams p) {
               const double2 l23 = *reinterpret_cast<const double2*>(&Lp[c * 4 + 2]);
               v = fma(-w3, l23.y, fma(-w2, l23.x, fma(-w1, l1, v)));
             }
-            a[tri][tc][h] = v;
+            if constexpr (ROLLED) {
+#pragma unroll
+              for (int q = 0; q < TR; ++q)
+                if (q == tri) a[q][tc][h] = v;
+            } else {
+              a[tri][tc][h] = v;
+            }
           }
       }
 #pragma unroll
@@ -776,24 +806,30 @@ band_mma_kernel(BandCholParams p) {
   if (tid == 0) band_epilogue(p, b, M, gram, logdet, info);
 }
 
-template <int WD, int WRG, int WCG>
-cudaError_t launch_band_mma_t(const BandCholParams& p, int B, cudaStream_t st) {
+template <int WD, int WRG, int WCG, bool ROLLED>
+cudaError_t launch_band_mma_tr(const BandCholParams& p, int B, cudaStream_t st) {
   const size_t smem = sizeof(double) * 2 * 16 * (WD + NRP);
   constexpr int NT = 32 * WRG * WCG;
   if (p.M + 1 <= 8) {
-    cudaError_t e = cudaFuncSetAttribute(band_mma_kernel<WD, WRG, WCG, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         64 * 1024);
-    if (e != cudaSuccess) return e;
-    band_mma_kernel<WD, WRG, WCG, 8><<<B, NT, smem, st>>>(p);
-  } else if constexpr (WD + kMaxM + 1 <= NT && (kMaxM + 1) * (kMaxM + 1) <= NT) {
-    cudaError_t e = cudaFuncSetAttribute(band_mma_kernel<WD, WRG, WCG, kMaxM + 1>,
+    cudaError_t e = cudaFuncSetAttribute(band_mma_kernel<WD, WRG, WCG, 8, ROLLED>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     if (e != cudaSuccess) return e;
-    band_mma_kernel<WD, WRG, WCG, kMaxM + 1><<<B, NT, smem, st>>>(p);
+    band_mma_kernel<WD, WRG, WCG, 8, ROLLED><<<B, NT, smem, st>>>(p);
+  } else if constexpr (WD + kMaxM + 1 <= NT && (kMaxM + 1) * (kMaxM + 1) <= NT) {
+    cudaError_t e = cudaFuncSetAttribute(band_mma_kernel<WD, WRG, WCG, kMaxM + 1, ROLLED>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (e != cudaSuccess) return e;
+    band_mma_kernel<WD, WRG, WCG, kMaxM + 1, ROLLED><<<B, NT, smem, st>>>(p);
   } else {
     return cudaErrorInvalidValue;  // launch_band_chol routes these to the rank-1 kernel
   }
   return cudaGetLastError();
+}
+
+template <int WD, int WRG, int WCG>
+cudaError_t launch_band_mma_t(const BandCholParams& p, int B, cudaStream_t st) {
+  static const bool rolled = getenv("SFB_BAND_MMA_ROLLED") != nullptr;  // unmeasured variant, opt-in only
+  return rolled ? launch_band_mma_tr<WD, WRG, WCG, true>(p, B, st) : launch_band_mma_tr<WD, WRG, WCG, false>(p, B, st);
 }
 
 // ------------------------------------------------------------------------------------------------
