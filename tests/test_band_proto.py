@@ -51,3 +51,32 @@ def test_sliding_window_restatement_matches_oracles():
     # an indefinite rank-M term is reported, not silently accepted
     _, info_bad = P.window_loglike(Sb, rhs, -1e9 * np.eye(M))
     assert info_bad == N
+
+
+def test_bench_ensemble_covers_the_late_row_path():
+    """bench.py reports max |lnL_structured - lnL_dense| / |lnL| over its 256 walkers; that figure pins the rank-4
+    kernel's late-row correction only if some walkers have a band within three pixels of their window (b > WD - 4).
+    The synthetic ensemble does, in every class it uses (host arithmetic only: the band widths follow from the
+    kernel hyper-parameters)."""
+    N, B, c = 8192, 256, 2.99792458e5
+    wave = synth.log_uniform_wave(N)
+    tight = {96: 0, 128: 0, 160: 0}
+    counts = {96: 0, 128: 0, 160: 0}
+    for b in range(B):
+        _, p = synth.walker_params(b, n_local=2, with_global=True)
+        r0 = 6 * np.exp(p["global_cov"]["log_ls"])
+        bw = 0
+        for d in range(40, 200):
+            r = c / 2 * np.abs((wave[:-d] - wave[d:]) / (wave[:-d] + wave[d:]))
+            if not np.any(r <= r0):
+                break
+            bw = d
+        for lk in p["local_cov"]:
+            m = c / lk["mu"] * np.abs(wave - lk["mu"])
+            bw = max(bw, int(np.sum(m <= 4 * np.exp(lk["log_sigma"]))) - 1)
+        WD = next(w for w in (64, 96, 128, 160, 192, 256) if bw + 1 <= w)
+        assert WD in counts, (b, bw)
+        counts[WD] += 1
+        tight[WD] += bw > WD - 4
+    assert counts == {96: 14, 128: 206, 160: 36}      # the routing bench.py reports (window_classes / 23 passes)
+    assert all(v >= 1 for v in tight.values()), tight
