@@ -36,3 +36,17 @@ def make_model_params(wave, grid, params, **kw):
         warnings.simplefilter("ignore")
         return SpectrumModel(emu, Spectrum(w, f, sigmas=s, name="synthetic"), grid_params=grid,
                              **copy.deepcopy(params), **kw)
+
+
+def ls_for_half_bandwidth(wave, b):
+    """Length scale (km/s) of the global kernel for which the covariance band has half-width exactly b pixels on
+    this (strictly increasing) grid: the support test is r <= 6·ls with r = (c/2)|λi−λk|/(λi+λk)
+    (Starfish/models/kernels.py:27-33), so 6·ls is put midway between the smallest r at offsets b and b+1."""
+    import numpy as np
+
+    c = 2.99792458e5
+
+    def rmin(d):
+        return float(np.min(c / 2 * np.abs((wave[:-d] - wave[d:]) / (wave[:-d] + wave[d:]))))
+
+    return (rmin(b) + rmin(b + 1)) / 12.0

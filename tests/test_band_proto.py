@@ -80,3 +80,29 @@ def test_bench_ensemble_covers_the_late_row_path():
         tight[WD] += bw > WD - 4
     assert counts == {96: 14, 128: 206, 160: 36}      # the routing bench.py reports (window_classes / 23 passes)
     assert all(v >= 1 for v in tight.values()), tight
+
+
+def test_tight_band_inputs_of_the_gpu_test_and_the_rank4_restatement():
+    """The inputs of tests/test_gpu_structured.py::test_band_within_three_pixels_of_every_window, checked without a
+    GPU: the length scales give exactly the half-bandwidths WD-4 .. WD-1, and the numpy restatement of the rank-4
+    kernel (late-row correction included) reproduces the dense oracle on the tightest walker of two classes."""
+    import band_proto as P
+    from _helpers import ls_for_half_bandwidth
+
+    N, B = 2048, 16
+    targets = [WD - k for WD in (64, 96, 128, 160) for k in (4, 3, 2, 1)]
+    d = synth.stage_inputs_direct(N, B, n_comp=6, n_local=2)
+    d["glob"][:, 1] = [ls_for_half_bandwidth(d["wave"], b) for b in targets]
+    for b in range(B):
+        Smat = O.assemble_covariance(d["wave"], d["sigma"], None, None, d["glob"][b], d["loc"][b])
+        i, k = np.nonzero(Smat)
+        assert int(np.max(i - k)) == targets[b], (b, targets[b])
+        if b not in (7, 15):          # b = 95 in the 96-pixel window, b = 159 in the 160-pixel window
+            continue
+        cov = Smat + d["X"][b].T @ d["A"][b] @ d["X"][b]
+        dense = O.log_likelihood(cov, d["model_flux"][b], d["data_flux"])[0]
+        np.fill_diagonal(Smat, Smat.diagonal() + O.JITTER)
+        Sb = P.band_storage(Smat, targets[b] + 1)
+        rhs = np.column_stack([d["model_flux"][b] - d["data_flux"], d["X"][b].T])
+        lnl4, info4 = P.window_loglike_blocked(Sb, rhs, d["A"][b])
+        assert info4 == 0 and abs(lnl4 - dense) <= 1e-11 * abs(dense)

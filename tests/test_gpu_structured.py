@@ -65,6 +65,31 @@ def test_every_window_class_and_dense_fallback_n2048():
     eng.close()
 
 
+def test_band_within_three_pixels_of_every_window():
+    """Half-bandwidths WD−4 … WD−1 for WD = 64, 96, 128, 160 (length scales from the support test itself): the band
+    fills its window, and for b > WD−4 the rank-4 kernel's entering rows reach pivots of the block that has just
+    been eliminated (late-row correction).  Same classes as the rank-1 kernel, same numbers as the dense path."""
+    from _helpers import ls_for_half_bandwidth
+
+    N, B = 2048, 16
+    targets = [WD - k for WD in (64, 96, 128, 160) for k in (4, 3, 2, 1)]
+    d = synth.stage_inputs_direct(N, B, n_comp=6, n_local=2)
+    d["glob"][:, 1] = [ls_for_half_bandwidth(d["wave"], b) for b in targets]
+    eng = _engine(N, 6, 2, B)
+    eng.set_data(d["wave"], d["sigma"], d["data_flux"])
+    lnL, info = _run(eng, d)
+    classes = eng.band_classes()
+    assert classes == {64: 4, 96: 4, 128: 4, 160: 4, 192: 0, 256: 0, 0: 0}, classes
+    assert (info == 0).all()
+    for b in range(B):
+        ref = _dense_ref(d, b)
+        assert abs(lnL[b] - ref) <= TOL * max(1.0, abs(ref)), (b, targets[b], lnL[b], ref)
+    eng.set_solver("dense")
+    lnL_d, _ = _run(eng, d)
+    assert np.abs(lnL - lnL_d).max() <= TOL * np.abs(lnL_d).max()
+    eng.close()
+
+
 def test_config2_shape_global_only_no_emulator_term():
     N, B = 4096, 5
     d = synth.stage_inputs_direct(N, B, n_comp=0, n_local=0)
