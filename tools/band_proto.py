@@ -161,3 +161,106 @@ def window_loglike_blocked(Sb, rhs, A=None):
         logdet += ldk
         quad -= u @ np.linalg.solve(K, A @ u)
     return (-(logdet + quad) / 2 if info == 0 else np.nan), info
+
+
+def window_loglike_lookahead(Sb, rhs, A=None):
+    """The SCHEDULE of band_mma_la_kernel at matrix level: block n's rank-4 update is applied to the tile column
+    (8 residues) that holds block n+1's pivots first, block n's entering rows enter in that tile column, the raw
+    panel of block n+1 is taken, its panel is solved, and only then the rest of block n's update and entering rows
+    follow.  Same arithmetic as window_loglike_blocked — this restatement pins the ordering argument (an entered row
+    must not receive block n's update; the entered values belong in the next panel)."""
+    N, WD = Sb.shape
+    NR = rhs.shape[1]
+    M = NR - 1
+
+    def row_of(i):
+        if i < N:
+            return Sb[i]
+        r = np.zeros(WD)
+        r[0] = 1.0
+        return r
+
+    def rhs_of(i):
+        return rhs[i] if i < N else np.zeros(NR)
+
+    W = np.zeros((WD, WD))
+    for i in range(WD):
+        for k in range(i + 1):
+            W[i, k] = row_of(i)[i - k]
+    rw = np.array([rhs_of(i) for i in range(WD)])
+    gram = np.zeros((NR, NR))
+    state = {"logdet": 0.0, "info": 0}
+
+    def panel(j, jr, P, zraw):
+        Lp = np.zeros((4, 4))
+        inv = np.zeros(4)
+        Wp = np.zeros((WD, 4))
+        for t in range(4):
+            Wp[:, t] = P[:, t]
+            for k in range(t):
+                Wp[:, t] -= Wp[:, k] * Lp[t, k]
+            d = Wp[jr + t, t]
+            if not d > 0 and state["info"] == 0:
+                state["info"] = j + t + 1
+            state["logdet"] += np.log(d) if d > 0 else np.nan
+            inv[t] = 1.0 / d
+            Lp[:, t] = Wp[jr:jr + 4, t] * inv[t]
+        zW = np.zeros((4, NR))
+        for t in range(4):
+            zW[t] = zraw[t]
+            for k in range(t):
+                zW[t] -= Wp[jr + t, k] * (zW[k] * inv[k])
+        return Wp, Wp * inv, Lp, zW, zW * inv[:, None]
+
+    def enter(j, jr, cols, L, Lp):
+        for s4 in range(4):
+            new = row_of(j + WD + s4)
+            Wl = np.zeros(4)
+            for t in range(s4 + 1, 4):
+                Wl[t] = new[WD + s4 - t]
+                for k in range(s4 + 1, t):
+                    Wl[t] -= Wl[k] * Lp[t, k]
+            for c in cols:
+                v = new[(jr + s4 - c) % WD]
+                if not (0 <= c - jr < 4):
+                    for t in range(1, 4):
+                        v -= Wl[t] * L[c, t]
+                W[jr + s4, c] = v
+        return
+
+    cur = panel(0, 0, W[:, 0:4].copy(), rw[0:4].copy())
+    for j in range(0, N, 4):
+        jr = j % WD
+        Wp, L, Lp, zW, zL = cur
+        jn, jrn = j + 4, (jr + 4) % WD
+        has_next = jn < N
+        rw -= Wp @ zL                                   # S1
+        gram += zL.T @ zW
+        first = list(range(8 * (jrn // 8), 8 * (jrn // 8) + 8)) if has_next else []
+        rest = [c for c in range(WD) if c not in first]
+        if has_next:                                    # S2: the next panel's tile column first
+            W[:, first] -= Wp @ L[first].T
+            enter(j, jr, first, L, Lp)
+            cur = panel(jn, jrn, W[:, jrn:jrn + 4].copy(), rw[jrn:jrn + 4].copy())   # NB + S4
+        W[:, rest] -= Wp @ L[rest].T                    # S5
+        enter(j, jr, rest, L, Lp)
+        for s4 in range(4):
+            new = row_of(j + WD + s4)
+            Wl = np.zeros(4)
+            for t in range(s4 + 1, 4):
+                Wl[t] = new[WD + s4 - t]
+                for k in range(s4 + 1, t):
+                    Wl[t] -= Wl[k] * Lp[t, k]
+            rw[jr + s4] = rhs_of(j + WD + s4) - Wl @ zL
+    logdet, info = state["logdet"], state["info"]
+    quad = gram[0, 0]
+    if M > 0 and info == 0:
+        G = gram[1:, 1:]
+        u = gram[1:, 0]
+        K = np.eye(M) + A @ G
+        sign, ldk = np.linalg.slogdet(K)
+        if sign <= 0:
+            info = N
+        logdet += ldk
+        quad -= u @ np.linalg.solve(K, A @ u)
+    return (-(logdet + quad) / 2 if info == 0 else np.nan), info
