@@ -38,6 +38,9 @@ def test_sliding_window_restatement_matches_oracles():
         # the rank-4 variant (four pivots per step, rows enter four at a time: b <= WD - 4)
         lnl4, info4 = P.window_loglike_blocked(Sb, rhs, d["A"][b])
         assert info4 == 0 and abs(lnl4 - dense) <= 1e-11 * abs(dense)
+        # ... and the look-ahead schedule (next panel's tile column updated, entered and published first)
+        lnla, infola = P.window_loglike_lookahead(Sb, rhs, d["A"][b])
+        assert infola == 0 and abs(lnla - lnl4) <= 1e-13 * abs(lnl4)
     # M = 0 (config-2 shape) and a band that does not fit
     lnl0, info0 = P.window_loglike(Sb, rhs[:, :1])
     ref0 = S.stage_log_likelihood(d["wave"], d["sigma"], d["data_flux"], None, None, d["model_flux"][B - 1],
@@ -106,3 +109,6 @@ def test_tight_band_inputs_of_the_gpu_test_and_the_rank4_restatement():
         rhs = np.column_stack([d["model_flux"][b] - d["data_flux"], d["X"][b].T])
         lnl4, info4 = P.window_loglike_blocked(Sb, rhs, d["A"][b])
         assert info4 == 0 and abs(lnl4 - dense) <= 1e-11 * abs(dense)
+        # ... and the look-ahead schedule (next panel's tile column updated, entered and published first)
+        lnla, infola = P.window_loglike_lookahead(Sb, rhs, d["A"][b])
+        assert infola == 0 and abs(lnla - lnl4) <= 1e-13 * abs(lnl4)
