@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--no-model", action="store_true", help="skip the parameter-level (drop-in model) legs")
     ap.add_argument("--no-structured", action="store_true", help="skip the structured-solver (row f4) legs")
     ap.add_argument("--cpu-sample", type=int, default=0, help="walkers in the CPU sample (0 = auto)")
+    ap.add_argument("--solver", default="dense", choices=["dense", "dense_i8"],
+                    help="trailing update of the dense factorisation: fp64 DMMA or the int8 tensor-core restatement")
     return ap.parse_args()
 
 
@@ -187,6 +189,7 @@ def run_b200(args, rank, world, local_rank):
     stage = synth.stage_inputs_direct(N, nb, n_comp=M, n_local=K, first_walker=lo)
     eng = LikelihoodEngine(N, M, K, max(nb, 1), device=local_rank)
     eng.set_data(stage["wave"], stage["sigma"], stage["data_flux"])
+    eng.set_solver(args.solver)
     X = torch.from_numpy(stage["X"]).to(dev)
     A = torch.from_numpy(stage["A"]).to(dev)
     F = torch.from_numpy(stage["model_flux"]).to(dev)
@@ -396,7 +399,7 @@ def run_b200(args, rank, world, local_rank):
                 "launches": bc["launches"], "ms": bc["ms"],
                 "band_build": {"launches": bb["launches"], "ms": bb["ms"],
                                "achieved_gbs": bb["work"] / (bb["ms"] * 1e-3) / 1e9 if bb["ms"] > 0 else None}}
-        eng.set_solver("dense")
+        eng.set_solver(args.solver)
     if not args.no_model:
         model._engine = None
 

@@ -179,7 +179,7 @@ int sfb_spline_halfwidth(void);
  * not positive definite — the dense path reports the same leading minor); N = S is fine but S + XᵀAX is not
  * positive definite (the dense path reports whichever leading minor fails first — both mean LinAlgError upstream).
  */
-enum sfb_solver { SFB_SOLVER_DENSE = 0, SFB_SOLVER_STRUCTURED = 1 };
+enum sfb_solver { SFB_SOLVER_DENSE = 0, SFB_SOLVER_STRUCTURED = 1, SFB_SOLVER_DENSE_I8 = 2 };
 int sfb_set_solver(sfb_t* h, int solver);
 int sfb_get_solver(const sfb_t* h);
 /* Walkers routed to each register-window width since creation; the last entry (width 0) is the dense
@@ -196,7 +196,7 @@ int sfb_sync(sfb_t* h);
  * (bytes for SFB_K_BUILD, FLOPs otherwise), and resets the counters.  `n` = capacity of out in doubles.
  */
 enum sfb_kernel_class { SFB_K_BUILD = 0, SFB_K_POTRF_DIAG = 1, SFB_K_TRSM = 2, SFB_K_SYRK = 3, SFB_K_UPSTREAM = 4,
-                        SFB_K_BAND_BUILD = 5, SFB_K_BAND_CHOL = 6, SFB_K_NCLASS = 7 };
+                        SFB_K_BAND_BUILD = 5, SFB_K_BAND_CHOL = 6, SFB_K_OZ_SLICE = 7, SFB_K_NCLASS = 8 };
 int sfb_profile_enable(sfb_t* h, int on);
 int sfb_profile_read(sfb_t* h, double* out, int n);
 

@@ -19,14 +19,14 @@ EXPORTS = [
     "sfb_set_solver", "sfb_get_solver", "sfb_band_classes",
 ]
 
-SOLVER_DENSE, SOLVER_STRUCTURED = 0, 1
+SOLVER_DENSE, SOLVER_STRUCTURED, SOLVER_DENSE_I8 = 0, 1, 2
 
 ABI_VERSION = 2
 
 # sfb_model_flags of include/sfb200.h
 MODEL_VSINI, MODEL_VZ, MODEL_LOG_SCALE, MODEL_NORM, MODEL_PAPER_TERM = 1, 2, 4, 8, 16
 
-KERNEL_CLASSES = ("build", "potrf_diag", "trsm", "syrk", "upstream", "band_build", "band_chol")
+KERNEL_CLASSES = ("build", "potrf_diag", "trsm", "syrk", "upstream", "band_build", "band_chol", "oz_slice")
 
 _p = C.c_void_p
 _i = C.c_int

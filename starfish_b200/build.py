@@ -9,7 +9,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["cov_build.cu", "chol.cu", "upstream.cu", "band.cu", "capi.cu"]
+SOURCES = ["cov_build.cu", "chol.cu", "ozaki.cu", "upstream.cu", "band.cu", "capi.cu"]
 HEADERS = ["sfb_internal.cuh", os.path.join("..", "..", "include", "sfb200.h")]
 LIB = os.path.join(HERE, "libsfb200.so")
 

@@ -56,6 +56,11 @@ struct sfb_ctx {
   int *bw_h = nullptr, *rowmap_h = nullptr;  // pinned
   cudaEvent_t ev_band = nullptr, ev_up = nullptr;
   long long band_rows[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // walkers per window class (last = dense fallback) since creation
+  // int8 tensor-core trailing update (SFB_SOLVER_DENSE_I8): sliced panels (two buffers per slot: the look-ahead
+  // slices block J+1 while the bulk update of block J still reads its own) and the per-row scales
+  int8_t* ozP = nullptr;
+  double* oz_rscale = nullptr;
+  size_t oz_bytes = 0;    // bytes of ONE panel buffer of one slot
   ModelState model;       // upstream of the covariance (rows f1/f2); empty until sfb_set_model_host
   bool have_model = false;
   std::string err;
@@ -153,10 +158,21 @@ int join_streams(sfb_ctx* h, cudaStream_t caller, int nstreams) {
 //
 // so the latency-bound panel work of block J+1 hides under the bulk update of block J (they touch
 // disjoint tile columns).  On entry and exit all ordering is expressed on the main stream `lo`.
+int ensure_ozaki(sfb_ctx* h) {
+  if (h->ozP) return SFB_OK;
+  h->oz_bytes = oz_panel_bytes_per_slot(h->Np, h->outer_tiles);
+  if (cudaMalloc((void**)&h->ozP, 2 * h->oz_bytes * (size_t)h->slots) != cudaSuccess ||
+      cudaMalloc((void**)&h->oz_rscale, sizeof(double) * (size_t)h->Np * h->slots) != cudaSuccess)
+    return fail(h, SFB_ERR_NOMEM, "int8 solver: sliced-panel workspace allocation failed");
+  SFB_CUDA(h, ozaki_init());
+  return SFB_OK;
+}
+
 int run_cholesky(sfb_ctx* h, int lane, int slot0, int nb, double* lnL_out, int* info_out) {
   cudaStream_t lo = h->streams[lane];
   cudaStream_t hi = (h->profile || (h->debug_mode & 1)) ? lo : h->hi[lane];
   const bool two = (hi != lo);
+  const bool i8 = (h->solver == SFB_SOLVER_DENSE_I8);
   CholParams p;
   p.Np = h->Np;
   p.strideW = (long long)h->Np * h->Np;
@@ -169,14 +185,32 @@ int run_cholesky(sfb_ctx* h, int lane, int slot0, int nb, double* lnL_out, int* 
   p.info = h->info_ws + slot0;
   p.k0 = 0;
   const int nt = h->Np / kTile;
+  OzParams oz{nullptr, 0, nullptr};
+  if (i8) {
+    int rc = ensure_ozaki(h);
+    if (rc != SFB_OK) return rc;
+    oz.strideP = (long long)(2 * h->oz_bytes);
+    oz.rscale = h->oz_rscale + (long long)slot0 * h->Np;
+    SFB_CUDA(h, launch_oz_rowscale(p, oz, nb, lo));  // from the diagonal of the matrix as built
+    h->launches++;
+  }
   if (two) {  // hi starts after whatever produced the matrices on lo (build / copy-in)
     SFB_CUDA(h, cudaEventRecord(h->ev_lo[lane], lo));
     SFB_CUDA(h, cudaStreamWaitEvent(hi, h->ev_lo[lane], 0));
   }
   const int OT = h->outer_tiles;
-  for (int J0 = 0; J0 < nt; J0 += OT) {
+  // update of tile columns [jt0, jt0+njt) by the K columns starting at kb (strip), or of everything right of jt0 (tri)
+  auto strip = [&](int kb, int K, int jt0, int njt, cudaStream_t st) {
+    return i8 ? launch_oz_syrk_strip(p, oz, K, jt0, njt, nb, st)
+              : launch_syrk_strip(p, h->maps, slot0, kb, K, jt0, njt, nb, st);
+  };
+  auto tri = [&](int kb, int K, int jt0, cudaStream_t st) {
+    return i8 ? launch_oz_syrk_tri(p, oz, K, jt0, nb, st) : launch_syrk_tri(p, h->maps, slot0, kb, K, jt0, nb, st);
+  };
+  for (int J0 = 0, blk = 0; J0 < nt; J0 += OT, ++blk) {
     const int q = std::min(OT, nt - J0);
     const int kb = J0 * kTile;
+    if (i8) oz.P = h->ozP + (size_t)slot0 * 2 * h->oz_bytes + (size_t)(blk & 1) * h->oz_bytes;
     // ---- PANEL(J) on hi
     for (int c = 0; c < q; ++c) {
       const int jt = J0 + c;
@@ -186,7 +220,7 @@ int run_cholesky(sfb_ctx* h, int lane, int slot0, int nb, double* lnL_out, int* 
       if (c > 0) {
         const double rows = (double)(h->Np - p.k0), K = (double)c * kTile;
         ProfScope ps(h, hi, SFB_K_SYRK, nb * (2.0 * K * kTile * rows - K * kTile * (kTile - 1.0)));
-        SFB_CUDA(h, launch_syrk_strip(p, h->maps, slot0, kb, c * kTile, jt, 1, nb, hi));
+        SFB_CUDA(h, strip(kb, c * kTile, jt, 1, hi));
         h->launches++;
       }
       {
@@ -195,9 +229,16 @@ int run_cholesky(sfb_ctx* h, int lane, int slot0, int nb, double* lnL_out, int* 
         h->launches++;
       }
       if (!last) {
-        ProfScope ps(h, hi, SFB_K_TRSM, nb * (rem * kTile * kTile));  // useful FLOPs of a triangular solve
-        SFB_CUDA(h, launch_trsm(p, h->maps, slot0, nb, hi));
-        h->launches++;
+        {
+          ProfScope ps(h, hi, SFB_K_TRSM, nb * (rem * kTile * kTile));  // useful FLOPs of a triangular solve
+          SFB_CUDA(h, launch_trsm(p, h->maps, slot0, nb, hi));
+          h->launches++;
+        }
+        if (i8) {  // fixed-point restatement of the panel just solved -> chunks [4c, 4c+4) of this block's buffer
+          ProfScope ps(h, hi, SFB_K_OZ_SLICE, nb * rem * kTile * (8.0 + kOzSlices));
+          SFB_CUDA(h, launch_oz_slice(p, oz, c * (kTile / kOzChunk), nb, hi));
+          h->launches++;
+        }
       }
     }
     const int jn = J0 + q;  // first tile column right of this block
@@ -212,13 +253,13 @@ int run_cholesky(sfb_ctx* h, int lane, int slot0, int nb, double* lnL_out, int* 
     {  // ---- NEXT(J): tile columns [jn, jn+qn), on hi
       const double rows = (double)(h->Np - jn * kTile), w = (double)qn * kTile;
       ProfScope ps(h, hi, SFB_K_SYRK, nb * (2.0 * K * w * rows - K * w * (w - 1.0)));
-      SFB_CUDA(h, launch_syrk_strip(p, h->maps, slot0, kb, q * kTile, jn, qn, nb, hi));
+      SFB_CUDA(h, strip(kb, q * kTile, jn, qn, hi));
       h->launches++;
     }
     if (jn + qn < nt) {  // ---- REST(J): everything right of the next block, on lo
       const double n = (double)(h->Np - (jn + qn) * kTile);
       ProfScope ps(h, lo, SFB_K_SYRK, nb * (n * (n + 1.0) * K));  // algorithmic syrk FLOPs: n(n+1)k
-      SFB_CUDA(h, launch_syrk_tri(p, h->maps, slot0, kb, q * kTile, jn + qn, nb, lo));
+      SFB_CUDA(h, tri(kb, q * kTile, jn + qn, lo));
       h->launches++;
     }
     if (two) SFB_CUDA(h, cudaEventRecord(h->ev_lo[lane], lo));
@@ -564,6 +605,8 @@ int sfb_destroy(sfb_t* h) {
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   free_gemm_maps(&h->maps);
   model_free(&h->model);
+  if (h->ozP) cudaFree(h->ozP);
+  if (h->oz_rscale) cudaFree(h->oz_rscale);
   if (h->Sb) cudaFree(h->Sb);
   if (h->bw_d) cudaFree(h->bw_d);
   if (h->overflow) cudaFree(h->overflow);
@@ -945,7 +988,8 @@ int sfb_spline_halfwidth(void) { return kSplineW; }
 
 int sfb_set_solver(sfb_t* h, int solver) {
   if (!h) return SFB_ERR_ARG;
-  if (solver != SFB_SOLVER_DENSE && solver != SFB_SOLVER_STRUCTURED) return fail(h, SFB_ERR_ARG, "unknown solver");
+  if (solver != SFB_SOLVER_DENSE && solver != SFB_SOLVER_STRUCTURED && solver != SFB_SOLVER_DENSE_I8)
+    return fail(h, SFB_ERR_ARG, "unknown solver");
   h->solver = solver;
   return SFB_OK;
 }

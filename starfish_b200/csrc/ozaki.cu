@@ -1,0 +1,364 @@
+// fp64-equivalent trailing update on the int8 tensor path (tcgen05.mma kind::i8, TMEM accumulators) — the
+// SFB_SOLVER_DENSE_I8 mode of the dense factorisation (sm_100a).
+//
+// The dense path is fp64-bound: A_ij −= L_ik·L_jkᵀ is N³/3 of its FLOPs and the fp64 tensor rate (DMMA,
+// 37.1 TFLOP/s) caps it at 201 evals/s per GPU (N=8192).  tcgen05 has no fp64 kind, but it multiplies int8
+// exactly into int32.  This file restates the update's OPERANDS in fixed point and keeps every product exact
+// (an Ozaki-style split; it is not iterative refinement — potrf_diag, trsm, the forward solve and logdet stay
+// true fp64, chol.cu):
+//
+//   row scale  2^e_i ∈ (2√C_ii, 4√C_ii]   (C_ii = the diagonal before the factorisation; |L_ik| ≤ √C_ii for an
+//                                          SPD matrix, so |L_ik|/2^e_i < ½ for every panel, fixed up front)
+//   q_ik     = rint(L_ik · 2^(47−e_i))     a 48-bit signed integer
+//   q_ik     = Σ_t b_ikt·256^(5−t)         six balanced radix-256 digits, b ∈ [−128, 127]  (int8 "slices")
+//   L_ik·L_jk ≈ 2^(e_i+e_j−14) · Σ_{d=0..6} 256^(−d) · S_d ,   S_d = Σ_k Σ_{s+t=d} b_iks·b_jkt
+//
+// Every S_d is exact in int32 (|S_d| ≤ 6·2^14·1024 < 2^27 for K ≤ 1024), so one TMEM accumulator per
+// anti-diagonal d: 7 accumulators × 64 columns = 448 of the 512 TMEM columns for a 128×64 tile, fed by 26 int8
+// MMAs per 32-deep k-chunk (pairs s,t ≤ 5, s+t ≤ 6).  What is dropped is the anti-diagonals d ≥ 7 and the
+// rounding of q: measured |ΔlnL|/|lnL| ≤ 1.6e-12 against the dense oracle up to cond 7e5 (tools/ozaki_experiment.py,
+// tests/test_gpu_ozaki.py; 5 accumulators give 1e-7 — the anti-diagonal count, not the digit count, is what
+// matters).  The epilogue recombines Σ_d 256^(−d)·S_d by Horner in fp64 and applies C −= 2^(e_i−7)·2^(e_j−7)·(…).
+//
+// Data layout.  The sliced panels of the current outer block live in P (per slot), pre-tiled so that an operand
+// tile is ONE contiguous block and already in the canonical K-major shared-memory layout of the MMA:
+//     P[chunk c (32 k)][row group g = row/8][slice t][row%8][32 bytes]        (NCH × Np/8 × 6 × 256 B)
+// -> the A operand (128 rows, all slices) of a chunk is 24 KB contiguous, the B operand (64 rows) 12 KB: two 1-D
+// bulk async copies (cp.async.bulk, SASS UBLKCP) per pipeline stage, no tensor map.  Inside a 256-byte row group
+// the two 16-byte halves of a row are XOR-swapped by bit 2 of the row (the 32-byte swizzle pattern, applied by
+// the slicing kernel), and the 8-row groups of one slice are 6·256 = 1536 B apart: UMMA descriptor
+// {SWIZZLE_32B, SBO = 1536}.
+//
+// Kernel shape: 192 threads = warp 0 bulk-copy producer (one lane), warp 1 MMA issuer (one lane) + TMEM
+// allocator, warps 2-5 epilogue (TMEM lane quarter = warp%4).  5-stage ring of 36 KB, full/empty mbarriers,
+// tcgen05.commit releases a stage / signals the epilogue.
+#include <cstdint>
+
+#include "sfb_internal.cuh"
+
+namespace sfb {
+
+namespace {
+
+constexpr int OZ_S = kOzSlices;      // 6
+constexpr int OZ_NACC = 7;           // anti-diagonals 0..6
+constexpr int OZ_KC = kOzChunk;      // 32
+constexpr int OZ_BM = 128, OZ_BN = 64;
+constexpr int OZ_STAGES = 5;
+constexpr int OZ_GROUP_BYTES = 8 * OZ_KC;                    // 256: 8 rows × 32 B of one slice
+constexpr int OZ_ROWGROUP_BYTES = OZ_S * OZ_GROUP_BYTES;     // 1536: all slices of 8 rows
+constexpr int OZ_A_BYTES = (OZ_BM / 8) * OZ_ROWGROUP_BYTES;  // 24576
+constexpr int OZ_B_BYTES = (OZ_BN / 8) * OZ_ROWGROUP_BYTES;  // 12288
+constexpr int OZ_STAGE_BYTES = OZ_A_BYTES + OZ_B_BYTES;      // 36864
+constexpr int OZ_THREADS = 192;
+constexpr int OZ_SMEM_BYTES = OZ_STAGES * OZ_STAGE_BYTES + 1024;  // + alignment slack
+constexpr uint32_t OZ_TMEM_COLS = 512;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_test(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem]·B[smem]ᵀ, int8 × int8 -> int32, one thread issues for the CTA (SASS UTCIMMA)
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier when every MMA issued so far by this thread has completed (implies
+// tcgen05.fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n.reg .b32 rx;\n.reg .pred px;\nelect.sync rx|px, %1;\n@px mov.s32 %0, 1;\n}\n"
+      : "+r"(pred)
+      : "r"(0xffffffffu));
+  return pred != 0;
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory matrix descriptor, K-major, SWIZZLE_32B (layout code 6), descriptor version 1:
+// start address, LBO (unused for swizzled K-major; canonical value 1) and SBO in 16-byte units.
+__device__ __forceinline__ uint64_t oz_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)1 << 16) | ((uint64_t)(OZ_ROWGROUP_BYTES >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)6 << 61);
+}
+// instruction descriptor: D = S32 (2 << 4), A = B = signed int8 (1 << 7, 1 << 10), both K-major, N >> 3, M >> 4
+constexpr uint32_t OZ_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BN >> 3) << 17) |
+                              ((uint32_t)(OZ_BM >> 4) << 24);
+
+// ------------------------------------------------------------------------------------------------
+// syrk on the int8 path: C[r0.., c0..] −= Σ_{chunks} (sliced L rows r0..) · (sliced L rows c0..)ᵀ.
+// Grid shapes as chol.cu's syrk_kernel (strip / triangle).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+    syrk_i8_kernel(CholParams p, OzParams oz, int nch, int jt0, int strip) {
+  const int s = blockIdx.z;
+  if (p.info[s] != 0) return;
+  int it, c0;
+  if (strip) {
+    const int jt = jt0 + (blockIdx.x >> 1);
+    it = jt0 + blockIdx.y;
+    if (it < jt) return;
+    c0 = jt * kTile + (blockIdx.x & 1) * 64;
+  } else {
+    const int L = blockIdx.x;
+    int t = (int)((sqrtf(4.0f * (float)L + 1.0f) - 1.0f) * 0.5f);
+    while (t * (t + 1) > L) --t;
+    while ((t + 1) * (t + 2) <= L) ++t;
+    it = jt0 + t;
+    c0 = jt0 * kTile + (L - t * (t + 1)) * 64;
+  }
+  const int r0 = it * kTile;
+
+  extern __shared__ uint8_t oz_smem_raw[];
+  __shared__ uint64_t bars[2 * OZ_STAGES + 1];
+  __shared__ uint32_t tmem_base_s;
+  const uint32_t ring = (smem_u32(oz_smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar0 = smem_u32(bars);  // full[s] at +8s, empty[s] at +8(STAGES+s), accfull at +16·STAGES
+  const uint32_t accfull = bar0 + 16 * OZ_STAGES;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < 2 * OZ_STAGES + 1; ++i) mbar_init(bar0 + 8 * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), OZ_TMEM_COLS);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+
+  const int8_t* Ps = oz.P + (long long)s * oz.strideP;
+  const long long chunk_bytes = (long long)(p.Np / 8) * OZ_ROWGROUP_BYTES;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ---- producer: two contiguous bulk copies per chunk
+      const int8_t* srcA = Ps + (long long)(r0 / 8) * OZ_ROWGROUP_BYTES;
+      const int8_t* srcB = Ps + (long long)(c0 / 8) * OZ_ROWGROUP_BYTES;
+      for (int c = 0; c < nch; ++c) {
+        const int st = c % OZ_STAGES;
+        if (c >= OZ_STAGES) mbar_wait(bar0 + 8 * (OZ_STAGES + st), ((c / OZ_STAGES) - 1) & 1);
+        const uint32_t full = bar0 + 8 * st;
+        const uint32_t dst = ring + st * OZ_STAGE_BYTES;
+        mbar_arrive_expect_tx(full, OZ_STAGE_BYTES);
+        bulk_g2s(dst, srcA + c * chunk_bytes, OZ_A_BYTES, full);
+        bulk_g2s(dst + OZ_A_BYTES, srcB + c * chunk_bytes, OZ_B_BYTES, full);
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer: 26 int8 MMAs per chunk into 7 accumulators.  The whole warp runs the loop (descriptor
+    // arithmetic stays warp-uniform, i.e. in uniform registers); one elected lane issues.
+    const bool leader = elect_one();
+    for (int c = 0; c < nch; ++c) {
+      const int st = c % OZ_STAGES;
+      mbar_wait(bar0 + 8 * st, (c / OZ_STAGES) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t a0 = ring + st * OZ_STAGE_BYTES, b0 = a0 + OZ_A_BYTES;
+      const uint64_t ad0 = oz_desc(a0), bd0 = oz_desc(b0);
+      const uint32_t acc = (c == 0) ? 0u : 1u;
+      if (leader) {
+#pragma unroll
+        for (int sa = 0; sa < OZ_S; ++sa) {
+#pragma unroll
+          for (int sb = 0; sb < OZ_S; ++sb) {
+            if (sa + sb >= OZ_NACC) continue;
+            // the start-address field counts 16-byte units and the ring never crosses its 14-bit range inside a
+            // stage, so the other slices' descriptors are the stage's plus a constant
+            const uint64_t ad = ad0 + (uint64_t)(sa * (OZ_GROUP_BYTES >> 4));
+            const uint64_t bd = bd0 + (uint64_t)(sb * (OZ_GROUP_BYTES >> 4));
+            // the first pair that touches anti-diagonal d is (sa = 0, sb = d) for d < 6 and (1, 5) for d = 6
+            const bool first = (sa == 0) || (sa == 1 && sb == OZ_S - 1);
+            umma_i8(tmem + (uint32_t)(sa + sb) * OZ_BN, ad, bd, OZ_IDESC, first ? acc : 1u);
+          }
+        }
+        umma_commit(bar0 + 8 * (OZ_STAGES + st));  // stage free once these MMAs have read it
+      }
+      __syncwarp();
+    }
+    if (leader) umma_commit(accfull);
+    __syncwarp();
+  } else {
+    // ---- epilogue: thread = tile row (TMEM lane), 4 blocks of 16 columns
+    const int q = warp & 3;             // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;      // tile row
+    const double* rs = oz.rscale + (long long)s * p.Np;
+    const double ri = rs[r0 + row];
+    double* Crow = p.W + (long long)s * p.strideW + (long long)(r0 + row) * p.Np + c0;
+    mbar_wait(accfull, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+    for (int cb = 0; cb < OZ_BN / 16; ++cb) {
+      double acc[16];
+      uint32_t v[16];
+      tmem_ld16(tlane + (OZ_NACC - 1) * OZ_BN + cb * 16, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] = (double)(int)v[j];
+#pragma unroll
+      for (int d = OZ_NACC - 2; d >= 0; --d) {
+        tmem_ld16(tlane + d * OZ_BN + cb * 16, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = fma(acc[j], 0.00390625, (double)(int)v[j]);
+      }
+      double2* Cv = reinterpret_cast<double2*>(Crow + cb * 16);
+      const double2* rj = reinterpret_cast<const double2*>(rs + c0 + cb * 16);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        double2 c = Cv[j];
+        const double2 sc = rj[j];
+        c.x -= acc[2 * j] * (ri * sc.x);
+        c.y -= acc[2 * j + 1] * (ri * sc.y);
+        Cv[j] = c;
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, OZ_TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// row scales from the diagonal of the (not yet factorised) matrix: rscale_i = 2^(e_i − 7)
+// ------------------------------------------------------------------------------------------------
+__global__ void oz_rowscale_kernel(CholParams p, OzParams oz) {
+  const int s = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.Np) return;
+  const double d = p.W[(long long)s * p.strideW + (long long)i * p.Np + i];
+  double r = 1.0;
+  if (d > 0.0 && d < 1e300) {
+    int ex;
+    frexp(sqrt(d), &ex);        // sqrt(d) = m·2^ex, m ∈ [0.5, 1)  ->  2^(ex+1) ∈ (2√d, 4√d]
+    r = ldexp(1.0, ex + 1 - 7);
+  }
+  oz.rscale[(long long)s * p.Np + i] = r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// slice the panel just produced by trsm (rows k0+128.., columns k0..k0+127) into chunks [ch0, ch0+4) of P.
+// A warp takes one row: lane l owns k = 4l..4l+3 (one coalesced 1 KB row read), six packed 4-byte stores.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) oz_slice_kernel(CholParams p, OzParams oz, int ch0) {
+  const int s = blockIdx.y;
+  if (p.info[s] != 0) return;
+  const int lane = threadIdx.x & 31;
+  const int row = p.k0 + kTile + blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= p.Np) return;
+  const double* src = p.W + (long long)s * p.strideW + (long long)row * p.Np + p.k0 + 4 * lane;
+  const double2 v01 = *reinterpret_cast<const double2*>(src);
+  const double2 v23 = *reinterpret_cast<const double2*>(src + 2);
+  const double inv = 1099511627776.0 / oz.rscale[(long long)s * p.Np + row];  // 2^40 / 2^(e−7) = 2^(47−e)
+  const double lim = 140737488355327.0;                                       // 2^47 − 1
+  long long qv[4];
+  qv[0] = __double2ll_rn(fmin(fmax(v01.x * inv, -lim), lim));
+  qv[1] = __double2ll_rn(fmin(fmax(v01.y * inv, -lim), lim));
+  qv[2] = __double2ll_rn(fmin(fmax(v23.x * inv, -lim), lim));
+  qv[3] = __double2ll_rn(fmin(fmax(v23.y * inv, -lim), lim));
+  uint32_t packed[OZ_S];
+#pragma unroll
+  for (int t = OZ_S - 1; t >= 0; --t) {  // least significant digit first
+    uint32_t w = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const long long dgt = (long long)(int8_t)(qv[e] & 0xff);
+      qv[e] = (qv[e] - dgt) >> 8;
+      w |= ((uint32_t)dgt & 0xffu) << (8 * e);
+    }
+    packed[t] = w;
+  }
+  const int chunk = ch0 + (lane >> 3);
+  const int kb = (4 * lane) & 31;                       // byte inside the 32-byte row
+  const int r8 = row & 7;
+  const int half = ((kb >> 4) ^ (r8 >> 2)) & 1;         // 32-byte swizzle: 16-byte halves swapped for rows 4-7
+  int8_t* dst = oz.P + (long long)s * oz.strideP +
+                ((long long)chunk * (p.Np / 8) + (row >> 3)) * OZ_ROWGROUP_BYTES + r8 * OZ_KC + half * 16 + (kb & 15);
+#pragma unroll
+  for (int t = 0; t < OZ_S; ++t) *reinterpret_cast<uint32_t*>(dst + t * OZ_GROUP_BYTES) = packed[t];
+}
+
+}  // namespace
+
+cudaError_t ozaki_init() {
+  return cudaFuncSetAttribute((const void*)syrk_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES);
+}
+
+size_t oz_panel_bytes_per_slot(int Np, int outer_tiles) {
+  return (size_t)(outer_tiles * (kTile / OZ_KC)) * (size_t)(Np / 8) * OZ_ROWGROUP_BYTES;
+}
+
+cudaError_t launch_oz_rowscale(const CholParams& p, const OzParams& oz, int B, cudaStream_t st) {
+  oz_rowscale_kernel<<<dim3((p.Np + 255) / 256, B), 256, 0, st>>>(p, oz);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_oz_slice(const CholParams& p, const OzParams& oz, int chunk0, int B, cudaStream_t st) {
+  const int rows = p.Np - p.k0 - kTile;
+  if (rows <= 0) return cudaSuccess;
+  oz_slice_kernel<<<dim3(rows / 8, B), 256, 0, st>>>(p, oz, chunk0);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_oz_syrk_strip(const CholParams& p, const OzParams& oz, int K, int jt0, int njt, int B,
+                                 cudaStream_t st) {
+  const int rows = p.Np / kTile - jt0;
+  if (rows <= 0 || K <= 0 || njt <= 0) return cudaSuccess;
+  syrk_i8_kernel<<<dim3(2 * njt, rows, B), OZ_THREADS, OZ_SMEM_BYTES, st>>>(p, oz, K / OZ_KC, jt0, 1);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_oz_syrk_tri(const CholParams& p, const OzParams& oz, int K, int jt0, int B, cudaStream_t st) {
+  const int T = p.Np / kTile - jt0;
+  if (T <= 0 || K <= 0) return cudaSuccess;
+  syrk_i8_kernel<<<dim3(T * (T + 1), 1, B), OZ_THREADS, OZ_SMEM_BYTES, st>>>(p, oz, K / OZ_KC, jt0, 0);
+  return cudaGetLastError();
+}
+
+}  // namespace sfb

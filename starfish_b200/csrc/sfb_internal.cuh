@@ -89,6 +89,22 @@ cudaError_t launch_solve_lower(const double* L, long long strideL, int ldl, cons
                                int N, int B, cudaStream_t st);
 cudaError_t kernels_init();  // sets max dynamic shared memory attributes
 
+// ---- int8 tensor-core trailing update (SFB_SOLVER_DENSE_I8, ozaki.cu) ----
+constexpr int kOzSlices = 6;   // balanced radix-256 digits per fp64 operand element (48-bit fixed point per row)
+constexpr int kOzChunk = 32;   // k per MMA / pipeline stage (bytes per row per slice)
+struct OzParams {
+  int8_t* P;             // sliced panels of the current outer block: slot s at P + s*strideP
+  long long strideP;     // bytes per slot
+  double* rscale;        // per slot, Np doubles: 2^(e_i - 7)
+};
+cudaError_t ozaki_init();
+size_t oz_panel_bytes_per_slot(int Np, int outer_tiles);
+cudaError_t launch_oz_rowscale(const CholParams& p, const OzParams& oz, int B, cudaStream_t st);
+cudaError_t launch_oz_slice(const CholParams& p, const OzParams& oz, int chunk0, int B, cudaStream_t st);
+cudaError_t launch_oz_syrk_strip(const CholParams& p, const OzParams& oz, int K, int jt0, int njt, int B,
+                                 cudaStream_t st);
+cudaError_t launch_oz_syrk_tri(const CholParams& p, const OzParams& oz, int K, int jt0, int B, cudaStream_t st);
+
 }  // namespace sfb
 
 // ---------------------------------------------------------------------------------------------

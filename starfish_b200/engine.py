@@ -223,14 +223,16 @@ class LikelihoodEngine:
     def set_solver(self, solver: str):
         """'dense' (default: blocked fp64 Cholesky of the N×N covariance) or 'structured' (banded Cholesky of
         diag + kernels, rank-M capacitance system; walkers whose band does not fit take the dense path)."""
-        code = {"dense": _lib.SOLVER_DENSE, "structured": _lib.SOLVER_STRUCTURED}.get(solver)
+        code = {"dense": _lib.SOLVER_DENSE, "structured": _lib.SOLVER_STRUCTURED,
+                "dense_i8": _lib.SOLVER_DENSE_I8}.get(solver)
         if code is None:
-            raise ValueError("solver must be 'dense' or 'structured'")
+            raise ValueError("solver must be 'dense', 'dense_i8' or 'structured'")
         self._check(self._lib.sfb_set_solver(self._h, code), "sfb_set_solver")
 
     @property
     def solver(self) -> str:
-        return "structured" if self._lib.sfb_get_solver(self._h) == _lib.SOLVER_STRUCTURED else "dense"
+        return {_lib.SOLVER_STRUCTURED: "structured", _lib.SOLVER_DENSE_I8: "dense_i8"}.get(
+            self._lib.sfb_get_solver(self._h), "dense")
 
     def band_classes(self):
         """{window width: walkers routed to it since creation}; key 0 is the dense fallback."""

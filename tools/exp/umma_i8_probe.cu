@@ -1,0 +1,321 @@
+// tcgen05.mma kind::i8 probe for sm_100a (B200): settles, in ONE box visit, the facts the int8 (Ozaki) trailing
+// update depends on and that cannot be checked without a GPU:
+//   1. which shared-memory descriptor encodings (no swizzle / 32B / 64B / 128B swizzle, K-major, arbitrary SBO)
+//      produce D = A·Bᵀ exactly (checked against a CPU int32 GEMM),
+//   2. the dispatch pace of 128×N×32 int8 MMAs from shared memory for N = 64, 128, 256 (is 128×64 smem-bound?),
+//   3. the TMEM→register read rate of the epilogue (tcgen05.ld 32x32b).
+// Build:  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/exp/umma_i8_probe tools/exp/umma_i8_probe.cu
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#define CK(x)                                                                      \
+  do {                                                                             \
+    cudaError_t e_ = (x);                                                          \
+    if (e_ != cudaSuccess) {                                                       \
+      printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+      exit(1);                                                                     \
+    }                                                                              \
+  } while (0)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_test(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout)
+__host__ __device__ inline uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  d |= (uint64_t)layout << 61;
+  return d;
+}
+__host__ __device__ inline uint32_t make_idesc_i8(int M, int N) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------
+// correctness: one CTA, operands written to shared memory by the threads in the layout under test
+// ------------------------------------------------------------------------------------------------
+struct Variant {
+  int layout;      // descriptor layout code: 0 none, 6 = 32B, 4 = 64B, 2 = 128B
+  int row_bytes;   // bytes of K per row held in one slab (16-byte interleave for layout 0)
+  int swz_bits;    // XOR bits [4,4+swz_bits) with bits [7,7+swz_bits)
+  int sbo;         // bytes between 8-row groups
+  int lbo;         // bytes between the two 16-byte K chunks (no swizzle only)
+  int ksteps;      // number of K=32 MMAs (start address advanced by 32 B each)
+};
+
+// byte offset of element (row r, byte k) inside a slab
+__host__ __device__ inline uint32_t slab_off(const Variant& v, int r, int k) {
+  if (v.layout == 0) {  // core matrices of 8 rows × 16 B
+    return (uint32_t)((r >> 3) * v.sbo + (k >> 4) * v.lbo + (r & 7) * 16 + (k & 15));
+  }
+  uint32_t off = (uint32_t)((r >> 3) * v.sbo + (r & 7) * v.row_bytes + k);
+  const uint32_t mask = (1u << v.swz_bits) - 1;
+  off ^= ((off >> 7) & mask) << 4;
+  return off;
+}
+
+constexpr int M_ = 128;
+
+__global__ void __launch_bounds__(128, 1)
+    probe_kernel(const int8_t* A, const int8_t* B, int N, int K, Variant v, int32_t* D, int a_bytes, int b_bytes) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + a_bytes;
+  for (int i = tid; i < a_bytes + b_bytes; i += blockDim.x) smem[i] = 0;
+  __syncthreads();
+  for (int i = tid; i < M_ * K; i += blockDim.x) sA[slab_off(v, i / K, i % K)] = (uint8_t)A[i];
+  for (int i = tid; i < N * K; i += blockDim.x) sB[slab_off(v, i / K, i % K)] = (uint8_t)B[i];
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (tid == 0) {
+    mbar_init(smem_u32(&bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_base), 256);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tb = tmem_base;
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc_i8(M_, N);
+    for (int ks = 0; ks < v.ksteps; ++ks) {
+      const uint32_t adv = (v.layout == 0) ? ks * 2 * v.lbo : ks * 32;
+      const uint64_t ad = make_desc(smem_u32(sA) + adv, v.lbo, v.sbo, v.layout);
+      const uint64_t bd = make_desc(smem_u32(sB) + adv, v.lbo, v.sbo, v.layout);
+      umma_i8(tb, ad, bd, idesc, ks > 0);
+    }
+    umma_commit(smem_u32(&bar));
+  }
+  mbar_wait(smem_u32(&bar), 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    uint32_t r[16];
+    tmem_ld16(tb + ((uint32_t)(warp * 32) << 16) + c0, r);
+    tmem_ld_wait();
+    for (int j = 0; j < 16; ++j) D[(size_t)tid * N + c0 + j] = (int32_t)r[j];
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, 256);
+}
+
+// ------------------------------------------------------------------------------------------------
+// pace: the issue loop of the real kernel (ozaki.cu): per chunk 26 MMAs of 128×N×32 over six A and six B slices
+// laid out [row group][slice][8 rows][32 B] (SW32, SBO = 1536), NACC accumulators, warp-uniform loop with one
+// elected lane; cycles by clock64 around the loop + final commit.  Then the epilogue read of 448 TMEM columns.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n.reg .b32 rx;\n.reg .pred px;\nelect.sync rx|px, %1;\n@px mov.s32 %0, 1;\n}\n" : "+r"(pred) : "r"(0xffffffffu));
+  return pred != 0;
+}
+__host__ __device__ inline uint64_t desc_sw32(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)1 << 16) | ((uint64_t)(1536 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)6 << 61);
+}
+template <int N>
+__global__ void __launch_bounds__(128, 1) pace_kernel(int chunks, int nstage, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  constexpr int NACC = (N == 64) ? 7 : (N == 128 ? 3 : 2);
+  constexpr int A_BYTES = 16 * 1536, B_BYTES = (N / 8) * 1536, STAGE = A_BYTES + B_BYTES;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < nstage * STAGE; i += blockDim.x) smem[i] = (uint8_t)(i * 7 + 3);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (tid == 0) {
+    mbar_init(smem_u32(&bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_base), 512);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tb = tmem_base;
+  if (warp == 1) {
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc_i8(M_, N);
+    const long long t0 = clock64();
+    for (int c = 0; c < chunks; ++c) {
+      const uint32_t a0 = smem_u32(smem) + (c % nstage) * STAGE, b0 = a0 + A_BYTES;
+      const uint64_t ad0 = desc_sw32(a0), bd0 = desc_sw32(b0);
+      if (leader) {
+#pragma unroll
+        for (int sa = 0; sa < 6; ++sa)
+#pragma unroll
+          for (int sb = 0; sb < 6; ++sb) {
+            if (sa + sb >= 7) continue;
+            umma_i8(tb + (uint32_t)((sa + sb) % NACC) * N, ad0 + sa * 16, bd0 + sb * 16, idesc, 1);
+          }
+      }
+      __syncwarp();
+    }
+    if (leader) umma_commit(smem_u32(&bar));
+    __syncwarp();
+    mbar_wait(smem_u32(&bar), 0);
+    if (leader) out[0] = clock64() - t0;
+  } else {
+    mbar_wait(smem_u32(&bar), 0);
+  }
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  __syncthreads();
+  long long e0 = clock64();
+  uint32_t sink = 0;
+  for (int c0 = 0; c0 < 448; c0 += 16) {
+    uint32_t r[16];
+    tmem_ld16(tb + ((uint32_t)(warp * 32) << 16) + c0, r);
+    tmem_ld_wait();
+    for (int j = 0; j < 16; ++j) sink ^= r[j];
+  }
+  long long e1 = clock64();
+  if (sink == 0x12345678u) out[3] = 1;
+  __syncthreads();
+  if (tid == 0) out[1] = e1 - e0;
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, 512);
+}
+
+template <int N>
+void run_pace(int sms) {
+  constexpr int STAGE = 16 * 1536 + (N / 8) * 1536;
+  const int nstage = (N == 256) ? 2 : 4;
+  long long* dout;
+  CK(cudaMalloc(&dout, 64));
+  CK(cudaFuncSetAttribute(pace_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  const int chunks = 256;
+  CK(cudaMemset(dout, 0, 64));
+  pace_kernel<N><<<1, 128, nstage * STAGE + 1024>>>(chunks, nstage, dout);
+  CK(cudaDeviceSynchronize());
+  long long h[4];
+  CK(cudaMemcpy(h, dout, 32, cudaMemcpyDeviceToHost));
+  printf("pace 128x%dx32 i8, real issue loop (26 MMAs/chunk): %.1f cycles per MMA (floor %d) -> %.0f MAC/clk/SM; epilogue read 448 cols: %lld cycles\n",
+         N, (double)h[0] / (chunks * 26.0), 128 * N / 256, 128.0 * N * 32 * chunks * 26.0 / (double)h[0], h[1]);
+  cudaEvent_t a, b;
+  CK(cudaEventCreate(&a));
+  CK(cudaEventCreate(&b));
+  const int big = 40000;
+  pace_kernel<N><<<sms, 128, nstage * STAGE + 1024>>>(100, nstage, dout);
+  CK(cudaEventRecord(a));
+  pace_kernel<N><<<sms, 128, nstage * STAGE + 1024>>>(big, nstage, dout);
+  CK(cudaEventRecord(b));
+  CK(cudaDeviceSynchronize());
+  float ms;
+  CK(cudaEventElapsedTime(&ms, a, b));
+  const double ops = 2.0 * 128 * N * 32 * 26.0 * (double)big * sms;
+  printf("chip 128x%dx32 i8 on %d SMs: %.2f ms -> %.1f TOP/s\n", N, sms, ms, ops / ms * 1e-9);
+  cudaFree(dout);
+}
+
+int main() {
+  int dev = 0;
+  CK(cudaSetDevice(dev));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, dev));
+  printf("device %s sm_%d%d, %d SMs\n", prop.name, prop.major, prop.minor, prop.multiProcessorCount);
+  CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+
+  const int N = 64;
+  struct Named { const char* name; Variant v; };
+  const Named vars[] = {
+      {"none  K=32  lbo=128 sbo=256", {0, 16, 0, 256, 128, 1}},
+      {"none  K=64  lbo=128 sbo=512 (2 steps)", {0, 16, 0, 512, 128, 2}},
+      {"sw32  K=32  sbo=256", {6, 32, 1, 256, 16, 1}},
+      {"sw32  K=32  sbo=1536 (slices interleaved)", {6, 32, 1, 1536, 16, 1}},
+      {"sw64  K=64  sbo=512  (2 steps)", {4, 64, 2, 512, 16, 2}},
+      {"sw128 K=128 sbo=1024 (4 steps)", {2, 128, 3, 1024, 16, 4}},
+      {"sw128 K=128 sbo=1024 lbo=0 (4 steps)", {2, 128, 3, 1024, 0, 4}},
+  };
+  for (const Named& nv : vars) {
+    const Variant v = nv.v;
+    const int K = 32 * v.ksteps;
+    std::vector<int8_t> A(M_ * K), B(N * K);
+    srand(1234);
+    for (auto& x : A) x = (int8_t)(rand() % 256 - 128);
+    for (auto& x : B) x = (int8_t)(rand() % 256 - 128);
+    const int a_bytes = ((M_ / 8) * v.sbo + 1023) / 1024 * 1024 + 1024;
+    const int b_bytes = ((N / 8) * v.sbo + 1023) / 1024 * 1024 + 1024;
+    int8_t *dA, *dB;
+    int32_t* dD;
+    CK(cudaMalloc(&dA, A.size()));
+    CK(cudaMalloc(&dB, B.size()));
+    CK(cudaMalloc(&dD, sizeof(int32_t) * M_ * N));
+    CK(cudaMemcpy(dA, A.data(), A.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dB, B.data(), B.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemset(dD, 0xff, sizeof(int32_t) * M_ * N));
+    probe_kernel<<<1, 128, a_bytes + b_bytes>>>(dA, dB, N, K, v, dD, a_bytes, b_bytes);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+      printf("%-45s : CUDA error %s\n", nv.name, cudaGetErrorString(e));
+      return 1;
+    }
+    std::vector<int32_t> D(M_ * N);
+    CK(cudaMemcpy(D.data(), dD, sizeof(int32_t) * M_ * N, cudaMemcpyDeviceToHost));
+    long long bad = 0, maxd = 0;
+    for (int i = 0; i < M_; ++i)
+      for (int j = 0; j < N; ++j) {
+        int32_t ref = 0;
+        for (int k = 0; k < K; ++k) ref += (int32_t)A[i * K + k] * (int32_t)B[j * K + k];
+        long long d = llabs((long long)ref - D[i * N + j]);
+        if (d) ++bad;
+        if (d > maxd) maxd = d;
+      }
+    printf("%-45s : %s (mismatches %lld of %d, max |diff| %lld)\n", nv.name, bad ? "WRONG" : "exact", bad, M_ * N, maxd);
+    cudaFree(dA); cudaFree(dB); cudaFree(dD);
+  }
+
+  run_pace<64>(prop.multiProcessorCount);
+  run_pace<128>(prop.multiProcessorCount);
+  run_pace<256>(prop.multiProcessorCount);
+  return 0;
+}

@@ -7,7 +7,7 @@
 set -u
 TAG=${1:-ab}
 mkdir -p gpurun_out
-for V in default rolled la rank1; do
+for V in default rolled rank1 la; do
   case $V in
     default) unset SFB_BAND_MMA_ROLLED SFB_BAND_MMA_LA SFB_BAND_RANK1 ;;
     rolled)  unset SFB_BAND_MMA_LA SFB_BAND_RANK1; export SFB_BAND_MMA_ROLLED=1 ;;
