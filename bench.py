@@ -389,9 +389,8 @@ def run_b200(args, rank, world, local_rank):
             bc, bb = pr["band_chol"], pr["band_build"]
             ach = bc["work"] / (bc["ms"] * 1e-3) / 1e12 if bc["ms"] > 0 else 0.0
             structured["roofline"] = {
-                "kernel": ("band_chol_kernel (rank-1, SFB_BAND_RANK1)" if os.environ.get("SFB_BAND_RANK1") else
-                           "band_mma_kernel (rank-4 DMMA)") +
-                          " — register-resident sliding-window banded Cholesky + forward solves",
+                "kernel": "band_mma_kernel (rank-4 DMMA) — register-resident sliding-window banded Cholesky + "
+                          "forward solves",
                 "bound": "serial pivot chain (panel solve + barriers), then fp64 issue", "achieved": ach, "peak": FP64_DFMA_PEAK_TFLOPS, "unit": "TFLOP/s",
                 "frac": ach / FP64_DFMA_PEAK_TFLOPS,
                 "peak_source": "DFMA peak measured by tools/fp64_peak.cu (profiles/r01_fp64_peak.txt)",

@@ -35,11 +35,16 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    """Build the shared library if it is missing or older than its sources. Returns its path."""
+def build(force=False, verbose=False, experiments=False):
+    """Build the shared library if it is missing or older than its sources. Returns its path.
+
+    ``experiments=True`` defines SFB_EXPERIMENTS: the A/B environment knobs (SFB_DEBUG_MODE, SFB_OUTER_TILES)
+    exist only in such a build; the shipped library reads no environment variables."""
     if not force and not needs_build():
         return LIB
     cmd = [_nvcc(), *NVCC_FLAGS]
+    if experiments:
+        cmd += ["-DSFB_EXPERIMENTS"]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
@@ -52,4 +57,5 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv or "--experiments" in sys.argv, verbose="-v" in sys.argv,
+                experiments="--experiments" in sys.argv))

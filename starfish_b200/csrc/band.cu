@@ -505,10 +505,10 @@ __device__ __forceinline__ double band_rcp(double x) {
   return fma(r, e, r);
 }
 
-// ROLLED = true (SFB_BAND_MMA_ROLLED=1, NOT YET RUN ON A GPU — prepared for the next A/B): one copy of the block body
-// instead of 2·lcm(TR,TC); the tile that holds the pivot columns / the retiring rows is then a run-time index and only
-// the publish and the entering-row code select it (a chain of TC resp. TR predicated copies).  Meant to bring the
-// 160-pixel kernel (30 k SASS instructions unrolled) back inside the instruction cache.
+// ROLLED = true (used for the 160-pixel window): one copy of the block body instead of 2·lcm(TR,TC); the tile that
+// holds the pivot columns / the retiring rows is then a run-time index and only the publish and the entering-row
+// code select it (a chain of TC resp. TR predicated copies).  It keeps the 160-pixel kernel (30 k SASS instructions
+// unrolled) inside the instruction cache (measured 6.89 vs 7.46 ms).
 template <int WD, int WRG, int WCG, int MAXNR, bool ROLLED>
 __global__ void __launch_bounds__(32 * WRG * WCG, 1)
 band_mma_kernel(BandCholParams p) {
@@ -806,330 +806,6 @@ band_mma_kernel(BandCholParams p) {
   if (tid == 0) band_epilogue(p, b, M, gram, logdet, info);
 }
 
-// ------------------------------------------------------------------------------------------------
-// Look-ahead variant of band_mma_kernel (SFB_BAND_MMA_LA=1, opt-in, NOT YET RUN ON A GPU — prepared for the next
-// A/B).  The ≈ 900-cycle panel of block n+1 runs while the other warps still issue block n's DMMAs:
-//   S1  every thread: right-hand sides and Gram matrix of block n;
-//   S2  the warp column that holds block n+1's pivot columns applies block n's DMMAs to THAT tile column first,
-//       lets block n's entering rows enter in that tile column (their values belong in the next panel, and an
-//       entered row must not receive block n's update afterwards), and publishes the raw panel of block n+1;
-//   NB  named barrier 1: everybody arrives, only the panel warps wait;
-//   S4  panel warps: panel of block n+1 into the other buffer set;
-//   S5  every warp: the remaining DMMAs of block n, the remaining entering rows;   one __syncthreads per block.
-// Indices are run-time (the ROLLED form): one copy of the body.
-// ------------------------------------------------------------------------------------------------
-template <int WD, int WRG, int WCG, int MAXNR>
-__global__ void __launch_bounds__(32 * WRG * WCG, 1)
-band_mma_la_kernel(BandCholParams p) {
-  constexpr int NT = 32 * WRG * WCG, TR = WD / 8 / WRG, TC = WD / 8 / WCG, ROWLEN = WD + NRP, BATCH = 16;
-  constexpr int NE = (WD * MAXNR + NT - 1) / NT;  // right-hand-side registers per thread
-  static_assert(TR <= TC && WD % (8 * WRG) == 0 && WD % (8 * WCG) == 0 && WD + MAXNR <= NT &&
-                    MAXNR * MAXNR <= NT && BATCH % (NT / 32) == 0,
-                "warp grid must tile the window; panel rows, Gram elements and ring rows need enough threads");
-  __shared__ __align__(16) double Praw[WD * 4];  // raw columns of the four pivots, [row residue][pivot]
-  __shared__ __align__(16) double Wn2[2][WD * 4];  // −W (unscaled panel): the DMMA A operand, per block parity
-  __shared__ __align__(16) double Lp2[2][WD * 4];  // L = W/d: the DMMA B operand
-  __shared__ double zraw[4][NRP], zW2[2][4][NRP], zL2[2][4][NRP];
-  __shared__ double facL2[2][4];  // L21, L31, L32 of a block (late-row correction)
-  __shared__ double gram[(kMaxM + 1) * (kMaxM + 1)];
-  extern __shared__ __align__(16) double ring[];  // [2][BATCH][ROWLEN]
-
-  const int b = p.rowmap ? p.rowmap[blockIdx.x] : blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wr = warp / WCG, wc = warp % WCG, g = lane >> 2, t = lane & 3;
-  const int N = p.N, M = p.M, NR = M + 1;
-  if (p.overflow[b] != 0 || *p.sorted == 0) {  // band wider than the window / grid not increasing: not ours
-    if (tid == 0) {
-      p.info[b] = p.overflow[b] != 0 ? -2 : -3;
-      p.lnL[b] = nan("");
-    }
-    return;
-  }
-  const double* Sb = p.Sb + (long long)b * p.strideSb;
-  const double* Xb = (M > 0) ? p.X + (long long)b * M * N : nullptr;
-  const double* Fb = p.model_flux + (long long)b * N;
-
-  auto rhs_at = [&](int i, int q) -> double {
-    if (i >= N) return 0.0;
-    return q == 0 ? Fb[i] - p.data_flux[i] : Xb[(long long)(q - 1) * N + i];
-  };
-  // Entering rows j0+WD … j0+WD+BATCH−1, one warp per ring row (BATCH == 16 warps): the band by 16-byte
-  // cp.async, X by 8-byte cp.async; the residual column is staged as its two terms (model flux in column WD,
-  // data flux in the spare column WD+NRP−1) and subtracted when the row is consumed, so nothing here waits for
-  // a global load; rows past the end of the matrix are the identity padding.
-  auto stage_issue = [&](int j0, double* dst) {
-   for (int rb = warp; rb < BATCH; rb += NT / 32) {
-    const int i = j0 + WD + rb;
-    double* drow = dst + rb * ROWLEN;
-    if (i < N) {
-      const double* srow = Sb + (long long)i * WD;
-      for (int c2 = lane; c2 < WD / 2; c2 += 32) cp_async16(drow + 2 * c2, srow + 2 * c2);
-      if (lane == 0) cp_async8(drow + WD, Fb + i);
-      else if (lane < NR) cp_async8(drow + WD + lane, Xb + (long long)(lane - 1) * N + i);
-      else if (lane == NRP - 1) cp_async8(drow + WD + NRP - 1, p.data_flux + i);
-    } else {
-      for (int c = lane; c < ROWLEN; c += 32) drow[c] = (c == 0) ? 1.0 : 0.0;
-    }
-   }
-    cp_async_commit();
-  };
-  static_assert(NRP <= 32, "one lane per right-hand-side column");
-
-  // ---- initial window: slot (r, c) = element (i = r, k = c) for k <= i
-  double a[TR][TC][2];
-#pragma unroll
-  for (int tr = 0; tr < TR; ++tr)
-#pragma unroll
-    for (int tc = 0; tc < TC; ++tc)
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int i = 8 * (wr * TR + tr) + g, k = 8 * (wc * TC + tc) + 2 * t + h;
-        double v = 0.0;
-        if (k <= i) v = (i < N) ? Sb[(long long)i * WD + (i - k)] : (k == i ? 1.0 : 0.0);
-        a[tr][tc][h] = v;
-      }
-  double rv[NE];
-  int rcode[NE];  // residue·32 + column of the right-hand-side element held in rv[e]; negative: none
-#pragma unroll
-  for (int e = 0; e < NE; ++e) {
-    const int idx = tid + NT * e;
-    const bool ok = idx < WD * NR;
-    const int res = idx / NR, q = idx - res * NR;
-    rcode[e] = ok ? res * 32 + q : -32;
-    rv[e] = ok ? rhs_at(res, q) : 0.0;
-  }
-  stage_issue(0, ring);
-
-  // Four rows enter together.  If the band comes within three pixels of the window width (b > WD − 4), an entering
-  // row j+WD+s reaches pivots j+s+1 … j+3 of the block that has just been eliminated without it; those updates are
-  // then applied as the row enters (below).  Whether this walker needs that is a CTA-uniform fact of its band.
-  int late_any = 0;
-  for (int idx = tid; idx < 3 * N; idx += NT) {
-    const int i = idx / 3, d = WD - 1 - (idx - 3 * i);
-    late_any |= (Sb[(long long)i * WD + d] != 0.0) ? 1 : 0;
-  }
-  const bool late = __syncthreads_or(late_any) != 0;
-
-  double logdet = 0.0, gacc = 0.0, mant = 1.0;
-  long long expo = 0;
-  int info = 0;
-  const int gp_ = tid / NR, gq_ = tid - (tid / NR) * NR;  // Gram element of this thread (tid < NR²)
-  const bool gram_on = tid < NR * NR;
-
-  constexpr int PANEL_WARPS = (WD + MAXNR + 31) / 32;  // warps that hold a panel row or right-hand-side column
-
-  // ---- pieces of a block --------------------------------------------------------------------------
-  // raw columns of the four pivots with residues jrp … jrp+3, and the pivot rows of the right-hand sides
-  auto publish = [&](int jrp) {
-    const int ct = jrp >> 3, tcp = ct % TC, ocp = ct / TC, ppp = (jrp >> 2) & 1;
-    if (wc == ocp && (t >> 1) == ppp) {
-#pragma unroll
-      for (int q = 0; q < TC; ++q)
-        if (q == tcp) {
-#pragma unroll
-          for (int tr = 0; tr < TR; ++tr)
-            *reinterpret_cast<double2*>(&Praw[(8 * (wr * TR + tr) + g) * 4 + 2 * (t & 1)]) =
-                make_double2(a[tr][q][0], a[tr][q][1]);
-        }
-    }
-#pragma unroll
-    for (int e = 0; e < NE; ++e) {
-      const int rs = rcode[e] >> 5;
-      if (rs >= jrp && rs < jrp + 4) zraw[rs - jrp][rcode[e] & 31] = rv[e];
-    }
-  };
-  // 4×4 LDLᵀ of the diagonal block (redundantly), then one row / one rhs column per thread (see band_mma_kernel)
-  auto panel = [&](int jp, int jrp, int buf) {
-    if (tid < WD + NR) {
-      const double* Dp = Praw + jrp * 4;
-      const double D00 = Dp[0], D10 = Dp[4], D11 = Dp[5], D20 = Dp[8], D21 = Dp[9], D22 = Dp[10];
-      const double D30 = Dp[12], D31 = Dp[13], D32 = Dp[14], D33 = Dp[15];
-      const double inv0 = band_rcp(D00);
-      const double L10 = D10 * inv0, L20 = D20 * inv0, L30 = D30 * inv0;
-      const double W11 = fma(-D10, L10, D11);
-      const double inv1 = band_rcp(W11);
-      const double W21 = fma(-D20, L10, D21), W31 = fma(-D30, L10, D31);
-      const double L21 = W21 * inv1, L31 = W31 * inv1;
-      const double W22 = fma(-W21, L21, fma(-D20, L20, D22));
-      const double inv2 = band_rcp(W22);
-      const double W32 = fma(-W31, L21, fma(-D30, L20, D32));
-      const double L32 = W32 * inv2;
-      const double W33 = fma(-W32, L32, fma(-W31, L31, fma(-D30, L30, D33)));
-      const double inv3 = band_rcp(W33);
-      if (tid < WD) {
-        const double2 p01 = *reinterpret_cast<const double2*>(&Praw[tid * 4]);
-        const double2 p23 = *reinterpret_cast<const double2*>(&Praw[tid * 4 + 2]);
-        const double w0 = p01.x;
-        const double w1 = fma(-w0, L10, p01.y);
-        const double w2 = fma(-w1, L21, fma(-w0, L20, p23.x));
-        const double w3 = fma(-w2, L32, fma(-w1, L31, fma(-w0, L30, p23.y)));
-        *reinterpret_cast<double2*>(&Wn2[buf][tid * 4]) = make_double2(-w0, -w1);
-        *reinterpret_cast<double2*>(&Wn2[buf][tid * 4 + 2]) = make_double2(-w2, -w3);
-        *reinterpret_cast<double2*>(&Lp2[buf][tid * 4]) = make_double2(w0 * inv0, w1 * inv1);
-        *reinterpret_cast<double2*>(&Lp2[buf][tid * 4 + 2]) = make_double2(w2 * inv2, w3 * inv3);
-      } else {
-        const int q = tid - WD;
-        const double z0 = zraw[0][q], zl0 = z0 * inv0;
-        const double z1 = fma(-D10, zl0, zraw[1][q]), zl1 = z1 * inv1;
-        const double z2 = fma(-W21, zl1, fma(-D20, zl0, zraw[2][q])), zl2 = z2 * inv2;
-        const double z3 = fma(-W32, zl2, fma(-W31, zl1, fma(-D30, zl0, zraw[3][q]))), zl3 = z3 * inv3;
-        zW2[buf][0][q] = z0; zW2[buf][1][q] = z1; zW2[buf][2][q] = z2; zW2[buf][3][q] = z3;
-        zL2[buf][0][q] = zl0; zL2[buf][1][q] = zl1; zL2[buf][2][q] = zl2; zL2[buf][3][q] = zl3;
-      }
-      if (tid == 0) {
-        facL2[buf][0] = L21;
-        facL2[buf][1] = L31;
-        facL2[buf][2] = L32;
-        const double piv[4] = {D00, W11, W22, W33};
-#pragma unroll
-        for (int s4 = 0; s4 < 4; ++s4) {
-          const double pj = piv[s4];
-          if (!(pj > 0.0) && info == 0) info = jp + s4 + 1;
-          const int hi = __double2hiint(pj);
-          expo += ((hi >> 20) & 0x7ff) - 1022;
-          mant *= __hiloint2double((hi & 0x800fffff) | 0x3fe00000, __double2loint(pj));
-        }
-        if ((jp & 511) == 508) {
-          const int h2 = __double2hiint(mant);
-          expo += ((h2 >> 20) & 0x7ff) - 1022;
-          mant = __hiloint2double((h2 & 0x800fffff) | 0x3fe00000, __double2loint(mant));
-        }
-      }
-    }
-  };
-  // block's DMMAs on the tile columns selected by (only, skip): only >= 0 → just that one; skip >= 0 → all but it
-  auto dmma_cols = [&](int buf, int only, int skip) {
-    double af[TR];
-#pragma unroll
-    for (int tr = 0; tr < TR; ++tr) af[tr] = Wn2[buf][(8 * (wr * TR + tr) + g) * 4 + t];
-#pragma unroll
-    for (int tc = 0; tc < TC; ++tc) {
-      if ((only >= 0 && tc != only) || tc == skip) continue;  // warp-uniform
-      const double bf = Lp2[buf][(8 * (wc * TC + tc) + g) * 4 + t];
-#pragma unroll
-      for (int tr = 0; tr < TR; ++tr) band_dmma(a[tr][tc][0], a[tr][tc][1], af[tr], bf);
-    }
-  };
-  // panel values of a late row (s = its position in the block), see band_mma_kernel
-  auto late_w = [&](const double* row, int sblk, int buf, double& w1, double& w2, double& w3) {
-    const double r1 = (sblk < 1) ? row[WD + sblk - 1] : 0.0;
-    const double r2 = (sblk < 2) ? row[WD + sblk - 2] : 0.0;
-    const double r3 = (sblk < 3) ? row[WD + sblk - 3] : 0.0;
-    w1 = r1;
-    w2 = fma(-w1, facL2[buf][0], r2);
-    w3 = fma(-w2, facL2[buf][2], fma(-w1, facL2[buf][1], r3));
-  };
-  // rows jb+WD … jb+WD+3 take over the residues jrb … jrb+3, in the selected tile columns
-  auto enter_cols = [&](int jb, int jrb, int buf, int only, int skip) {
-    const int ct = jrb >> 3, trb = ct % TR, orb = ct / TR, ppb = (jrb >> 2) & 1;
-    if (wr == orb && (g >> 2) == ppb) {
-      const double* row = ring + ((jb / BATCH) & 1) * (BATCH * ROWLEN) + ((jb & (BATCH - 1)) + (g & 3)) * ROWLEN;
-      const int rres_new = jrb + (g & 3);
-      double w1 = 0.0, w2 = 0.0, w3 = 0.0;
-      if (late) late_w(row, g & 3, buf, w1, w2, w3);
-#pragma unroll
-      for (int tc = 0; tc < TC; ++tc) {
-        if ((only >= 0 && tc != only) || tc == skip) continue;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int c = 8 * (wc * TC + tc) + 2 * t + h;
-          int dd = rres_new - c;
-          if (dd < 0) dd += WD;
-          double v = row[dd];
-          if (late && (unsigned)(c - jrb) >= 4u) {
-            const double l1 = Lp2[buf][c * 4 + 1];
-            const double2 l23 = *reinterpret_cast<const double2*>(&Lp2[buf][c * 4 + 2]);
-            v = fma(-w3, l23.y, fma(-w2, l23.x, fma(-w1, l1, v)));
-          }
-#pragma unroll
-          for (int q = 0; q < TR; ++q)
-            if (q == trb) a[q][tc][h] = v;
-        }
-      }
-    }
-  };
-
-  // ---- prologue: panel of block 0
-  publish(0);
-  cp_async_wait_all();
-  __syncthreads();
-  stage_issue(BATCH, ring + BATCH * ROWLEN);
-  panel(0, 0, 0);
-  __syncthreads();
-
-  for (int j = 0, jr = 0; j < N; j += 4, jr = (jr + 4 == WD) ? 0 : jr + 4) {
-    const int buf = (j >> 2) & 1;
-    const int jn = j + 4, jrn = (jr + 4 == WD) ? 0 : jr + 4;
-    const bool has_next = jn < N;
-    const int tcn = (jrn >> 3) % TC, ocn = (jrn >> 3) / TC;  // tile column / warp column of block n+1's pivots
-    // ---- S1: right-hand sides and Gram matrix of block n
-#pragma unroll
-    for (int e = 0; e < NE; ++e)
-      if (rcode[e] >= 0) {
-        const int rs = rcode[e] >> 5, q = rcode[e] & 31;
-        const double2 w01 = *reinterpret_cast<const double2*>(&Wn2[buf][rs * 4]);
-        const double2 w23 = *reinterpret_cast<const double2*>(&Wn2[buf][rs * 4 + 2]);
-        double r = rv[e];
-        r = fma(w01.x, zL2[buf][0][q], r);
-        r = fma(w01.y, zL2[buf][1][q], r);
-        r = fma(w23.x, zL2[buf][2][q], r);
-        r = fma(w23.y, zL2[buf][3][q], r);
-        rv[e] = r;
-      }
-    if (gram_on) {
-#pragma unroll
-      for (int s4 = 0; s4 < 4; ++s4) gacc = fma(zL2[buf][s4][gp_], zW2[buf][s4][gq_], gacc);
-    }
-    // ---- S2: the next panel's tile column first, its entering rows, then publish the next raw panel
-    const bool next_owner = has_next && wc == ocn;
-    if (next_owner) {
-      dmma_cols(buf, tcn, -1);
-      enter_cols(j, jr, buf, tcn, -1);
-    }
-    if (has_next) {
-      publish(jrn);
-      // ---- NB: everybody arrives, the panel warps wait and compute the panel of block n+1
-      __threadfence_block();
-      if (warp < PANEL_WARPS) {
-        asm volatile("bar.sync 1, %0;" ::"r"(NT) : "memory");
-        panel(jn, jrn, buf ^ 1);
-      } else {
-        asm volatile("bar.arrive 1, %0;" ::"r"(NT) : "memory");
-      }
-    }
-    // ---- S5: the rest of block n
-    dmma_cols(buf, -1, next_owner ? tcn : -1);
-    enter_cols(j, jr, buf, -1, next_owner ? tcn : -1);
-    {
-      const double* rowbase = ring + ((j / BATCH) & 1) * (BATCH * ROWLEN) + (j & (BATCH - 1)) * ROWLEN;
-#pragma unroll
-      for (int e = 0; e < NE; ++e) {
-        const int rs = rcode[e] >> 5, q = rcode[e] & 31;
-        if (rs >= jr && rs < jr + 4) {
-          const double* row = rowbase + (rs - jr) * ROWLEN;
-          const double* rr = row + WD;
-          double v = (q == 0) ? rr[0] - rr[NRP - 1] : rr[q];
-          if (late) {
-            double w1, w2, w3;
-            late_w(row, rs - jr, buf, w1, w2, w3);
-            v = fma(-w3, zL2[buf][3][q], fma(-w2, zL2[buf][2][q], fma(-w1, zL2[buf][1][q], v)));
-          }
-          rv[e] = v;
-        }
-      }
-    }
-    const bool boundary_next = has_next && (jn & (BATCH - 1)) == 0;
-    if (boundary_next) cp_async_wait_all();  // the next batch's entering rows have landed (visible after the barrier)
-    __syncthreads();
-    if (boundary_next) stage_issue(jn + BATCH, ring + (((jn / BATCH) & 1) ^ 1) * (BATCH * ROWLEN));
-  }
-  if (tid == 0) logdet = log(mant) + (double)expo * 0.6931471805599453;
-
-  if (gram_on) gram[tid] = gacc;
-  __syncthreads();
-  if (tid == 0) band_epilogue(p, b, M, gram, logdet, info);
-}
-
 template <int WD, int WRG, int WCG, bool ROLLED>
 cudaError_t launch_band_mma_tr(const BandCholParams& p, int B, cudaStream_t st) {
   const size_t smem = sizeof(double) * 2 * 16 * (WD + NRP);
@@ -1150,20 +826,13 @@ cudaError_t launch_band_mma_tr(const BandCholParams& p, int B, cudaStream_t st) 
   return cudaGetLastError();
 }
 
+// The unrolled body (tile indices are compile-time register indices) is the faster one while it fits the instruction
+// cache: 96 px 2.76 ms vs 2.99 rolled, 128 px 4.22 vs 4.41.  At 160 px the unrolled loop is 30 k SASS instructions and
+// misses the cache; the rolled form (one copy of the block body, run-time tile index) runs 6.89 ms vs 7.46
+// (profiles/r2a_band_ab.txt, one wave of CTAs each).
 template <int WD, int WRG, int WCG>
 cudaError_t launch_band_mma_t(const BandCholParams& p, int B, cudaStream_t st) {
-  static const bool rolled = getenv("SFB_BAND_MMA_ROLLED") != nullptr;  // unmeasured variant, opt-in only
-  static const bool la = getenv("SFB_BAND_MMA_LA") != nullptr;          // unmeasured look-ahead variant, opt-in only
-  if (la && p.M + 1 <= 8) {
-    constexpr int NT = 32 * WRG * WCG;
-    const size_t smem = sizeof(double) * 2 * 16 * (WD + NRP);
-    cudaError_t e = cudaFuncSetAttribute(band_mma_la_kernel<WD, WRG, WCG, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         64 * 1024);
-    if (e != cudaSuccess) return e;
-    band_mma_la_kernel<WD, WRG, WCG, 8><<<B, NT, smem, st>>>(p);
-    return cudaGetLastError();
-  }
-  return rolled ? launch_band_mma_tr<WD, WRG, WCG, true>(p, B, st) : launch_band_mma_tr<WD, WRG, WCG, false>(p, B, st);
+  return launch_band_mma_tr<WD, WRG, WCG, (WD >= 160)>(p, B, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1407,22 +1076,9 @@ cudaError_t launch_band_build(const BandBuildParams& p, int B, cudaStream_t st) 
   return cudaGetLastError();
 }
 
-// Windows up to 160 pixels use the full-square register window (rank-4 DMMA kernel, or the rank-1 kernel for
-// more than 8 right-hand sides at 160 pixels); the symmetric window serves the 192- and 256-pixel classes,
-// which do not fit the register file as a square.
-// SFB_BAND_SYM=1 forces the symmetric kernel for every class (A/B measurements).
-static bool band_use_sym(int WD) {
-  static const bool force = getenv("SFB_BAND_SYM") != nullptr;
-  return force || WD > 160;
-}
-
-// The classes up to 160 pixels run the rank-4 DMMA kernel (measured faster for every class);
-// SFB_BAND_RANK1=1 keeps the rank-1 kernel for A/B measurements.
-static bool band_use_mma(int WD) {
-  static const bool off = getenv("SFB_BAND_RANK1") != nullptr;
-  return !off && WD <= 160 && !band_use_sym(WD);
-}
-
+// Windows up to 160 pixels use the full-square register window: the rank-4 DMMA kernel, or the rank-1 kernel for
+// more than 8 right-hand sides at 160 pixels (the 256-thread 160-pixel DMMA kernel carries at most 8).  The
+// symmetric window serves the 192- and 256-pixel classes, which do not fit the register file as a square.
 // pixels of slack a window needs beyond the half-bandwidth: b + slack <= WD
 int band_slack(int WD) {
   (void)WD;
@@ -1431,31 +1087,13 @@ int band_slack(int WD) {
 
 cudaError_t launch_band_chol(const BandCholParams& p, int WD, int B, cudaStream_t st) {
   if (B <= 0) return cudaSuccess;
-  if (band_use_mma(WD) && (WD < 160 || p.M + 1 <= 8)) {  // (the 256-thread 160-pixel kernel carries <= 8 right-hand sides)
-    switch (WD) {
-      case 64: return launch_band_mma_t<64, 4, 4>(p, B, st);
-      case 96: return launch_band_mma_t<96, 4, 4>(p, B, st);
-      case 128: return launch_band_mma_t<128, 4, 4>(p, B, st);
-      case 160: return launch_band_mma_t<160, 4, 2>(p, B, st);
-      default: return cudaErrorInvalidValue;
-    }
-  }
-  if (band_use_sym(WD)) {
-    switch (WD) {
-      case 64: return launch_band_sym_t<2>(p, B, st);
-      case 96: return launch_band_sym_t<3>(p, B, st);
-      case 128: return launch_band_sym_t<4>(p, B, st);
-      case 160: return launch_band_sym_t<5>(p, B, st);
-      case 192: return launch_band_sym_t<6>(p, B, st);
-      case 256: return launch_band_sym_t<8>(p, B, st);
-      default: return cudaErrorInvalidValue;
-    }
-  }
   switch (WD) {
-    case 64: return launch_band_t<64, 8>(p, B, st);
-    case 96: return launch_band_t<96, 8>(p, B, st);
-    case 128: return launch_band_t<128, 8>(p, B, st);
-    case 160: return launch_band_t<160, 10>(p, B, st);
+    case 64: return launch_band_mma_t<64, 4, 4>(p, B, st);
+    case 96: return launch_band_mma_t<96, 4, 4>(p, B, st);
+    case 128: return launch_band_mma_t<128, 4, 4>(p, B, st);
+    case 160: return (p.M + 1 <= 8) ? launch_band_mma_t<160, 4, 2>(p, B, st) : launch_band_t<160, 10>(p, B, st);
+    case 192: return launch_band_sym_t<6>(p, B, st);
+    case 256: return launch_band_sym_t<8>(p, B, st);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -44,8 +44,8 @@ struct sfb_ctx {
   cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
   cudaEvent_t ev_hi[2] = {nullptr, nullptr}, ev_lo[2] = {nullptr, nullptr};
   bool profile = false;
-  int outer_tiles = kOuterTiles;  // SFB_OUTER_TILES overrides (experiments)
-  int debug_mode = 0;  // SFB_DEBUG_MODE: bit0 = no high-priority stream, bit1 = single lane
+  int outer_tiles = kOuterTiles;  // (experiments build only: SFB_OUTER_TILES overrides)
+  int debug_mode = 0;  // (experiments build only: SFB_DEBUG_MODE, bit0 = no high-priority stream, bit1 = single lane)
   std::vector<ProfEvent> prof;
   std::vector<cudaEvent_t> ev_pool;
   long long launches = 0;
@@ -529,8 +529,10 @@ int sfb_create(int device, int N, int M, int Kmax, int Bmax, int workspace_walke
   h->M = M;
   h->Kmax = std::max(Kmax, 1);
   h->Bmax = Bmax;
+#ifdef SFB_EXPERIMENTS  // A/B knobs exist only in an experiments build (python -m starfish_b200.build --experiments)
   if (const char* dbg = getenv("SFB_DEBUG_MODE")) h->debug_mode = atoi(dbg);
   if (const char* ot = getenv("SFB_OUTER_TILES")) h->outer_tiles = std::max(1, atoi(ot));
+#endif
   DeviceGuard guard(device);
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) {

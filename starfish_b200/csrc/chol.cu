@@ -611,10 +611,6 @@ cudaError_t kernels_init() {
   for (const Item& it : items) {
     cudaError_t e = cudaFuncSetAttribute(it.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, it.bytes);
     if (e != cudaSuccess) return e;
-    if (getenv("SFB_MAX_CARVEOUT")) {
-      e = cudaFuncSetAttribute(it.fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-      if (e != cudaSuccess) return e;
-    }
   }
   return cudaSuccess;
 }

@@ -6,7 +6,6 @@ set -u
 TAG=${1:-final}
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests -m gpu -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/${TAG}_pytest.log
-SFB_BAND_RANK1=1 timeout 300 python -m pytest tests/test_gpu_structured.py -q > gpurun_out/${TAG}_pytest_rank1.log 2>&1; echo "pytest rank1 rc=$?"; tail -2 gpurun_out/${TAG}_pytest_rank1.log
 timeout 300 python __graft_entry__.py --smoke > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/${TAG}_smoke.log
 timeout 600 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"; cat gpurun_out/${TAG}_bench.json; tail -3 gpurun_out/${TAG}_bench.err
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_reference.json 2>> gpurun_out/${TAG}_bench.err; echo "reference rc=$?"
@@ -14,4 +13,3 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --
   python bench.py --walkers 32 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/${TAG}_ncu_launch.log 2>&1; echo "ncu launches rc=$?"
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:'band_mma_kernel' -c 3 \
   -o gpurun_out/${TAG}_band_mma python bench.py --walkers 64 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-model > gpurun_out/${TAG}_ncu_band.log 2>&1; echo "ncu band rc=$?"
-SFB_BAND_RANK1=1 timeout 200 python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-model > gpurun_out/${TAG}_bench_rank1.json 2>> gpurun_out/${TAG}_bench.err; echo "rank1 bench rc=$?"
