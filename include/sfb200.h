@@ -186,6 +186,23 @@ int sfb_get_solver(const sfb_t* h);
  * fallback.  Returns the number of entries written (n must be >= 5). */
 int sfb_band_classes(const sfb_t* h, int* widths, long long* walkers, int n);
 
+/*
+ * ---- Multi-GPU: walkers are independent, so every rank (one handle, one GPU, one process or
+ * thread) evaluates its own contiguous shard and the ONLY exchange per ensemble step is one all-gather of the
+ * log-likelihood scalars — the reference evaluates the walkers serially (examples/single.ipynb:458-470) and has no
+ * counterpart.  NCCL is bound at run time (dlopen of libnccl.so.2), so a host that never calls sfb_comm_init does
+ * not need it.
+ *   sfb_comm_unique_id   rank 0 creates the 128-byte NCCL unique id; the host distributes it (MPI, files, sockets …)
+ *   sfb_comm_init        every rank, collectively: ncclCommInitRank on the handle's device
+ *   sfb_allgather_lnL    lnL_all[r·count + i] = lnL_local[i] of rank r (ncclAllGather of `count` doubles per rank,
+ *                        equal on every rank), enqueued on the caller's `stream` — after sfb_loglike on the same
+ *                        stream it follows the last factorisation epilogue without a host round trip
+ */
+int sfb_comm_unique_id(void* unique_id_h /* 128 bytes out */);
+int sfb_comm_init(sfb_t* h, int rank, int nranks, const void* unique_id_h);
+int sfb_allgather_lnL(sfb_t* h, const double* lnL_local, int count, double* lnL_all, void* stream);
+int sfb_comm_destroy(sfb_t* h);
+
 /* Block the host until all work queued on the handle has finished. */
 int sfb_sync(sfb_t* h);
 

@@ -17,11 +17,12 @@ EXPORTS = [
     "sfb_set_model_host", "sfb_upstream", "sfb_loglike_params", "sfb_loglike_params_host",
     "sfb_host_rfft", "sfb_host_spline_inverse_band", "sfb_host_cholesky_lower", "sfb_spline_halfwidth",
     "sfb_set_solver", "sfb_get_solver", "sfb_band_classes",
+    "sfb_comm_unique_id", "sfb_comm_init", "sfb_allgather_lnL", "sfb_comm_destroy",
 ]
 
 SOLVER_DENSE, SOLVER_STRUCTURED, SOLVER_DENSE_I8 = 0, 1, 2
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # sfb_model_flags of include/sfb200.h
 MODEL_VSINI, MODEL_VZ, MODEL_LOG_SCALE, MODEL_NORM, MODEL_PAPER_TERM = 1, 2, 4, 8, 16
@@ -65,6 +66,10 @@ def load():
     lib.sfb_set_solver.argtypes = [_p, _i]
     lib.sfb_get_solver.argtypes = [_p]
     lib.sfb_band_classes.argtypes = [_p, _p, _p, _i]
+    lib.sfb_comm_unique_id.argtypes = [_p]
+    lib.sfb_comm_init.argtypes = [_p, _i, _i, _p]
+    lib.sfb_allgather_lnL.argtypes = [_p, _p, _i, _p, _p]
+    lib.sfb_comm_destroy.argtypes = [_p]
     lib.sfb_sync.argtypes = [_p]
     lib.sfb_profile_enable.argtypes = [_p, _i]
     lib.sfb_profile_read.argtypes = [_p, _p, _i]

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <dlfcn.h>
 
 #include "sfb_internal.cuh"
 
@@ -61,6 +62,10 @@ struct sfb_ctx {
   int8_t* ozP = nullptr;
   double* oz_rscale = nullptr;
   size_t oz_bytes = 0;    // bytes of ONE panel buffer of one slot
+  // multi-GPU: one NCCL communicator per handle, created by sfb_comm_init; NCCL is bound at run time
+  // (dlopen) so that a host that never calls sfb_comm_init needs no NCCL, and a torch host shares torch's copy
+  void* nccl_comm = nullptr;
+  int comm_rank = 0, comm_size = 1;
   ModelState model;       // upstream of the covariance (rows f1/f2); empty until sfb_set_model_host
   bool have_model = false;
   std::string err;
@@ -514,7 +519,7 @@ int structured_device(sfb_ctx* h, int B, const double* X, const double* A, const
 
 extern "C" {
 
-int sfb_abi_version(void) { return 2; }
+int sfb_abi_version(void) { return 3; }
 
 int sfb_create(int device, int N, int M, int Kmax, int Bmax, int workspace_walkers, sfb_t** out) {
   if (!out) return SFB_ERR_ARG;
@@ -607,6 +612,7 @@ int sfb_destroy(sfb_t* h) {
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   free_gemm_maps(&h->maps);
   model_free(&h->model);
+  sfb_comm_destroy(h);
   if (h->ozP) cudaFree(h->ozP);
   if (h->oz_rscale) cudaFree(h->oz_rscale);
   if (h->Sb) cudaFree(h->Sb);
@@ -1004,6 +1010,85 @@ int sfb_band_classes(const sfb_t* h, int* widths, long long* walkers, int n) {
   widths[kNumBandWidths] = 0;  // dense fallback
   walkers[kNumBandWidths] = h->band_rows[kNumBandWidths];
   return kNumBandWidths + 1;
+}
+
+// ---- NCCL, bound lazily ---------------------------------------------------------------------------
+namespace {
+struct NcclUniqueId { char b[128]; };  // layout of ncclUniqueId (nccl.h: struct { char internal[128]; })
+struct NcclApi {
+  // the few entry points of nccl.h this path needs (ncclResult_t / ncclDataType_t are ints)
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclUniqueId, int) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+NcclApi* nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return api.ok ? &api : nullptr;
+  tried = true;
+  void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);   // the copy already in the process (torch's) if any
+  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) return nullptr;
+  api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+  api.CommInitRank = (decltype(api.CommInitRank))dlsym(lib, "ncclCommInitRank");
+  api.AllGather = (decltype(api.AllGather))dlsym(lib, "ncclAllGather");
+  api.CommDestroy = (decltype(api.CommDestroy))dlsym(lib, "ncclCommDestroy");
+  api.GetErrorString = (decltype(api.GetErrorString))dlsym(lib, "ncclGetErrorString");
+  api.ok = api.GetUniqueId && api.CommInitRank && api.AllGather && api.CommDestroy && api.GetErrorString;
+  return api.ok ? &api : nullptr;
+}
+int nccl_fail(sfb_ctx* h, NcclApi* n, const char* what, int code) {
+  h->err = std::string(what) + ": " + n->GetErrorString(code);
+  return SFB_ERR_CUDA;
+}
+}  // namespace
+
+int sfb_comm_unique_id(void* id_h) {
+  NcclApi* n = nccl_api();
+  if (!n || !id_h) return SFB_ERR_STATE;
+  return n->GetUniqueId(id_h) == 0 ? SFB_OK : SFB_ERR_CUDA;
+}
+
+int sfb_comm_init(sfb_t* h, int rank, int nranks, const void* unique_id_h) {
+  if (!h || !unique_id_h || nranks < 1 || rank < 0 || rank >= nranks) return fail(h, SFB_ERR_ARG, "sfb_comm_init: bad argument");
+  NcclApi* n = nccl_api();
+  if (!n) return fail(h, SFB_ERR_STATE, "sfb_comm_init: libnccl.so.2 not found");
+  DeviceGuard guard(h->device);
+  if (h->nccl_comm) { n->CommDestroy(h->nccl_comm); h->nccl_comm = nullptr; }
+  NcclUniqueId id;
+  memcpy(id.b, unique_id_h, sizeof(id.b));
+  const int rc = n->CommInitRank(&h->nccl_comm, nranks, id, rank);
+  if (rc != 0) return nccl_fail(h, n, "ncclCommInitRank", rc);
+  h->comm_rank = rank;
+  h->comm_size = nranks;
+  return SFB_OK;
+}
+
+int sfb_comm_destroy(sfb_t* h) {
+  if (!h) return SFB_ERR_ARG;
+  if (h->nccl_comm) {
+    NcclApi* n = nccl_api();
+    DeviceGuard guard(h->device);
+    if (n) n->CommDestroy(h->nccl_comm);
+    h->nccl_comm = nullptr;
+    h->comm_size = 1;
+    h->comm_rank = 0;
+  }
+  return SFB_OK;
+}
+
+int sfb_allgather_lnL(sfb_t* h, const double* lnL_local, int count, double* lnL_all, void* stream) {
+  if (!h || !lnL_local || !lnL_all || count < 0) return fail(h, SFB_ERR_ARG, "sfb_allgather_lnL: bad argument");
+  if (!h->nccl_comm) return fail(h, SFB_ERR_STATE, "sfb_allgather_lnL: call sfb_comm_init first");
+  if (count == 0) return SFB_OK;
+  NcclApi* n = nccl_api();
+  DeviceGuard guard(h->device);
+  const int rc = n->AllGather(lnL_local, lnL_all, (size_t)count, /* ncclFloat64 */ 8, h->nccl_comm, (cudaStream_t)stream);
+  if (rc != 0) return nccl_fail(h, n, "ncclAllGather", rc);
+  return SFB_OK;
 }
 
 int sfb_sync(sfb_t* h) {

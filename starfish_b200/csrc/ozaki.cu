@@ -29,9 +29,11 @@
 // the slicing kernel), and the 8-row groups of one slice are 6·256 = 1536 B apart: UMMA descriptor
 // {SWIZZLE_32B, SBO = 1536}.
 //
-// Kernel shape: 192 threads = warp 0 bulk-copy producer (one lane), warp 1 MMA issuer (one lane) + TMEM
+// Kernel shape: 192 threads = warp 0 bulk-copy producer (one lane), warp 1 MMA issuer (one elected lane) + TMEM
 // allocator, warps 2-5 epilogue (TMEM lane quarter = warp%4).  5-stage ring of 36 KB, full/empty mbarriers,
-// tcgen05.commit releases a stage / signals the epilogue.
+// tcgen05.commit releases a stage / signals the epilogue.  The epilogue warps prefetch the C tile (coalesced,
+// into registers) while the main loop runs, transpose the recombined update through the idle ring and finish
+// the read-modify-write with coalesced streaming stores.
 #include <cstdint>
 
 #include "sfb_internal.cuh"
@@ -224,15 +226,25 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
     if (leader) umma_commit(accfull);
     __syncwarp();
   } else {
-    // ---- epilogue: thread = tile row (TMEM lane), 4 blocks of 16 columns
-    const int q = warp & 3;             // TMEM lane quarter this warp may access
-    const int row = q * 32 + lane;      // tile row
+    // ---- epilogue (4 warps; warp q owns tile rows 32q..32q+31 = its TMEM lane quarter).
+    // Two thread mappings: TMEM hands a thread ONE ROW (lane = row, 16 columns per load), global memory wants a
+    // warp on one row (lane = column pair, 512 contiguous bytes).  The C tile is therefore fetched in the global
+    // mapping BEFORE the accumulators are ready (32 independent 16-byte loads per thread, in flight under the whole
+    // main loop), the recombined update goes through a warp-private transpose buffer in the (by then idle)
+    // operand ring, and the read-modify-write finishes with coalesced streaming stores.
+    const int q = warp & 3;
     const double* rs = oz.rscale + (long long)s * p.Np;
-    const double ri = rs[r0 + row];
-    double* Crow = p.W + (long long)s * p.strideW + (long long)(r0 + row) * p.Np + c0;
+    const double ri = rs[r0 + q * 32 + lane];                                            // row scale, TMEM mapping
+    const double2 rj = *reinterpret_cast<const double2*>(rs + c0 + 2 * lane);           // column scales, global mapping
+    double* Cw = p.W + (long long)s * p.strideW + (long long)(r0 + q * 32) * p.Np + c0 + 2 * lane;
+    double2 creg[32];
+#pragma unroll
+    for (int r = 0; r < 32; ++r) creg[r] = __ldcs(reinterpret_cast<const double2*>(Cw + (long long)r * p.Np));
     mbar_wait(accfull, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+    constexpr uint32_t TROW = 66 * 8;  // padded row of the transpose buffer: 528 B -> conflict-free 16-byte accesses
+    const uint32_t tbuf = ring + (uint32_t)q * (32 * TROW);
 #pragma unroll 1
     for (int cb = 0; cb < OZ_BN / 16; ++cb) {
       double acc[16];
@@ -248,16 +260,21 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
 #pragma unroll
         for (int j = 0; j < 16; ++j) acc[j] = fma(acc[j], 0.00390625, (double)(int)v[j]);
       }
-      double2* Cv = reinterpret_cast<double2*>(Crow + cb * 16);
-      const double2* rj = reinterpret_cast<const double2*>(rs + c0 + cb * 16);
+      const uint32_t dst = tbuf + (uint32_t)lane * TROW + (uint32_t)cb * 128;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        double2 c = Cv[j];
-        const double2 sc = rj[j];
-        c.x -= acc[2 * j] * (ri * sc.x);
-        c.y -= acc[2 * j + 1] * (ri * sc.y);
-        Cv[j] = c;
-      }
+      for (int j = 0; j < 8; ++j)
+        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(dst + 16 * j), "d"(acc[2 * j] * ri), "d"(acc[2 * j + 1] * ri)
+                     : "memory");
+    }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+      double tx, ty;
+      asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(tx), "=d"(ty) : "r"(tbuf + (uint32_t)r * TROW + 16 * lane) : "memory");
+      double2 c = creg[r];
+      c.x = fma(-tx, rj.x, c.x);
+      c.y = fma(-ty, rj.y, c.y);
+      __stcs(reinterpret_cast<double2*>(Cw + (long long)r * p.Np), c);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

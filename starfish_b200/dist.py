@@ -45,3 +45,19 @@ def gather_lnl(local, n_walkers: int, group=None):
     buf = torch.empty(world * mx, dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(buf, padded, group=group)
     return torch.cat([buf[r * mx: r * mx + sizes[r]] for r in range(world)])
+
+
+def init_engine_comm(engine, group=None):
+    """Give ``engine`` (a LikelihoodEngine) its own NCCL communicator, created INSIDE libsfb200 (sfb_comm_init):
+    rank 0 makes the unique id, ``torch.distributed`` only carries those 128 bytes to the other ranks once at
+    set-up.  After this ``engine.allgather_lnl`` is the per-step exchange and no torch collective is on the path.
+    Without an initialised process group a single-rank communicator is created."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        engine.comm_init(0, 1, engine.comm_unique_id())
+        return
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    box = [engine.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    engine.comm_init(rank, world, box[0])

@@ -243,6 +243,34 @@ class LikelihoodEngine:
             self._check(k, "sfb_band_classes")
         return {int(w[i]): int(n[i]) for i in range(k)}
 
+    # -- multi-GPU: the one exchange per ensemble step --------------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """128-byte NCCL unique id (call on rank 0, hand it to every rank by any host-side means)."""
+        buf = C.create_string_buffer(128)
+        rc = _lib.lib().sfb_comm_unique_id(buf)
+        if rc != 0:
+            raise _lib.SfbError(f"sfb_comm_unique_id failed ({rc}): is libnccl.so.2 loadable?")
+        return buf.raw
+
+    def comm_init(self, rank: int, world: int, unique_id: bytes):
+        """Collective: create this handle's NCCL communicator (ncclCommInitRank inside the library)."""
+        if len(unique_id) != 128:
+            raise ValueError("unique_id must be the 128 bytes returned by comm_unique_id()")
+        self._check(self._lib.sfb_comm_init(self._h, int(rank), int(world), C.c_char_p(unique_id)), "sfb_comm_init")
+        self.comm_rank, self.comm_world = int(rank), int(world)
+
+    def allgather_lnl(self, local, out=None):
+        """``out[r·n + i] = local[i]`` of rank r — one ncclAllGather of the lnL shard, enqueued on the current
+        stream by the library itself (no torch collective on the path).  Shards must have equal length."""
+        torch = _torch()
+        n = local.numel()
+        if out is None:
+            out = torch.empty(n * self.comm_world, dtype=torch.float64, device=self.device)
+        self._check(self._lib.sfb_allgather_lnL(self._h, self._ptr(local), n, self._ptr(out), self._stream()),
+                    "sfb_allgather_lnL")
+        return out
+
     # -- upstream of the covariance (rows f1/f2/f3): parameters in, log-likelihood out --------------
     def set_model(self, fine_wave, bulk_fluxes, grid_points, variances, lengthscales, v11, w_hat,
                   ncheb_max: int = 0, flags: int = 0):

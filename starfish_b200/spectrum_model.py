@@ -76,8 +76,8 @@ class SpectrumModel:
             raise ValueError("Multiple orders detected in data, please use EchelleModel")
         if emulator_term not in ("reference", "paper"):
             raise ValueError("emulator_term must be 'reference' (XᵀΣ_w⁻¹X, as coded) or 'paper' (XᵀΣ_wX)")
-        if solver not in ("dense", "structured"):
-            raise ValueError("solver must be 'dense' or 'structured'")
+        if solver not in ("dense", "dense_i8", "structured"):
+            raise ValueError("solver must be 'dense', 'dense_i8' or 'structured'")
         self.solver = solver
         self.emulator = emulator
         self.data_name = data.name

@@ -18,7 +18,7 @@ def built_lib():
 def _declared():
     text = open(os.path.join(ROOT, "include", "sfb200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(sfb_[a-z_0-9]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(sfb_[A-Za-z_0-9]+)\s*\(", text)))
 
 
 def test_header_and_binding_agree(built_lib):
@@ -32,7 +32,7 @@ def test_library_exports_every_symbol(built_lib):
     for name in _declared():
         assert hasattr(lib, name), name
     lib.sfb_abi_version.restype = ctypes.c_int
-    assert lib.sfb_abi_version() == 2
+    assert lib.sfb_abi_version() == 3
 
 
 def test_library_is_sm100a_only(built_lib):
