@@ -1,11 +1,23 @@
 #!/bin/bash
-# Full single-GPU visit: every GPU test, smoke, the default bench line, the reference arm, an ncu launch list.
+# every GPU test, smoke, the default bench line and the reference arm
 set -u
 TAG=${1:-full}
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/${TAG}_pytest.log
+timeout 1200 python -m pytest tests -m gpu -q -x > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/${TAG}_pytest.log
 timeout 300 python __graft_entry__.py --smoke > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/${TAG}_smoke.log
-timeout 900 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"; cat gpurun_out/${TAG}_bench.json; tail -3 gpurun_out/${TAG}_bench.err
-timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_reference.json 2>> gpurun_out/${TAG}_bench.err; echo "reference rc=$?"; cat gpurun_out/${TAG}_bench_reference.json
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/${TAG}_launches.csv \
-  python bench.py --walkers 32 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/${TAG}_ncu_launch.log 2>&1; echo "ncu launches rc=$?"
+timeout 900 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"; tail -3 gpurun_out/${TAG}_bench.err
+python - <<PY
+import json
+d = json.load(open("gpurun_out/${TAG}_bench.json"))
+print("value", d["value"], "e2e", d["e2e"]["value"], "model", d["e2e_model"]["value"], "parity", d["parity"])
+print("roofline", {k: d["roofline"][k] for k in ("achieved", "peak", "frac", "achieved_fp64_equivalent_tflops", "share_of_step") if k in d["roofline"]})
+print("kernels", d["kernels"])
+alt = d.get("fp64_dmma") or d.get("int8_tensor")
+print("alt", alt["solver"], alt["value"], alt["max_rel_diff_vs_headline_lnL"])
+print("structured", d["structured"]["value"], d["structured"]["max_rel_diff_vs_dense_lnL"])
+for k, c in (d.get("configs") or {}).items():
+    for s in ("dense_i8", "dense"):
+        print(k, s, round(c[s]["value"], 2), "frac of fp64 floor", round(c[s]["frac_of_fp64_floor"], 3), c[s].get("kernels"), c[s].get("max_rel_diff_vs_dense_i8"))
+print("cpu", d["cpu_baseline"]["sample"])
+print("clocks", d["clocks"])
+PY
