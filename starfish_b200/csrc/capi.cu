@@ -136,8 +136,20 @@ struct ProfScope {  // brackets one launch with events when profiling is on
   }
 };
 
-// fork: internal streams wait for everything queued on the caller's stream
+// A new call may arrive on a different caller stream while the previous call's work is still running on the
+// handle's lanes; per-handle scratch (the upstream stage's X/A/flux, staging buffers) is shared by the lanes, so
+// lane 0 must not start the new call before lane 1 has finished the old one (and vice versa).
+int order_after_previous_call(sfb_ctx* h) {
+  for (int i = 0; i < 2; ++i) SFB_CUDA(h, cudaEventRecord(h->ev_join[i], h->streams[i]));
+  SFB_CUDA(h, cudaStreamWaitEvent(h->streams[0], h->ev_join[1], 0));
+  SFB_CUDA(h, cudaStreamWaitEvent(h->streams[1], h->ev_join[0], 0));
+  return SFB_OK;
+}
+
+// fork: internal streams wait for everything queued on the caller's stream (and for the handle's previous call)
 int fork_streams(sfb_ctx* h, cudaStream_t caller, int nstreams) {
+  int rc = order_after_previous_call(h);
+  if (rc != SFB_OK) return rc;
   SFB_CUDA(h, cudaEventRecord(h->ev_fork, caller));
   for (int i = 0; i < nstreams; ++i) SFB_CUDA(h, cudaStreamWaitEvent(h->streams[i], h->ev_fork, 0));
   return SFB_OK;
@@ -916,6 +928,7 @@ int sfb_loglike_params(sfb_t* h, int B, const double* theta, int ncheb, const do
     return SFB_OK;
   }
   // the upstream stage runs once for the whole batch on stream 0; the other lane waits for it
+  if ((rc = order_after_previous_call(h)) != SFB_OK) return rc;
   SFB_CUDA(h, cudaEventRecord(h->ev_fork, caller));
   SFB_CUDA(h, cudaStreamWaitEvent(h->streams[0], h->ev_fork, 0));
   if ((rc = run_upstream(h, B, theta, ncheb, ms.X, ms.A, ms.flux, log_scale_out ? log_scale_out : ms.log_scale,

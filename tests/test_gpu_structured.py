@@ -207,7 +207,7 @@ def test_model_level_structured_solver(golden_dir):
     g = dict(np.load(os.path.join(golden_dir, "model_n2048_w0.npz"), allow_pickle=False))
     m = make_model(2048, 0, solver="structured")
     lnl = m.log_likelihood()
-    assert abs(lnl - g["lnL"]) <= 1e-8 * abs(g["lnL"])
+    assert abs(lnl - g["lnL"]) <= 1e-10 * abs(g["lnL"])
     md = make_model(2048, 0)
     P = np.tile(m.get_param_vector(), (4, 1))
     P[1:, list(m.labels).index("vz")] = [5.0, -20.0, 60.0]

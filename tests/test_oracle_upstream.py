@@ -11,6 +11,7 @@ import warnings
 import numpy as np
 import pytest
 
+from oracle import starfish_oracle as O
 from oracle import upstream_oracle as U
 from oracle.make_golden import UPSTREAM_VARIANTS, upstream_variant_params
 from oracle import ref_loader
@@ -185,3 +186,98 @@ def test_doppler_knot_rounding_floor(golden_dir):
     assert 1e-13 < rel < 1e-10
     smooth = np.abs(U.resample(shifted, bulk_f[6:7], wave) - U.resample(jig, bulk_f[6:7], wave)).max()
     assert smooth < 1e-13  # the smooth rows (flux mean) are insensitive
+
+
+def _variant_lnl(name, knot_jitter=False, lu_route=False, sb_jitter=False):
+    """lnL of one recorded upstream variant through the CPU oracle, optionally with ONE of the reference's own
+    ill-conditioned steps evaluated by an equally valid fp64 route:
+      knot_jitter  the Doppler-scaled knots fl(λ·s) moved up by one ulp at random (any other evaluation order of
+                   λ·sqrt((c+v)/(c−v)) does that);
+      lu_route     Σ_w = v22 − v21·v11⁻¹·v12 through scipy's getrf/getrs instead of numpy's gesv;
+      sb_jitter    Gray's transfer function with cos/sin/j1 perturbed by one ulp at random (glibc vs cephes vs CUDA
+                   libm differ by that much)."""
+    from scipy.linalg import lu_factor, lu_solve
+    from scipy.special import j1
+
+    n_pix, wave, grid, p = upstream_variant_params(name)
+    emu = synth.make_emulator_arrays()
+    bulk = np.vstack([emu["eigenspectra"], emu["flux_mean"], emu["flux_std"]])
+    fine, bulk_f = U.model_setup(emu["wavelength"], bulk, wave)
+    w, data_flux, sigma = synth.make_data(n_pix, wave=wave)
+    var, ls = np.full(6, 1e4), np.full((6, 3), 1.0)
+    from starfish_b200.emulator import Emulator
+    import copy
+
+    e = Emulator(**copy.deepcopy(emu))
+    rng = np.random.default_rng(17)
+    v12 = U.batch_kernel(e.grid_points, np.atleast_2d(grid), e.variances, e.lengthscales)
+    v22 = U.batch_kernel(np.atleast_2d(grid), np.atleast_2d(grid), e.variances, e.lengthscales)
+    v21 = v12.T
+    if lu_route:
+        f = lu_factor(e.v11)
+        mu = v21 @ lu_solve(f, e.w_hat)
+        wcov = v22 - v21 @ lu_solve(f, v12)
+    else:
+        mu = v21 @ np.linalg.solve(e.v11, e.w_hat)
+        wcov = v22 - v21 @ np.linalg.solve(e.v11, v12)
+    fluxes, wv = bulk_f, fine
+    if "vsini" in p:
+        dv = U.calculate_dv(wv)
+        freq = np.fft.rfftfreq(fluxes.shape[-1], dv)
+        ff = np.fft.rfft(fluxes)
+        ub = (2.0 * np.pi * p["vsini"] * freq)[1:]
+        c, s, j = np.cos(ub), np.sin(ub), j1(ub)
+        if sb_jitter:
+            c = np.where(rng.random(c.size) < 0.5, np.nextafter(c, np.inf), c)
+            s = np.where(rng.random(s.size) < 0.5, np.nextafter(s, np.inf), s)
+            j = np.where(rng.random(j.size) < 0.5, np.nextafter(j, np.inf), j)
+        sb = j / ub - 3 * c / (2 * ub**2) + 3.0 * s / (2 * ub**3)
+        ff *= np.insert(sb, 0, 1.0)
+        fluxes = np.fft.irfft(ff, n=fluxes.shape[-1])
+    if "vz" in p:
+        wv = U.doppler_shift(wv, p["vz"])
+        if knot_jitter:
+            wv = np.where(rng.random(wv.size) < 0.5, np.nextafter(wv, np.inf), wv)
+    fluxes = U.resample(wv, fluxes, wave)
+    if "cheb" in p:
+        fluxes = U.chebyshev_correct(wave, fluxes, [1, *p["cheb"]])
+    *eig, fmean, fstd = fluxes
+    X = np.array(eig) * fstd
+    flux = mu @ X + fmean
+    if "log_scale" in p:
+        scale = np.exp(p["log_scale"])
+    else:
+        scale = U.renorm_factor(wave, flux, data_flux)
+    flux, X = flux * scale, X * scale
+    glob = (np.exp(p["global_cov"]["log_amp"]), np.exp(p["global_cov"]["log_ls"]))
+    loc = np.array([(np.exp(k["log_amp"]), k["mu"], np.exp(k["log_sigma"])) for k in p.get("local_cov", [])]).reshape(-1, 3)
+    cov = O.assemble_covariance(wave, sigma, X, wcov, glob, loc)
+    return O.log_likelihood(cov, flux, data_flux)[0], X, wcov
+
+
+REFERENCE_LNL_FLOOR = {}   # variant -> relative lnL spread of the reference's own arithmetic (filled by the test below)
+
+
+@pytest.mark.parametrize("name", ["a", "c", "d", "e"])
+def test_reference_lnl_conditioning_floor(name, golden_dir):
+    """Quantifies the end-to-end tolerance granted to the device model path (tests/test_gpu_upstream.py,
+    MODEL_LNL_RTOL): the REFERENCE's own lnL moves by this much when one of its ill-conditioned steps is evaluated by
+    an equally valid fp64 route.  The unperturbed run must reproduce the recorded reference value; the perturbed runs
+    give the floor (measured: 1e-15 … 5e-14 — X moves by up to 4e-11 but lnL hardly sees it).  The tolerance granted
+    to the device path must be at least 100x this floor and no looser than the stage-boundary bar 1e-10."""
+    g = dict(np.load(os.path.join(golden_dir, f"upstream_{name}.npz"), allow_pickle=False))
+    base, X0, wc0 = _variant_lnl(name)
+    assert abs(base - g["lnL"]) <= 1e-12 * abs(g["lnL"])
+    spread = {}
+    for key in ("knot_jitter", "lu_route", "sb_jitter"):
+        v, X1, wc1 = _variant_lnl(name, **{key: True})
+        spread[key] = (abs(v - base) / abs(base), np.abs(X1 - X0).max() / np.abs(X0).max(),
+                       np.abs(wc1 - wc0).max() / np.abs(wc0).max())
+    worst = max(s[0] for s in spread.values())
+    REFERENCE_LNL_FLOOR[name] = worst
+    print(f"variant {name}: lnL={base:.6f}; relative lnL spread of the reference under equivalent fp64 routes: " +
+          ", ".join(f"{k}={s[0]:.1e} (dX {s[1]:.1e}, dSigma_w {s[2]:.1e})" for k, s in spread.items()))
+    assert worst < 1e-12
+    from test_gpu_upstream import MODEL_LNL_RTOL
+
+    assert 100 * worst <= MODEL_LNL_RTOL <= 1e-10
