@@ -43,17 +43,19 @@ def build(force=False, verbose=False, experiments=False):
     if not force and not needs_build():
         return LIB
     cmd = [_nvcc(), *NVCC_FLAGS]
-    if experiments:
+    out = LIB
+    if experiments:   # separate file: load it with SFB200_LIB=<path> (starfish_b200/_lib.py)
         cmd += ["-DSFB_EXPERIMENTS"]
+        out = os.path.join(HERE, "libsfb200_exp.so")
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd += ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose:
         sys.stderr.write(res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

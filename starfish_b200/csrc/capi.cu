@@ -549,6 +549,7 @@ int sfb_create(int device, int N, int M, int Kmax, int Bmax, int workspace_walke
 #ifdef SFB_EXPERIMENTS  // A/B knobs exist only in an experiments build (python -m starfish_b200.build --experiments)
   if (const char* dbg = getenv("SFB_DEBUG_MODE")) h->debug_mode = atoi(dbg);
   if (const char* ot = getenv("SFB_OUTER_TILES")) h->outer_tiles = std::max(1, atoi(ot));
+  ozaki_set_ts(getenv("SFB_OZ_TS") != nullptr);
 #endif
   DeviceGuard guard(device);
   cudaDeviceProp prop;

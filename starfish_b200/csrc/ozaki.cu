@@ -34,6 +34,7 @@
 // tcgen05.commit releases a stage / signals the epilogue.  The epilogue warps prefetch the C tile (coalesced,
 // into registers) while the main loop runs, transpose the recombined update through the idle ring and finish
 // the read-modify-write with coalesced streaming stores.
+#include <algorithm>
 #include <cstdint>
 
 #include "sfb_internal.cuh"
@@ -46,14 +47,13 @@ constexpr int OZ_S = kOzSlices;      // 6
 constexpr int OZ_NACC = 7;           // anti-diagonals 0..6
 constexpr int OZ_KC = kOzChunk;      // 32
 constexpr int OZ_BM = 128, OZ_BN = 64;
-constexpr int OZ_STAGES = 5;
+constexpr int OZ_STAGES = 4;
 constexpr int OZ_GROUP_BYTES = 8 * OZ_KC;                    // 256: 8 rows × 32 B of one slice
 constexpr int OZ_ROWGROUP_BYTES = OZ_S * OZ_GROUP_BYTES;     // 1536: all slices of 8 rows
 constexpr int OZ_A_BYTES = (OZ_BM / 8) * OZ_ROWGROUP_BYTES;  // 24576
 constexpr int OZ_B_BYTES = (OZ_BN / 8) * OZ_ROWGROUP_BYTES;  // 12288
 constexpr int OZ_STAGE_BYTES = OZ_A_BYTES + OZ_B_BYTES;      // 36864
 constexpr int OZ_THREADS = 192;
-constexpr int OZ_SMEM_BYTES = OZ_STAGES * OZ_STAGE_BYTES + 1024;  // + alignment slack
 constexpr uint32_t OZ_TMEM_COLS = 512;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -113,6 +113,26 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// shared memory -> TMEM, 128 lanes × 256 bits (one K-major 128×32-byte operand slab; SASS UTCCP)
+__device__ __forceinline__ void utccp_128x256b(uint32_t taddr, uint64_t sdesc) {
+  asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+}
+// D[tmem] (+)= A[tmem]·B[smem]ᵀ
+__device__ __forceinline__ void umma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// exact int32 -> double on the full-rate fp64 add pipe: (2^52 + 2^31 + v) − (2^52 + 2^31)
+__device__ __forceinline__ double i2d(uint32_t v) {
+  return __hiloint2double(0x43300000, (int)(v ^ 0x80000000u)) - 4503601774854144.0;
+}
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
   asm volatile(
@@ -135,39 +155,63 @@ constexpr uint32_t OZ_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(O
 
 // ------------------------------------------------------------------------------------------------
 // syrk on the int8 path: C[r0.., c0..] −= Σ_{chunks} (sliced L rows r0..) · (sliced L rows c0..)ᵀ.
-// Grid shapes as chol.cu's syrk_kernel (strip / triangle).
+//
+// A CTA works through `tpc` consecutive tiles of one walker (semi-persistent: long enough to amortise the TMEM
+// allocation / barrier set-up and to overlap a tile's epilogue with the next tile's operand loads, short enough —
+// a few hundred µs — that the high-priority panel kernels of the look-ahead still find free SMs).
+// Tile enumeration (`l` = linear tile index inside the walker):
+//   strip    update of tile columns [jt0, jt0+njt) from their diagonal tile down: l -> (x = l % (2·njt), y = l / (2·njt)),
+//            row tile jt0+y, 64-column block x; tiles above the diagonal of their tile column (y < x/2) are skipped
+//   triangle trailing update of every tile column >= jt0: l in [0, T(T+1)), decoded to (row tile t, 64-column block)
+// Roles: warp 0 = bulk-copy producer (runs ahead across tile boundaries), warp 1 = MMA issuer (waits for the previous
+// tile's accumulators to be drained), warps 2-5 = epilogue.
 // ------------------------------------------------------------------------------------------------
+struct OzTile { int r0, c0, live; };
+
+__device__ __forceinline__ OzTile oz_tile(int l, int jt0, int njt, int strip) {
+  OzTile t;
+  if (strip) {
+    const int x = l % (2 * njt), y = l / (2 * njt);
+    t.live = (y >= (x >> 1));
+    t.r0 = (jt0 + y) * kTile;
+    t.c0 = (jt0 + (x >> 1)) * kTile + (x & 1) * 64;
+  } else {
+    int q = (int)((sqrtf(4.0f * (float)l + 1.0f) - 1.0f) * 0.5f);
+    while (q * (q + 1) > l) --q;
+    while ((q + 1) * (q + 2) <= l) ++q;
+    t.live = 1;
+    t.r0 = (jt0 + q) * kTile;
+    t.c0 = jt0 * kTile + (l - q * (q + 1)) * 64;
+  }
+  return t;
+}
+
+constexpr uint32_t OZ_TROW = 66 * 8;                 // padded row of the transpose buffer (528 B: conflict-free 16-byte accesses)
+constexpr int OZ_TBUF_BYTES = 4 * 32 * OZ_TROW;     // 4 epilogue warps × 32 rows
+constexpr int OZ_SMEM_BYTES = OZ_STAGES * OZ_STAGE_BYTES + OZ_TBUF_BYTES + 1024;  // + alignment slack
+constexpr uint32_t OZ_TMEM_A = OZ_NACC * OZ_BN;     // first TMEM column of the A operand (TS form): 448..495
+
+template <bool TS>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
-    syrk_i8_kernel(CholParams p, OzParams oz, int nch, int jt0, int strip) {
+    syrk_i8_kernel(CholParams p, OzParams oz, int nch, int jt0, int njt, int strip, int ntiles, int tpc) {
   const int s = blockIdx.z;
   if (p.info[s] != 0) return;
-  int it, c0;
-  if (strip) {
-    const int jt = jt0 + (blockIdx.x >> 1);
-    it = jt0 + blockIdx.y;
-    if (it < jt) return;
-    c0 = jt * kTile + (blockIdx.x & 1) * 64;
-  } else {
-    const int L = blockIdx.x;
-    int t = (int)((sqrtf(4.0f * (float)L + 1.0f) - 1.0f) * 0.5f);
-    while (t * (t + 1) > L) --t;
-    while ((t + 1) * (t + 2) <= L) ++t;
-    it = jt0 + t;
-    c0 = jt0 * kTile + (L - t * (t + 1)) * 64;
-  }
-  const int r0 = it * kTile;
+  const int l0 = blockIdx.x * tpc;
+  const int l1 = min(ntiles, l0 + tpc);
 
   extern __shared__ uint8_t oz_smem_raw[];
-  __shared__ uint64_t bars[2 * OZ_STAGES + 1];
+  __shared__ uint64_t bars[2 * OZ_STAGES + 2];
   __shared__ uint32_t tmem_base_s;
   const uint32_t ring = (smem_u32(oz_smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar0 = smem_u32(bars);  // full[s] at +8s, empty[s] at +8(STAGES+s), accfull at +16·STAGES
-  const uint32_t accfull = bar0 + 16 * OZ_STAGES;
+  const uint32_t tbuf0 = ring + OZ_STAGES * OZ_STAGE_BYTES;
+  const uint32_t bar0 = smem_u32(bars);  // full[s] at +8s, empty[s] at +8(STAGES+s), then accfull, tmem_empty
+  const uint32_t accfull = bar0 + 16 * OZ_STAGES, tmem_empty = accfull + 8;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
 #pragma unroll
     for (int i = 0; i < 2 * OZ_STAGES + 1; ++i) mbar_init(bar0 + 8 * i, 1);
+    mbar_init(tmem_empty, 4);  // one arrival per epilogue warp
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), OZ_TMEM_COLS);
@@ -180,101 +224,137 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
   const long long chunk_bytes = (long long)(p.Np / 8) * OZ_ROWGROUP_BYTES;
 
   if (warp == 0) {
-    if (lane == 0) {  // ---- producer: two contiguous bulk copies per chunk
-      const int8_t* srcA = Ps + (long long)(r0 / 8) * OZ_ROWGROUP_BYTES;
-      const int8_t* srcB = Ps + (long long)(c0 / 8) * OZ_ROWGROUP_BYTES;
-      for (int c = 0; c < nch; ++c) {
-        const int st = c % OZ_STAGES;
-        if (c >= OZ_STAGES) mbar_wait(bar0 + 8 * (OZ_STAGES + st), ((c / OZ_STAGES) - 1) & 1);
-        const uint32_t full = bar0 + 8 * st;
-        const uint32_t dst = ring + st * OZ_STAGE_BYTES;
-        mbar_arrive_expect_tx(full, OZ_STAGE_BYTES);
-        bulk_g2s(dst, srcA + c * chunk_bytes, OZ_A_BYTES, full);
-        bulk_g2s(dst + OZ_A_BYTES, srcB + c * chunk_bytes, OZ_B_BYTES, full);
+    if (lane == 0) {  // ---- producer: two contiguous bulk copies per chunk, continuous over the CTA's tiles
+      int g = 0;      // chunks issued so far (ring position)
+      for (int l = l0; l < l1; ++l) {
+        const OzTile t = oz_tile(l, jt0, njt, strip);
+        if (!t.live) continue;
+        const int8_t* srcA = Ps + (long long)(t.r0 / 8) * OZ_ROWGROUP_BYTES;
+        const int8_t* srcB = Ps + (long long)(t.c0 / 8) * OZ_ROWGROUP_BYTES;
+        for (int c = 0; c < nch; ++c, ++g) {
+          const int st = g % OZ_STAGES;
+          if (g >= OZ_STAGES) mbar_wait(bar0 + 8 * (OZ_STAGES + st), ((g / OZ_STAGES) - 1) & 1);
+          const uint32_t full = bar0 + 8 * st;
+          const uint32_t dst = ring + st * OZ_STAGE_BYTES;
+          mbar_arrive_expect_tx(full, OZ_STAGE_BYTES);
+          bulk_g2s(dst, srcA + c * chunk_bytes, OZ_A_BYTES, full);
+          bulk_g2s(dst + OZ_A_BYTES, srcB + c * chunk_bytes, OZ_B_BYTES, full);
+        }
       }
     }
   } else if (warp == 1) {
     // ---- MMA issuer: 26 int8 MMAs per chunk into 7 accumulators.  The whole warp runs the loop (descriptor
     // arithmetic stays warp-uniform, i.e. in uniform registers); one elected lane issues.
     const bool leader = elect_one();
-    for (int c = 0; c < nch; ++c) {
-      const int st = c % OZ_STAGES;
-      mbar_wait(bar0 + 8 * st, (c / OZ_STAGES) & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t a0 = ring + st * OZ_STAGE_BYTES, b0 = a0 + OZ_A_BYTES;
-      const uint64_t ad0 = oz_desc(a0), bd0 = oz_desc(b0);
-      const uint32_t acc = (c == 0) ? 0u : 1u;
-      if (leader) {
-#pragma unroll
-        for (int sa = 0; sa < OZ_S; ++sa) {
-#pragma unroll
-          for (int sb = 0; sb < OZ_S; ++sb) {
-            if (sa + sb >= OZ_NACC) continue;
-            // the start-address field counts 16-byte units and the ring never crosses its 14-bit range inside a
-            // stage, so the other slices' descriptors are the stage's plus a constant
-            const uint64_t ad = ad0 + (uint64_t)(sa * (OZ_GROUP_BYTES >> 4));
-            const uint64_t bd = bd0 + (uint64_t)(sb * (OZ_GROUP_BYTES >> 4));
-            // the first pair that touches anti-diagonal d is (sa = 0, sb = d) for d < 6 and (1, 5) for d = 6
-            const bool first = (sa == 0) || (sa == 1 && sb == OZ_S - 1);
-            umma_i8(tmem + (uint32_t)(sa + sb) * OZ_BN, ad, bd, OZ_IDESC, first ? acc : 1u);
-          }
-        }
-        umma_commit(bar0 + 8 * (OZ_STAGES + st));  // stage free once these MMAs have read it
+    int g = 0, k = 0;  // ring position, live tiles done
+    for (int l = l0; l < l1; ++l) {
+      if (!oz_tile(l, jt0, njt, strip).live) continue;
+      if (k > 0) {  // the epilogue must have drained the accumulators of the previous tile
+        mbar_wait(tmem_empty, (k - 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       }
+      for (int c = 0; c < nch; ++c, ++g) {
+        const int st = g % OZ_STAGES;
+        mbar_wait(bar0 + 8 * st, (g / OZ_STAGES) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a0 = ring + st * OZ_STAGE_BYTES, b0 = a0 + OZ_A_BYTES;
+        const uint64_t ad0 = oz_desc(a0), bd0 = oz_desc(b0);
+        const uint32_t acc = (c == 0) ? 0u : 1u;
+        if (leader) {
+          if constexpr (TS) {
+            // A slices shared memory -> TMEM once per chunk (the SS form re-reads each A slice for every pair and
+            // is shared-memory-bandwidth-bound); copies and MMAs of one thread execute in issue order, so the
+            // copies of this chunk follow the previous chunk's MMAs without a wait
+#pragma unroll
+            for (int sa = 0; sa < OZ_S; ++sa)
+              utccp_128x256b(tmem + OZ_TMEM_A + sa * (OZ_KC / 4), ad0 + (uint64_t)(sa * (OZ_GROUP_BYTES >> 4)));
+          }
+#pragma unroll
+          for (int sa = 0; sa < OZ_S; ++sa) {
+#pragma unroll
+            for (int sb = 0; sb < OZ_S; ++sb) {
+              if (sa + sb >= OZ_NACC) continue;
+              // the start-address field counts 16-byte units and never leaves its 14-bit range inside the ring, so
+              // the other slices' descriptors are the stage's plus a constant
+              const uint64_t bd = bd0 + (uint64_t)(sb * (OZ_GROUP_BYTES >> 4));
+              // the first pair that touches anti-diagonal d is (sa = 0, sb = d) for d < 6 and (1, 5) for d = 6
+              const bool first = (sa == 0) || (sa == 1 && sb == OZ_S - 1);
+              const uint32_t dcol = tmem + (uint32_t)(sa + sb) * OZ_BN;
+              if constexpr (TS) {
+                umma_i8_ts(dcol, tmem + OZ_TMEM_A + sa * (OZ_KC / 4), bd, OZ_IDESC, first ? acc : 1u);
+              } else {
+                umma_i8(dcol, ad0 + (uint64_t)(sa * (OZ_GROUP_BYTES >> 4)), bd, OZ_IDESC, first ? acc : 1u);
+              }
+            }
+          }
+          umma_commit(bar0 + 8 * (OZ_STAGES + st));  // stage free once these MMAs (and copies) have read it
+        }
+        __syncwarp();
+      }
+      if (leader) umma_commit(accfull);
       __syncwarp();
+      ++k;
     }
-    if (leader) umma_commit(accfull);
-    __syncwarp();
   } else {
     // ---- epilogue (4 warps; warp q owns tile rows 32q..32q+31 = its TMEM lane quarter).
     // Two thread mappings: TMEM hands a thread ONE ROW (lane = row, 16 columns per load), global memory wants a
     // warp on one row (lane = column pair, 512 contiguous bytes).  The C tile is therefore fetched in the global
-    // mapping BEFORE the accumulators are ready (32 independent 16-byte loads per thread, in flight under the whole
-    // main loop), the recombined update goes through a warp-private transpose buffer in the (by then idle)
-    // operand ring, and the read-modify-write finishes with coalesced streaming stores.
+    // mapping BEFORE the accumulators are ready (32 independent 16-byte loads per thread, in flight under the
+    // main loop), the recombined update goes through a warp-private transpose buffer, the accumulators are handed
+    // back to the MMA warp, and the read-modify-write finishes with coalesced streaming stores while the next
+    // tile's MMAs already run.
     const int q = warp & 3;
     const double* rs = oz.rscale + (long long)s * p.Np;
-    const double ri = rs[r0 + q * 32 + lane];                                            // row scale, TMEM mapping
-    const double2 rj = *reinterpret_cast<const double2*>(rs + c0 + 2 * lane);           // column scales, global mapping
-    double* Cw = p.W + (long long)s * p.strideW + (long long)(r0 + q * 32) * p.Np + c0 + 2 * lane;
-    double2 creg[32];
-#pragma unroll
-    for (int r = 0; r < 32; ++r) creg[r] = __ldcs(reinterpret_cast<const double2*>(Cw + (long long)r * p.Np));
-    mbar_wait(accfull, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
-    constexpr uint32_t TROW = 66 * 8;  // padded row of the transpose buffer: 528 B -> conflict-free 16-byte accesses
-    const uint32_t tbuf = ring + (uint32_t)q * (32 * TROW);
+    const uint32_t tbuf = tbuf0 + (uint32_t)q * (32 * OZ_TROW);
+    int k = 0;
+    for (int l = l0; l < l1; ++l) {
+      const OzTile t = oz_tile(l, jt0, njt, strip);
+      if (!t.live) continue;
+      const double ri = rs[t.r0 + q * 32 + lane];                                         // row scale, TMEM mapping
+      const double2 rj = *reinterpret_cast<const double2*>(rs + t.c0 + 2 * lane);        // column scales, global mapping
+      double* Cw = p.W + (long long)s * p.strideW + (long long)(t.r0 + q * 32) * p.Np + t.c0 + 2 * lane;
+      double2 creg[32];
+#pragma unroll
+      for (int r = 0; r < 32; ++r) creg[r] = __ldcs(reinterpret_cast<const double2*>(Cw + (long long)r * p.Np));
+      mbar_wait(accfull, k & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-    for (int cb = 0; cb < OZ_BN / 16; ++cb) {
-      double acc[16];
-      uint32_t v[16];
-      tmem_ld16(tlane + (OZ_NACC - 1) * OZ_BN + cb * 16, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 16; ++j) acc[j] = (double)(int)v[j];
-#pragma unroll
-      for (int d = OZ_NACC - 2; d >= 0; --d) {
-        tmem_ld16(tlane + d * OZ_BN + cb * 16, v);
+      for (int cb = 0; cb < OZ_BN / 16; ++cb) {
+        double acc[16];
+        uint32_t v[16];
+        tmem_ld16(tlane + (OZ_NACC - 1) * OZ_BN + cb * 16, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = fma(acc[j], 0.00390625, (double)(int)v[j]);
+        for (int j = 0; j < 16; ++j) acc[j] = i2d(v[j]);
+#pragma unroll
+        for (int d = OZ_NACC - 2; d >= 0; --d) {
+          tmem_ld16(tlane + d * OZ_BN + cb * 16, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] = fma(acc[j], 0.00390625, i2d(v[j]));
+        }
+        const uint32_t dst = tbuf + (uint32_t)lane * OZ_TROW + (uint32_t)cb * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(dst + 16 * j), "d"(acc[2 * j] * ri), "d"(acc[2 * j + 1] * ri)
+                       : "memory");
       }
-      const uint32_t dst = tbuf + (uint32_t)lane * TROW + (uint32_t)cb * 128;
+      // accumulators drained: hand TMEM back to the MMA warp (which orders its next MMAs after this arrive)
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty);
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(dst + 16 * j), "d"(acc[2 * j] * ri), "d"(acc[2 * j + 1] * ri)
-                     : "memory");
-    }
-    __syncwarp();
-#pragma unroll
-    for (int r = 0; r < 32; ++r) {
-      double tx, ty;
-      asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(tx), "=d"(ty) : "r"(tbuf + (uint32_t)r * TROW + 16 * lane) : "memory");
-      double2 c = creg[r];
-      c.x = fma(-tx, rj.x, c.x);
-      c.y = fma(-ty, rj.y, c.y);
-      __stcs(reinterpret_cast<double2*>(Cw + (long long)r * p.Np), c);
+      for (int r = 0; r < 32; ++r) {
+        double tx, ty;
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(tx), "=d"(ty) : "r"(tbuf + (uint32_t)r * OZ_TROW + 16 * lane) : "memory");
+        double2 c = creg[r];
+        c.x = fma(-tx, rj.x, c.x);
+        c.y = fma(-ty, rj.y, c.y);
+        __stcs(reinterpret_cast<double2*>(Cw + (long long)r * p.Np), c);
+      }
+      __syncwarp();  // the transpose buffer is rewritten by the next tile
+      ++k;
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -343,13 +423,44 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(CholParams p, OzParams oz
 
 }  // namespace
 
+namespace {
+bool g_oz_ts = false;  // A operand from TMEM (tcgen05.cp + .ts MMAs) instead of shared memory
+}
+void ozaki_set_ts(bool on) { g_oz_ts = on; }
+
 cudaError_t ozaki_init() {
-  return cudaFuncSetAttribute((const void*)syrk_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES);
+  cudaError_t e = cudaFuncSetAttribute((const void*)syrk_i8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       OZ_SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute((const void*)syrk_i8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              OZ_SMEM_BYTES);
 }
 
 size_t oz_panel_bytes_per_slot(int Np, int outer_tiles) {
   return (size_t)(outer_tiles * (kTile / OZ_KC)) * (size_t)(Np / 8) * OZ_ROWGROUP_BYTES;
 }
+
+namespace {
+// tiles per CTA: enough CTAs for ~4 waves over the SMs, at most 8 tiles each
+cudaError_t launch_syrk_i8(const CholParams& p, const OzParams& oz, int K, int jt0, int njt, int strip, int ntiles, int B,
+                           cudaStream_t st) {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  long long total = (long long)ntiles * B;
+  int tpc = (int)std::min<long long>(8, std::max<long long>(1, total / (4LL * sms)));
+  tpc = std::min(tpc, ntiles);
+  const dim3 grid((ntiles + tpc - 1) / tpc, 1, B);
+  if (g_oz_ts)
+    syrk_i8_kernel<true><<<grid, OZ_THREADS, OZ_SMEM_BYTES, st>>>(p, oz, K / OZ_KC, jt0, njt, strip, ntiles, tpc);
+  else
+    syrk_i8_kernel<false><<<grid, OZ_THREADS, OZ_SMEM_BYTES, st>>>(p, oz, K / OZ_KC, jt0, njt, strip, ntiles, tpc);
+  return cudaGetLastError();
+}
+}  // namespace
 
 cudaError_t launch_oz_rowscale(const CholParams& p, const OzParams& oz, int B, cudaStream_t st) {
   oz_rowscale_kernel<<<dim3((p.Np + 255) / 256, B), 256, 0, st>>>(p, oz);
@@ -367,15 +478,13 @@ cudaError_t launch_oz_syrk_strip(const CholParams& p, const OzParams& oz, int K,
                                  cudaStream_t st) {
   const int rows = p.Np / kTile - jt0;
   if (rows <= 0 || K <= 0 || njt <= 0) return cudaSuccess;
-  syrk_i8_kernel<<<dim3(2 * njt, rows, B), OZ_THREADS, OZ_SMEM_BYTES, st>>>(p, oz, K / OZ_KC, jt0, 1);
-  return cudaGetLastError();
+  return launch_syrk_i8(p, oz, K, jt0, njt, 1, 2 * njt * rows, B, st);
 }
 
 cudaError_t launch_oz_syrk_tri(const CholParams& p, const OzParams& oz, int K, int jt0, int B, cudaStream_t st) {
   const int T = p.Np / kTile - jt0;
   if (T <= 0 || K <= 0) return cudaSuccess;
-  syrk_i8_kernel<<<dim3(T * (T + 1), 1, B), OZ_THREADS, OZ_SMEM_BYTES, st>>>(p, oz, K / OZ_KC, jt0, 0);
-  return cudaGetLastError();
+  return launch_syrk_i8(p, oz, K, jt0, 1, 0, T * (T + 1), B, st);
 }
 
 }  // namespace sfb

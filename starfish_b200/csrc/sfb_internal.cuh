@@ -98,6 +98,7 @@ struct OzParams {
   double* rscale;        // per slot, Np doubles: 2^(e_i - 7)
 };
 cudaError_t ozaki_init();
+void ozaki_set_ts(bool on);  // A operand of the int8 MMAs from TMEM (tcgen05.cp) instead of shared memory
 size_t oz_panel_bytes_per_slot(int Np, int outer_tiles);
 cudaError_t launch_oz_rowscale(const CholParams& p, const OzParams& oz, int B, cudaStream_t st);
 cudaError_t launch_oz_slice(const CholParams& p, const OzParams& oz, int chunk0, int B, cudaStream_t st);

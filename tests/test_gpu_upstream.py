@@ -14,7 +14,7 @@ perturbed by one ulp (knot spacing 0.045 Å against ulp(5000 Å) = 9e-13 Å → 
 by tests/test_oracle_upstream.py::test_doppler_knot_rounding_floor).  The device fits the spline once in the
 unshifted frame — exact in real arithmetic — so it sits inside that floor, not on the reference's rounding.
 Hence: X and model flux to 2e-9·max|·| with rotation, 1e-10 with a Doppler shift only, 1e-12 with neither;
-Σ_w and weights to 1e-10; lnL end to end to MODEL_LNL_RTOL = 1e-10·|lnL| — the SAME bar as the stage boundary:
+Σ_w and weights to 1e-10; lnL end to end to MODEL_LNL_RTOL = 1e-11·|lnL| — the SAME bar as the stage boundary:
 the 1e-11 movements of X barely reach lnL (measured floor of the reference itself: 5e-14, see below).
 """
 import copy
@@ -36,10 +36,11 @@ pytestmark = pytest.mark.gpu
 #   * tests/test_oracle_upstream.py::test_reference_lnl_conditioning_floor measures how far the REFERENCE's own lnL
 #     moves when one of its ill-conditioned steps is evaluated by an equally valid fp64 route (knots by one ulp,
 #     getrf/getrs instead of gesv, libm ulps in Gray's transfer function) — the floor — and asserts
-#     100·floor <= MODEL_LNL_RTOL <= 1e-10 (the floor is ~5e-14: X moves by 1e-11 but lnL hardly sees it);
-#   * OBSERVED_* below are the device-vs-reference errors measured on a B200 (profiles/r2_model_tolerance.txt); every test
-#     prints its observed error and asserts it stays within 10x of the recorded one as well as within MODEL_LNL_RTOL.
-MODEL_LNL_RTOL = 1e-10
+#     10·floor <= MODEL_LNL_RTOL <= 1e-10 (the floor is ~5e-14: X moves by 1e-11 but lnL hardly sees it);
+#   * the device-vs-reference errors measured on a B200 are 6.6e-16 … 4.7e-14 over the five recorded variants and the
+#     three config fixtures (profiles/r2f_model_tolerance.txt); every test prints its observed error.  1e-11 is 200x the
+#     largest observed value and 10x tighter than the stage-boundary bar.
+MODEL_LNL_RTOL = 1e-11
 
 
 def _load(golden_dir, name):

@@ -257,6 +257,204 @@ void run_pace(int sms) {
   cudaFree(dout);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// A operand from TMEM: tcgen05.cp (smem -> TMEM, 128 lanes x 256 bit) of a K-major SW32 A slab, read back with
+// tcgen05.ld (layout check), then the .ts form of the MMA (A in TMEM, B in smem) against the CPU GEMM.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void utccp_128x256b(uint32_t taddr, uint64_t sdesc) {
+  asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+}
+__device__ __forceinline__ void umma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(128, 1) ts_kernel(const int8_t* A, const int8_t* B, int N, int32_t* D, uint32_t* Aback) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const Variant v{6, 32, 1, 256, 16, 1};
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + 8192;
+  for (int i = tid; i < 16384; i += blockDim.x) smem[i] = 0;
+  __syncthreads();
+  for (int i = tid; i < M_ * 32; i += blockDim.x) sA[slab_off(v, i / 32, i % 32)] = (uint8_t)A[i];
+  for (int i = tid; i < N * 32; i += blockDim.x) sB[slab_off(v, i / 32, i % 32)] = (uint8_t)B[i];
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (tid == 0) {
+    mbar_init(smem_u32(&bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_base), 512);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tb = tmem_base;
+  const uint32_t ta = tb + 256;   // A operand columns
+  if (tid == 0) {
+    utccp_128x256b(ta, make_desc(smem_u32(sA), 16, 256, 6));
+    umma_i8_ts(tb, ta, make_desc(smem_u32(sB), 16, 256, 6), make_idesc_i8(M_, N), 0);
+    umma_commit(smem_u32(&bar));
+  }
+  mbar_wait(smem_u32(&bar), 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  {
+    uint32_t r[8];
+    tmem_ld8(ta + ((uint32_t)(warp * 32) << 16), r);
+    tmem_ld_wait();
+    for (int j = 0; j < 8; ++j) Aback[tid * 8 + j] = r[j];
+  }
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    uint32_t r[16];
+    tmem_ld16(tb + ((uint32_t)(warp * 32) << 16) + c0, r);
+    tmem_ld_wait();
+    for (int j = 0; j < 16; ++j) D[(size_t)tid * N + c0 + j] = (int32_t)r[j];
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, 512);
+}
+
+// pace of the TS form: per chunk 6 tcgen05.cp (A slices -> 48 TMEM columns) + 26 MMAs with A from TMEM
+__global__ void __launch_bounds__(128, 1) pace_ts_kernel(int chunks, int nstage, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  constexpr int N = 64, A_BYTES = 16 * 1536, B_BYTES = (N / 8) * 1536, STAGE = A_BYTES + B_BYTES;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < nstage * STAGE; i += blockDim.x) smem[i] = (uint8_t)(i * 7 + 3);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (tid == 0) {
+    mbar_init(smem_u32(&bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_base), 512);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tb = tmem_base;
+  if (warp == 1) {
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc_i8(M_, N);
+    const long long t0 = clock64();
+    for (int c = 0; c < chunks; ++c) {
+      const uint32_t a0 = smem_u32(smem) + (c % nstage) * STAGE, b0 = a0 + A_BYTES;
+      const uint64_t ad0 = desc_sw32(a0), bd0 = desc_sw32(b0);
+      if (leader) {
+#pragma unroll
+        for (int sa = 0; sa < 6; ++sa) utccp_128x256b(tb + 448 + sa * 8, ad0 + sa * 16);
+#pragma unroll
+        for (int sa = 0; sa < 6; ++sa)
+#pragma unroll
+          for (int sb = 0; sb < 6; ++sb) {
+            if (sa + sb >= 7) continue;
+            umma_i8_ts(tb + (uint32_t)(sa + sb) * N, tb + 448 + sa * 8, bd0 + sb * 16, idesc, 1);
+          }
+      }
+      __syncwarp();
+    }
+    if (leader) umma_commit(smem_u32(&bar));
+    __syncwarp();
+    mbar_wait(smem_u32(&bar), 0);
+    if (leader) out[0] = clock64() - t0;
+  } else {
+    mbar_wait(smem_u32(&bar), 0);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, 512);
+}
+
+void run_ts(int sms) {
+  const int N = 64;
+  std::vector<int8_t> A(M_ * 32), B(N * 32);
+  srand(77);
+  for (auto& x : A) x = (int8_t)(rand() % 256 - 128);
+  for (auto& x : B) x = (int8_t)(rand() % 256 - 128);
+  int8_t *dA, *dB;
+  int32_t* dD;
+  uint32_t* dAb;
+  CK(cudaMalloc(&dA, A.size()));
+  CK(cudaMalloc(&dB, B.size()));
+  CK(cudaMalloc(&dD, sizeof(int32_t) * M_ * N));
+  CK(cudaMalloc(&dAb, sizeof(uint32_t) * M_ * 8));
+  CK(cudaMemcpy(dA, A.data(), A.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, B.data(), B.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemset(dD, 0xff, sizeof(int32_t) * M_ * N));
+  CK(cudaFuncSetAttribute(ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  ts_kernel<<<1, 128, 20 * 1024>>>(dA, dB, N, dD, dAb);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    printf("TS form: CUDA error %s\n", cudaGetErrorString(e));
+    exit(1);
+  }
+  std::vector<int32_t> D(M_ * N);
+  std::vector<uint32_t> Ab(M_ * 8);
+  CK(cudaMemcpy(D.data(), dD, sizeof(int32_t) * M_ * N, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(Ab.data(), dAb, sizeof(uint32_t) * M_ * 8, cudaMemcpyDeviceToHost));
+  long long badA = 0;
+  for (int r = 0; r < M_; ++r)
+    for (int j = 0; j < 8; ++j) {
+      uint32_t w = 0;
+      for (int b = 0; b < 4; ++b) w |= (uint32_t)(uint8_t)A[r * 32 + 4 * j + b] << (8 * b);
+      if (w != Ab[r * 8 + j]) ++badA;
+    }
+  printf("tcgen05.cp 128x256b (SW32 K-major slab -> TMEM): lane r / column j = bytes 4j..4j+3 of row r: %s (%lld of %d words differ)\n",
+         badA ? "NO" : "yes", badA, M_ * 8);
+  if (badA) {
+    printf("  row 0 got: ");
+    for (int j = 0; j < 8; ++j) printf("%08x ", Ab[j]);
+    printf("\n  row 0 exp: ");
+    for (int j = 0; j < 8; ++j) {
+      uint32_t w = 0;
+      for (int b = 0; b < 4; ++b) w |= (uint32_t)(uint8_t)A[4 * j + b] << (8 * b);
+      printf("%08x ", w);
+    }
+    printf("\n");
+  }
+  long long bad = 0;
+  for (int i = 0; i < M_; ++i)
+    for (int j = 0; j < N; ++j) {
+      int32_t ref = 0;
+      for (int k = 0; k < 32; ++k) ref += (int32_t)A[i * 32 + k] * (int32_t)B[j * 32 + k];
+      if (ref != D[i * N + j]) ++bad;
+    }
+  printf("tcgen05.mma .ts form (A from TMEM): %s (%lld mismatches of %d)\n", bad ? "WRONG" : "exact", bad, M_ * N);
+  long long* dout;
+  CK(cudaMalloc(&dout, 64));
+  CK(cudaFuncSetAttribute(pace_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  const int STAGE = 16 * 1536 + 8 * 1536, nstage = 4, chunks = 256;
+  pace_ts_kernel<<<1, 128, nstage * STAGE + 1024>>>(chunks, nstage, dout);
+  CK(cudaDeviceSynchronize());
+  long long h[2];
+  CK(cudaMemcpy(h, dout, 16, cudaMemcpyDeviceToHost));
+  printf("pace TS 128x64x32 i8 (6 cp + 26 MMAs per chunk): %.1f cycles per MMA incl. copies (SS form: 52.4; floor 32)\n",
+         (double)h[0] / (chunks * 26.0));
+  cudaEvent_t a, b;
+  CK(cudaEventCreate(&a));
+  CK(cudaEventCreate(&b));
+  const int big = 40000;
+  pace_ts_kernel<<<sms, 128, nstage * STAGE + 1024>>>(100, nstage, dout);
+  CK(cudaEventRecord(a));
+  pace_ts_kernel<<<sms, 128, nstage * STAGE + 1024>>>(big, nstage, dout);
+  CK(cudaEventRecord(b));
+  CK(cudaDeviceSynchronize());
+  float ms;
+  CK(cudaEventElapsedTime(&ms, a, b));
+  printf("chip TS 128x64x32 i8 on %d SMs: %.2f ms -> %.1f TOP/s\n", sms, ms, 2.0 * 128 * N * 32 * 26.0 * big * sms / ms * 1e-9);
+}
+
 int main() {
   int dev = 0;
   CK(cudaSetDevice(dev));
@@ -314,6 +512,7 @@ int main() {
     cudaFree(dA); cudaFree(dB); cudaFree(dD);
   }
 
+  run_ts(prop.multiProcessorCount);
   run_pace<64>(prop.multiProcessorCount);
   run_pace<128>(prop.multiProcessorCount);
   run_pace<256>(prop.multiProcessorCount);

@@ -1,0 +1,15 @@
+#!/bin/bash
+# probe (TS form), model-level tolerance observations, NCCL C-ABI test, compute-sanitizer passes
+set -u
+TAG=${1:-misc}
+mkdir -p gpurun_out
+timeout 120 ./tools/exp/umma_i8_probe > gpurun_out/${TAG}_probe.txt 2>&1; echo "probe rc=$?"; grep -E "tcgen05|TS|pace|chip" gpurun_out/${TAG}_probe.txt
+timeout 600 python -m pytest tests/test_gpu_upstream.py tests/test_gpu_model.py tests/test_gpu_structured.py tests/test_gpu_comm.py -q -s > gpurun_out/${TAG}_pytest_model.log 2>&1; echo "pytest model rc=$?"
+grep -E "dlnL|rel err|passed|failed|Error|assert" gpurun_out/${TAG}_pytest_model.log | head -60
+SEL='n256 or not_positive or cho_factor or odd_sizes or ragged or 384'
+timeout 900 compute-sanitizer --tool memcheck --print-limit 10 python -m pytest tests/test_gpu_parity.py tests/test_gpu_edge.py tests/test_gpu_ozaki.py -q -x -k "$SEL" > gpurun_out/${TAG}_memcheck.log 2>&1; echo "memcheck rc=$?"
+grep -E "ERROR SUMMARY|passed|failed|Invalid|Hazard" gpurun_out/${TAG}_memcheck.log | head -20
+timeout 900 compute-sanitizer --tool racecheck --print-limit 10 python -m pytest tests/test_gpu_parity.py tests/test_gpu_edge.py tests/test_gpu_ozaki.py -q -x -k "$SEL" > gpurun_out/${TAG}_racecheck.log 2>&1; echo "racecheck rc=$?"
+grep -E "RACECHECK SUMMARY|passed|failed|hazard|Hazard" gpurun_out/${TAG}_racecheck.log | head -20
+timeout 600 compute-sanitizer --tool synccheck --print-limit 10 python -m pytest tests/test_gpu_ozaki.py tests/test_gpu_parity.py -q -x -k "$SEL" > gpurun_out/${TAG}_synccheck.log 2>&1; echo "synccheck rc=$?"
+grep -E "ERROR SUMMARY|passed|failed|Barrier|barrier" gpurun_out/${TAG}_synccheck.log | head -20
