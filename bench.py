@@ -21,6 +21,7 @@ Prints ONE JSON line (rank 0):
   roofline     the dominant kernel (trailing update) against its tensor peak
   configs      BASELINE.json configs[1] (64 walkers, N=4096, global kernel only) and a configs[4] shard
                (64 walkers per GPU, N=16384, 16 local kernels): value, fraction of the fp64 floor, kernel shares
+  frozen_shared  the reference's frozen-kernel mode: all walkers share the kernel hyper-parameters, S factorised once
   structured   the structure-exploiting solver (row f4) on the same inputs
   cpu_baseline the CPU oracle port on this box's host cores, both threading modes, on a bounded sample
 """
@@ -66,6 +67,7 @@ def parse_args():
     ap.add_argument("--no-structured", action="store_true", help="skip the structured-solver (row f4) legs")
     ap.add_argument("--no-configs", action="store_true", help="skip the configs[1] / configs[4] legs")
     ap.add_argument("--no-alt", action="store_true", help="skip the leg with the other dense trailing-update mode")
+    ap.add_argument("--no-frozen", action="store_true", help="skip the frozen-kernel (shared factor) leg")
     ap.add_argument("--cpu-sample", type=int, default=0, help="walkers in the CPU sample (0 = one per usable core)")
     return ap.parse_args()
 
@@ -589,6 +591,40 @@ def run_b200(args, rank, world, local_rank, cpu_sample):
             alt["kernels"] = kernel_shares(pa)
         eng.set_solver(args.solver)
 
+    # ---- frozen kernel groups: every walker shares the hyper-parameter row -> S factorised once per step ------
+    frozen = None
+    if not args.no_frozen:
+        g1, n1, l1 = eng.pack_hyper(nb, stage["glob"][:1], stage["nloc"][:1], stage["loc"][:1], True)
+
+        def step_frozen():
+            eng.log_likelihood_resident(nb, X, A, F, g1, n1, l1, lnL, info, shared_hyper=True)
+            return gather(lnL)
+
+        f_steps = max(10, 2 * args.steps)
+        ms_f, launches_f, _ = timed(step_frozen, f_steps, 2)
+        lnl_frozen = lnL.clone()
+        eng.set_shared_factor(False)      # the same call, every walker's full covariance factorised: the check
+        step_frozen()
+        torch.cuda.synchronize(dev)
+        diff = float(((lnl_frozen - lnL).abs() / lnL.abs().clamp(min=1.0)).max().item())
+        eng.set_shared_factor(True)
+        fl_f = N ** 3 / 3 + nb * float(N) ** 2 * (M + 1)   # per step and GPU: one factorisation + the forward solves
+        v_f = B / (ms_f / f_steps * 1e-3)
+        frozen = {"value": v_f, "unit": "evals/s", "ms_per_step": ms_f / f_steps, "steps": f_steps,
+                  "gpu_launches": int(launches_f), "max_rel_diff_vs_per_walker_factorisation": diff,
+                  "not_positive_definite": int((info != 0).sum().item()),
+                  "flop_model": "N^3/3 (one factorisation of S) + B*N^2*(M+1) (forward solves of [R | X^T]) per step",
+                  "path_tflops": fl_f / (ms_f / f_steps * 1e-3) / 1e12,
+                  "frac_of_fp64_peak": fl_f / (ms_f / f_steps * 1e-3) / 1e12 / FP64_DMMA_PEAK_TFLOPS,
+                  "api": "sfb_loglike(shared_hyper=1): the reference's frozen global_cov/local_cov mode "
+                         "(spectrum_model.py:341-363); S built and factorised once, all walkers' right-hand sides "
+                         "solved together, M x M capacitance system per walker"}
+        if rank == 0:
+            eng.profile(True)
+            step_frozen()
+            frozen["kernels"] = kernel_shares(eng.profile_read())
+            eng.profile(False)
+
     # ---- the structure-exploiting solver (row f4): same stage boundary, banded Cholesky + capacitance ------
     structured = None
     if not args.no_structured:
@@ -667,7 +703,7 @@ def run_b200(args, rank, world, local_rank, cpu_sample):
             "path_tflops_fp64_equivalent": value * fl / 1e12,
             "path_frac_of_fp64_peak": value * fl / 1e12 / (FP64_DMMA_PEAK_TFLOPS * world),
             ("fp64_dmma" if args.solver == "dense_i8" else "int8_tensor"): alt,
-            "structured": structured, "configs": configs,
+            "frozen_shared": frozen, "structured": structured, "configs": configs,
             "not_positive_definite": bad,
             "lnL_checksum": checksum,
             "workspace_walkers": ws_walkers,

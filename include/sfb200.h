@@ -182,6 +182,18 @@ int sfb_spline_halfwidth(void);
 enum sfb_solver { SFB_SOLVER_DENSE = 0, SFB_SOLVER_STRUCTURED = 1, SFB_SOLVER_DENSE_I8 = 2 };
 int sfb_set_solver(sfb_t* h, int solver);
 int sfb_get_solver(const sfb_t* h);
+/*
+ * Shared-factor path — the reference's frozen-kernel cache (Starfish/models/spectrum_model.py:341-363: with
+ * "global_cov" and "local_cov" frozen the cached kernel matrices are reused, its production MCMC mode,
+ * examples/single.ipynb:436).  With shared_hyper != 0 every walker has the same S = diag(σ²+1e-10) + K_global +
+ * ΣK_local; the dense solvers then build and factorise S ONCE per call and solve L⁻¹[R_b | X_bᵀ] for all walkers
+ * together (N³/3 + B·N²(M+1) FLOP instead of B·N³/3), finishing with the M×M capacitance system per walker.
+ * Same lnL to rounding (|ΔlnL| <= 1e-10·|lnL|, tests/test_gpu_shared_factor.py).  On by default for B >= 2;
+ * sfb_set_shared_factor(h, 0) makes shared_hyper calls factorise every walker's full covariance again.
+ */
+int sfb_set_shared_factor(sfb_t* h, int on);
+long long sfb_shared_factor_calls(const sfb_t* h);
+
 /* Walkers routed to each register-window width since creation; the last entry (width 0) is the dense
  * fallback.  Returns the number of entries written (n must be >= 5). */
 int sfb_band_classes(const sfb_t* h, int* widths, long long* walkers, int n);
@@ -213,7 +225,7 @@ int sfb_sync(sfb_t* h);
  * (bytes for SFB_K_BUILD, FLOPs otherwise), and resets the counters.  `n` = capacity of out in doubles.
  */
 enum sfb_kernel_class { SFB_K_BUILD = 0, SFB_K_POTRF_DIAG = 1, SFB_K_TRSM = 2, SFB_K_SYRK = 3, SFB_K_UPSTREAM = 4,
-                        SFB_K_BAND_BUILD = 5, SFB_K_BAND_CHOL = 6, SFB_K_OZ_SLICE = 7, SFB_K_NCLASS = 8 };
+                        SFB_K_BAND_BUILD = 5, SFB_K_BAND_CHOL = 6, SFB_K_OZ_SLICE = 7, SFB_K_FWD_ROWS = 8, SFB_K_NCLASS = 9 };
 int sfb_profile_enable(sfb_t* h, int on);
 int sfb_profile_read(sfb_t* h, double* out, int n);
 

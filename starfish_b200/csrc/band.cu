@@ -1056,6 +1056,44 @@ __global__ void residual_only_kernel(const double* __restrict__ F, const double*
   if (i < N) resid[(long long)b * N + i] = F[(long long)b * N + i] - data[i];
 }
 
+// ------------------------------------------------------------------------------------------------
+// Shared-factor path (frozen kernels): the right-hand sides of walker b, already solved against the shared factor
+// (rows b·(M+1) .. b·(M+1)+M of Zt), give its Gram matrix; band_epilogue turns it into lnL with the shared logdet.
+// One CTA per walker, one warp per Gram entry at a time, fixed summation order (deterministic).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gram_capacitance_kernel(const double* __restrict__ Zt, int ldz, int N, int M,
+                                                               const double* A, const double* logdet_S,
+                                                               const int* info_S, double* lnL, int* info) {
+  __shared__ double gram[(kMaxM + 1) * (kMaxM + 1)];
+  const int b = blockIdx.x, NR = M + 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double* Zb = Zt + (long long)b * NR * ldz;
+  for (int pq = warp; pq < NR * NR; pq += 8) {
+    const int i = pq / NR, j = pq % NR;
+    if (j > i) continue;
+    const double* zi = Zb + (long long)i * ldz;
+    const double* zj = Zb + (long long)j * ldz;
+    double acc = 0.0;
+    for (int c = lane; c < N; c += 32) acc = fma(zi[c], zj[c], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) { gram[i * NR + j] = acc; gram[j * NR + i] = acc; }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    BandCholParams p;
+    p.N = N; p.M = M; p.A = A; p.lnL = lnL; p.info = info;
+    band_epilogue(p, b, M, gram, *logdet_S, *info_S);
+  }
+}
+
+cudaError_t launch_gram_capacitance(const double* Zt, int ldz, int N, int M, int B, const double* A,
+                                    const double* logdet_S, const int* info_S, double* lnL, int* info, cudaStream_t st) {
+  if (B <= 0) return cudaSuccess;
+  gram_capacitance_kernel<<<B, 256, 0, st>>>(Zt, ldz, N, M, A, logdet_S, info_S, lnL, info);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_residual_only(const double* model_flux, const double* data_flux, int N, int B, double* resid,
                                  cudaStream_t st) {
   if (B <= 0) return cudaSuccess;

@@ -62,6 +62,13 @@ struct sfb_ctx {
   int8_t* ozP = nullptr;
   double* oz_rscale = nullptr;
   size_t oz_bytes = 0;    // bytes of ONE panel buffer of one slot
+  // shared-factor path (frozen kernel groups): right-hand sides of all walkers as rows, per-panel L_kk^-1 blocks
+  bool shared_factor = true;   // sfb_set_shared_factor
+  double* Zt = nullptr;
+  double* MinvAll = nullptr;
+  int Jp_max = 0;
+  FwdMaps fwd_maps;
+  long long shared_factor_calls = 0;
   // multi-GPU: one NCCL communicator per handle, created by sfb_comm_init; NCCL is bound at run time
   // (dlopen) so that a host that never calls sfb_comm_init needs no NCCL, and a torch host shares torch's copy
   void* nccl_comm = nullptr;
@@ -185,7 +192,7 @@ int ensure_ozaki(sfb_ctx* h) {
   return SFB_OK;
 }
 
-int run_cholesky(sfb_ctx* h, int lane, int slot0, int nb, double* lnL_out, int* info_out) {
+int run_cholesky(sfb_ctx* h, int lane, int slot0, int nb, double* lnL_out, int* info_out, double* minv_all = nullptr) {
   cudaStream_t lo = h->streams[lane];
   cudaStream_t hi = (h->profile || (h->debug_mode & 1)) ? lo : h->hi[lane];
   const bool two = (hi != lo);
@@ -244,6 +251,9 @@ int run_cholesky(sfb_ctx* h, int lane, int slot0, int nb, double* lnL_out, int* 
         ProfScope ps(h, hi, SFB_K_POTRF_DIAG, nb * (2.0 * kTile * kTile * kTile / 3.0));
         SFB_CUDA(h, launch_potrf_diag(p, nb, last, lnL_out, info_out, hi));
         h->launches++;
+        if (minv_all)  // shared-factor path (nb == 1): keep every panel's L_kk^-1 for the forward substitution
+          SFB_CUDA(h, cudaMemcpyAsync(minv_all + (size_t)jt * kTile * kTile, p.Minv, sizeof(double) * kTile * kTile,
+                                      cudaMemcpyDeviceToDevice, hi));
       }
       if (!last) {
         {
@@ -527,11 +537,70 @@ int structured_device(sfb_ctx* h, int B, const double* X, const double* A, const
   return join_streams(h, caller, 2);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Shared-factor path: all walkers share the kernel hyper-parameters (the reference's frozen-group cache,
+// spectrum_model.py:341-363), so S = diag(σ²+jitter) + K_global + ΣK_local is built and factorised ONCE;
+// per walker only Z_b = L⁻¹[R_b | X_bᵀ] (N²(M+1) FLOP instead of N³/3) and the M×M capacitance system remain:
+//   log det C_b = log det S + log det(I + A_b G_b),   R_bᵀC_b⁻¹R_b = ‖z_R‖² − uᵀ(I + A_b G_b)⁻¹A_b u,
+//   G_b = Z_XᵀZ_X,  u = Z_Xᵀz_R   (determinant lemma / Woodbury; the same identity the structured solver uses).
+// ---------------------------------------------------------------------------------------------------
+int shared_factor_device(sfb_ctx* h, int B, const double* X, const double* A, const double* model_flux,
+                         const double* glob, const int* nloc, const double* loc, double* lnL, int* info, double* resid,
+                         cudaStream_t caller) {
+  const int N = h->N, Np = h->Np, M = X ? h->M : 0;
+  const int J = B * (M + 1), Jp = ((J + 127) / 128) * 128;
+  const int nt = Np / kTile;
+  if (!h->Zt || Jp > h->Jp_max) {
+    if (h->Zt) { cudaFree(h->Zt); free_fwd_maps(&h->fwd_maps); h->Zt = nullptr; }
+    const int want = ((h->Bmax * (h->M + 1) + 127) / 128) * 128;
+    if (cudaMalloc((void**)&h->Zt, sizeof(double) * (size_t)want * Np) != cudaSuccess)
+      return fail(h, SFB_ERR_NOMEM, "shared-factor path: right-hand-side workspace allocation failed");
+    if (!h->MinvAll && cudaMalloc((void**)&h->MinvAll, sizeof(double) * (size_t)nt * kTile * kTile) != cudaSuccess)
+      return fail(h, SFB_ERR_NOMEM, "shared-factor path: L_kk^-1 workspace allocation failed");
+    h->Jp_max = want;
+    SFB_CUDA(h, make_fwd_maps(&h->fwd_maps, h->Zt, Np, want, h->MinvAll, nt));
+  }
+  int rc = fork_streams(h, caller, 1);
+  if (rc != SFB_OK) return rc;
+  cudaStream_t st = h->streams[0];
+  // 1. S into slot 0 (no emulator term), factorised with the handle's dense solver (fp64 or int8 trailing update)
+  BuildParams bp = make_build_params(h, nullptr, nullptr, glob, nloc, loc, 1, 1e-10);
+  bp.ldc = Np;
+  bp.strideC = (long long)Np * Np;
+  bp.padN = Np;
+  bp.lower_only = 1;
+  bp.vec2 = 1;
+  bp.C = h->W;
+  SFB_CUDA(h, launch_residual(nullptr, nullptr, N, Np, 1, h->rhs, nullptr, h->logdet, h->sqmah, h->info_ws, st));
+  {
+    ProfScope ps(h, st, SFB_K_BUILD, 4.0 * Np * ((double)Np + kTile));
+    SFB_CUDA(h, launch_cov_build(bp, 1, st));
+  }
+  h->launches += 2;
+  if ((rc = run_cholesky(h, 0, 0, 1, nullptr, nullptr, h->MinvAll)) != SFB_OK) return rc;
+  // 2. right-hand sides of every walker as rows, 3. Z = L^-1 RHS panel by panel
+  SFB_CUDA(h, launch_pack_rhs(model_flux, h->data_flux, X, N, Np, M, J, Jp, h->Zt, resid, st));
+  h->launches++;
+  {
+    ProfScope ps(h, st, SFB_K_FWD_ROWS, (double)J * Np * Np);
+    SFB_CUDA(h, launch_forward_rows(h->fwd_maps, h->maps, h->Zt, Np, Jp, 0, st, &h->launches));
+  }
+  // 4. Gram matrices + capacitance systems -> lnL, info
+  SFB_CUDA(h, launch_gram_capacitance(h->Zt, Np, N, M, B, A, h->logdet, h->info_ws, lnL, info, st));
+  h->launches++;
+  h->shared_factor_calls++;
+  return join_streams(h, caller, 1);
+}
+
+bool use_shared_factor(const sfb_ctx* h, int B, int shared_hyper) {
+  return shared_hyper && h->shared_factor && B >= 2 && h->solver != SFB_SOLVER_STRUCTURED;
+}
+
 }  // namespace
 
 extern "C" {
 
-int sfb_abi_version(void) { return 3; }
+int sfb_abi_version(void) { return 4; }
 
 int sfb_create(int device, int N, int M, int Kmax, int Bmax, int workspace_walkers, sfb_t** out) {
   if (!out) return SFB_ERR_ARG;
@@ -549,7 +618,8 @@ int sfb_create(int device, int N, int M, int Kmax, int Bmax, int workspace_walke
 #ifdef SFB_EXPERIMENTS  // A/B knobs exist only in an experiments build (python -m starfish_b200.build --experiments)
   if (const char* dbg = getenv("SFB_DEBUG_MODE")) h->debug_mode = atoi(dbg);
   if (const char* ot = getenv("SFB_OUTER_TILES")) h->outer_tiles = std::max(1, atoi(ot));
-  ozaki_set_ts(getenv("SFB_OZ_TS") != nullptr);
+  if (const char* v = getenv("SFB_OZ_TS")) ozaki_set_ts(atoi(v) != 0);
+  if (const char* v = getenv("SFB_OZ_TPC")) ozaki_set_tpc(atoi(v));
 #endif
   DeviceGuard guard(device);
   cudaDeviceProp prop;
@@ -626,6 +696,9 @@ int sfb_destroy(sfb_t* h) {
   free_gemm_maps(&h->maps);
   model_free(&h->model);
   sfb_comm_destroy(h);
+  if (h->Zt) cudaFree(h->Zt);
+  if (h->MinvAll) cudaFree(h->MinvAll);
+  free_fwd_maps(&h->fwd_maps);
   if (h->ozP) cudaFree(h->ozP);
   if (h->oz_rscale) cudaFree(h->oz_rscale);
   if (h->Sb) cudaFree(h->Sb);
@@ -762,6 +835,8 @@ int sfb_loglike(sfb_t* h, int B, const double* X, const double* A, const double*
   cudaStream_t caller = (cudaStream_t)stream;
   if (h->solver == SFB_SOLVER_STRUCTURED)
     return structured_device(h, B, X, A, model_flux, glob, nloc, loc, shared_hyper, lnL, info, resid, caller);
+  if (use_shared_factor(h, B, shared_hyper))
+    return shared_factor_device(h, B, X, A, model_flux, glob, nloc, loc, lnL, info, resid, caller);
   const int nstreams = (h->profile || h->slots < 2 || (h->debug_mode & 2)) ? 1 : 2;
   if ((rc = fork_streams(h, caller, nstreams)) != SFB_OK) return rc;
   rc = loglike_device(h, B, X, A, model_flux, glob, nloc, loc, shared_hyper, lnL, info, resid, nstreams, nullptr,
@@ -796,7 +871,8 @@ int sfb_loglike_host(sfb_t* h, int B, const double* X_h, const double* A_h, cons
   ok &= lazy((void**)&h->dinfo, sizeof(int) * Bm);
   if (resid_h) ok &= lazy((void**)&h->dresid, sizeof(double) * (size_t)Bm * N);
   if (!ok) return fail(h, SFB_ERR_NOMEM, "sfb_loglike_host: staging allocation failed");
-  if (h->solver == SFB_SOLVER_STRUCTURED) {  // inputs up on lane 0, structured solve, results down
+  const bool shared_path = use_shared_factor(h, B, shared_hyper);
+  if (h->solver == SFB_SOLVER_STRUCTURED || shared_path) {  // inputs up on lane 0, one device call, results down
     cudaStream_t st = h->streams[0];
     const int Bh = shared_hyper ? 1 : B;
     SFB_CUDA(h, cudaStreamSynchronize(h->streams[1]));
@@ -808,8 +884,11 @@ int sfb_loglike_host(sfb_t* h, int B, const double* X_h, const double* A_h, cons
     SFB_CUDA(h, cudaMemcpyAsync(h->dglob, glob_h, sizeof(double) * 2 * Bh, cudaMemcpyHostToDevice, st));
     SFB_CUDA(h, cudaMemcpyAsync(h->dnloc, nloc_h, sizeof(int) * Bh, cudaMemcpyHostToDevice, st));
     SFB_CUDA(h, cudaMemcpyAsync(h->dloc, loc_h, sizeof(double) * 3 * (size_t)K * Bh, cudaMemcpyHostToDevice, st));
-    rc = structured_device(h, B, X_h ? h->dX : nullptr, X_h ? h->dA : nullptr, h->dflux, h->dglob, h->dnloc, h->dloc,
-                           shared_hyper, h->dlnL, h->dinfo, resid_h ? h->dresid : nullptr, st);
+    rc = shared_path
+             ? shared_factor_device(h, B, X_h ? h->dX : nullptr, X_h ? h->dA : nullptr, h->dflux, h->dglob, h->dnloc,
+                                    h->dloc, h->dlnL, h->dinfo, resid_h ? h->dresid : nullptr, st)
+             : structured_device(h, B, X_h ? h->dX : nullptr, X_h ? h->dA : nullptr, h->dflux, h->dglob, h->dnloc,
+                                 h->dloc, shared_hyper, h->dlnL, h->dinfo, resid_h ? h->dresid : nullptr, st);
     if (rc != SFB_OK) return rc;
     SFB_CUDA(h, cudaMemcpyAsync(lnL_h, h->dlnL, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
     SFB_CUDA(h, cudaMemcpyAsync(info_h, h->dinfo, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
@@ -1017,6 +1096,14 @@ int sfb_set_solver(sfb_t* h, int solver) {
 }
 
 int sfb_get_solver(const sfb_t* h) { return h ? h->solver : -1; }
+
+int sfb_set_shared_factor(sfb_t* h, int on) {
+  if (!h) return SFB_ERR_ARG;
+  h->shared_factor = (on != 0);
+  return SFB_OK;
+}
+
+long long sfb_shared_factor_calls(const sfb_t* h) { return h ? h->shared_factor_calls : -1; }
 
 int sfb_band_classes(const sfb_t* h, int* widths, long long* walkers, int n) {
   if (!h || !widths || !walkers || n < kNumBandWidths + 1) return SFB_ERR_ARG;

@@ -342,6 +342,86 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2)
 }
 
 // ------------------------------------------------------------------------------------------------
+// Shared-factor path (frozen kernel groups, Starfish/models/spectrum_model.py:341-363): every walker has the same
+// S = diag + K_global + ΣK_local, so S is factorised ONCE and the walkers only differ in their right-hand sides
+// [R_b | X_bᵀ].  Zt holds all of them as rows (row j = one right-hand side, Np contiguous doubles); the forward
+// substitution Z = L⁻¹·RHS runs panel by panel with the two GEMM shapes of the factorisation itself:
+//   fwd_diag    Zt[j][k0..k0+127] = Σ_c Zt[j][k0+c]·M_k[r][c]       (M_k = L_kk⁻¹ kept per panel)   == trsm_kernel
+//   fwd_update  Zt[j][i] −= Σ_c Zt[j][k0+c]·L[i][k0+c]   for i ≥ k0+128                           == syrk_kernel
+// Both operands are K-contiguous rows again (right-hand sides are stored as rows for exactly that reason).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+    fwd_diag_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmMall, double* Zt,
+                    int ldz, int k0, int panel) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const int j0 = blockIdx.x * 64;
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wm = warp / 4, wn = warp % 4, g = lane >> 2, t = lane & 3;
+  const GemmOperand opA{&tmZ, k0, j0, 0}, opB{&tmMall, 0, 0, panel};
+  gemm_mainloop<64, 128>(acc, smem_raw, opA, opB, kTile, 2 * (wn + 1));  // M_k is lower triangular
+  const int rho = (g >> 1) | ((g & 1) << 2);
+  double* Cg = Zt + (long long)(j0 + wm * 32 + rho) * ldz + k0 + wn * 32 + t;
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+      Cg[(long long)mt * 8 * ldz + nt * 8] = acc[mt][nt][0];
+      Cg[(long long)mt * 8 * ldz + nt * 8 + 4] = acc[mt][nt][1];
+    }
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+    fwd_update_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmW, double* Zt, int ldz,
+                      int k0, int slotL) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const int j0 = blockIdx.x * 128;
+  const int i0 = k0 + kTile + blockIdx.y * 64;
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  const GemmOperand opA{&tmZ, k0, j0, 0}, opB{&tmW, k0, i0, slotL};
+  gemm_mainloop<128, 64>(acc, smem_raw, opA, opB, kTile, kTile / BK);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wm = warp / 2, wn = warp % 2, g = lane >> 2, t = lane & 3;
+  const int rho = (g >> 1) | ((g & 1) << 2);
+  double* Cg = Zt + (long long)(j0 + wm * 32 + rho) * ldz + i0 + wn * 32 + t;
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      Cg[(long long)mt * 8 * ldz + nt * 8] -= acc[mt][nt][0];
+      Cg[(long long)mt * 8 * ldz + nt * 8 + 4] -= acc[mt][nt][1];
+    }
+}
+
+// Right-hand sides as rows: row b·(M+1) = model_flux_b − data_flux (also written to resid_out), rows b·(M+1)+1+m =
+// X_b[m]; columns N..Np−1 and rows J..Jp−1 are zero (the identity padding of the factor leaves them zero).
+__global__ void pack_rhs_kernel(const double* __restrict__ model_flux, const double* __restrict__ data_flux,
+                                const double* __restrict__ X, int N, int Np, int M, int J, double* Zt, double* resid_out) {
+  const int j = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Np) return;
+  double v = 0.0;
+  if (j < J && i < N) {
+    const int b = j / (M + 1), m = j % (M + 1);
+    if (m == 0) {
+      v = model_flux[(long long)b * N + i] - data_flux[i];
+      if (resid_out) resid_out[(long long)b * N + i] = v;
+    } else {
+      v = X[((long long)b * M + (m - 1)) * N + i];
+    }
+  }
+  Zt[(long long)j * Np + i] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
 // potrf_diag: factor + invert the diagonal tile, solve the panel's slice of the right-hand side
 // ------------------------------------------------------------------------------------------------
 constexpr int PD_THREADS = 512;
@@ -695,6 +775,73 @@ void free_gemm_maps(GemmMaps* m) {
   delete m->W;
   delete m->Minv;
   m->W = m->Minv = nullptr;
+}
+
+// ---- shared-factor path -----------------------------------------------------------------------------
+cudaError_t make_fwd_maps(FwdMaps* out, double* Zt, int Np, int Jp, double* MinvAll, int panels) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                               const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+  if (e != cudaSuccess) return e;
+  if (!fn || q != cudaDriverEntryPointSuccess) return cudaErrorNotSupported;
+  EncodeFn encode = reinterpret_cast<EncodeFn>(fn);
+  out->Z = new CUtensorMap;
+  out->Mall = new CUtensorMap;
+  const cuuint32_t box[3] = {BK, 64, 1}, estr[3] = {1, 1, 1};
+  {
+    const cuuint64_t dims[3] = {(cuuint64_t)Np, (cuuint64_t)Jp, 1};
+    const cuuint64_t strides[2] = {(cuuint64_t)Np * 8, (cuuint64_t)Np * Jp * 8};
+    if (encode(out->Z, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, Zt, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return cudaErrorInvalidValue;
+  }
+  {
+    const cuuint64_t dims[3] = {(cuuint64_t)kTile, (cuuint64_t)kTile, (cuuint64_t)panels};
+    const cuuint64_t strides[2] = {(cuuint64_t)kTile * 8, (cuuint64_t)kTile * kTile * 8};
+    if (encode(out->Mall, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, MinvAll, dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return cudaErrorInvalidValue;
+  }
+  return cudaSuccess;
+}
+
+void free_fwd_maps(FwdMaps* m) {
+  delete m->Z;
+  delete m->Mall;
+  m->Z = m->Mall = nullptr;
+}
+
+cudaError_t launch_pack_rhs(const double* model_flux, const double* data_flux, const double* X, int N, int Np, int M,
+                            int J, int Jp, double* Zt, double* resid_out, cudaStream_t st) {
+  pack_rhs_kernel<<<dim3((Np + 255) / 256, Jp), 256, 0, st>>>(model_flux, data_flux, X, N, Np, M, J, Zt, resid_out);
+  return cudaGetLastError();
+}
+
+// Z = L⁻¹·RHS for the Jp rows of Zt, L = the factor in workspace slot `slotL`, M_k = MinvAll[k]
+cudaError_t launch_forward_rows(const FwdMaps& fm, const GemmMaps& gm, double* Zt, int Np, int Jp, int slotL,
+                                cudaStream_t st, long long* launches) {
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute((const void*)fwd_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute((const void*)fwd_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  const int nt = Np / kTile;
+  for (int k = 0; k < nt; ++k) {
+    const int k0 = k * kTile;
+    fwd_diag_kernel<<<Jp / 64, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(*fm.Z, *fm.Mall, Zt, Np, k0, k);
+    if (k + 1 < nt)
+      fwd_update_kernel<<<dim3(Jp / 128, (Np - k0 - kTile) / 64), GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(*fm.Z, *gm.W, Zt, Np,
+                                                                                                    k0, slotL);
+    if (launches) *launches += (k + 1 < nt) ? 2 : 1;
+  }
+  return cudaGetLastError();
 }
 
 cudaError_t launch_copy_in_lower(const double* C, int N, double* W, int Np, long long strideW, int B,

@@ -424,9 +424,14 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(CholParams p, OzParams oz
 }  // namespace
 
 namespace {
-bool g_oz_ts = false;  // A operand from TMEM (tcgen05.cp + .ts MMAs) instead of shared memory
+// A operand from TMEM (tcgen05.cp + .ts MMAs) instead of shared memory: measured 418 vs 398 evals/s on the 256-walker
+// step (profiles/r2g_i8_ss_vs_ts.txt) — the copy replaces 26 shared-memory reads of A slabs by 6, which matters once
+// the chip runs at its power cap.  The SS form stays selectable in an experiments build.
+bool g_oz_ts = true;
+int g_oz_tpc = 8;      // most tiles a CTA works through
 }
 void ozaki_set_ts(bool on) { g_oz_ts = on; }
+void ozaki_set_tpc(int n) { g_oz_tpc = n < 1 ? 1 : n; }
 
 cudaError_t ozaki_init() {
   cudaError_t e = cudaFuncSetAttribute((const void*)syrk_i8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -451,7 +456,7 @@ cudaError_t launch_syrk_i8(const CholParams& p, const OzParams& oz, int K, int j
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
   long long total = (long long)ntiles * B;
-  int tpc = (int)std::min<long long>(8, std::max<long long>(1, total / (4LL * sms)));
+  int tpc = (int)std::min<long long>(g_oz_tpc, std::max<long long>(1, total / (4LL * sms)));
   tpc = std::min(tpc, ntiles);
   const dim3 grid((ntiles + tpc - 1) / tpc, 1, B);
   if (g_oz_ts)

@@ -89,6 +89,22 @@ cudaError_t launch_solve_lower(const double* L, long long strideL, int ldl, cons
                                int N, int B, cudaStream_t st);
 cudaError_t kernels_init();  // sets max dynamic shared memory attributes
 
+// ---- shared-factor path (frozen kernel groups): one factorisation of S, right-hand sides of all walkers as rows ----
+struct FwdMaps {  // TMA tensor maps over the right-hand-side rows and over the per-panel L_kk⁻¹ blocks
+  CUtensorMap_st* Z = nullptr;
+  CUtensorMap_st* Mall = nullptr;
+};
+cudaError_t make_fwd_maps(FwdMaps* out, double* Zt, int Np, int Jp, double* MinvAll, int panels);
+void free_fwd_maps(FwdMaps* m);
+cudaError_t launch_pack_rhs(const double* model_flux, const double* data_flux, const double* X, int N, int Np, int M,
+                            int J, int Jp, double* Zt, double* resid_out, cudaStream_t st);
+cudaError_t launch_forward_rows(const FwdMaps& fm, const GemmMaps& gm, double* Zt, int Np, int Jp, int slotL,
+                                cudaStream_t st, long long* launches);
+// Gram matrix of every walker's solved right-hand sides + the M×M capacitance system (band.cu's epilogue):
+// lnL_b = −½[logdet S + logdet(I + A_b G_b) + ‖z_R‖² − uᵀ(I + A_b G_b)⁻¹A_b u]
+cudaError_t launch_gram_capacitance(const double* Zt, int ldz, int N, int M, int B, const double* A,
+                                    const double* logdet_S, const int* info_S, double* lnL, int* info, cudaStream_t st);
+
 // ---- int8 tensor-core trailing update (SFB_SOLVER_DENSE_I8, ozaki.cu) ----
 constexpr int kOzSlices = 6;   // balanced radix-256 digits per fp64 operand element (48-bit fixed point per row)
 constexpr int kOzChunk = 32;   // k per MMA / pipeline stage (bytes per row per slice)
@@ -98,7 +114,8 @@ struct OzParams {
   double* rscale;        // per slot, Np doubles: 2^(e_i - 7)
 };
 cudaError_t ozaki_init();
-void ozaki_set_ts(bool on);  // A operand of the int8 MMAs from TMEM (tcgen05.cp) instead of shared memory
+void ozaki_set_ts(bool on);  // A operand of the int8 MMAs from TMEM (tcgen05.cp, default) or shared memory
+void ozaki_set_tpc(int n);   // most tiles per CTA (experiments)
 size_t oz_panel_bytes_per_slot(int Np, int outer_tiles);
 cudaError_t launch_oz_rowscale(const CholParams& p, const OzParams& oz, int B, cudaStream_t st);
 cudaError_t launch_oz_slice(const CholParams& p, const OzParams& oz, int chunk0, int B, cudaStream_t st);

@@ -234,6 +234,15 @@ class LikelihoodEngine:
         return {_lib.SOLVER_STRUCTURED: "structured", _lib.SOLVER_DENSE_I8: "dense_i8"}.get(
             self._lib.sfb_get_solver(self._h), "dense")
 
+    def set_shared_factor(self, on: bool):
+        """Frozen-kernel calls (``shared_hyper=True``): factorise the shared S once per call and solve all walkers'
+        right-hand sides against it (default), or factorise every walker's full covariance (``on=False``)."""
+        self._check(self._lib.sfb_set_shared_factor(self._h, int(bool(on))), "sfb_set_shared_factor")
+
+    @property
+    def shared_factor_calls(self) -> int:
+        return int(self._lib.sfb_shared_factor_calls(self._h))
+
     def band_classes(self):
         """{window width: walkers routed to it since creation}; key 0 is the dense fallback."""
         w = (C.c_int * 8)()

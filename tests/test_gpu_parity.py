@@ -127,12 +127,20 @@ def test_batch_vs_oracle_and_shared_hyper():
         ref, _, _, R = O.log_likelihood(cov, d["model_flux"][b], d["data_flux"])
         assert abs(lnL[b] - ref) <= LNL_RTOL * max(1.0, abs(ref)), (b, lnL[b], ref)
         assert np.array_equal(resid[b], R)
-    # frozen-kernel sharing: one hyper-parameter row for all walkers
-    lnL2, info2 = eng.log_likelihood(d["X"], d["A"], d["model_flux"], glob=d["glob"][:1], loc=d["loc"][:1],
-                                     shared_hyper=True)
+    # frozen-kernel sharing: one hyper-parameter row for all walkers.  With the shared-factor path off the shared row
+    # is just broadcast (bit-identical to repeating it); with it on (the default, tests/test_gpu_shared_factor.py) S is
+    # factorised once and the results agree to rounding.
     lnL3, _ = eng.log_likelihood(d["X"], d["A"], d["model_flux"], glob=np.repeat(d["glob"][:1], B, 0),
                                  loc=np.repeat(d["loc"][:1], B, 0))
+    eng.set_shared_factor(False)
+    lnL2, info2 = eng.log_likelihood(d["X"], d["A"], d["model_flux"], glob=d["glob"][:1], loc=d["loc"][:1],
+                                     shared_hyper=True)
     assert np.array_equal(lnL2.cpu().numpy(), lnL3.cpu().numpy())
+    eng.set_shared_factor(True)
+    lnL4, _ = eng.log_likelihood(d["X"], d["A"], d["model_flux"], glob=d["glob"][:1], loc=d["loc"][:1],
+                                 shared_hyper=True)
+    l3 = lnL3.cpu().numpy()
+    assert (np.abs(lnL4.cpu().numpy() - l3) <= LNL_RTOL * np.maximum(1.0, np.abs(l3))).all()
     eng.close()
 
 

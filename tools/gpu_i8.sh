@@ -5,7 +5,7 @@ TAG=${1:-i8}
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_ozaki.py -q -x -s > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?"; tail -12 gpurun_out/${TAG}_pytest.log
 run_bench () {  # name, extra env
-  timeout 600 env $2 python bench.py --solver dense_i8 --steps 3 --warmup 1 --no-cpu-baseline --no-e2e --no-model --no-structured --no-configs --no-alt > gpurun_out/${TAG}_bench_$1.json 2> gpurun_out/${TAG}_bench_$1.err; echo "bench $1 rc=$?"
+  timeout 600 env $2 python bench.py --solver dense_i8 --steps 3 --warmup 1 --no-cpu-baseline --no-e2e --no-model --no-structured --no-configs --no-alt --no-frozen > gpurun_out/${TAG}_bench_$1.json 2> gpurun_out/${TAG}_bench_$1.err; echo "bench $1 rc=$?"
   python - <<PY
 import json
 try:
@@ -24,5 +24,5 @@ if [ -f starfish_b200/libsfb200_exp.so ]; then
   run_bench ts "SFB200_LIB=$PWD/starfish_b200/libsfb200_exp.so SFB_OZ_TS=1"
 fi
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv \
-  --log-file gpurun_out/${TAG}_launches.csv python bench.py --solver dense_i8 --walkers 32 --steps 1 --warmup 0 --no-e2e --no-cpu-baseline --no-model --no-structured --no-configs --no-alt > gpurun_out/${TAG}_l.log 2>&1; echo "ncu launches rc=$?"
+  --log-file gpurun_out/${TAG}_launches.csv python bench.py --solver dense_i8 --walkers 32 --steps 1 --warmup 0 --no-e2e --no-cpu-baseline --no-model --no-structured --no-configs --no-alt --no-frozen > gpurun_out/${TAG}_l.log 2>&1; echo "ncu launches rc=$?"
 python tools/ncu_summary.py launches gpurun_out/${TAG}_launches.csv | head -9
