@@ -6,6 +6,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <dlfcn.h>
+#include <nvtx3/nvToolsExt.h>  // header-only (NVTX v3): ranges cost nothing unless a profiler attaches
 
 #include "sfb_internal.cuh"
 
@@ -96,6 +97,11 @@ int fail(sfb_ctx* h, int code, const char* what, cudaError_t e = cudaSuccess) {
     cudaError_t e__ = (call);                                          \
     if (e__ != cudaSuccess) return fail(h, SFB_ERR_CUDA, #call, e__); \
   } while (0)
+
+struct NvtxRange {  // one named range per C-ABI call (visible in Nsight Systems / ncu --nvtx)
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 struct DeviceGuard {
   int prev = -1;
@@ -719,6 +725,7 @@ int sfb_destroy(sfb_t* h) {
 }
 
 int sfb_set_static(sfb_t* h, const double* wave, const double* sigma, const double* data_flux, void* stream) {
+  NvtxRange nvtx_range("sfb_set_static");
   if (!h || !wave || !sigma || !data_flux) return fail(h, SFB_ERR_ARG, "sfb_set_static: NULL argument");
   DeviceGuard guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
@@ -738,6 +745,7 @@ int sfb_set_static(sfb_t* h, const double* wave, const double* sigma, const doub
 }
 
 int sfb_set_static_host(sfb_t* h, const double* wave_h, const double* sigma_h, const double* data_flux_h) {
+  NvtxRange nvtx_range("sfb_set_static_host");
   if (!h || !wave_h || !sigma_h || !data_flux_h) return fail(h, SFB_ERR_ARG, "sfb_set_static_host: NULL argument");
   DeviceGuard guard(h->device);
   for (int i = 0; i < 2; ++i) SFB_CUDA(h, cudaStreamSynchronize(h->streams[i]));
@@ -755,6 +763,7 @@ int sfb_set_static_host(sfb_t* h, const double* wave_h, const double* sigma_h, c
 
 int sfb_build_cov(sfb_t* h, int B, const double* X, const double* A, const double* glob, const int* nloc,
                   const double* loc, int shared_hyper, double jitter, double* C, void* stream) {
+  NvtxRange nvtx_range("sfb_build_cov");
   int rc = check_batch(h, B);
   if (rc != SFB_OK) return rc;
   if (!h->have_static) return fail(h, SFB_ERR_STATE, "sfb_build_cov: call sfb_set_static first");
@@ -779,6 +788,7 @@ int sfb_build_cov(sfb_t* h, int B, const double* X, const double* A, const doubl
 }
 
 int sfb_potrf(sfb_t* h, int B, double* C, int* info, double* logdet, void* stream) {
+  NvtxRange nvtx_range("sfb_potrf");
   int rc = check_batch(h, B);
   if (rc != SFB_OK) return rc;
   if (!C || !info) return fail(h, SFB_ERR_ARG, "sfb_potrf: NULL argument");
@@ -810,6 +820,7 @@ int sfb_potrf(sfb_t* h, int B, double* C, int* info, double* logdet, void* strea
 }
 
 int sfb_solve_lower(sfb_t* h, int B, const double* L, const double* r, double* z, void* stream) {
+  NvtxRange nvtx_range("sfb_solve_lower");
   int rc = check_batch(h, B);
   if (rc != SFB_OK) return rc;
   if (!L || !r || !z) return fail(h, SFB_ERR_ARG, "sfb_solve_lower: NULL argument");
@@ -825,6 +836,7 @@ int sfb_solve_lower(sfb_t* h, int B, const double* L, const double* r, double* z
 int sfb_loglike(sfb_t* h, int B, const double* X, const double* A, const double* model_flux, const double* glob,
                 const int* nloc, const double* loc, int shared_hyper, double* lnL, int* info, double* resid,
                 void* stream) {
+  NvtxRange nvtx_range("sfb_loglike");
   int rc = check_batch(h, B);
   if (rc != SFB_OK) return rc;
   if (!h->have_static) return fail(h, SFB_ERR_STATE, "sfb_loglike: call sfb_set_static first");
@@ -848,6 +860,7 @@ int sfb_loglike(sfb_t* h, int B, const double* X, const double* A, const double*
 int sfb_loglike_host(sfb_t* h, int B, const double* X_h, const double* A_h, const double* model_flux_h,
                      const double* glob_h, const int* nloc_h, const double* loc_h, int shared_hyper,
                      double* lnL_h, int* info_h, double* resid_h) {
+  NvtxRange nvtx_range("sfb_loglike_host");
   int rc = check_batch(h, B);
   if (rc != SFB_OK) return rc;
   if (!h->have_static) return fail(h, SFB_ERR_STATE, "sfb_loglike_host: call sfb_set_static first");
@@ -912,6 +925,7 @@ int sfb_loglike_host(sfb_t* h, int B, const double* X_h, const double* A_h, cons
 int sfb_set_model_host(sfb_t* h, int nf, const double* fine_wave_h, const double* bulk_h, int G, int D,
                        const double* grid_points_h, const double* variances_h, const double* lengthscales_h,
                        const double* v11_h, const double* w_hat_h, int ncheb_max, int flags) {
+  NvtxRange nvtx_range("sfb_set_model_host");
   if (!h) return SFB_ERR_ARG;
   if (!fine_wave_h || !bulk_h || !grid_points_h || !variances_h || !lengthscales_h || !v11_h || !w_hat_h)
     return fail(h, SFB_ERR_ARG, "sfb_set_model_host: NULL argument");
@@ -970,6 +984,7 @@ int run_upstream(sfb_ctx* h, int B, const double* theta, int ncheb, double* X, d
 
 int sfb_upstream(sfb_t* h, int B, const double* theta, int ncheb, double* X, double* A, double* model_flux,
                  double* log_scale_out, int* status, double* weights, double* weights_cov, void* stream) {
+  NvtxRange nvtx_range("sfb_upstream");
   int rc = check_upstream(h, B, ncheb, "sfb_upstream");
   if (rc != SFB_OK) return rc;
   if (!theta || !X || !A || !model_flux || !log_scale_out || !status)
@@ -990,6 +1005,7 @@ int sfb_upstream(sfb_t* h, int B, const double* theta, int ncheb, double* X, dou
 int sfb_loglike_params(sfb_t* h, int B, const double* theta, int ncheb, const double* glob, const int* nloc,
                        const double* loc, int shared_hyper, double* lnL, int* info, double* resid,
                        double* log_scale_out, void* stream) {
+  NvtxRange nvtx_range("sfb_loglike_params");
   int rc = check_upstream(h, B, ncheb, "sfb_loglike_params");
   if (rc != SFB_OK) return rc;
   if (!theta || !glob || !nloc || !loc || !lnL || !info) return fail(h, SFB_ERR_ARG, "sfb_loglike_params: NULL argument");
@@ -1028,6 +1044,7 @@ int sfb_loglike_params(sfb_t* h, int B, const double* theta, int ncheb, const do
 int sfb_loglike_params_host(sfb_t* h, int B, const double* theta_h, int ncheb, const double* glob_h,
                             const int* nloc_h, const double* loc_h, int shared_hyper, double* lnL_h, int* info_h,
                             double* resid_h, double* log_scale_h) {
+  NvtxRange nvtx_range("sfb_loglike_params_host");
   int rc = check_upstream(h, B, ncheb, "sfb_loglike_params_host");
   if (rc != SFB_OK) return rc;
   if (!theta_h || !glob_h || !nloc_h || !loc_h || !lnL_h || !info_h)
@@ -1154,6 +1171,7 @@ int sfb_comm_unique_id(void* id_h) {
 }
 
 int sfb_comm_init(sfb_t* h, int rank, int nranks, const void* unique_id_h) {
+  NvtxRange nvtx_range("sfb_comm_init");
   if (!h || !unique_id_h || nranks < 1 || rank < 0 || rank >= nranks) return fail(h, SFB_ERR_ARG, "sfb_comm_init: bad argument");
   NcclApi* n = nccl_api();
   if (!n) return fail(h, SFB_ERR_STATE, "sfb_comm_init: libnccl.so.2 not found");
@@ -1182,6 +1200,7 @@ int sfb_comm_destroy(sfb_t* h) {
 }
 
 int sfb_allgather_lnL(sfb_t* h, const double* lnL_local, int count, double* lnL_all, void* stream) {
+  NvtxRange nvtx_range("sfb_allgather_lnL");
   if (!h || !lnL_local || !lnL_all || count < 0) return fail(h, SFB_ERR_ARG, "sfb_allgather_lnL: bad argument");
   if (!h->nccl_comm) return fail(h, SFB_ERR_STATE, "sfb_allgather_lnL: call sfb_comm_init first");
   if (count == 0) return SFB_OK;
