@@ -51,7 +51,8 @@ int sfb_abi_version(void);
  * Create a handle on `device` for spectra of N pixels, up to M eigenspectra (rank of the emulator term),
  * up to Kmax local kernels per walker and batches of up to Bmax walkers per call.
  * `workspace_walkers` = how many N×N fp64 factorisation slots to allocate (0 = choose automatically:
- * enough to keep the GPU full, bounded by free memory).
+ * enough to keep the GPU full, bounded by free memory; < 0 = none yet — a build-only handle for sfb_build_cov,
+ * the workspace is then allocated, automatically sized, by the first call that factorises).
  */
 int sfb_create(int device, int N, int M, int Kmax, int Bmax, int workspace_walkers, sfb_t** out);
 int sfb_destroy(sfb_t* h);

@@ -188,6 +188,39 @@ int join_streams(sfb_ctx* h, cudaStream_t caller, int nstreams) {
 //
 // so the latency-bound panel work of block J+1 hides under the bulk update of block J (they touch
 // disjoint tile columns).  On entry and exit all ordering is expressed on the main stream `lo`.
+// Factorisation workspace: `slots` N×N fp64 matrices + the per-slot panel buffers + the TMA tensor maps over them.
+// sfb_create allocates it unless asked not to (workspace_walkers < 0: a build-only handle, e.g. the kernel-builder
+// seam); every entry point that factorises calls ensure_workspace first.
+int alloc_workspace(sfb_ctx* h, long long slots) {
+  const size_t per_slot = sizeof(double) * (size_t)h->Np * h->Np;
+  size_t free_b = 0, total_b = 0;
+  cudaMemGetInfo(&free_b, &total_b);
+  if (slots <= 0) {
+    const size_t budget = std::min<size_t>((size_t)48 << 30, (size_t)(0.6 * (double)free_b));
+    slots = (long long)std::max<size_t>(2, std::min<size_t>(1024, budget / per_slot));
+    slots = std::min<long long>(slots, std::max(h->Bmax, 1));
+  }
+  if (slots > 1) slots -= slots % 2;  // two equal halves, one per stream
+  if ((size_t)slots * per_slot > (size_t)(0.9 * (double)free_b))
+    return fail(h, SFB_ERR_NOMEM, "factorisation workspace does not fit in free device memory");
+  auto alloc = [&](void** p, size_t bytes) { return cudaMalloc(p, std::max<size_t>(bytes, 16)) == cudaSuccess; };
+  bool ok = true;
+  ok &= alloc((void**)&h->W, per_slot * slots);
+  ok &= alloc((void**)&h->Minv, sizeof(double) * kTile * kTile * slots);
+  ok &= alloc((void**)&h->rhs, sizeof(double) * h->Np * slots);
+  ok &= alloc((void**)&h->zk, sizeof(double) * kTile * slots);
+  ok &= alloc((void**)&h->logdet, sizeof(double) * slots);
+  ok &= alloc((void**)&h->sqmah, sizeof(double) * slots);
+  ok &= alloc((void**)&h->info_ws, sizeof(int) * slots);
+  if (!ok) return fail(h, SFB_ERR_NOMEM, "factorisation workspace allocation failed");
+  h->slots = (int)slots;
+  if (make_gemm_maps(&h->maps, h->W, h->Np, h->Minv, h->slots) != cudaSuccess)
+    return fail(h, SFB_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  return SFB_OK;
+}
+
+int ensure_workspace(sfb_ctx* h) { return h->W ? SFB_OK : alloc_workspace(h, 0); }
+
 int ensure_ozaki(sfb_ctx* h) {
   if (h->ozP) return SFB_OK;
   h->oz_bytes = oz_panel_bytes_per_slot(h->Np, h->outer_tiles);
@@ -633,30 +666,15 @@ int sfb_create(int device, int N, int M, int Kmax, int Bmax, int workspace_walke
     delete h;
     return SFB_ERR_CUDA;  // sm_100a only
   }
-  const size_t per_slot = sizeof(double) * (size_t)h->Np * h->Np;
-  size_t free_b = 0, total_b = 0;
-  cudaMemGetInfo(&free_b, &total_b);
-  long long slots = workspace_walkers;
-  if (slots <= 0) {
-    const size_t budget = std::min<size_t>((size_t)48 << 30, (size_t)(0.6 * (double)free_b));
-    slots = (long long)std::max<size_t>(2, std::min<size_t>(1024, budget / per_slot));
-    slots = std::min<long long>(slots, std::max(Bmax, 1));
+  if (workspace_walkers >= 0) {
+    const int rc = alloc_workspace(h, workspace_walkers);
+    if (rc != SFB_OK) {
+      sfb_destroy(h);
+      return rc;
+    }
   }
-  if (slots > 1) slots -= slots % 2;  // two equal halves, one per stream
-  if ((size_t)slots * per_slot > (size_t)(0.9 * (double)free_b)) {
-    delete h;
-    return SFB_ERR_NOMEM;
-  }
-  h->slots = (int)slots;
   auto alloc = [&](void** p, size_t bytes) { return cudaMalloc(p, std::max<size_t>(bytes, 16)) == cudaSuccess; };
   bool ok = true;
-  ok &= alloc((void**)&h->W, per_slot * slots);
-  ok &= alloc((void**)&h->Minv, sizeof(double) * kTile * kTile * slots);
-  ok &= alloc((void**)&h->rhs, sizeof(double) * h->Np * slots);
-  ok &= alloc((void**)&h->zk, sizeof(double) * kTile * slots);
-  ok &= alloc((void**)&h->logdet, sizeof(double) * slots);
-  ok &= alloc((void**)&h->sqmah, sizeof(double) * slots);
-  ok &= alloc((void**)&h->info_ws, sizeof(int) * slots);
   ok &= alloc((void**)&h->wave, sizeof(double) * N);
   ok &= alloc((void**)&h->sigma, sizeof(double) * N);
   ok &= alloc((void**)&h->data_flux, sizeof(double) * N);
@@ -673,7 +691,6 @@ int sfb_create(int device, int N, int M, int Kmax, int Bmax, int workspace_walke
   ok = ok && cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess;
   ok = ok && kernels_init() == cudaSuccess;
   ok = ok && upstream_init() == cudaSuccess;
-  ok = ok && make_gemm_maps(&h->maps, h->W, h->Np, h->Minv, h->slots) == cudaSuccess;
   if (!ok) {
     sfb_destroy(h);
     return SFB_ERR_NOMEM;
@@ -794,6 +811,7 @@ int sfb_potrf(sfb_t* h, int B, double* C, int* info, double* logdet, void* strea
   if (!C || !info) return fail(h, SFB_ERR_ARG, "sfb_potrf: NULL argument");
   if (B == 0) return SFB_OK;
   DeviceGuard guard(h->device);
+  if ((rc = ensure_workspace(h)) != SFB_OK) return rc;
   cudaStream_t caller = (cudaStream_t)stream;
   const int nstreams = (h->profile || h->slots < 2 || (h->debug_mode & 2)) ? 1 : 2;
   if ((rc = fork_streams(h, caller, nstreams)) != SFB_OK) return rc;
@@ -844,6 +862,7 @@ int sfb_loglike(sfb_t* h, int B, const double* X, const double* A, const double*
     return fail(h, SFB_ERR_ARG, "sfb_loglike: NULL argument");
   if (B == 0) return SFB_OK;
   DeviceGuard guard(h->device);
+  if ((rc = ensure_workspace(h)) != SFB_OK) return rc;
   cudaStream_t caller = (cudaStream_t)stream;
   if (h->solver == SFB_SOLVER_STRUCTURED)
     return structured_device(h, B, X, A, model_flux, glob, nloc, loc, shared_hyper, lnL, info, resid, caller);
@@ -868,6 +887,7 @@ int sfb_loglike_host(sfb_t* h, int B, const double* X_h, const double* A_h, cons
     return fail(h, SFB_ERR_ARG, "sfb_loglike_host: NULL argument");
   if (B == 0) return SFB_OK;
   DeviceGuard guard(h->device);
+  if ((rc = ensure_workspace(h)) != SFB_OK) return rc;
   const int N = h->N, M = h->M, K = h->Kmax, Bm = h->Bmax;
   auto lazy = [&](void** p, size_t bytes) {
     if (*p) return true;
@@ -1011,6 +1031,7 @@ int sfb_loglike_params(sfb_t* h, int B, const double* theta, int ncheb, const do
   if (!theta || !glob || !nloc || !loc || !lnL || !info) return fail(h, SFB_ERR_ARG, "sfb_loglike_params: NULL argument");
   if (B == 0) return SFB_OK;
   DeviceGuard guard(h->device);
+  if ((rc = ensure_workspace(h)) != SFB_OK) return rc;
   cudaStream_t caller = (cudaStream_t)stream;
   const int nstreams = (h->profile || h->slots < 2 || (h->debug_mode & 2)) ? 1 : 2;
   ModelState& ms = h->model;
@@ -1051,6 +1072,7 @@ int sfb_loglike_params_host(sfb_t* h, int B, const double* theta_h, int ncheb, c
     return fail(h, SFB_ERR_ARG, "sfb_loglike_params_host: NULL argument");
   if (B == 0) return SFB_OK;
   DeviceGuard guard(h->device);
+  if ((rc = ensure_workspace(h)) != SFB_OK) return rc;
   const int N = h->N, K = h->Kmax, Bm = h->Bmax;
   auto lazy = [&](void** p, size_t bytes) {
     if (*p) return true;

@@ -49,14 +49,14 @@ class _CachedKernel:
         self.shape = (n, n)
 
     def __array__(self, dtype=None, copy=None):
-        eng = self._model._get_engine(1)
-        self._model._sync_static(eng)
-        zeros = np.zeros(self.shape[0])
-        # kernels only: σ is part of the static data, so build with the kernel terms and subtract σ²
-        C = eng.build_covariance(None, None, glob=None if self.glob is None else np.array([self.glob]),
-                                 loc=None if self.loc is None else self.loc[None], n_walkers=1)[0]
-        out = C.cpu().numpy()
-        out[np.diag_indices_from(out)] -= np.asarray(self._model.data.sigma) ** 2
+        # the kernel-only matrix, built directly (zero noise term) — bit-identical to what
+        # kernels.global_covariance_matrix / local_covariance_matrix return, as the reference's cache is
+        from .kernels import _build
+
+        out = _build(np.asarray(self._model.data.wave, dtype=np.float64),
+                     None if self.glob is None else np.array([self.glob], dtype=np.float64),
+                     None if self.loc is None else np.asarray(self.loc, dtype=np.float64)[None],
+                     False, self._model.device)
         return out if dtype is None else out.astype(dtype)
 
 
@@ -327,8 +327,15 @@ class SpectrumModel:
         """Upload the static model tables (fine-grid bulk fluxes, emulator GP) when they changed: new
         engine, re-trained emulator hyper-parameters, a parameter group added or removed."""
         emu = self.emulator
-        sig = (id(eng), id(self.bulk_fluxes), id(emu.v11), id(emu.w_hat), emu.get_param_vector().tobytes(),
-               self._model_flags(), self._n_cheb())
+        # content, not identity: in-place edits (emu.w_hat[:] = ..., model.bulk_fluxes[...] = ...) must be seen, as the
+        # reference re-reads these arrays on every call (crc32 of ~1 MB: 0.3 ms per call)
+        import zlib
+
+        def crc(a):
+            return zlib.crc32(np.ascontiguousarray(a, dtype=np.float64).view(np.uint8))
+
+        sig = (id(eng), crc(self.bulk_fluxes), crc(self.min_dv_wave), crc(emu.v11), crc(emu.w_hat), crc(emu.grid_points),
+               emu.get_param_vector().tobytes(), self._model_flags(), self._n_cheb())
         if getattr(self, "_model_sig", None) != sig:
             eng.set_model(self.min_dv_wave, self.bulk_fluxes, emu.grid_points, emu.variances, emu.lengthscales,
                           emu.v11, emu.w_hat, ncheb_max=self._n_cheb(), flags=self._model_flags())

@@ -116,3 +116,49 @@ def test_frozen_groups_shared_hyper_batch(golden_dir):
     from oracle import starfish_oracle as O
 
     assert np.abs(kg - O.global_covariance_matrix(g["wave"], *g["glob"])).max() <= 1e-13 * g["glob"][0] + 1e-18
+
+
+def test_cached_kernel_matrices_are_bit_identical_to_the_builders(golden_dir):
+    """The reference's _glob_cov/_loc_cov ARE the builders' outputs (spectrum_model.py:343-360)."""
+    from starfish_b200.kernels import global_covariance_matrix, local_covariance_matrix
+
+    g = _load(golden_dir, "model_n256_w0.npz")
+    m = make_model(256, 0, wave=g["wave"], mus=(5098.0, 5103.0))
+    m.freeze(["global_cov", "local_cov"])
+    m.log_likelihood()
+    kg, kl = np.asarray(m._glob_cov), np.asarray(m._loc_cov)
+    assert np.array_equal(kg, global_covariance_matrix(g["wave"], *g["glob"]))
+    ref = sum(local_covariance_matrix(g["wave"], *row) for row in g["loc"])
+    assert np.abs(kl - ref).max() <= 1e-16 * max(1.0, np.abs(ref).max())   # one fused sum vs a sum of builder calls
+    assert kg.diagonal().min() == kg.diagonal().max() == g["glob"][0]       # diag = amplitude exactly: no σ² round trip
+
+
+def test_inplace_edits_of_the_emulator_tables_are_seen(golden_dir):
+    """The reference re-reads emulator.w_hat / bulk_fluxes on every call; the device tables must follow in-place edits."""
+    g = _load(golden_dir, "model_n256_w0.npz")
+    m = make_model(256, 0, wave=g["wave"], mus=(5098.0, 5103.0))
+    a = m.log_likelihood()
+    m.emulator.w_hat[:] = m.emulator.w_hat * 1.05          # in place: same object id
+    b = m.log_likelihood()
+    assert b != a
+    m2 = make_model(256, 0, wave=g["wave"], mus=(5098.0, 5103.0))
+    m2.emulator.w_hat = m2.emulator.w_hat * 1.05            # re-assigned: the path that always worked
+    assert m2.log_likelihood() == b
+    m.bulk_fluxes[0] *= 1.01
+    assert m.log_likelihood() != b
+
+
+def test_build_only_handle_allocates_its_workspace_on_first_factorisation():
+    import torch
+
+    from starfish_b200.engine import LikelihoodEngine
+
+    eng = LikelihoodEngine(300, 0, 1, 2, workspace_walkers=-1)
+    assert eng.workspace_walkers == 0
+    wave = np.linspace(5000.0, 5010.0, 300)
+    eng.set_data(wave, np.full(300, 0.01), np.zeros(300))
+    C = eng.build_covariance(None, None, glob=np.array([[1e-4, 20.0]]), n_walkers=1)
+    assert eng.workspace_walkers == 0 and C.shape == (1, 300, 300)
+    _, info = eng.cho_factor(C.clone().contiguous())
+    assert info.cpu().tolist() == [0] and eng.workspace_walkers >= 2
+    eng.close()
