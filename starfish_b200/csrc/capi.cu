@@ -12,6 +12,8 @@
 
 using namespace sfb;
 
+constexpr int kMaxLanes = 4;
+
 struct ProfEvent {
   cudaEvent_t a, b;
   int cls;
@@ -41,10 +43,11 @@ struct sfb_ctx {
   int *dnloc = nullptr, *dinfo = nullptr;
   // two lanes; each lane = a main stream (bulk trailing updates, copies) + a high-priority stream for the
   // panel work that is on the critical path (look-ahead)
-  cudaStream_t streams[2] = {nullptr, nullptr};
-  cudaStream_t hi[2] = {nullptr, nullptr};
-  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
-  cudaEvent_t ev_hi[2] = {nullptr, nullptr}, ev_lo[2] = {nullptr, nullptr};
+  cudaStream_t streams[kMaxLanes] = {};
+  cudaStream_t hi[kMaxLanes] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[kMaxLanes] = {};
+  cudaEvent_t ev_hi[kMaxLanes] = {}, ev_lo[kMaxLanes] = {};
+  int nlanes = 2;  // lanes the walker chunks of one call alternate over (experiments build: SFB_LANES)
   bool profile = false;
   int outer_tiles = kOuterTiles;  // (experiments build only: SFB_OUTER_TILES overrides)
   int debug_mode = 0;  // (experiments build only: SFB_DEBUG_MODE, bit0 = no high-priority stream, bit1 = single lane)
@@ -153,9 +156,10 @@ struct ProfScope {  // brackets one launch with events when profiling is on
 // handle's lanes; per-handle scratch (the upstream stage's X/A/flux, staging buffers) is shared by the lanes, so
 // lane 0 must not start the new call before lane 1 has finished the old one (and vice versa).
 int order_after_previous_call(sfb_ctx* h) {
-  for (int i = 0; i < 2; ++i) SFB_CUDA(h, cudaEventRecord(h->ev_join[i], h->streams[i]));
-  SFB_CUDA(h, cudaStreamWaitEvent(h->streams[0], h->ev_join[1], 0));
-  SFB_CUDA(h, cudaStreamWaitEvent(h->streams[1], h->ev_join[0], 0));
+  for (int i = 0; i < kMaxLanes; ++i) SFB_CUDA(h, cudaEventRecord(h->ev_join[i], h->streams[i]));
+  for (int i = 0; i < kMaxLanes; ++i)
+    for (int j = 0; j < kMaxLanes; ++j)
+      if (i != j) SFB_CUDA(h, cudaStreamWaitEvent(h->streams[i], h->ev_join[j], 0));
   return SFB_OK;
 }
 
@@ -557,7 +561,7 @@ int structured_device(sfb_ctx* h, int B, const double* X, const double* A, const
   if (count[nclass] && up) SFB_CUDA(h, cudaStreamWaitEvent(s0, h->ev_up, 0));
   if (count[nclass]) {
     h->band_rows[nclass] += count[nclass];
-    const int nstreams = (h->profile || h->slots < 2 || (h->debug_mode & 2)) ? 1 : 2;
+    const int nstreams = (h->profile || h->slots < 2 || (h->debug_mode & 2)) ? 1 : std::min(h->nlanes, h->slots);
     const int M = h->M;
     int q = 0;
     while (q < count[nclass]) {
@@ -659,6 +663,7 @@ int sfb_create(int device, int N, int M, int Kmax, int Bmax, int workspace_walke
   if (const char* ot = getenv("SFB_OUTER_TILES")) h->outer_tiles = std::max(1, atoi(ot));
   if (const char* v = getenv("SFB_OZ_TS")) ozaki_set_ts(atoi(v) != 0);
   if (const char* v = getenv("SFB_OZ_TPC")) ozaki_set_tpc(atoi(v));
+  if (const char* v = getenv("SFB_LANES")) h->nlanes = std::max(1, std::min(kMaxLanes, atoi(v)));
 #endif
   DeviceGuard guard(device);
   cudaDeviceProp prop;
@@ -681,7 +686,7 @@ int sfb_create(int device, int N, int M, int Kmax, int Bmax, int workspace_walke
   ok &= alloc((void**)&h->sorted, sizeof(int));
   int prio_lo = 0, prio_hi = 0;
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-  for (int i = 0; i < 2 && ok; ++i) {
+  for (int i = 0; i < kMaxLanes && ok; ++i) {
     ok &= cudaStreamCreateWithPriority(&h->streams[i], cudaStreamNonBlocking, prio_lo) == cudaSuccess;
     ok &= cudaStreamCreateWithPriority(&h->hi[i], cudaStreamNonBlocking, prio_hi) == cudaSuccess;
     ok &= cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
@@ -708,7 +713,7 @@ int sfb_destroy(sfb_t* h) {
                   h->dnloc, h->dinfo};
   for (void* p : ptrs)
     if (p) cudaFree(p);
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < kMaxLanes; ++i) {
     if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
     if (h->hi[i]) cudaStreamDestroy(h->hi[i]);
     if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
@@ -747,7 +752,7 @@ int sfb_set_static(sfb_t* h, const double* wave, const double* sigma, const doub
   DeviceGuard guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   // earlier work on the handle's own streams may still read the old static data
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < kMaxLanes; ++i) {
     SFB_CUDA(h, cudaEventRecord(h->ev_join[i], h->streams[i]));
     SFB_CUDA(h, cudaStreamWaitEvent(st, h->ev_join[i], 0));
   }
@@ -765,7 +770,7 @@ int sfb_set_static_host(sfb_t* h, const double* wave_h, const double* sigma_h, c
   NvtxRange nvtx_range("sfb_set_static_host");
   if (!h || !wave_h || !sigma_h || !data_flux_h) return fail(h, SFB_ERR_ARG, "sfb_set_static_host: NULL argument");
   DeviceGuard guard(h->device);
-  for (int i = 0; i < 2; ++i) SFB_CUDA(h, cudaStreamSynchronize(h->streams[i]));
+  for (int i = 0; i < kMaxLanes; ++i) SFB_CUDA(h, cudaStreamSynchronize(h->streams[i]));
   const size_t nb = sizeof(double) * h->N;
   cudaStream_t st = h->streams[0];
   SFB_CUDA(h, cudaMemcpyAsync(h->wave, wave_h, nb, cudaMemcpyHostToDevice, st));
@@ -813,7 +818,7 @@ int sfb_potrf(sfb_t* h, int B, double* C, int* info, double* logdet, void* strea
   DeviceGuard guard(h->device);
   if ((rc = ensure_workspace(h)) != SFB_OK) return rc;
   cudaStream_t caller = (cudaStream_t)stream;
-  const int nstreams = (h->profile || h->slots < 2 || (h->debug_mode & 2)) ? 1 : 2;
+  const int nstreams = (h->profile || h->slots < 2 || (h->debug_mode & 2)) ? 1 : std::min(h->nlanes, h->slots);
   if ((rc = fork_streams(h, caller, nstreams)) != SFB_OK) return rc;
   const int per = std::max(1, h->slots / nstreams);
   const long long strideW = (long long)h->Np * h->Np;
@@ -868,7 +873,7 @@ int sfb_loglike(sfb_t* h, int B, const double* X, const double* A, const double*
     return structured_device(h, B, X, A, model_flux, glob, nloc, loc, shared_hyper, lnL, info, resid, caller);
   if (use_shared_factor(h, B, shared_hyper))
     return shared_factor_device(h, B, X, A, model_flux, glob, nloc, loc, lnL, info, resid, caller);
-  const int nstreams = (h->profile || h->slots < 2 || (h->debug_mode & 2)) ? 1 : 2;
+  const int nstreams = (h->profile || h->slots < 2 || (h->debug_mode & 2)) ? 1 : std::min(h->nlanes, h->slots);
   if ((rc = fork_streams(h, caller, nstreams)) != SFB_OK) return rc;
   rc = loglike_device(h, B, X, A, model_flux, glob, nloc, loc, shared_hyper, lnL, info, resid, nstreams, nullptr,
                       nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
@@ -908,7 +913,7 @@ int sfb_loglike_host(sfb_t* h, int B, const double* X_h, const double* A_h, cons
   if (h->solver == SFB_SOLVER_STRUCTURED || shared_path) {  // inputs up on lane 0, one device call, results down
     cudaStream_t st = h->streams[0];
     const int Bh = shared_hyper ? 1 : B;
-    SFB_CUDA(h, cudaStreamSynchronize(h->streams[1]));
+    for (int i = 1; i < kMaxLanes; ++i) SFB_CUDA(h, cudaStreamSynchronize(h->streams[i]));
     if (X_h) {
       SFB_CUDA(h, cudaMemcpyAsync(h->dX, X_h, sizeof(double) * (size_t)B * M * N, cudaMemcpyHostToDevice, st));
       SFB_CUDA(h, cudaMemcpyAsync(h->dA, A_h, sizeof(double) * (size_t)B * M * M, cudaMemcpyHostToDevice, st));
@@ -930,7 +935,7 @@ int sfb_loglike_host(sfb_t* h, int B, const double* X_h, const double* A_h, cons
     SFB_CUDA(h, cudaStreamSynchronize(st));
     return SFB_OK;
   }
-  const int nstreams = (h->profile || h->slots < 2 || (h->debug_mode & 2)) ? 1 : 2;
+  const int nstreams = (h->profile || h->slots < 2 || (h->debug_mode & 2)) ? 1 : std::min(h->nlanes, h->slots);
   rc = loglike_device(h, B, X_h ? h->dX : nullptr, X_h ? h->dA : nullptr, h->dflux, h->dglob, h->dnloc, h->dloc,
                       shared_hyper, h->dlnL, h->dinfo, resid_h ? h->dresid : nullptr, nstreams, X_h, A_h,
                       model_flux_h, glob_h, nloc_h, loc_h, lnL_h, info_h, resid_h);
@@ -953,7 +958,7 @@ int sfb_set_model_host(sfb_t* h, int nf, const double* fine_wave_h, const double
   if (h->M < 1 || G < 1 || D < 1 || D > 16 || ncheb_max < 0 || ncheb_max > 32)
     return fail(h, SFB_ERR_ARG, "sfb_set_model_host: sizes out of range (needs M >= 1)");
   DeviceGuard guard(h->device);
-  for (int i = 0; i < 2; ++i) SFB_CUDA(h, cudaStreamSynchronize(h->streams[i]));
+  for (int i = 0; i < kMaxLanes; ++i) SFB_CUDA(h, cudaStreamSynchronize(h->streams[i]));
   h->have_model = false;
   std::string why;
   cudaError_t e = model_setup(&h->model, h->N, h->M, h->Bmax, nf, fine_wave_h, bulk_h, G, D, grid_points_h,
@@ -1033,7 +1038,7 @@ int sfb_loglike_params(sfb_t* h, int B, const double* theta, int ncheb, const do
   DeviceGuard guard(h->device);
   if ((rc = ensure_workspace(h)) != SFB_OK) return rc;
   cudaStream_t caller = (cudaStream_t)stream;
-  const int nstreams = (h->profile || h->slots < 2 || (h->debug_mode & 2)) ? 1 : 2;
+  const int nstreams = (h->profile || h->slots < 2 || (h->debug_mode & 2)) ? 1 : std::min(h->nlanes, h->slots);
   ModelState& ms = h->model;
   if (h->solver == SFB_SOLVER_STRUCTURED) {  // upstream on lane 1, overlapped with the band set-up on lane 0
     UpstreamJob job{theta, ncheb, log_scale_out ? log_scale_out : ms.log_scale};
@@ -1090,7 +1095,8 @@ int sfb_loglike_params_host(sfb_t* h, int B, const double* theta_h, int ncheb, c
   cudaStream_t st = h->streams[0];
   const int Bh = shared_hyper ? 1 : B;
   const int ntheta = ms.D + 4 + ncheb;
-  SFB_CUDA(h, cudaStreamSynchronize(h->streams[1]));  // staging buffers may still be read by the other lane
+  for (int i = 1; i < kMaxLanes; ++i)
+    SFB_CUDA(h, cudaStreamSynchronize(h->streams[i]));  // staging buffers may still be read by the other lanes
   SFB_CUDA(h, cudaMemcpyAsync(ms.theta, theta_h, sizeof(double) * (size_t)B * ntheta, cudaMemcpyHostToDevice, st));
   SFB_CUDA(h, cudaMemcpyAsync(h->dglob, glob_h, sizeof(double) * 2 * Bh, cudaMemcpyHostToDevice, st));
   SFB_CUDA(h, cudaMemcpyAsync(h->dnloc, nloc_h, sizeof(int) * Bh, cudaMemcpyHostToDevice, st));
@@ -1236,7 +1242,7 @@ int sfb_allgather_lnL(sfb_t* h, const double* lnL_local, int count, double* lnL_
 int sfb_sync(sfb_t* h) {
   if (!h) return SFB_ERR_ARG;
   DeviceGuard guard(h->device);
-  for (int i = 0; i < 2; ++i) SFB_CUDA(h, cudaStreamSynchronize(h->streams[i]));
+  for (int i = 0; i < kMaxLanes; ++i) SFB_CUDA(h, cudaStreamSynchronize(h->streams[i]));
   return SFB_OK;
 }
 
@@ -1249,7 +1255,7 @@ int sfb_profile_enable(sfb_t* h, int on) {
 int sfb_profile_read(sfb_t* h, double* out, int n) {
   if (!h || !out || n < 3 * SFB_K_NCLASS) return fail(h, SFB_ERR_ARG, "sfb_profile_read: buffer too small");
   DeviceGuard guard(h->device);
-  for (int i = 0; i < 2; ++i) SFB_CUDA(h, cudaStreamSynchronize(h->streams[i]));
+  for (int i = 0; i < kMaxLanes; ++i) SFB_CUDA(h, cudaStreamSynchronize(h->streams[i]));
   for (int i = 0; i < 3 * SFB_K_NCLASS; ++i) out[i] = 0.0;
   for (auto& pe : h->prof) {
     float ms = 0.f;

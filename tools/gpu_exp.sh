@@ -25,3 +25,6 @@ run_bench tpc16 "SFB_OZ_TPC=16"
 run_bench ot16 "SFB_OUTER_TILES=16"
 run_bench ot4 "SFB_OUTER_TILES=4"
 run_bench nohi "SFB_DEBUG_MODE=1"
+run_bench lanes3 "SFB_LANES=3"
+run_bench lanes4 "SFB_LANES=4"
+run_bench lanes1 "SFB_LANES=1"
