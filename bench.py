@@ -295,7 +295,7 @@ def kernel_shares(prof):
             for k, v in prof.items() if v["launches"]}
 
 
-def roofline_block(prof, solver, peaks):
+def roofline_block(prof, solver, peaks, issued_frac=1.0):
     sy = prof["syrk"]
     total_ms = sum(v["ms"] for v in prof.values())
     ach = sy["work"] / (sy["ms"] * 1e-3) / 1e12 if sy["ms"] > 0 else 0.0   # fp64(-equivalent) TFLOP/s
@@ -325,19 +325,22 @@ def roofline_block(prof, solver, peaks):
               "timing": "one extra profiled step after the timed region: single stream, CUDA events around every "
                         "launch", "other_kernels": other}
     if solver == "dense_i8":
-        i8 = ach * I8_PRODUCTS   # int8 TOP/s actually executed on the tensor pipe
+        i8 = ach * I8_PRODUCTS * issued_frac   # int8 TOP/s actually executed on the tensor pipe
         peak = 2.0 * peaks["bf16_tflops_sustained"] if peaks.get("bf16_tflops_sustained") else 2.0 * 1400.0
         common.update({
             "kernel": "syrk_i8_kernel (trailing update A_ij -= L_ik L_jk^T as 26 exact int8 MMAs per fp64 product "
                       "term: tcgen05.mma kind::i8, 7 int32 TMEM accumulators, fp64 recombination)",
             "achieved": i8, "peak": peak, "frac": i8 / peak,
             "achieved_fp64_equivalent_tflops": ach, "fp64_dmma_peak_tflops": FP64_DMMA_PEAK_TFLOPS,
+            "int8_mma_issued_frac": issued_frac,
             "speedup_over_fp64_tensor_peak": ach / FP64_DMMA_PEAK_TFLOPS,
             "peak_source": "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (int8 dense rate = 2 x bf16 on sm_100a; the "
                            "file has no int8 entry" + ("" if peaks.get("bf16_tflops_sustained") else "; FALLBACK 1.4 PF") +
                            "); this kernel's 128x64 MMA shape is shared-memory-bandwidth-bound at 0.61 of the int8 "
                            "issue peak (tools/exp/umma_i8_probe.cu: 2789 of 4596 TOP/s measured on the chip)",
-            "algorithmic_work": "n(n+1)K fp64 FLOP per trailing update x 26 int8 MMA terms"})
+            "algorithmic_work": "n(n+1)K fp64 FLOP per trailing update x 26 int8 MMA terms x int8_mma_issued_frac "
+                                "(products with an all-zero digit slab are skipped — exact; the fraction is measured "
+                                "by the kernel itself over the profiled step)"})
     else:
         common.update({
             "kernel": "syrk_kernel (trailing update A_ij -= L_ik L_jk^T, DMMA m8n8k4 fp64)",
@@ -386,8 +389,12 @@ def run_config_leg(torch, dist, dev, local_rank, world, rank, stage, N, M, K, nb
             leg["max_rel_diff_vs_" + solvers[0]] = float(((cur - ref).abs() / ref.abs().clamp(min=1.0)).max().item())
         if rank == 0:
             eng.profile(True)
+            eng.i8_mma_counts()
             step()
             leg["kernels"] = kernel_shares(eng.profile_read())
+            if solver == "dense_i8":
+                iss, den = eng.i8_mma_counts()
+                leg["int8_mma_issued_frac"] = iss / den if den else None
             eng.profile(False)
         out[solver] = leg
     eng.close()
@@ -562,10 +569,12 @@ def run_b200(args, rank, world, local_rank, cpu_sample):
     shares = None
     if rank == 0:
         eng.profile(True)
+        eng.i8_mma_counts()                      # reset
         eng.log_likelihood_resident(nb, X, A, F, g, n, l, lnL, info)
         prof = eng.profile_read()
+        issued, dense_cnt = eng.i8_mma_counts()
         eng.profile(False)
-        roof = roofline_block(prof, args.solver, peaks)
+        roof = roofline_block(prof, args.solver, peaks, issued / dense_cnt if dense_cnt else 1.0)
         shares = kernel_shares(prof)
 
     # ---- the other dense trailing-update mode on the same inputs -------------------------------------
@@ -584,10 +593,12 @@ def run_b200(args, rank, world, local_rank, cpu_sample):
                "not_positive_definite": int((info != 0).sum().item())}
         if rank == 0:
             eng.profile(True)
+            eng.i8_mma_counts()
             eng.log_likelihood_resident(nb, X, A, F, g, n, l, lnL, info)
             pa = eng.profile_read()
+            issued_a, dense_a = eng.i8_mma_counts()
             eng.profile(False)
-            alt["roofline"] = roofline_block(pa, other, peaks)
+            alt["roofline"] = roofline_block(pa, other, peaks, issued_a / dense_a if dense_a else 1.0)
             alt["kernels"] = kernel_shares(pa)
         eng.set_solver(args.solver)
 

@@ -111,6 +111,7 @@ int sfb_loglike_host(sfb_t* h, int B, const double* X_h, const double* A_h, cons
  *                        rotational_broaden   Starfish/transforms.py:93-134
  *                        doppler_shift        Starfish/transforms.py:137-158
  *                        resample (k=5)       Starfish/transforms.py:11-42
+ *                        extinct (ccm89)      Starfish/transforms.py:161-206
  *                        chebyshev_correct    Starfish/transforms.py:271-304
  *                        Emulator.__call__    Starfish/emulator/emulator.py:330-394 (weights, Σ_w)
  *                        X = eig·std, flux = w·X + mean, rescale / renorm   spectrum_model.py:306-332
@@ -125,7 +126,9 @@ enum sfb_model_flags {
   SFB_MODEL_VZ = 2,         /* Doppler shift (theta column D+1)                                        */
   SFB_MODEL_LOG_SCALE = 4,  /* log_scale given (column D+2); otherwise renormalise to the data flux    */
   SFB_MODEL_NORM = 8,       /* multiply by the emulator's norm factor (column D+3, host-interpolated)   */
-  SFB_MODEL_PAPER_TERM = 16 /* A = Σ_w (paper) instead of Σ_w⁻¹ (as the reference codes it)            */
+  SFB_MODEL_PAPER_TERM = 16,/* A = Σ_w (paper) instead of Σ_w⁻¹ (as the reference codes it)            */
+  SFB_MODEL_AV = 32         /* interstellar extinction (LAST theta column): Starfish/transforms.py:161-206 with
+                               the defaults SpectrumModel uses (law ccm89, R_V = 3.1), spectrum_model.py:298-299   */
 };
 
 /*
@@ -142,7 +145,8 @@ int sfb_set_model_host(sfb_t* h, int nf, const double* fine_wave_h, const double
                        const double* v11_h, const double* w_hat_h, int ncheb_max, int flags);
 
 /*
- * theta: B×ntheta (ntheta = D+4+ncheb), row b = [grid params (D) | vsini | vz | log_scale | norm | c1..c_ncheb];
+ * theta: B×ntheta (ntheta = D+4+ncheb, +1 with SFB_MODEL_AV), row b = [grid params (D) | vsini | vz | log_scale | norm |
+ * c1..c_ncheb | Av];
  * columns the model's flags do not use are ignored.  Outputs (device): X B×M×N, A B×M×M, model_flux B×N,
  * log_scale_out B (the fitted value when SFB_MODEL_LOG_SCALE is off), status B (0 ok, 1 = Σ_w not
  * positive definite — the reference raises LinAlgError there).  weights/weights_cov (B×M, B×M×M) may be NULL.
@@ -192,6 +196,13 @@ int sfb_get_solver(const sfb_t* h);
  * Same lnL to rounding (|ΔlnL| <= 1e-10·|lnL|, tests/test_gpu_shared_factor.py).  On by default for B >= 2;
  * sfb_set_shared_factor(h, 0) makes shared_hyper calls factorise every walker's full covariance again.
  */
+/*
+ * SFB_SOLVER_DENSE_I8 skips every int8 product one of whose digit slabs is identically zero (exact: a product with
+ * zero).  Counts since the last call: MMAs issued, and MMAs a dense digit pattern would have needed (26 per tile and
+ * 32-deep chunk).  Resets the counters; synchronises the handle.
+ */
+int sfb_i8_mma_counts(sfb_t* h, unsigned long long* issued, unsigned long long* dense);
+
 int sfb_set_shared_factor(sfb_t* h, int on);
 long long sfb_shared_factor_calls(const sfb_t* h);
 

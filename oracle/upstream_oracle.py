@@ -108,8 +108,39 @@ def model_setup(emu_wl, emu_bulk_fluxes, data_wave):
     return fine, resample(emu_wl, emu_bulk_fluxes, fine)
 
 
+def ccm89(wave, a_v, r_v=3.1):
+    """A_λ of Cardelli, Clayton & Mathis (1989) — what ``extinction.ccm89(wave, a_v, r_v)`` returns and
+    Starfish/transforms.py:199-205 multiplies in.  The ``extinction`` package (v0.4.x, a dependency of the reference,
+    setup.py) is ABSENT from this image, so this restates the published law (eqs. 2a-5b of the paper, Horner
+    evaluation as in the package's C source): PARITY UNPINNED against the package itself; pinned against the paper's
+    Table 3 (tests/test_oracle_upstream.py::test_ccm89_matches_the_papers_table3)."""
+    x = 1e4 / np.asarray(wave, dtype=np.float64)
+    a = np.zeros_like(x)
+    b = np.zeros_like(x)
+    for i, xi in enumerate(x):          # plain per-pixel restatement, deliberately not sharing code with the product
+        if 0.3 <= xi < 1.1:
+            a[i], b[i] = 0.574 * xi**1.61, -0.527 * xi**1.61
+        elif xi < 3.3:
+            y = xi - 1.82
+            a[i] = ((((((0.32999 * y - 0.77530) * y + 0.01979) * y + 0.72085) * y - 0.02427) * y - 0.50447) * y
+                    + 0.17699) * y + 1.0
+            b[i] = ((((((-2.09002 * y + 5.30260) * y - 0.62251) * y - 5.38434) * y + 1.07233) * y + 2.28305) * y
+                    + 1.41338) * y
+        elif xi < 8.0:
+            d = xi - 5.9 if xi >= 5.9 else 0.0
+            a[i] = 1.752 - 0.316 * xi - 0.104 / ((xi - 4.67) ** 2 + 0.341) - 0.04473 * d**2 - 0.009779 * d**3
+            b[i] = -3.090 + 1.825 * xi + 1.206 / ((xi - 4.62) ** 2 + 0.263) + 0.2130 * d**2 + 0.1207 * d**3
+        elif xi <= 11.0:
+            z = xi - 8.0
+            a[i] = -1.073 - 0.628 * z + 0.137 * z**2 - 0.070 * z**3
+            b[i] = 13.670 + 4.257 * z - 0.420 * z**2 + 0.374 * z**3
+        else:
+            raise ValueError("ccm89: wavelength out of range")
+    return a_v * (a + b / r_v)
+
+
 def model_call(fine_wave, bulk_fluxes, data_wave, data_flux, weights, *, vsini=None, vz=None, cheb=None,
-               log_scale=None, norm=1.0):
+               log_scale=None, norm=1.0, Av=None):
     """-> (flux[N], X[M,N], log_scale) for one walker; ``None`` = parameter absent from the model."""
     wave, fluxes = fine_wave, bulk_fluxes
     if vsini is not None:
@@ -117,6 +148,8 @@ def model_call(fine_wave, bulk_fluxes, data_wave, data_flux, weights, *, vsini=N
     if vz is not None:
         wave = doppler_shift(wave, vz)
     fluxes = resample(wave, fluxes, data_wave)
+    if Av is not None:                                   # spectrum_model.py:298-299, transforms.py:199-205
+        fluxes = fluxes * 10 ** (-0.4 * ccm89(data_wave, Av))
     if cheb is not None:
         fluxes = chebyshev_correct(data_wave, fluxes, [1, *cheb])
     *eigenspectra, flux_mean, flux_std = fluxes

@@ -18,15 +18,15 @@ EXPORTS = [
     "sfb_host_rfft", "sfb_host_spline_inverse_band", "sfb_host_cholesky_lower", "sfb_spline_halfwidth",
     "sfb_set_solver", "sfb_get_solver", "sfb_band_classes",
     "sfb_comm_unique_id", "sfb_comm_init", "sfb_allgather_lnL", "sfb_comm_destroy",
-    "sfb_set_shared_factor", "sfb_shared_factor_calls",
+    "sfb_set_shared_factor", "sfb_shared_factor_calls", "sfb_i8_mma_counts",
 ]
 
 SOLVER_DENSE, SOLVER_STRUCTURED, SOLVER_DENSE_I8 = 0, 1, 2
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # sfb_model_flags of include/sfb200.h
-MODEL_VSINI, MODEL_VZ, MODEL_LOG_SCALE, MODEL_NORM, MODEL_PAPER_TERM = 1, 2, 4, 8, 16
+MODEL_VSINI, MODEL_VZ, MODEL_LOG_SCALE, MODEL_NORM, MODEL_PAPER_TERM, MODEL_AV = 1, 2, 4, 8, 16, 32
 
 KERNEL_CLASSES = ("build", "potrf_diag", "trsm", "syrk", "upstream", "band_build", "band_chol", "oz_slice", "fwd_rows")
 
@@ -74,6 +74,7 @@ def load():
     lib.sfb_set_shared_factor.argtypes = [_p, _i]
     lib.sfb_shared_factor_calls.argtypes = [_p]
     lib.sfb_shared_factor_calls.restype = C.c_longlong
+    lib.sfb_i8_mma_counts.argtypes = [_p, _p, _p]
     lib.sfb_sync.argtypes = [_p]
     lib.sfb_profile_enable.argtypes = [_p, _i]
     lib.sfb_profile_read.argtypes = [_p, _p, _i]

@@ -65,7 +65,10 @@ struct sfb_ctx {
   // slices block J+1 while the bulk update of block J still reads its own) and the per-row scales
   int8_t* ozP = nullptr;
   double* oz_rscale = nullptr;
+  uint8_t* ozF = nullptr;                 // non-zero digit-slab flags, same two-buffer scheme as ozP
+  unsigned long long* oz_stats = nullptr; // [issued, dense-pattern] int8 MMA counts since the last read
   size_t oz_bytes = 0;    // bytes of ONE panel buffer of one slot
+  size_t oz_fbytes = 0;   // bytes of ONE flag buffer of one slot
   // shared-factor path (frozen kernel groups): right-hand sides of all walkers as rows, per-panel L_kk^-1 blocks
   bool shared_factor = true;   // sfb_set_shared_factor
   double* Zt = nullptr;
@@ -228,9 +231,13 @@ int ensure_workspace(sfb_ctx* h) { return h->W ? SFB_OK : alloc_workspace(h, 0);
 int ensure_ozaki(sfb_ctx* h) {
   if (h->ozP) return SFB_OK;
   h->oz_bytes = oz_panel_bytes_per_slot(h->Np, h->outer_tiles);
+  h->oz_fbytes = oz_flag_bytes_per_slot(h->Np, h->outer_tiles);
   if (cudaMalloc((void**)&h->ozP, 2 * h->oz_bytes * (size_t)h->slots) != cudaSuccess ||
-      cudaMalloc((void**)&h->oz_rscale, sizeof(double) * (size_t)h->Np * h->slots) != cudaSuccess)
+      cudaMalloc((void**)&h->oz_rscale, sizeof(double) * (size_t)h->Np * h->slots) != cudaSuccess ||
+      cudaMalloc((void**)&h->ozF, 2 * h->oz_fbytes * (size_t)h->slots) != cudaSuccess ||
+      cudaMalloc((void**)&h->oz_stats, 2 * sizeof(unsigned long long)) != cudaSuccess)
     return fail(h, SFB_ERR_NOMEM, "int8 solver: sliced-panel workspace allocation failed");
+  SFB_CUDA(h, cudaMemset(h->oz_stats, 0, 2 * sizeof(unsigned long long)));
   SFB_CUDA(h, ozaki_init());
   return SFB_OK;
 }
@@ -252,11 +259,13 @@ int run_cholesky(sfb_ctx* h, int lane, int slot0, int nb, double* lnL_out, int* 
   p.info = h->info_ws + slot0;
   p.k0 = 0;
   const int nt = h->Np / kTile;
-  OzParams oz{nullptr, 0, nullptr};
+  OzParams oz{nullptr, 0, nullptr, nullptr, 0, nullptr};
   if (i8) {
     int rc = ensure_ozaki(h);
     if (rc != SFB_OK) return rc;
     oz.strideP = (long long)(2 * h->oz_bytes);
+    oz.strideF = (long long)(2 * h->oz_fbytes);
+    oz.stats = h->oz_stats;
     oz.rscale = h->oz_rscale + (long long)slot0 * h->Np;
     SFB_CUDA(h, launch_oz_rowscale(p, oz, nb, lo));  // from the diagonal of the matrix as built
     h->launches++;
@@ -277,7 +286,10 @@ int run_cholesky(sfb_ctx* h, int lane, int slot0, int nb, double* lnL_out, int* 
   for (int J0 = 0, blk = 0; J0 < nt; J0 += OT, ++blk) {
     const int q = std::min(OT, nt - J0);
     const int kb = J0 * kTile;
-    if (i8) oz.P = h->ozP + (size_t)slot0 * 2 * h->oz_bytes + (size_t)(blk & 1) * h->oz_bytes;
+    if (i8) {
+      oz.P = h->ozP + (size_t)slot0 * 2 * h->oz_bytes + (size_t)(blk & 1) * h->oz_bytes;
+      oz.F = h->ozF + (size_t)slot0 * 2 * h->oz_fbytes + (size_t)(blk & 1) * h->oz_fbytes;
+    }
     // ---- PANEL(J) on hi
     for (int c = 0; c < q; ++c) {
       const int jt = J0 + c;
@@ -643,7 +655,7 @@ bool use_shared_factor(const sfb_ctx* h, int B, int shared_hyper) {
 
 extern "C" {
 
-int sfb_abi_version(void) { return 4; }
+int sfb_abi_version(void) { return 5; }
 
 int sfb_create(int device, int N, int M, int Kmax, int Bmax, int workspace_walkers, sfb_t** out) {
   if (!out) return SFB_ERR_ARG;
@@ -728,6 +740,8 @@ int sfb_destroy(sfb_t* h) {
   if (h->MinvAll) cudaFree(h->MinvAll);
   free_fwd_maps(&h->fwd_maps);
   if (h->ozP) cudaFree(h->ozP);
+  if (h->ozF) cudaFree(h->ozF);
+  if (h->oz_stats) cudaFree(h->oz_stats);
   if (h->oz_rscale) cudaFree(h->oz_rscale);
   if (h->Sb) cudaFree(h->Sb);
   if (h->bw_d) cudaFree(h->bw_d);
@@ -989,7 +1003,7 @@ int run_upstream(sfb_ctx* h, int B, const double* theta, int ncheb, double* X, d
   UpstreamArgs a;
   a.B = B;
   a.ncheb = ncheb;
-  a.ntheta = h->model.D + 4 + ncheb;
+  a.ntheta = h->model.D + 4 + ncheb + ((h->model.flags & SFB_MODEL_AV) ? 1 : 0);
   a.theta = theta;
   a.wave = h->wave;
   a.data_flux = h->data_flux;
@@ -1094,7 +1108,7 @@ int sfb_loglike_params_host(sfb_t* h, int B, const double* theta_h, int ncheb, c
   ModelState& ms = h->model;
   cudaStream_t st = h->streams[0];
   const int Bh = shared_hyper ? 1 : B;
-  const int ntheta = ms.D + 4 + ncheb;
+  const int ntheta = ms.D + 4 + ncheb + ((ms.flags & SFB_MODEL_AV) ? 1 : 0);
   for (int i = 1; i < kMaxLanes; ++i)
     SFB_CUDA(h, cudaStreamSynchronize(h->streams[i]));  // staging buffers may still be read by the other lanes
   SFB_CUDA(h, cudaMemcpyAsync(ms.theta, theta_h, sizeof(double) * (size_t)B * ntheta, cudaMemcpyHostToDevice, st));
@@ -1149,6 +1163,20 @@ int sfb_set_shared_factor(sfb_t* h, int on) {
 }
 
 long long sfb_shared_factor_calls(const sfb_t* h) { return h ? h->shared_factor_calls : -1; }
+
+int sfb_i8_mma_counts(sfb_t* h, unsigned long long* issued, unsigned long long* dense) {
+  if (!h || !issued || !dense) return SFB_ERR_ARG;
+  *issued = *dense = 0;
+  if (!h->oz_stats) return SFB_OK;
+  DeviceGuard guard(h->device);
+  for (int i = 0; i < kMaxLanes; ++i) SFB_CUDA(h, cudaStreamSynchronize(h->streams[i]));
+  unsigned long long v[2];
+  SFB_CUDA(h, cudaMemcpy(v, h->oz_stats, sizeof(v), cudaMemcpyDeviceToHost));
+  SFB_CUDA(h, cudaMemset(h->oz_stats, 0, sizeof(v)));
+  *issued = v[0];
+  *dense = v[1];
+  return SFB_OK;
+}
 
 int sfb_band_classes(const sfb_t* h, int* widths, long long* walkers, int n) {
   if (!h || !widths || !walkers || n < kNumBandWidths + 1) return SFB_ERR_ARG;

@@ -200,18 +200,20 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
   const int l1 = min(ntiles, l0 + tpc);
 
   extern __shared__ uint8_t oz_smem_raw[];
-  __shared__ uint64_t bars[2 * OZ_STAGES + 2];
+  __shared__ uint64_t bars[2 * OZ_STAGES + 3];
   __shared__ uint32_t tmem_base_s;
+  __shared__ uint32_t touched_s;
   const uint32_t ring = (smem_u32(oz_smem_raw) + 1023u) & ~1023u;
   const uint32_t tbuf0 = ring + OZ_STAGES * OZ_STAGE_BYTES;
   const uint32_t bar0 = smem_u32(bars);  // full[s] at +8s, empty[s] at +8(STAGES+s), then accfull, tmem_empty
-  const uint32_t accfull = bar0 + 16 * OZ_STAGES, tmem_empty = accfull + 8;
+  const uint32_t accfull = bar0 + 16 * OZ_STAGES, tmem_empty = accfull + 8, meta = accfull + 16;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
 #pragma unroll
     for (int i = 0; i < 2 * OZ_STAGES + 1; ++i) mbar_init(bar0 + 8 * i, 1);
     mbar_init(tmem_empty, 4);  // one arrival per epilogue warp
+    mbar_init(meta, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), OZ_TMEM_COLS);
@@ -246,20 +248,39 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
     // ---- MMA issuer: 26 int8 MMAs per chunk into 7 accumulators.  The whole warp runs the loop (descriptor
     // arithmetic stays warp-uniform, i.e. in uniform registers); one elected lane issues.
     const bool leader = elect_one();
+    const uint8_t* Fs = oz.F + (long long)s * oz.strideF;
+    const int nrb = p.Np / 64;
+    unsigned long long issued = 0;
     int g = 0, k = 0;  // ring position, live tiles done
     for (int l = l0; l < l1; ++l) {
-      if (!oz_tile(l, jt0, njt, strip).live) continue;
+      const OzTile t = oz_tile(l, jt0, njt, strip);
+      if (!t.live) continue;
+      // which digit slabs of this tile's operands are not identically zero, chunk by chunk (written by the slicing
+      // kernel; lane j holds chunks j and j+32) — fetched while the previous tile's accumulators are being drained
+      uint32_t fa0 = 0, fb0 = 0, fa1 = 0, fb1 = 0;
+      if (lane < nch) {
+        const uint8_t* f = Fs + (long long)lane * nrb;
+        fa0 = f[t.r0 / 64] | f[t.r0 / 64 + 1];
+        fb0 = f[t.c0 / 64];
+      }
+      if (lane + 32 < nch) {
+        const uint8_t* f = Fs + (long long)(lane + 32) * nrb;
+        fa1 = f[t.r0 / 64] | f[t.r0 / 64 + 1];
+        fb1 = f[t.c0 / 64];
+      }
       if (k > 0) {  // the epilogue must have drained the accumulators of the previous tile
         mbar_wait(tmem_empty, (k - 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       }
+      uint32_t touched = 0;  // accumulators that have received a product in this tile
       for (int c = 0; c < nch; ++c, ++g) {
         const int st = g % OZ_STAGES;
+        const uint32_t fa = __shfl_sync(0xffffffffu, c < 32 ? fa0 : fa1, c & 31);
+        const uint32_t fb = __shfl_sync(0xffffffffu, c < 32 ? fb0 : fb1, c & 31);
         mbar_wait(bar0 + 8 * st, (g / OZ_STAGES) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t a0 = ring + st * OZ_STAGE_BYTES, b0 = a0 + OZ_A_BYTES;
         const uint64_t ad0 = oz_desc(a0), bd0 = oz_desc(b0);
-        const uint32_t acc = (c == 0) ? 0u : 1u;
         if (leader) {
           if constexpr (TS) {
             // A slices shared memory -> TMEM once per chunk (the SS form re-reads each A slice for every pair and
@@ -267,33 +288,46 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
             // copies of this chunk follow the previous chunk's MMAs without a wait
 #pragma unroll
             for (int sa = 0; sa < OZ_S; ++sa)
-              utccp_128x256b(tmem + OZ_TMEM_A + sa * (OZ_KC / 4), ad0 + (uint64_t)(sa * (OZ_GROUP_BYTES >> 4)));
+              if ((fa >> sa) & 1u)
+                utccp_128x256b(tmem + OZ_TMEM_A + sa * (OZ_KC / 4), ad0 + (uint64_t)(sa * (OZ_GROUP_BYTES >> 4)));
           }
 #pragma unroll
           for (int sa = 0; sa < OZ_S; ++sa) {
 #pragma unroll
             for (int sb = 0; sb < OZ_S; ++sb) {
               if (sa + sb >= OZ_NACC) continue;
+              // a product with an all-zero digit slab contributes nothing: skipped (exactly, not approximately)
+              if (!(((fa >> sa) & 1u) && ((fb >> sb) & 1u))) continue;
               // the start-address field counts 16-byte units and never leaves its 14-bit range inside the ring, so
               // the other slices' descriptors are the stage's plus a constant
               const uint64_t bd = bd0 + (uint64_t)(sb * (OZ_GROUP_BYTES >> 4));
-              // the first pair that touches anti-diagonal d is (sa = 0, sb = d) for d < 6 and (1, 5) for d = 6
-              const bool first = (sa == 0) || (sa == 1 && sb == OZ_S - 1);
-              const uint32_t dcol = tmem + (uint32_t)(sa + sb) * OZ_BN;
+              const uint32_t d = sa + sb;
+              const uint32_t dcol = tmem + d * OZ_BN;
+              const uint32_t acc = (touched >> d) & 1u;   // the first product into an accumulator overwrites it
               if constexpr (TS) {
-                umma_i8_ts(dcol, tmem + OZ_TMEM_A + sa * (OZ_KC / 4), bd, OZ_IDESC, first ? acc : 1u);
+                umma_i8_ts(dcol, tmem + OZ_TMEM_A + sa * (OZ_KC / 4), bd, OZ_IDESC, acc);
               } else {
-                umma_i8(dcol, ad0 + (uint64_t)(sa * (OZ_GROUP_BYTES >> 4)), bd, OZ_IDESC, first ? acc : 1u);
+                umma_i8(dcol, ad0 + (uint64_t)(sa * (OZ_GROUP_BYTES >> 4)), bd, OZ_IDESC, acc);
               }
+              touched |= 1u << d;
+              ++issued;
             }
           }
           umma_commit(bar0 + 8 * (OZ_STAGES + st));  // stage free once these MMAs (and copies) have read it
         }
         __syncwarp();
       }
-      if (leader) umma_commit(accfull);
+      if (leader) {
+        touched_s = touched;               // which accumulators hold a sum (the others are stale: treated as zero)
+        mbar_arrive(meta);                 // release: the epilogue reads touched_s after acquiring this barrier
+        umma_commit(accfull);
+      }
       __syncwarp();
       ++k;
+    }
+    if (leader && oz.stats) {
+      atomicAdd(oz.stats, issued);
+      atomicAdd(oz.stats + 1, (unsigned long long)k * nch * 26ull);
     }
   } else {
     // ---- epilogue (4 warps; warp q owns tile rows 32q..32q+31 = its TMEM lane quarter).
@@ -317,22 +351,27 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
       double2 creg[32];
 #pragma unroll
       for (int r = 0; r < 32; ++r) creg[r] = __ldcs(reinterpret_cast<const double2*>(Cw + (long long)r * p.Np));
+      mbar_wait(meta, k & 1);
+      const uint32_t touched = touched_s;
       mbar_wait(accfull, k & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
       for (int cb = 0; cb < OZ_BN / 16; ++cb) {
         double acc[16];
         uint32_t v[16];
-        tmem_ld16(tlane + (OZ_NACC - 1) * OZ_BN + cb * 16, v);
-        tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = i2d(v[j]);
+        for (int j = 0; j < 16; ++j) acc[j] = 0.0;
 #pragma unroll
-        for (int d = OZ_NACC - 2; d >= 0; --d) {
-          tmem_ld16(tlane + d * OZ_BN + cb * 16, v);
-          tmem_ld_wait();
+        for (int d = OZ_NACC - 1; d >= 0; --d) {   // Horner from the least significant anti-diagonal
+          if ((touched >> d) & 1u) {
+            tmem_ld16(tlane + d * OZ_BN + cb * 16, v);
+            tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) acc[j] = fma(acc[j], 0.00390625, i2d(v[j]));
+            for (int j = 0; j < 16; ++j) acc[j] = fma(acc[j], 0.00390625, i2d(v[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j] *= 0.00390625;
+          }
         }
         const uint32_t dst = tbuf + (uint32_t)lane * OZ_TROW + (uint32_t)cb * 128;
 #pragma unroll
@@ -381,44 +420,64 @@ __global__ void oz_rowscale_kernel(CholParams p, OzParams oz) {
 
 // ------------------------------------------------------------------------------------------------
 // slice the panel just produced by trsm (rows k0+128.., columns k0..k0+127) into chunks [ch0, ch0+4) of P.
-// A warp takes one row: lane l owns k = 4l..4l+3 (one coalesced 1 KB row read), six packed 4-byte stores.
+// A CTA takes 64 rows (one flag block), a warp 8 of them; per row lane l owns k = 4l..4l+3 (one coalesced 1 KB row
+// read), six packed 4-byte stores.  Per (64-row block, chunk) the CTA also records which digit slabs are not
+// identically zero (F): |L_ik| is usually far below its row's scale away from the band, so the leading digit slab
+// of most operand blocks is all zero and the update kernel skips every product with it.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) oz_slice_kernel(CholParams p, OzParams oz, int ch0) {
   const int s = blockIdx.y;
   if (p.info[s] != 0) return;
-  const int lane = threadIdx.x & 31;
-  const int row = p.k0 + kTile + blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= p.Np) return;
-  const double* src = p.W + (long long)s * p.strideW + (long long)row * p.Np + p.k0 + 4 * lane;
-  const double2 v01 = *reinterpret_cast<const double2*>(src);
-  const double2 v23 = *reinterpret_cast<const double2*>(src + 2);
-  const double inv = 1099511627776.0 / oz.rscale[(long long)s * p.Np + row];  // 2^40 / 2^(e−7) = 2^(47−e)
-  const double lim = 140737488355327.0;                                       // 2^47 − 1
-  long long qv[4];
-  qv[0] = __double2ll_rn(fmin(fmax(v01.x * inv, -lim), lim));
-  qv[1] = __double2ll_rn(fmin(fmax(v01.y * inv, -lim), lim));
-  qv[2] = __double2ll_rn(fmin(fmax(v23.x * inv, -lim), lim));
-  qv[3] = __double2ll_rn(fmin(fmax(v23.y * inv, -lim), lim));
-  uint32_t packed[OZ_S];
-#pragma unroll
-  for (int t = OZ_S - 1; t >= 0; --t) {  // least significant digit first
-    uint32_t w = 0;
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const long long dgt = (long long)(int8_t)(qv[e] & 0xff);
-      qv[e] = (qv[e] - dgt) >> 8;
-      w |= ((uint32_t)dgt & 0xffu) << (8 * e);
-    }
-    packed[t] = w;
-  }
+  __shared__ uint32_t wmask[8][4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row_base = p.k0 + kTile + blockIdx.x * 64;
   const int chunk = ch0 + (lane >> 3);
   const int kb = (4 * lane) & 31;                       // byte inside the 32-byte row
-  const int r8 = row & 7;
-  const int half = ((kb >> 4) ^ (r8 >> 2)) & 1;         // 32-byte swizzle: 16-byte halves swapped for rows 4-7
-  int8_t* dst = oz.P + (long long)s * oz.strideP +
-                ((long long)chunk * (p.Np / 8) + (row >> 3)) * OZ_ROWGROUP_BYTES + r8 * OZ_KC + half * 16 + (kb & 15);
+  uint32_t nz = 0;                                      // bit t: slab t of this lane's chunk has a non-zero digit
+  for (int i = 0; i < 8; ++i) {
+    const int row = row_base + warp * 8 + i;
+    const double* src = p.W + (long long)s * p.strideW + (long long)row * p.Np + p.k0 + 4 * lane;
+    const double2 v01 = *reinterpret_cast<const double2*>(src);
+    const double2 v23 = *reinterpret_cast<const double2*>(src + 2);
+    const double inv = 1099511627776.0 / oz.rscale[(long long)s * p.Np + row];  // 2^40 / 2^(e−7) = 2^(47−e)
+    const double lim = 140737488355327.0;                                       // 2^47 − 1
+    long long qv[4];
+    qv[0] = __double2ll_rn(fmin(fmax(v01.x * inv, -lim), lim));
+    qv[1] = __double2ll_rn(fmin(fmax(v01.y * inv, -lim), lim));
+    qv[2] = __double2ll_rn(fmin(fmax(v23.x * inv, -lim), lim));
+    qv[3] = __double2ll_rn(fmin(fmax(v23.y * inv, -lim), lim));
+    uint32_t packed[OZ_S];
 #pragma unroll
-  for (int t = 0; t < OZ_S; ++t) *reinterpret_cast<uint32_t*>(dst + t * OZ_GROUP_BYTES) = packed[t];
+    for (int t = OZ_S - 1; t >= 0; --t) {  // least significant digit first
+      uint32_t w = 0;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const long long dgt = (long long)(int8_t)(qv[e] & 0xff);
+        qv[e] = (qv[e] - dgt) >> 8;
+        w |= ((uint32_t)dgt & 0xffu) << (8 * e);
+      }
+      packed[t] = w;
+      nz |= (w != 0u) << t;
+    }
+    const int r8 = row & 7;
+    const int half = ((kb >> 4) ^ (r8 >> 2)) & 1;         // 32-byte swizzle: 16-byte halves swapped for rows 4-7
+    int8_t* dst = oz.P + (long long)s * oz.strideP +
+                  ((long long)chunk * (p.Np / 8) + (row >> 3)) * OZ_ROWGROUP_BYTES + r8 * OZ_KC + half * 16 + (kb & 15);
+#pragma unroll
+    for (int t = 0; t < OZ_S; ++t) *reinterpret_cast<uint32_t*>(dst + t * OZ_GROUP_BYTES) = packed[t];
+  }
+  // OR over the 8 lanes of a chunk, then over the CTA's 8 warps
+  nz |= __shfl_xor_sync(0xffffffffu, nz, 1);
+  nz |= __shfl_xor_sync(0xffffffffu, nz, 2);
+  nz |= __shfl_xor_sync(0xffffffffu, nz, 4);
+  if ((lane & 7) == 0) wmask[warp][lane >> 3] = nz;
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) m |= wmask[w][threadIdx.x];
+    oz.F[(long long)s * oz.strideF + (long long)(ch0 + threadIdx.x) * (p.Np / 64) + row_base / 64] = (uint8_t)m;
+  }
 }
 
 }  // namespace
@@ -443,6 +502,9 @@ cudaError_t ozaki_init() {
 
 size_t oz_panel_bytes_per_slot(int Np, int outer_tiles) {
   return (size_t)(outer_tiles * (kTile / OZ_KC)) * (size_t)(Np / 8) * OZ_ROWGROUP_BYTES;
+}
+size_t oz_flag_bytes_per_slot(int Np, int outer_tiles) {
+  return (size_t)(outer_tiles * (kTile / OZ_KC)) * (size_t)(Np / 64);
 }
 
 namespace {
@@ -475,7 +537,7 @@ cudaError_t launch_oz_rowscale(const CholParams& p, const OzParams& oz, int B, c
 cudaError_t launch_oz_slice(const CholParams& p, const OzParams& oz, int chunk0, int B, cudaStream_t st) {
   const int rows = p.Np - p.k0 - kTile;
   if (rows <= 0) return cudaSuccess;
-  oz_slice_kernel<<<dim3(rows / 8, B), 256, 0, st>>>(p, oz, chunk0);
+  oz_slice_kernel<<<dim3(rows / 64, B), 256, 0, st>>>(p, oz, chunk0);
   return cudaGetLastError();
 }
 

@@ -112,11 +112,15 @@ struct OzParams {
   int8_t* P;             // sliced panels of the current outer block: slot s at P + s*strideP
   long long strideP;     // bytes per slot
   double* rscale;        // per slot, Np doubles: 2^(e_i - 7)
+  uint8_t* F;            // per slot: [chunk][row/64] bit t = digit slab t of that 64-row × 32-k block is not all zero
+  long long strideF;     // bytes per slot
+  unsigned long long* stats;  // optional [2]: int8 MMAs issued / MMAs a dense digit pattern would issue
 };
 cudaError_t ozaki_init();
 void ozaki_set_ts(bool on);  // A operand of the int8 MMAs from TMEM (tcgen05.cp, default) or shared memory
 void ozaki_set_tpc(int n);   // most tiles per CTA (experiments)
 size_t oz_panel_bytes_per_slot(int Np, int outer_tiles);
+size_t oz_flag_bytes_per_slot(int Np, int outer_tiles);
 cudaError_t launch_oz_rowscale(const CholParams& p, const OzParams& oz, int B, cudaStream_t st);
 cudaError_t launch_oz_slice(const CholParams& p, const OzParams& oz, int chunk0, int B, cudaStream_t st);
 cudaError_t launch_oz_syrk_strip(const CholParams& p, const OzParams& oz, int K, int jt0, int njt, int B,

@@ -443,6 +443,31 @@ __device__ double block_sum(double v, double* red) {
   return s;
 }
 
+// A_λ/A_V of Cardelli, Clayton & Mathis (1989) for R_V = 3.1 (the reference calls extinct() with its defaults,
+// spectrum_model.py:298-299): a(x) + b(x)/R_V, x = 1e4/λ[Å].  Same Horner evaluation as the oracle restatement.
+__device__ __forceinline__ double ccm89_curve(double wave_aa) {
+  const double x = 1e4 / wave_aa;
+  double a, b;
+  if (x < 1.1) {
+    const double p = pow(x, 1.61);
+    a = 0.574 * p;
+    b = -0.527 * p;
+  } else if (x < 3.3) {
+    const double y = x - 1.82;
+    a = ((((((0.32999 * y - 0.77530) * y + 0.01979) * y + 0.72085) * y - 0.02427) * y - 0.50447) * y + 0.17699) * y + 1.0;
+    b = ((((((-2.09002 * y + 5.30260) * y - 0.62251) * y - 5.38434) * y + 1.07233) * y + 2.28305) * y + 1.41338) * y;
+  } else if (x < 8.0) {
+    const double d = x >= 5.9 ? x - 5.9 : 0.0;
+    a = 1.752 - 0.316 * x - 0.104 / ((x - 4.67) * (x - 4.67) + 0.341) - 0.04473 * d * d - 0.009779 * d * d * d;
+    b = -3.090 + 1.825 * x + 1.206 / ((x - 4.62) * (x - 4.62) + 0.263) + 0.2130 * d * d + 0.1207 * d * d * d;
+  } else {
+    const double z = x - 8.0;
+    a = -1.073 - 0.628 * z + 0.137 * z * z - 0.070 * z * z * z;
+    b = 13.670 + 4.257 * z - 0.420 * z * z + 0.374 * z * z * z;
+  }
+  return a + b / 3.1;
+}
+
 __global__ void __launch_bounds__(CB_THREADS)
 combine_kernel(int N, int M, int R, int ncheb, int flags, const double* __restrict__ wave,
                const double* __restrict__ wave_max, const double* __restrict__ data_flux,
@@ -461,15 +486,22 @@ combine_kernel(int N, int M, int R, int ncheb, int flags, const double* __restri
   const bool fit = !(flags & SFB_MODEL_LOG_SCALE);
   double* fb = flux + (long long)b * N;
 
+  // one resampled row at pixel p: (Y · extinction) · Chebyshev, in the reference's order (spectrum_model.py:296-304)
+  const bool has_av = (flags & SFB_MODEL_AV) != 0;
+  const double av = has_av ? th[D + 4 + ncheb] : 0.0;
+  auto row = [&](int r, int p, double ext, double pc) {
+    double v = Yb[(long long)r * N + p];
+    if (has_av) v *= ext;
+    if (ncheb > 0) v *= pc;
+    return v;
+  };
   for (int p = tid; p < N; p += CB_THREADS) {
     const double pc = ncheb > 0 ? chebval1(wave[p] / wmax, cheb, ncheb) : 1.0;
-    const double sd = ncheb > 0 ? Yb[(long long)(M + 1) * N + p] * pc : Yb[(long long)(M + 1) * N + p];
-    const double mean = ncheb > 0 ? Yb[(long long)M * N + p] * pc : Yb[(long long)M * N + p];
+    const double ext = has_av ? exp10(-0.4 * (av * ccm89_curve(wave[p]))) : 1.0;
+    const double sd = row(M + 1, p, ext, pc);
+    const double mean = row(M, p, ext, pc);
     double f = 0.0;
-    for (int m = 0; m < M; ++m) {
-      const double e = ncheb > 0 ? Yb[(long long)m * N + p] * pc : Yb[(long long)m * N + p];
-      f = fma(w[m], e * sd, f);
-    }
+    for (int m = 0; m < M; ++m) f = fma(w[m], row(m, p, ext, pc) * sd, f);
     fb[p] = f + mean;
   }
   __syncthreads();
@@ -496,11 +528,9 @@ combine_kernel(int N, int M, int R, int ncheb, int flags, const double* __restri
   scale = s_scale;
   for (int p = tid; p < N; p += CB_THREADS) {
     const double pc = ncheb > 0 ? chebval1(wave[p] / wmax, cheb, ncheb) : 1.0;
-    const double sd = ncheb > 0 ? Yb[(long long)(M + 1) * N + p] * pc : Yb[(long long)(M + 1) * N + p];
-    for (int m = 0; m < M; ++m) {
-      const double e = ncheb > 0 ? Yb[(long long)m * N + p] * pc : Yb[(long long)m * N + p];
-      X[((long long)b * M + m) * N + p] = (e * sd) * scale;
-    }
+    const double ext = has_av ? exp10(-0.4 * (av * ccm89_curve(wave[p]))) : 1.0;
+    const double sd = row(M + 1, p, ext, pc);
+    for (int m = 0; m < M; ++m) X[((long long)b * M + m) * N + p] = (row(m, p, ext, pc) * sd) * scale;
     fb[p] = fb[p] * scale;
   }
 }
@@ -751,7 +781,7 @@ cudaError_t model_setup(ModelState* ms, int N, int M, int Bmax, int nf, const do
   UP(upload(&ms->gp_ls, ls_h, (size_t)M * D));
   UP(upload(&ms->L, L.data(), L.size()));
   UP(upload(&ms->zw, zw.data(), zw.size()));
-  const size_t nth = (size_t)D + 4 + ncheb_max;
+  const size_t nth = (size_t)D + 5 + ncheb_max;  // [grid | vsini | vz | log_scale | norm | cheb.. | Av]
   UP(upload(&ms->theta, (const double*)nullptr, (size_t)Bmax * nth));
   if (flags & SFB_MODEL_VSINI) {
     UP(upload(&ms->sb, (const double*)nullptr, (size_t)Bmax * (n2 + 1)));

@@ -243,6 +243,13 @@ class LikelihoodEngine:
     def shared_factor_calls(self) -> int:
         return int(self._lib.sfb_shared_factor_calls(self._h))
 
+    def i8_mma_counts(self):
+        """(issued, dense) int8 MMA counts of the dense_i8 trailing update since the last call: products with an
+        all-zero digit slab are skipped, `dense` is what a dense digit pattern would have needed."""
+        a, b = C.c_ulonglong(0), C.c_ulonglong(0)
+        self._check(self._lib.sfb_i8_mma_counts(self._h, C.byref(a), C.byref(b)), "sfb_i8_mma_counts")
+        return int(a.value), int(b.value)
+
     def band_classes(self):
         """{window width: walkers routed to it since creation}; key 0 is the dense fallback."""
         w = (C.c_int * 8)()
@@ -307,7 +314,7 @@ class LikelihoodEngine:
         self.D, self.model_flags, self.ncheb_max = D, int(flags), int(ncheb_max)
 
     def theta_width(self, ncheb):
-        return self.D + 4 + int(ncheb)
+        return self.D + 4 + int(ncheb) + (1 if self.model_flags & _lib.MODEL_AV else 0)
 
     def upstream(self, theta, ncheb: int):
         """Device tensors of everything SpectrumModel.__call__ computes before the rank-M term:

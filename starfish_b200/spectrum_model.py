@@ -293,6 +293,8 @@ class SpectrumModel:
             flags |= _lib.MODEL_NORM
         if self.emulator_term == "paper":
             flags |= _lib.MODEL_PAPER_TERM
+        if "Av" in self.params:
+            flags |= _lib.MODEL_AV
         return flags
 
     def _get_engine(self, n_walkers, n_local=None):
@@ -361,9 +363,11 @@ class SpectrumModel:
 
     def _theta(self, B, cols):
         """Pack the per-walker parameters the device upstream stage reads (include/sfb200.h, sfb_upstream):
-        [grid params | vsini | vz | log_scale | norm | c1..c_ncheb]."""
+        [grid params | vsini | vz | log_scale | norm | c1..c_ncheb | Av]."""
         D, nc = len(self.emulator.param_names), self._n_cheb()
-        th = np.zeros((B, D + 4 + nc))
+        th = np.zeros((B, D + 4 + nc + (1 if "Av" in self.params else 0)))
+        if "Av" in self.params:
+            th[:, D + 4 + nc] = cols["Av"]
         for d, name in enumerate(self.emulator.param_names):
             th[:, d] = cols[name]
         if "vsini" in self.params:
@@ -416,8 +420,6 @@ class SpectrumModel:
         return pad
 
     def _check_transforms(self, cols):
-        if "Av" in self.params and np.any(cols["Av"] != 0):
-            raise NotImplementedError("extinction needs the `extinction` package, absent from this image")
         if "vsini" in self.params and np.any(cols["vsini"] <= 0):
             raise ValueError("vsini must be positive")
 

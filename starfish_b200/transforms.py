@@ -4,7 +4,9 @@ These produce the per-walker inputs of the GPU stage boundary (``X[M,N]``, ``mod
 They mirror the behaviour of Starfish/transforms.py (function names, argument meaning, errors):
 ``resample`` :11-42, ``instrumental_broaden`` :45-90, ``rotational_broaden`` :93-134,
 ``doppler_shift`` :137-158, ``rescale`` :209-230, ``renorm`` :233-262, ``chebyshev_correct`` :271-304.
-``extinct`` is not provided: the ``extinction`` package is absent from this image.
+``extinct`` :161-206 for the two closed-form laws (ccm89, odonnell94); the reference delegates to the
+``extinction`` package (absent from this image) — its spline-based laws (fitzpatrick99, fm07) and calzetti00 are
+not provided.
 """
 import numpy as np
 from numpy.polynomial.chebyshev import chebval
@@ -59,6 +61,56 @@ def rotational_broaden(wave, flux, vsini):
 def doppler_shift(wave, vz):
     """λ·sqrt((c+vz)/(c−vz))."""
     return wave * np.sqrt((c_kms + vz) / (c_kms - vz))
+
+
+def _ccm89_ab(x, optical="ccm89"):
+    """a(x), b(x) of Cardelli, Clayton & Mathis (1989, ApJ 345, 245) eqs. 2-5, x = 1/λ [µm⁻¹] in [0.3, 11];
+    ``optical="odonnell94"`` swaps in O'Donnell's (1994, ApJ 422, 158) optical/NIR polynomials (1.1 <= x < 3.3)."""
+    x = np.asarray(x, dtype=np.float64)
+    a = np.empty_like(x)
+    b = np.empty_like(x)
+    if np.any((x < 0.3) | (x > 11.0)):
+        raise ValueError("ccm89 is defined for 0.3 <= 1/λ[µm] <= 11 (909 Å … 33333 Å)")
+    ir = x < 1.1
+    a[ir] = 0.574 * x[ir] ** 1.61
+    b[ir] = -0.527 * x[ir] ** 1.61
+    op = (x >= 1.1) & (x < 3.3)
+    y = x[op] - 1.82
+    if optical == "odonnell94":
+        ca = [1.0, 0.104, -0.609, 0.701, 1.137, -1.718, -0.827, 1.647, -0.505]
+        cb = [0.0, 1.952, 2.908, -3.989, -7.985, 11.102, 5.491, -10.805, 3.347]
+    else:
+        ca = [1.0, 0.17699, -0.50447, -0.02427, 0.72085, 0.01979, -0.77530, 0.32999]
+        cb = [0.0, 1.41338, 2.28305, 1.07233, -5.38434, -0.62251, 5.30260, -2.09002]
+    pa = np.zeros_like(y)
+    pb = np.zeros_like(y)
+    for c_a, c_b in zip(ca[::-1], cb[::-1]):   # Horner
+        pa = pa * y + c_a
+        pb = pb * y + c_b
+    a[op], b[op] = pa, pb
+    uv = (x >= 3.3) & (x < 8.0)
+    xu = x[uv]
+    d = np.where(xu >= 5.9, xu - 5.9, 0.0)
+    a[uv] = 1.752 - 0.316 * xu - 0.104 / ((xu - 4.67) ** 2 + 0.341) + (-0.04473 * d**2 - 0.009779 * d**3)
+    b[uv] = -3.090 + 1.825 * xu + 1.206 / ((xu - 4.62) ** 2 + 0.263) + (0.2130 * d**2 + 0.1207 * d**3)
+    fuv = x >= 8.0
+    z = x[fuv] - 8.0
+    a[fuv] = -1.073 - 0.628 * z + 0.137 * z**2 - 0.070 * z**3
+    b[fuv] = 13.670 + 4.257 * z - 0.420 * z**2 + 0.374 * z**3
+    return a, b
+
+
+def extinct(wave, flux, Av, Rv=3.1, law="ccm89"):
+    """``flux · 10^(−0.4·A_λ)``, ``A_λ = Av·(a(x) + b(x)/Rv)`` (Starfish/transforms.py:161-206).  The reference
+    evaluates the law with the ``extinction`` package; here the two closed-form laws are restated from the papers."""
+    if law not in ["ccm89", "odonnell94", "calzetti00", "fitzpatrick99", "fm07"]:
+        raise ValueError("Invalid extinction law given")
+    if Rv <= 0:
+        raise ValueError("Rv must be positive")
+    if law not in ("ccm89", "odonnell94"):
+        raise NotImplementedError(f"extinction law {law!r} needs the `extinction` package (absent from this image)")
+    a, b = _ccm89_ab(1e4 / np.asarray(wave, dtype=np.float64), optical=law)
+    return flux * 10 ** (-0.4 * (Av * (a + b / Rv)))
 
 
 def rescale(flux, scale):

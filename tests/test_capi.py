@@ -32,7 +32,7 @@ def test_library_exports_every_symbol(built_lib):
     for name in _declared():
         assert hasattr(lib, name), name
     lib.sfb_abi_version.restype = ctypes.c_int
-    assert lib.sfb_abi_version() == 4
+    assert lib.sfb_abi_version() == 5
 
 
 def test_library_is_sm100a_only(built_lib):

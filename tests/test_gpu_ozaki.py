@@ -137,3 +137,32 @@ def test_config3_n8192_against_independent_checker_and_fp64_mode():
     print("N=8192: max |lnL_i8 - lnL_fp64| / |lnL| =", rel.max())
     assert rel.max() <= 1e-11
     eng.close()
+
+
+def test_zero_digit_slabs_are_skipped_exactly():
+    """The update kernel skips every int8 product with an all-zero digit slab.  (a) a matrix whose factor has large
+    entries everywhere (no slab is zero): every MMA is issued; (b) a strongly diagonally dominant matrix (off-diagonal
+    factor entries below 2^-8 of the row scale: leading slab zero): fewer are issued — and both factors are exact."""
+    import torch
+    from scipy.linalg import cho_factor
+
+    rng = np.random.default_rng(5)
+    N, B = 1280, 2
+    eng = _engine(N, 0, 1, B)
+    a = rng.standard_normal((N, N))
+    dense_like = a @ a.T / N + 0.5 * np.eye(N)                     # correlations ~ N^-1/2 ≈ 0.03 > 2^-8
+    sparse_like = 1e-4 * (a @ a.T) / N + np.eye(N)                 # off-diagonal ~ 3e-6 of the diagonal
+    fracs = []
+    for mat in (dense_like, sparse_like):
+        Cd = torch.from_numpy(np.stack([mat, mat])).cuda()
+        eng.i8_mma_counts()
+        _, info = eng.cho_factor(Cd)
+        issued, dense = eng.i8_mma_counts()
+        assert info.cpu().tolist() == [0, 0] and dense > 0
+        fracs.append(issued / dense)
+        Lr = np.tril(cho_factor(mat, lower=True)[0])
+        Lg = np.tril(Cd.cpu().numpy()[0])
+        assert (np.abs(Lg - Lr) / np.sqrt(np.diag(mat))[:, None]).max() <= 1e-12
+    print("issued / dense-pattern int8 MMAs:", fracs)
+    assert fracs[0] > 0.95 and fracs[1] < 0.75
+    eng.close()

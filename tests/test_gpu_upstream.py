@@ -110,7 +110,8 @@ def _oracle_lnl(m, P_row):
                                   mm.grid_params)
     cheb = [p[f"cheb:{k}"] for k in p["cheb"].keys()] if "cheb" in p else None
     flux, X, _ = U.model_call(m.min_dv_wave, m.bulk_fluxes, m.data.wave, m.data.flux, mu,
-                              vsini=p.get("vsini"), vz=p.get("vz"), cheb=cheb, log_scale=p.get("log_scale"))
+                              vsini=p.get("vsini"), vz=p.get("vz"), cheb=cheb, log_scale=p.get("log_scale"),
+                              Av=p.get("Av"))
     glob = (np.exp(p["global_cov:log_amp"]), np.exp(p["global_cov:log_ls"])) if "global_cov" in p else None
     loc = [(np.exp(k["log_amp"]), k["mu"], np.exp(k["log_sigma"])) for k in p.as_dict().get("local_cov", [])]
     cov = O.assemble_covariance(m.data.wave, m.data.sigma, X, wcov, glob, np.array(loc).reshape(-1, 3))
@@ -311,3 +312,30 @@ def test_parameter_level_entry_error_behaviour():
     out = eng.upstream(theta, 2)
     assert out["status"].cpu().numpy().tolist() == [0, 0] and np.isfinite(out["X"].cpu().numpy()).all()
     eng.close()
+
+
+@pytest.mark.parametrize("av", [0.35, 0.0])
+def test_extinction_stage_on_the_device(golden_dir, av):
+    """`Av` in the model (spectrum_model.py:298-299 -> transforms.py:161-206, law ccm89, R_V = 3.1): resampled rows
+    times 10^(−0.4·A_λ) before the Chebyshev correction.  Checked against the upstream oracle's restatement of the
+    published law (the `extinction` package is absent: see oracle/upstream_oracle.py::ccm89)."""
+    g = _load(golden_dir, "model_n256_w0.npz")
+    m = make_model(256, 0, wave=g["wave"], mus=(5098.0, 5103.0), Av=av)
+    up = _device_upstream(m)
+    p = m.params
+    emu = m.emulator
+    mu, wcov = U.emulator_predict(emu.grid_points, emu.variances, emu.lengthscales, emu.v11, emu.w_hat, m.grid_params)
+    cheb = [p[f"cheb:{k}"] for k in p["cheb"].keys()]
+    flux, X, _ = U.model_call(m.min_dv_wave, m.bulk_fluxes, m.data.wave, m.data.flux, mu, vsini=p.get("vsini"),
+                              vz=p.get("vz"), cheb=cheb, log_scale=p.get("log_scale"), Av=av)
+    assert np.abs(up["X"] - X).max() <= 2e-9 * np.abs(X).max()
+    assert np.abs(up["flux"] - flux).max() <= 2e-9 * np.abs(flux).max()
+    ref = _oracle_lnl(m, m.get_param_vector())
+    got = m.log_likelihood()
+    print(f"Av={av}: end-to-end |dlnL|/|lnL| = {abs(got - ref) / abs(ref):.2e}")
+    assert abs(got - ref) <= MODEL_LNL_RTOL * abs(ref)
+    if av:
+        m0 = make_model(256, 0, wave=g["wave"], mus=(5098.0, 5103.0))
+        assert abs(m0.log_likelihood() - got) > 1e-3 * abs(got)       # extinction really changes the likelihood
+    else:
+        assert abs(got - g["lnL"]) <= MODEL_LNL_RTOL * abs(g["lnL"])   # Av = 0 is the recorded reference value

@@ -281,3 +281,30 @@ def test_reference_lnl_conditioning_floor(name, golden_dir):
     from test_gpu_upstream import MODEL_LNL_RTOL
 
     assert 10 * worst <= MODEL_LNL_RTOL <= 1e-10
+
+
+def test_ccm89_matches_the_papers_table3():
+    """Known answers for the extinction law (the `extinction` package the reference calls is absent, so the law is
+    pinned on Cardelli, Clayton & Mathis 1989, Table 3, R_V = 3.1): A_λ/A_V at the Johnson filter wavelengths, the
+    defining identities a(V) = 1, b(V) = 0 and A_B/A_V = 1 + 1/R_V, and product == oracle on a dense grid."""
+    from starfish_b200.transforms import extinct
+
+    x_inv_um = np.array([2.78, 2.27, 1.82, 1.43, 1.11, 0.80, 0.625, 1.0 / 2.2])   # U B V R I J H K as tabulated
+    table = np.array([1.569, 1.0 + 1.0 / 3.1, 1.000, 0.751, 0.479, 0.282, 0.190, 0.114])
+    got = U.ccm89(1e4 / x_inv_um, 1.0)
+    assert np.abs(got - table).max() <= 1.5e-3, got
+    assert abs(U.ccm89(np.array([1e4 / 1.82]), 1.0)[0] - 1.0) <= 1e-15          # y = 0: a = 1, b = 0 exactly
+    w = np.linspace(1000.0, 33000.0, 4001)
+    f = np.full_like(w, 2.0)
+    for av in (0.0, 0.3, 2.5):
+        ref = f * 10 ** (-0.4 * U.ccm89(w, av))
+        assert np.abs(extinct(w, f, av) - ref).max() <= 4e-16 * 2.0
+    assert np.array_equal(extinct(w, f, 0.0), f)
+    with pytest.raises(ValueError):
+        extinct(w, f, 0.1, law="nope")
+    with pytest.raises(ValueError):
+        extinct(w, f, 0.1, Rv=0.0)
+    with pytest.raises(NotImplementedError):
+        extinct(w, f, 0.1, law="fm07")
+    # O'Donnell's optical polynomials share the V-band normalisation
+    assert abs(-2.5 * np.log10(extinct(np.array([1e4 / 1.82]), np.ones(1), 1.0, law="odonnell94"))[0] - 1.0) <= 1e-15

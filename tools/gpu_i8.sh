@@ -12,7 +12,7 @@ try:
     d = json.load(open("gpurun_out/${TAG}_bench_$1.json"))
     r = d["roofline"]
     print("$1", "evals/s", round(d["value"], 2), "ms/step", round(d["ms_per_step"], 1), "syrk TFLOP/s(fp64-equiv)", round(r["achieved_fp64_equivalent_tflops"], 2),
-          "share", round(r["share_of_step"], 3), "clocks", d["clocks"], "kernels", json.dumps(d["kernels"]))
+          "share", round(r["share_of_step"], 3), "issued_frac", r.get("int8_mma_issued_frac"), "clocks", d["clocks"], "kernels", json.dumps(d["kernels"]))
 except Exception as e:
     print("$1 bench unreadable:", e)
 PY
