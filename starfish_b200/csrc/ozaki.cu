@@ -191,6 +191,46 @@ constexpr int OZ_TBUF_BYTES = 4 * 32 * OZ_TROW;     // 4 epilogue warps × 32 ro
 constexpr int OZ_SMEM_BYTES = OZ_STAGES * OZ_STAGE_BYTES + OZ_TBUF_BYTES + 1024;  // + alignment slack
 constexpr uint32_t OZ_TMEM_A = OZ_NACC * OZ_BN;     // first TMEM column of the A operand (TS form): 448..495
 
+// One 32-deep chunk: the six A slices shared memory -> TMEM once (TS form; the SS form re-reads each A slice for every
+// pair), then one int8 MMA per digit pair (sa, sb), sa + sb <= 6, into the accumulator of anti-diagonal sa + sb.
+// fa / fb: bit t set = digit slab t of the A / B operand block has a non-zero entry; a product with an all-zero slab
+// contributes nothing and is skipped (exactly).  Called with literal masks the tests fold away at compile time.
+// Copies and MMAs of one thread execute in issue order, so this chunk's copies follow the previous chunk's MMAs
+// without a wait.  Returns the number of MMAs issued.
+template <bool TS>
+__device__ __forceinline__ uint32_t oz_issue_chunk(uint32_t fa, uint32_t fb, uint32_t& touched, uint32_t tmem,
+                                                   uint64_t ad0, uint64_t bd0) {
+  if constexpr (TS) {
+#pragma unroll
+    for (int sa = 0; sa < OZ_S; ++sa)
+      if ((fa >> sa) & 1u)
+        utccp_128x256b(tmem + OZ_TMEM_A + sa * (OZ_KC / 4), ad0 + (uint64_t)(sa * (OZ_GROUP_BYTES >> 4)));
+  }
+  uint32_t local = 0, n = 0;  // accumulators touched by this chunk so far (compile-time known for literal masks)
+#pragma unroll
+  for (int sa = 0; sa < OZ_S; ++sa) {
+#pragma unroll
+    for (int sb = 0; sb < OZ_S; ++sb) {
+      if (sa + sb >= OZ_NACC) continue;
+      if (!(((fa >> sa) & 1u) && ((fb >> sb) & 1u))) continue;
+      // the start-address field counts 16-byte units and never leaves its 14-bit range inside the ring, so the
+      // other slices' descriptors are the stage's plus a constant
+      const uint64_t bd = bd0 + (uint64_t)(sb * (OZ_GROUP_BYTES >> 4));
+      const uint32_t d = sa + sb;
+      const uint32_t acc = ((touched | local) >> d) & 1u;   // the first product into an accumulator overwrites it
+      if constexpr (TS) {
+        umma_i8_ts(tmem + d * OZ_BN, tmem + OZ_TMEM_A + sa * (OZ_KC / 4), bd, OZ_IDESC, acc);
+      } else {
+        umma_i8(tmem + d * OZ_BN, ad0 + (uint64_t)(sa * (OZ_GROUP_BYTES >> 4)), bd, OZ_IDESC, acc);
+      }
+      local |= 1u << d;
+      ++n;
+    }
+  }
+  touched |= local;
+  return n;
+}
+
 template <bool TS>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
     syrk_i8_kernel(CholParams p, OzParams oz, int nch, int jt0, int njt, int strip, int ntiles, int tpc) {
@@ -282,37 +322,14 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
         const uint32_t a0 = ring + st * OZ_STAGE_BYTES, b0 = a0 + OZ_A_BYTES;
         const uint64_t ad0 = oz_desc(a0), bd0 = oz_desc(b0);
         if (leader) {
-          if constexpr (TS) {
-            // A slices shared memory -> TMEM once per chunk (the SS form re-reads each A slice for every pair and
-            // is shared-memory-bandwidth-bound); copies and MMAs of one thread execute in issue order, so the
-            // copies of this chunk follow the previous chunk's MMAs without a wait
-#pragma unroll
-            for (int sa = 0; sa < OZ_S; ++sa)
-              if ((fa >> sa) & 1u)
-                utccp_128x256b(tmem + OZ_TMEM_A + sa * (OZ_KC / 4), ad0 + (uint64_t)(sa * (OZ_GROUP_BYTES >> 4)));
-          }
-#pragma unroll
-          for (int sa = 0; sa < OZ_S; ++sa) {
-#pragma unroll
-            for (int sb = 0; sb < OZ_S; ++sb) {
-              if (sa + sb >= OZ_NACC) continue;
-              // a product with an all-zero digit slab contributes nothing: skipped (exactly, not approximately)
-              if (!(((fa >> sa) & 1u) && ((fb >> sb) & 1u))) continue;
-              // the start-address field counts 16-byte units and never leaves its 14-bit range inside the ring, so
-              // the other slices' descriptors are the stage's plus a constant
-              const uint64_t bd = bd0 + (uint64_t)(sb * (OZ_GROUP_BYTES >> 4));
-              const uint32_t d = sa + sb;
-              const uint32_t dcol = tmem + d * OZ_BN;
-              const uint32_t acc = (touched >> d) & 1u;   // the first product into an accumulator overwrites it
-              if constexpr (TS) {
-                umma_i8_ts(dcol, tmem + OZ_TMEM_A + sa * (OZ_KC / 4), bd, OZ_IDESC, acc);
-              } else {
-                umma_i8(dcol, ad0 + (uint64_t)(sa * (OZ_GROUP_BYTES >> 4)), bd, OZ_IDESC, acc);
-              }
-              touched |= 1u << d;
-              ++issued;
-            }
-          }
+          // The two digit patterns that dominate (nothing zero / leading slab zero), for either operand, get fully
+          // unrolled code with compile-time masks: a single thread issues every MMA of the CTA, so per-product
+          // run-time tests would make the issue loop the bottleneck.  Anything else takes the generic path.
+          if (fa == 0x3fu && fb == 0x3fu) issued += oz_issue_chunk<TS>(0x3fu, 0x3fu, touched, tmem, ad0, bd0);
+          else if (fa == 0x3eu && fb == 0x3eu) issued += oz_issue_chunk<TS>(0x3eu, 0x3eu, touched, tmem, ad0, bd0);
+          else if (fa == 0x3eu && fb == 0x3fu) issued += oz_issue_chunk<TS>(0x3eu, 0x3fu, touched, tmem, ad0, bd0);
+          else if (fa == 0x3fu && fb == 0x3eu) issued += oz_issue_chunk<TS>(0x3fu, 0x3eu, touched, tmem, ad0, bd0);
+          else issued += oz_issue_chunk<TS>(fa, fb, touched, tmem, ad0, bd0);
           umma_commit(bar0 + 8 * (OZ_STAGES + st));  // stage free once these MMAs (and copies) have read it
         }
         __syncwarp();

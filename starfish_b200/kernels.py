@@ -23,7 +23,7 @@ def _engine_for(n_pix: int, device: int = 0) -> LikelihoodEngine:
     if eng is None:
         if len(_ENGINES) >= 4:  # handles own GPU workspace; keep only a few sizes alive
             _ENGINES.pop(next(iter(_ENGINES))).close()
-        eng = LikelihoodEngine(n_pix, 0, 1, 1, device=device, workspace_walkers=-1)  # build-only: no N×N slots
+        eng = LikelihoodEngine(n_pix, 0, 32, 1, device=device, workspace_walkers=-1)  # build-only: no N×N slots
         _ENGINES[key] = eng
     return eng
 
