@@ -49,6 +49,7 @@ class LikelihoodEngine:
                                 f"Kmax={max_local}, Bmax={max_walkers})")
         self._h = h
         self._static = None
+        self.D, self.model_flags, self.ncheb_max = 0, 0, 0   # set by set_model
 
     # -- plumbing ---------------------------------------------------------------------------------
     def close(self):
