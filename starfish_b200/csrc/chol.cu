@@ -594,6 +594,298 @@ __global__ void __launch_bounds__(PD_THREADS, 1) potrf_diag_kernel(CholParams p,
 }
 
 // ------------------------------------------------------------------------------------------------
+// potrf_diag, blocked (the default): the tile lives in SHARED memory and is factorised right-looking in 32-column
+// blocks — the only sequential part left is the 32-column sweep of a 32×32 diagonal block, done by ONE warp in
+// registers with shuffles (no barrier per column); panel substitution, trailing update and the assembly of the
+// explicit inverse are 4×4-register-tile GEMM sweeps by the whole CTA.  The register-resident one-sweep kernel above
+// spends ≈ 2000 cycles per column on a barrier, a square root, a division and a full-square predicated update
+// (131 µs per tile); here the column chain is shuffle → rsqrt → 31−c shuffled FMAs.
+//   T (128 × P2_LD doubles): lower triangle A → L; the strict upper triangle receives (L⁻¹)ᵀ (M[r][c], r > c, at
+//   T[c][r]) as in the one-sweep kernel, the diagonal of L⁻¹ is dinv.
+// ------------------------------------------------------------------------------------------------
+constexpr int P2_THREADS = 256;
+constexpr int P2_LD = 129;
+constexpr int P2_SMEM_DOUBLES = kTile * P2_LD + 3 * kTile + 3 * 32 * 33;
+constexpr size_t kPotrf2Smem = sizeof(double) * P2_SMEM_DOUBLES;
+
+// acc[4][4] += Σ_{q<K} A[(4·ty+a)·lda + q] · B[(4·tx+b)·ldb + q]   (both operands contiguous in q)
+__device__ __forceinline__ void nt_tile_4x4(double (&acc)[4][4], const double* __restrict__ A, int lda,
+                                            const double* __restrict__ B, int ldb, int K) {
+#pragma unroll 4
+  for (int q = 0; q < K; ++q) {
+    double a[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      a[i] = A[i * lda + q];
+      b[i] = B[i * ldb + q];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+  }
+}
+
+__global__ void __launch_bounds__(P2_THREADS, 1) potrf_diag2_kernel(CholParams p, int last, double* lnL_out,
+                                                                     int* info_out) {
+  extern __shared__ __align__(16) double p2_smem[];
+  double* T = p2_smem;                   // [128][P2_LD]
+  double* rk = T + kTile * P2_LD;        // right-hand-side slice of this panel
+  double* dinv = rk + kTile;             // 1 / L_jj
+  double* dg = dinv + kTile;             // L_jj
+  double* Wb = dg + kTile;               // 3 scratch blocks [32][33] for the inverse assembly
+  __shared__ int fail_col;
+  __shared__ double red[16];
+  const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  if (p.info[s] != 0) {
+    if (last && tid == 0) {
+      if (lnL_out) lnL_out[s] = __longlong_as_double(0x7ff8000000000000LL);
+      if (info_out) info_out[s] = p.info[s];
+    }
+    return;
+  }
+  double* Wm = p.W + (long long)s * p.strideW;
+  const long long ld = p.Np;
+  double* Ag = Wm + (long long)p.k0 * ld + p.k0;
+
+  for (int idx = tid; idx < kTile * kTile; idx += P2_THREADS) {
+    const int r = idx >> 7, c = idx & 127;
+    T[r * P2_LD + c] = (c <= r) ? Ag[(long long)r * ld + c] : 0.0;
+  }
+  if (tid < kTile) rk[tid] = p.rhs[(long long)s * p.Np + p.k0 + tid];
+  if (tid == 0) fail_col = -1;
+  __syncthreads();
+
+  for (int bj = 0; bj < 4; ++bj) {
+    const int j0 = 32 * bj;
+    // ---- S1: the 32×32 diagonal block, one warp, row `lane` in registers, columns fully unrolled
+    if (warp == 0) {
+      double a[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) a[c] = T[(j0 + lane) * P2_LD + j0 + c];
+      int bad = -1;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const double piv = __shfl_sync(0xffffffffu, a[c], c);
+        if (bad < 0 && (!(piv > 0.0) || isinf(piv))) bad = c;   // also catches NaN; uniform across the warp
+        const double rs = rsqrt(piv);                            // two independent chains: 1/√piv for the scaling,
+        const double d = sqrt(piv);                              // √piv (IEEE) for the diagonal itself
+        const double lc = (lane == c) ? d : a[c] * rs;           // column c of L (rows >= c meaningful)
+        a[c] = lc;
+        if (lane == c) {
+          dinv[j0 + c] = rs;
+          dg[j0 + c] = d;
+        }
+#pragma unroll
+        for (int c2 = c + 1; c2 < 32; ++c2) {
+          const double other = __shfl_sync(0xffffffffu, lc, c2);  // L[c2][c]
+          a[c2] = fma(-lc, other, a[c2]);                          // meaningful for lane >= c2
+        }
+      }
+      if (bad >= 0) {
+        if (lane == 0) fail_col = j0 + bad;
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+          if (c <= lane) T[(j0 + lane) * P2_LD + j0 + c] = a[c];
+      }
+    }
+    __syncthreads();
+    if (fail_col >= 0) break;
+    const int nrows = kTile - j0 - 32;  // rows below the diagonal block
+    // ---- S2: L[i][j0..j0+31] for the rows below, one thread per row (forward substitution against L_d)
+    if (tid < nrows) {
+      double* row = T + (j0 + 32 + tid) * P2_LD + j0;
+      double x[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) x[c] = row[c];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        double v = x[c];
+#pragma unroll
+        for (int q = 0; q < c; ++q) v = fma(-x[q], T[(j0 + c) * P2_LD + j0 + q], v);   // broadcast reads of L_d
+        x[c] = v * dinv[j0 + c];
+      }
+#pragma unroll
+      for (int c = 0; c < 32; ++c) row[c] = x[c];
+    }
+    __syncthreads();
+    // ---- S3: trailing update T[i][k] −= Σ_c L[i][j0+c]·L[k][j0+c], i >= k >= j0+32, 4×4 tiles of the lower triangle
+    {
+      const int nt4 = nrows / 4;                 // tile rows
+      const int ntile = nt4 * (nt4 + 1) / 2;
+      for (int tl = tid; tl < ntile; tl += P2_THREADS) {
+        int ti = (int)((sqrtf(8.0f * (float)tl + 1.0f) - 1.0f) * 0.5f);
+        while (ti * (ti + 1) / 2 > tl) --ti;
+        while ((ti + 1) * (ti + 2) / 2 <= tl) ++ti;
+        const int tk = tl - ti * (ti + 1) / 2;
+        const int i0 = j0 + 32 + 4 * ti, k0 = j0 + 32 + 4 * tk;
+        double acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+        nt_tile_4x4(acc, T + i0 * P2_LD + j0, P2_LD, T + k0 * P2_LD + j0, P2_LD, 32);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (k0 + j <= i0 + i) T[(i0 + i) * P2_LD + k0 + j] -= acc[i][j];
+      }
+    }
+    __syncthreads();
+  }
+  if (fail_col >= 0) {
+    if (tid == 0) {
+      const int code = p.k0 + fail_col + 1;
+      p.info[s] = code;
+      if (last) {
+        if (lnL_out) lnL_out[s] = __longlong_as_double(0x7ff8000000000000LL);
+        if (info_out) info_out[s] = code;
+      }
+    }
+    return;
+  }
+
+  // ---- inverse, diagonal blocks: warp b inverts L_d of block b (row `lane` of X = L_d⁻¹ in registers):
+  // X[l][c] = −(Σ_{m=c+1..l} X[l][m]·L[m][c])·dinv[c] for c = l−1 … 0, X[l][l] = dinv[l]; stored transposed in the
+  // strict upper triangle of T
+  if (warp < 4) {
+    const int j0 = 32 * warp;
+    double Lr[32], X[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) Lr[c] = T[(j0 + lane) * P2_LD + j0 + c];   // row `lane` of L_d (c <= lane meaningful)
+#pragma unroll
+    for (int c = 0; c < 32; ++c) X[c] = 0.0;
+#pragma unroll
+    for (int c = 31; c >= 0; --c) {
+      double sum = 0.0;
+#pragma unroll
+      for (int m = c + 1; m < 32; ++m) {
+        const double lmc = __shfl_sync(0xffffffffu, Lr[c], m);   // L[m][c]
+        sum = fma(X[m], lmc, sum);                               // X[l][m] is zero for m > l
+      }
+      const double di = dinv[j0 + c];
+      X[c] = (lane == c) ? di : ((lane > c) ? -sum * di : 0.0);
+    }
+#pragma unroll
+    for (int c = 0; c < 32; ++c)
+      if (c < lane) T[(j0 + c) * P2_LD + j0 + lane] = X[c];
+  }
+  __syncthreads();
+  // ---- inverse, off-diagonal blocks, block row by block row:
+  //   W_bj = Σ_{bk=bj..bi−1} L[bi][bk]·M[bk][bj]   (one NT product of depth 32·(bi−bj): L rows and (Mᵀ) rows are both
+  //   contiguous in the summation index; the triangular block M[bj][bj] is masked),  M[bi][bj] = −M[bi][bi]·W_bj
+  for (int bi = 1; bi < 4; ++bi) {
+    const int i0 = 32 * bi;
+    const int grp = tid >> 6, t64 = tid & 63;      // 64 threads per 32×32 block: 8×8 tiles of 4×4
+    const int ty = t64 >> 3, tx = t64 & 7;
+    if (grp < bi) {
+      const int bj = grp, j0 = 32 * bj;
+      double acc[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+      // depth part 1: q in block bj (M[bj][bj] lower triangular with diagonal dinv) — masked scalar loop
+      for (int q = 0; q < 32; ++q) {
+        double a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = T[(i0 + 4 * ty + i) * P2_LD + j0 + q];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int y = 4 * tx + j;               // column of M[bj][bj]; row is q
+          b[j] = (q > y) ? T[(j0 + y) * P2_LD + j0 + q] : ((q == y) ? dinv[j0 + q] : 0.0);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+      }
+      // depth part 2: blocks bj+1 .. bi−1 (full blocks of M, stored transposed)
+      if (bi - bj > 1)
+        nt_tile_4x4(acc, T + (i0 + 4 * ty) * P2_LD + j0 + 32, P2_LD, T + (j0 + 4 * tx) * P2_LD + j0 + 32, P2_LD,
+                    32 * (bi - bj - 1));
+      double* Wg = Wb + grp * (32 * 33);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) Wg[(4 * ty + i) * 33 + 4 * tx + j] = acc[i][j];
+    }
+    __syncthreads();
+    if (grp < bi) {
+      const int bj = grp, j0 = 32 * bj;
+      const double* Wg = Wb + grp * (32 * 33);
+      double acc[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+      // M[bi][bj][x][y] = −Σ_{q<=x} M[bi][bi][x][q]·W[q][y]
+      for (int q = 0; q < 32; ++q) {
+        double a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int x = 4 * ty + i;
+          a[i] = (x > q) ? T[(i0 + q) * P2_LD + i0 + x] : ((x == q) ? dinv[i0 + q] : 0.0);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = Wg[q * 33 + 4 * tx + j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) T[(j0 + 4 * tx + j) * P2_LD + i0 + 4 * ty + i] = -acc[i][j];   // transposed store
+    }
+    __syncthreads();
+  }
+
+  // ---- outputs: L back to the workspace, M = L⁻¹ to the per-slot buffer, z = M·r, logdet, sqmah
+  double* Mg = p.Minv + (long long)s * kTile * kTile;
+  for (int idx = tid; idx < kTile * kTile; idx += P2_THREADS) {
+    const int r = idx >> 7, c = idx & 127;
+    if (c <= r) Ag[(long long)r * ld + c] = T[r * P2_LD + c];
+    Mg[idx] = (c < r) ? T[c * P2_LD + r] : ((c == r) ? dinv[r] : 0.0);
+  }
+  double zz = 0.0, lg = 0.0;
+  if (tid < kTile) {
+    double z = dinv[tid] * rk[tid];
+    for (int q = 0; q < tid; ++q) z = fma(T[q * P2_LD + tid], rk[q], z);   // M[tid][q], consecutive threads -> consecutive words
+    zz = z * z;
+    lg = log(dg[tid]);
+    p.zk[(long long)s * kTile + tid] = z;
+    p.rhs[(long long)s * p.Np + p.k0 + tid] = z;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    zz += __shfl_xor_sync(0xffffffffu, zz, o);
+    lg += __shfl_xor_sync(0xffffffffu, lg, o);
+  }
+  if (tid < kTile && lane == 0) {
+    red[warp] = zz;
+    red[4 + warp] = lg;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const double zsum = ((red[0] + red[1]) + red[2]) + red[3];
+    const double lsum = ((red[4] + red[5]) + red[6]) + red[7];
+    const double sq = p.sqmah[s] + zsum;
+    const double ldt = p.logdet[s] + 2.0 * lsum;
+    p.sqmah[s] = sq;
+    p.logdet[s] = ldt;
+    if (last) {
+      if (lnL_out) lnL_out[s] = -(ldt + sq) / 2;
+      if (info_out) info_out[s] = 0;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // small helpers
 // ------------------------------------------------------------------------------------------------
 __global__ void residual_kernel(const double* __restrict__ model_flux, const double* __restrict__ data_flux,
@@ -677,6 +969,7 @@ __global__ void __launch_bounds__(256) solve_lower_kernel(const double* __restri
 }
 
 constexpr size_t kPotrfSmem = 0;  // static shared memory only
+bool g_potrf_blocked = true;      // potrf_diag2_kernel (blocked, shared-memory resident); experiments build can switch
 
 }  // namespace
 
@@ -687,6 +980,7 @@ cudaError_t kernels_init() {
   struct Item { const void* fn; int bytes; };
   const Item items[] = {{(const void*)syrk_kernel, GEMM_SMEM_BYTES},
                         {(const void*)trsm_kernel, GEMM_SMEM_BYTES},
+                        {(const void*)potrf_diag2_kernel, (int)kPotrf2Smem},
                         {(const void*)solve_lower_kernel, 200 * 1024}};
   for (const Item& it : items) {
     cudaError_t e = cudaFuncSetAttribute(it.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, it.bytes);
@@ -694,6 +988,8 @@ cudaError_t kernels_init() {
   }
   return cudaSuccess;
 }
+
+void potrf_set_blocked(bool on) { g_potrf_blocked = on; }
 
 cudaError_t launch_residual(const double* model_flux, const double* data_flux, int N, int Np, int B,
                             double* rhs, double* resid_out, double* logdet, double* sqmah, int* info,
@@ -709,7 +1005,10 @@ cudaError_t launch_residual(const double* model_flux, const double* data_flux, i
 
 cudaError_t launch_potrf_diag(const CholParams& p, int B, int last, double* lnL_out, int* info_out,
                               cudaStream_t st) {
-  potrf_diag_kernel<<<B, PD_THREADS, kPotrfSmem, st>>>(p, last, lnL_out, info_out);
+  if (g_potrf_blocked)
+    potrf_diag2_kernel<<<B, P2_THREADS, kPotrf2Smem, st>>>(p, last, lnL_out, info_out);
+  else
+    potrf_diag_kernel<<<B, PD_THREADS, kPotrfSmem, st>>>(p, last, lnL_out, info_out);
   return cudaGetLastError();
 }
 

@@ -88,6 +88,7 @@ cudaError_t launch_copy_out_lower(double* C, int N, const double* W, int Np, lon
 cudaError_t launch_solve_lower(const double* L, long long strideL, int ldl, const double* r, double* z,
                                int N, int B, cudaStream_t st);
 cudaError_t kernels_init();  // sets max dynamic shared memory attributes
+void potrf_set_blocked(bool on);  // experiments: blocked shared-memory potrf_diag (default) or the one-sweep register kernel
 
 // ---- shared-factor path (frozen kernel groups): one factorisation of S, right-hand sides of all walkers as rows ----
 struct FwdMaps {  // TMA tensor maps over the right-hand-side rows and over the per-panel L_kk⁻¹ blocks
