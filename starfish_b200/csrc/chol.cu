@@ -116,7 +116,12 @@ struct GemmOperand {
   int slot;   // walker slot (3rd tensor coordinate)
 };
 
-template <int BM, int BN>
+// TRI = false: every warp consumes `warp_slabs` slabs.  TRI = true (trsm: B = L_kk⁻¹ is lower triangular, so output
+// column c only needs k <= c): the warp's four 8-column tiles are columns 16·wn, 16·wn+8 (need slabs 0..wn) and
+// 16·(7−wn), 16·(7−wn)+8 (need slabs 0..7−wn) — pairing column group g with 7−g gives every warp the same 9
+// half-slabs of work (the contiguous 32-column assignment left the warps with 2, 4, 6 and 8 slabs: the CTA ran at the
+// pace of the slowest and the tensor pipe at 62 %).
+template <int BM, int BN, bool TRI = false>
 __device__ __forceinline__ void gemm_mainloop(double (&acc)[4][4][2], uint8_t* smem_raw, const GemmOperand A,
                                               const GemmOperand B, int K, int warp_slabs) {
   static_assert(BM + BN == 192 && BM % 64 == 0 && BN % 64 == 0, "tile shape");
@@ -176,7 +181,11 @@ __device__ __forceinline__ void gemm_mainloop(double (&acc)[4][4][2], uint8_t* s
 
   const int rho = (g >> 1) | ((g & 1) << 2);
   const uint32_t a_off = (wm * 32 + rho) * ROW_BYTES;
-  const uint32_t b_off = (BM + wn * 32 + rho) * ROW_BYTES;
+  uint32_t b_off[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    b_off[i] = TRI ? (BM + (i < 2 ? 16 * wn : 16 * (7 - wn)) + 8 * (i & 1) + rho) * ROW_BYTES
+                   : (BM + wn * 32 + 8 * i + rho) * ROW_BYTES;
   const uint32_t x0 = (t ^ rho) << 4, x1 = ((t + 4) ^ rho) << 4;
 
   for (int it = 0; it < KT; ++it) {
@@ -186,8 +195,9 @@ __device__ __forceinline__ void gemm_mainloop(double (&acc)[4][4][2], uint8_t* s
       try_issue(false);
     }
     mbar_wait(bar_base + 8 * slot, (it / STAGES) & 1);
-    if (it < warp_slabs) {
+    if (TRI ? (it <= 7 - wn) : (it < warp_slabs)) {
       const uint32_t st = smem_base + slot * STAGE_BYTES;
+      const int nt0 = (TRI && it > wn) ? 2 : 0;   // first active column tile of this warp for this slab
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const uint32_t x = h ? x1 : x0;
@@ -195,16 +205,27 @@ __device__ __forceinline__ void gemm_mainloop(double (&acc)[4][4][2], uint8_t* s
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           a[i] = lds128(st + a_off + i * 8 * ROW_BYTES + x);
-          b[i] = lds128(st + b_off + i * 8 * ROW_BYTES + x);
+          if (!TRI || i >= 2 || nt0 == 0) b[i] = lds128(st + b_off[i] + x);
         }
+        if (!TRI || nt0 == 0) {
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt)
+          for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-          for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt].x, b[nt].x);
+            for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt].x, b[nt].x);
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt)
+          for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-          for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt].y, b[nt].y);
+            for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt].y, b[nt].y);
+        } else {
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+            for (int nt = 2; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt].x, b[nt].x);
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+            for (int nt = 2; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt].y, b[nt].y);
+        }
         if (h == 0 && tid == 0) try_issue(false);
       }
     }
@@ -307,19 +328,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wm = warp / 4, wn = warp % 4, g = lane >> 2, t = lane & 3;
   const GemmOperand opA{&tmW, p.k0, r0, slot0 + s}, opB{&tmM, 0, 0, slot0 + s};
-  gemm_mainloop<64, 128>(acc, smem_raw, opA, opB, kTile, 2 * (wn + 1));
+  gemm_mainloop<64, 128, true>(acc, smem_raw, opA, opB, kTile, 0);
 
   const int rho = (g >> 1) | ((g & 1) << 2);
-  double* Cg = Wm + (long long)(r0 + wm * 32 + rho) * ld + p.k0 + wn * 32 + t;
-  const double* zk = p.zk + (long long)s * kTile + wn * 32 + t;
+  double* Cg = Wm + (long long)(r0 + wm * 32 + rho) * ld + p.k0 + t;
+  const double* zk = p.zk + (long long)s * kTile + t;
   double part[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
   for (int nt = 0; nt < 4; ++nt) {
-    const double z0 = zk[nt * 8], z1 = zk[nt * 8 + 4];
+    const int cb = (nt < 2 ? 16 * wn : 16 * (7 - wn)) + 8 * (nt & 1);   // first column of this warp's tile nt
+    const double z0 = zk[cb], z1 = zk[cb + 4];
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt) {
-      Cg[(long long)mt * 8 * ld + nt * 8] = acc[mt][nt][0];
-      Cg[(long long)mt * 8 * ld + nt * 8 + 4] = acc[mt][nt][1];
+      Cg[(long long)mt * 8 * ld + cb] = acc[mt][nt][0];
+      Cg[(long long)mt * 8 * ld + cb + 4] = acc[mt][nt][1];
       part[mt] = fma(acc[mt][nt][0], z0, part[mt]);
       part[mt] = fma(acc[mt][nt][1], z1, part[mt]);
     }
@@ -363,16 +385,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wm = warp / 4, wn = warp % 4, g = lane >> 2, t = lane & 3;
   const GemmOperand opA{&tmZ, k0, j0, 0}, opB{&tmMall, 0, 0, panel};
-  gemm_mainloop<64, 128>(acc, smem_raw, opA, opB, kTile, 2 * (wn + 1));  // M_k is lower triangular
+  gemm_mainloop<64, 128, true>(acc, smem_raw, opA, opB, kTile, 0);  // M_k is lower triangular
   const int rho = (g >> 1) | ((g & 1) << 2);
-  double* Cg = Zt + (long long)(j0 + wm * 32 + rho) * ldz + k0 + wn * 32 + t;
+  double* Cg = Zt + (long long)(j0 + wm * 32 + rho) * ldz + k0 + t;
 #pragma unroll
-  for (int nt = 0; nt < 4; ++nt)
+  for (int nt = 0; nt < 4; ++nt) {
+    const int cb = (nt < 2 ? 16 * wn : 16 * (7 - wn)) + 8 * (nt & 1);
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt) {
-      Cg[(long long)mt * 8 * ldz + nt * 8] = acc[mt][nt][0];
-      Cg[(long long)mt * 8 * ldz + nt * 8 + 4] = acc[mt][nt][1];
+      Cg[(long long)mt * 8 * ldz + cb] = acc[mt][nt][0];
+      Cg[(long long)mt * 8 * ldz + cb + 4] = acc[mt][nt][1];
     }
+  }
 }
 
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
