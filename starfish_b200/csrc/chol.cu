@@ -20,6 +20,7 @@
 // row permutation of the fragments makes the swizzled 16-byte loads bank-conflict-free.
 #include <cuda.h>
 
+#include <cstdio>
 #include <cstdlib>
 
 #include "sfb_internal.cuh"
@@ -650,8 +651,17 @@ __device__ __forceinline__ void nt_tile_4x4(double (&acc)[4][4], const double* _
   }
 }
 
+#ifdef SFB_EXPERIMENTS   // phase timing of the first tile of a factorisation (experiments build only)
+#define P2_MARK(i) do { if (tid == 0) tph[i] = clock64(); } while (0)
+#else
+#define P2_MARK(i) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(P2_THREADS, 1) potrf_diag2_kernel(CholParams p, int last, double* lnL_out,
                                                                      int* info_out) {
+#ifdef SFB_EXPERIMENTS
+  long long tph[16];
+#endif
   extern __shared__ __align__(16) double p2_smem[];
   double* T = p2_smem;                   // [128][P2_LD]
   double* rk = T + kTile * P2_LD;        // right-hand-side slice of this panel
@@ -673,13 +683,30 @@ __global__ void __launch_bounds__(P2_THREADS, 1) potrf_diag2_kernel(CholParams p
   const long long ld = p.Np;
   double* Ag = Wm + (long long)p.k0 * ld + p.k0;
 
-  for (int idx = tid; idx < kTile * kTile; idx += P2_THREADS) {
-    const int r = idx >> 7, c = idx & 127;
-    T[r * P2_LD + c] = (c <= r) ? Ag[(long long)r * ld + c] : 0.0;
+  P2_MARK(0);
+  // thread -> (column pair, rows r0, r0+2, ...): 16 independent 16-byte loads in flight per batch
+  {
+    const int c2 = (tid & 63) * 2, rq = tid >> 6;          // columns c2, c2+1; rows rq, rq+4, ...
+#pragma unroll
+    for (int batch = 0; batch < 2; ++batch) {
+      double2 v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int r = rq + 4 * (batch * 16 + i);
+        v[i] = (c2 <= r) ? *reinterpret_cast<const double2*>(Ag + (long long)r * ld + c2) : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int r = rq + 4 * (batch * 16 + i);
+        T[r * P2_LD + c2] = v[i].x;
+        T[r * P2_LD + c2 + 1] = (c2 + 1 <= r) ? v[i].y : 0.0;
+      }
+    }
   }
   if (tid < kTile) rk[tid] = p.rhs[(long long)s * p.Np + p.k0 + tid];
   if (tid == 0) fail_col = -1;
   __syncthreads();
+  P2_MARK(1);
 
   for (int bj = 0; bj < 4; ++bj) {
     const int j0 = 32 * bj;
@@ -693,8 +720,9 @@ __global__ void __launch_bounds__(P2_THREADS, 1) potrf_diag2_kernel(CholParams p
       for (int c = 0; c < 32; ++c) {
         const double piv = __shfl_sync(0xffffffffu, a[c], c);
         if (bad < 0 && (!(piv > 0.0) || isinf(piv))) bad = c;   // also catches NaN; uniform across the warp
-        const double rs = rsqrt(piv);                            // two independent chains: 1/√piv for the scaling,
-        const double d = sqrt(piv);                              // √piv (IEEE) for the diagonal itself
+        const double rs = rsqrt(piv);                            // 1/√piv for the scaling (one MUFU chain), and
+        double d = piv * rs;                                     // √piv from it with one Newton correction
+        d = fma(0.5 * rs, fma(-d, d, piv), d);
         const double lc = (lane == c) ? d : a[c] * rs;           // column c of L (rows >= c meaningful)
         a[c] = lc;
         if (lane == c) {
@@ -716,6 +744,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) potrf_diag2_kernel(CholParams p
       }
     }
     __syncthreads();
+    if (bj == 0) P2_MARK(2);
     if (fail_col >= 0) break;
     const int nrows = kTile - j0 - 32;  // rows below the diagonal block
     // ---- S2: L[i][j0..j0+31] for the rows below, one thread per row (forward substitution against L_d)
@@ -735,6 +764,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) potrf_diag2_kernel(CholParams p
       for (int c = 0; c < 32; ++c) row[c] = x[c];
     }
     __syncthreads();
+    if (bj == 0) P2_MARK(3);
     // ---- S3: trailing update T[i][k] −= Σ_c L[i][j0+c]·L[k][j0+c], i >= k >= j0+32, 4×4 tiles of the lower triangle
     {
       const int nt4 = nrows / 4;                 // tile rows
@@ -759,7 +789,9 @@ __global__ void __launch_bounds__(P2_THREADS, 1) potrf_diag2_kernel(CholParams p
       }
     }
     __syncthreads();
+    if (bj == 0) P2_MARK(4);
   }
+  P2_MARK(5);
   if (fail_col >= 0) {
     if (tid == 0) {
       const int code = p.k0 + fail_col + 1;
@@ -798,6 +830,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) potrf_diag2_kernel(CholParams p
       if (c < lane) T[(j0 + c) * P2_LD + j0 + lane] = X[c];
   }
   __syncthreads();
+  P2_MARK(6);
   // ---- inverse, off-diagonal blocks, block row by block row:
   //   W_bj = Σ_{bk=bj..bi−1} L[bi][bk]·M[bk][bj]   (one NT product of depth 32·(bi−bj): L rows and (Mᵀ) rows are both
   //   contiguous in the summation index; the triangular block M[bj][bj] is masked),  M[bi][bj] = −M[bi][bi]·W_bj
@@ -869,6 +902,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) potrf_diag2_kernel(CholParams p
     __syncthreads();
   }
 
+  P2_MARK(7);
   // ---- outputs: L back to the workspace, M = L⁻¹ to the per-slot buffer, z = M·r, logdet, sqmah
   double* Mg = p.Minv + (long long)s * kTile * kTile;
   for (int idx = tid; idx < kTile * kTile; idx += P2_THREADS) {
@@ -876,6 +910,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) potrf_diag2_kernel(CholParams p
     if (c <= r) Ag[(long long)r * ld + c] = T[r * P2_LD + c];
     Mg[idx] = (c < r) ? T[c * P2_LD + r] : ((c == r) ? dinv[r] : 0.0);
   }
+  P2_MARK(8);
   double zz = 0.0, lg = 0.0;
   if (tid < kTile) {
     double z = dinv[tid] * rk[tid];
@@ -906,6 +941,14 @@ __global__ void __launch_bounds__(P2_THREADS, 1) potrf_diag2_kernel(CholParams p
       if (lnL_out) lnL_out[s] = -(ldt + sq) / 2;
       if (info_out) info_out[s] = 0;
     }
+#ifdef SFB_EXPERIMENTS
+    tph[9] = clock64();
+    if (s == 0 && p.k0 == 0)
+      printf("potrf_diag2 cycles: load %lld | S1(b0) %lld | S2(b0) %lld | S3(b0) %lld | blocks1-3 %lld | inv diag %lld | inv off %lld | "
+             "store %lld | z,logdet %lld | total %lld\n",
+             tph[1] - tph[0], tph[2] - tph[1], tph[3] - tph[2], tph[4] - tph[3], tph[5] - tph[4], tph[6] - tph[5],
+             tph[7] - tph[6], tph[8] - tph[7], tph[9] - tph[8], tph[9] - tph[0]);
+#endif
   }
 }
 
