@@ -765,27 +765,29 @@ __global__ void __launch_bounds__(P2_THREADS, 1) potrf_diag2_kernel(CholParams p
     }
     __syncthreads();
     if (bj == 0) P2_MARK(3);
-    // ---- S3: trailing update T[i][k] −= Σ_c L[i][j0+c]·L[k][j0+c], i >= k >= j0+32, 4×4 tiles of the lower triangle
+    // ---- S3: trailing update T[i][k] −= Σ_c L[i][j0+c]·L[k][j0+c] on the 32×32 blocks (bi, bk), bi >= bk > bj.
+    // 64 threads per block, each a 4×4 register tile with rows ty+8i and columns tx+8j: a warp's loads then touch
+    // consecutive rows of T (stride 129 doubles -> distinct banks); 4 consecutive rows per thread were 8-way conflicts.
     {
-      const int nt4 = nrows / 4;                 // tile rows
-      const int ntile = nt4 * (nt4 + 1) / 2;
-      for (int tl = tid; tl < ntile; tl += P2_THREADS) {
-        int ti = (int)((sqrtf(8.0f * (float)tl + 1.0f) - 1.0f) * 0.5f);
-        while (ti * (ti + 1) / 2 > tl) --ti;
-        while ((ti + 1) * (ti + 2) / 2 <= tl) ++ti;
-        const int tk = tl - ti * (ti + 1) / 2;
-        const int i0 = j0 + 32 + 4 * ti, k0 = j0 + 32 + 4 * tk;
+      const int nb = 3 - bj;                       // trailing blocks per side
+      const int nblk = nb * (nb + 1) / 2;
+      const int grp = tid >> 6, t64 = tid & 63, ty = t64 >> 3, tx = t64 & 7;
+      for (int bl = grp; bl < nblk; bl += 4) {
+        int bi = 0;
+        while ((bi + 1) * (bi + 2) / 2 <= bl) ++bi;
+        const int bk = bl - bi * (bi + 1) / 2;
+        const int i0 = j0 + 32 * (bi + 1), k0 = j0 + 32 * (bk + 1);
         double acc[4][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
           for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-        nt_tile_4x4(acc, T + i0 * P2_LD + j0, P2_LD, T + k0 * P2_LD + j0, P2_LD, 32);
+        nt_tile_4x4(acc, T + (i0 + ty) * P2_LD + j0, 8 * P2_LD, T + (k0 + tx) * P2_LD + j0, 8 * P2_LD, 32);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            if (k0 + j <= i0 + i) T[(i0 + i) * P2_LD + k0 + j] -= acc[i][j];
+            if (k0 + tx + 8 * j <= i0 + ty + 8 * i) T[(i0 + ty + 8 * i) * P2_LD + k0 + tx + 8 * j] -= acc[i][j];
       }
     }
     __syncthreads();
@@ -845,15 +847,18 @@ __global__ void __launch_bounds__(P2_THREADS, 1) potrf_diag2_kernel(CholParams p
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-      // depth part 1: q in block bj (M[bj][bj] lower triangular with diagonal dinv) — masked scalar loop
+      // rows x = ty + 8i of L[bi][·], columns y = tx + 8j of M[·][bj] (interleaved: conflict-free shared loads)
+      // depth part 1: q in block bj (M[bj][bj] lower triangular with diagonal dinv) — masked
       for (int q = 0; q < 32; ++q) {
         double a[4], b[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = T[(i0 + 4 * ty + i) * P2_LD + j0 + q];
+        for (int i = 0; i < 4; ++i) a[i] = T[(i0 + ty + 8 * i) * P2_LD + j0 + q];
+        const double dq = dinv[j0 + q];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int y = 4 * tx + j;               // column of M[bj][bj]; row is q
-          b[j] = (q > y) ? T[(j0 + y) * P2_LD + j0 + q] : ((q == y) ? dinv[j0 + q] : 0.0);
+          const int y = tx + 8 * j;               // column of M[bj][bj]; row is q
+          const double v = T[(j0 + y) * P2_LD + j0 + q];
+          b[j] = (q > y) ? v : ((q == y) ? dq : 0.0);
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -862,13 +867,13 @@ __global__ void __launch_bounds__(P2_THREADS, 1) potrf_diag2_kernel(CholParams p
       }
       // depth part 2: blocks bj+1 .. bi−1 (full blocks of M, stored transposed)
       if (bi - bj > 1)
-        nt_tile_4x4(acc, T + (i0 + 4 * ty) * P2_LD + j0 + 32, P2_LD, T + (j0 + 4 * tx) * P2_LD + j0 + 32, P2_LD,
+        nt_tile_4x4(acc, T + (i0 + ty) * P2_LD + j0 + 32, 8 * P2_LD, T + (j0 + tx) * P2_LD + j0 + 32, 8 * P2_LD,
                     32 * (bi - bj - 1));
       double* Wg = Wb + grp * (32 * 33);
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) Wg[(4 * ty + i) * 33 + 4 * tx + j] = acc[i][j];
+        for (int j = 0; j < 4; ++j) Wg[(ty + 8 * i) * 33 + tx + 8 * j] = acc[i][j];
     }
     __syncthreads();
     if (grp < bi) {
@@ -879,16 +884,18 @@ __global__ void __launch_bounds__(P2_THREADS, 1) potrf_diag2_kernel(CholParams p
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-      // M[bi][bj][x][y] = −Σ_{q<=x} M[bi][bi][x][q]·W[q][y]
+      // M[bi][bj][x][y] = −Σ_{q<=x} M[bi][bi][x][q]·W[q][y],  x = ty + 8i, y = tx + 8j
       for (int q = 0; q < 32; ++q) {
         double a[4], b[4];
+        const double dq = dinv[i0 + q];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int x = 4 * ty + i;
-          a[i] = (x > q) ? T[(i0 + q) * P2_LD + i0 + x] : ((x == q) ? dinv[i0 + q] : 0.0);
+          const int x = ty + 8 * i;
+          const double v = T[(i0 + q) * P2_LD + i0 + x];
+          a[i] = (x > q) ? v : ((x == q) ? dq : 0.0);
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) b[j] = Wg[q * 33 + 4 * tx + j];
+        for (int j = 0; j < 4; ++j) b[j] = Wg[q * 33 + tx + 8 * j];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -897,7 +904,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) potrf_diag2_kernel(CholParams p
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) T[(j0 + 4 * tx + j) * P2_LD + i0 + 4 * ty + i] = -acc[i][j];   // transposed store
+        for (int j = 0; j < 4; ++j) T[(j0 + tx + 8 * j) * P2_LD + i0 + ty + 8 * i] = -acc[i][j];   // transposed store
     }
     __syncthreads();
   }
