@@ -630,7 +630,7 @@ __global__ void __launch_bounds__(PD_THREADS, 1) potrf_diag_kernel(CholParams p,
 // ------------------------------------------------------------------------------------------------
 constexpr int P2_THREADS = 256;
 constexpr int P2_LD = 129;
-constexpr int P2_SMEM_DOUBLES = kTile * P2_LD + 3 * kTile + 3 * 32 * 33;
+constexpr int P2_SMEM_DOUBLES = kTile * P2_LD + 3 * kTile + 64 * 65;
 constexpr size_t kPotrf2Smem = sizeof(double) * P2_SMEM_DOUBLES;
 
 // acc[4][4] += Σ_{q<K} A[(4·ty+a)·lda + q] · B[(4·tx+b)·ldb + q]   (both operands contiguous in q)
@@ -667,7 +667,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) potrf_diag2_kernel(CholParams p
   double* rk = T + kTile * P2_LD;        // right-hand-side slice of this panel
   double* dinv = rk + kTile;             // 1 / L_jj
   double* dg = dinv + kTile;             // L_jj
-  double* Wb = dg + kTile;               // 3 scratch blocks [32][33] for the inverse assembly
+  double* Wb = dg + kTile;               // scratch: column buffers of S1, then [64][65] for the inverse assembly
   __shared__ int fail_col;
   __shared__ double red[16];
   const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -716,6 +716,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) potrf_diag2_kernel(CholParams p
 #pragma unroll
       for (int c = 0; c < 32; ++c) a[c] = T[(j0 + lane) * P2_LD + j0 + c];
       int bad = -1;
+      double* colb = Wb;   // two 32-double column buffers (parity of c): column c of L_d, published for the warp
 #pragma unroll
       for (int c = 0; c < 32; ++c) {
         const double piv = __shfl_sync(0xffffffffu, a[c], c);
@@ -729,11 +730,13 @@ __global__ void __launch_bounds__(P2_THREADS, 1) potrf_diag2_kernel(CholParams p
           dinv[j0 + c] = rs;
           dg[j0 + c] = d;
         }
+        // L[c2][c] for every c2 > c: one shared-memory broadcast read each (the shuffle version issued 62 SHFL per
+        // column and was bound by their throughput: 312 cycles per column)
+        double* cb = colb + 32 * (c & 1);
+        cb[lane] = lc;
+        __syncwarp();
 #pragma unroll
-        for (int c2 = c + 1; c2 < 32; ++c2) {
-          const double other = __shfl_sync(0xffffffffu, lc, c2);  // L[c2][c]
-          a[c2] = fma(-lc, other, a[c2]);                          // meaningful for lane >= c2
-        }
+        for (int c2 = c + 1; c2 < 32; ++c2) a[c2] = fma(-lc, cb[c2], a[c2]);   // meaningful for lane >= c2
       }
       if (bad >= 0) {
         if (lane == 0) fail_col = j0 + bad;
@@ -811,103 +814,141 @@ __global__ void __launch_bounds__(P2_THREADS, 1) potrf_diag2_kernel(CholParams p
   // strict upper triangle of T
   if (warp < 4) {
     const int j0 = 32 * warp;
-    double Lr[32], X[32];
-#pragma unroll
-    for (int c = 0; c < 32; ++c) Lr[c] = T[(j0 + lane) * P2_LD + j0 + c];   // row `lane` of L_d (c <= lane meaningful)
+    double X[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) X[c] = 0.0;
 #pragma unroll
     for (int c = 31; c >= 0; --c) {
       double sum = 0.0;
 #pragma unroll
-      for (int m = c + 1; m < 32; ++m) {
-        const double lmc = __shfl_sync(0xffffffffu, Lr[c], m);   // L[m][c]
-        sum = fma(X[m], lmc, sum);                               // X[l][m] is zero for m > l
-      }
+      for (int m = c + 1; m < 32; ++m)
+        sum = fma(X[m], T[(j0 + m) * P2_LD + j0 + c], sum);     // L[m][c]: broadcast read; X[l][m] is zero for m > l
       const double di = dinv[j0 + c];
       X[c] = (lane == c) ? di : ((lane > c) ? -sum * di : 0.0);
     }
+    __syncwarp();   // every lane has read L_d's column entries it needs before the transposed stores below
 #pragma unroll
     for (int c = 0; c < 32; ++c)
       if (c < lane) T[(j0 + c) * P2_LD + j0 + lane] = X[c];
   }
   __syncthreads();
   P2_MARK(6);
-  // ---- inverse, off-diagonal blocks, block row by block row:
-  //   W_bj = Σ_{bk=bj..bi−1} L[bi][bk]·M[bk][bj]   (one NT product of depth 32·(bi−bj): L rows and (Mᵀ) rows are both
-  //   contiguous in the summation index; the triangular block M[bj][bj] is masked),  M[bi][bj] = −M[bi][bi]·W_bj
-  for (int bi = 1; bi < 4; ++bi) {
-    const int i0 = 32 * bi;
-    const int grp = tid >> 6, t64 = tid & 63;      // 64 threads per 32×32 block: 8×8 tiles of 4×4
-    const int ty = t64 >> 3, tx = t64 & 7;
-    if (grp < bi) {
-      const int bj = grp, j0 = 32 * bj;
-      double acc[4][4];
+  // ---- inverse, off-diagonal part, by recursive halving (every level uses the whole CTA):
+  //   L = [[L1, 0], [B, L2]]  =>  L⁻¹ = [[M1, 0], [−M2·B·M1, M2]]
+  // level 1: inside each 64×64 half, the 32×32 block below the diagonal (two halves side by side, 128 threads each);
+  // level 2: the 64×64 block M[64..127][0..63] = −M2·(B·M1), all 256 threads, 4×4 register tiles.
+  // Register tiles are interleaved (rows ty + 8i or 16i, columns tx + 16j) so that a warp's shared-memory loads
+  // touch consecutive rows / words: no bank conflicts.  M[r][c] (r > c) lives at T[c][r]; its diagonal is dinv.
+  {
+    const int h = tid >> 7, t128 = tid & 127, ty = t128 >> 4, tx = t128 & 15;
+    const int j0 = 64 * h, i0 = j0 + 32;
+    double* Wh = Wb + h * (32 * 33);
+    double acc[4][2];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = 0.0;
+    for (int q = 0; q < 32; ++q) {            // W = L[i0.., j0..]·M[j0.., j0..]   (M lower triangular)
+      double a[4], bb[2];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-      // rows x = ty + 8i of L[bi][·], columns y = tx + 8j of M[·][bj] (interleaved: conflict-free shared loads)
-      // depth part 1: q in block bj (M[bj][bj] lower triangular with diagonal dinv) — masked
-      for (int q = 0; q < 32; ++q) {
-        double a[4], b[4];
+      for (int i = 0; i < 4; ++i) a[i] = T[(i0 + ty + 8 * i) * P2_LD + j0 + q];
+      const double dq = dinv[j0 + q];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = T[(i0 + ty + 8 * i) * P2_LD + j0 + q];
-        const double dq = dinv[j0 + q];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int y = tx + 8 * j;               // column of M[bj][bj]; row is q
-          const double v = T[(j0 + y) * P2_LD + j0 + q];
-          b[j] = (q > y) ? v : ((q == y) ? dq : 0.0);
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
-      }
-      // depth part 2: blocks bj+1 .. bi−1 (full blocks of M, stored transposed)
-      if (bi - bj > 1)
-        nt_tile_4x4(acc, T + (i0 + ty) * P2_LD + j0 + 32, 8 * P2_LD, T + (j0 + tx) * P2_LD + j0 + 32, 8 * P2_LD,
-                    32 * (bi - bj - 1));
-      double* Wg = Wb + grp * (32 * 33);
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) Wg[(ty + 8 * i) * 33 + tx + 8 * j] = acc[i][j];
-    }
-    __syncthreads();
-    if (grp < bi) {
-      const int bj = grp, j0 = 32 * bj;
-      const double* Wg = Wb + grp * (32 * 33);
-      double acc[4][4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-      // M[bi][bj][x][y] = −Σ_{q<=x} M[bi][bi][x][q]·W[q][y],  x = ty + 8i, y = tx + 8j
-      for (int q = 0; q < 32; ++q) {
-        double a[4], b[4];
-        const double dq = dinv[i0 + q];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int x = ty + 8 * i;
-          const double v = T[(i0 + q) * P2_LD + i0 + x];
-          a[i] = (x > q) ? v : ((x == q) ? dq : 0.0);
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) b[j] = Wg[q * 33 + tx + 8 * j];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+      for (int j = 0; j < 2; ++j) {
+        const int y = tx + 16 * j;
+        const double v = T[(j0 + y) * P2_LD + j0 + q];
+        bb[j] = (q > y) ? v : ((q == y) ? dq : 0.0);
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 4; ++i) {
+        acc[i][0] = fma(a[i], bb[0], acc[i][0]);
+        acc[i][1] = fma(a[i], bb[1], acc[i][1]);
+      }
+    }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) T[(j0 + tx + 8 * j) * P2_LD + i0 + ty + 8 * i] = -acc[i][j];   // transposed store
+    for (int i = 0; i < 4; ++i) {
+      Wh[(ty + 8 * i) * 33 + tx] = acc[i][0];
+      Wh[(ty + 8 * i) * 33 + tx + 16] = acc[i][1];
     }
     __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = 0.0;
+    for (int q = 0; q < 32; ++q) {            // M[i0+x][j0+y] = −Σ_{q<=x} M[i0+x][i0+q]·W[q][y]
+      double a[4];
+      const double dq = dinv[i0 + q];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int x = ty + 8 * i;
+        const double v = T[(i0 + q) * P2_LD + i0 + x];
+        a[i] = (x > q) ? v : ((x == q) ? dq : 0.0);
+      }
+      const double b0 = Wh[q * 33 + tx], b1 = Wh[q * 33 + tx + 16];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        acc[i][0] = fma(a[i], b0, acc[i][0]);
+        acc[i][1] = fma(a[i], b1, acc[i][1]);
+      }
+    }
+    __syncthreads();   // all reads of the diagonal blocks' stored inverses done before the stores below? (disjoint blocks: kept for the scratch reuse)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      T[(j0 + tx) * P2_LD + i0 + ty + 8 * i] = -acc[i][0];
+      T[(j0 + tx + 16) * P2_LD + i0 + ty + 8 * i] = -acc[i][1];
+    }
   }
+  __syncthreads();
+  {
+    const int ty = tid >> 4, tx = tid & 15;     // rows x = ty + 16i, columns y = tx + 16j of the 64×64 block
+    double acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+    for (int q = 0; q < 64; ++q) {              // W2 = B·M1,  B = L[64.., 0..63],  M1 lower triangular
+      double a[4], bb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = T[(64 + ty + 16 * i) * P2_LD + q];
+      const double dq = dinv[q];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int y = tx + 16 * j;
+        const double v = T[y * P2_LD + q];
+        bb[j] = (q > y) ? v : ((q == y) ? dq : 0.0);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], bb[j], acc[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) Wb[(ty + 16 * i) * 65 + tx + 16 * j] = acc[i][j];
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+    for (int q = 0; q < 64; ++q) {              // M[64+x][y] = −Σ_{q<=x} M2[x][q]·W2[q][y]
+      double a[4], bb[4];
+      const double dq = dinv[64 + q];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int x = ty + 16 * i;
+        const double v = T[(64 + q) * P2_LD + 64 + x];
+        a[i] = (x > q) ? v : ((x == q) ? dq : 0.0);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bb[j] = Wb[q * 65 + tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], bb[j], acc[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) T[(tx + 16 * j) * P2_LD + 64 + ty + 16 * i] = -acc[i][j];   // transposed store
+  }
+  __syncthreads();
 
   P2_MARK(7);
   // ---- outputs: L back to the workspace, M = L⁻¹ to the per-slot buffer, z = M·r, logdet, sqmah
