@@ -846,6 +846,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) potrf_diag2_kernel(CholParams p
     double acc[4][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = 0.0;
+#pragma unroll 4
     for (int q = 0; q < 32; ++q) {            // W = L[i0.., j0..]·M[j0.., j0..]   (M lower triangular)
       double a[4], bb[2];
 #pragma unroll
@@ -871,6 +872,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) potrf_diag2_kernel(CholParams p
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = 0.0;
+#pragma unroll 4
     for (int q = 0; q < 32; ++q) {            // M[i0+x][j0+y] = −Σ_{q<=x} M[i0+x][i0+q]·W[q][y]
       double a[4];
       const double dq = dinv[i0 + q];
@@ -902,6 +904,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) potrf_diag2_kernel(CholParams p
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+#pragma unroll 4
     for (int q = 0; q < 64; ++q) {              // W2 = B·M1,  B = L[64.., 0..63],  M1 lower triangular
       double a[4], bb[4];
 #pragma unroll
@@ -927,6 +930,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) potrf_diag2_kernel(CholParams p
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+#pragma unroll 4
     for (int q = 0; q < 64; ++q) {              // M[64+x][y] = −Σ_{q<=x} M2[x][q]·W2[q][y]
       double a[4], bb[4];
       const double dq = dinv[64 + q];
