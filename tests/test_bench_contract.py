@@ -29,8 +29,8 @@ def test_reference_arm_json_line():
 
 
 def test_committed_b200_line_has_the_contract_keys():
-    """A default `python bench.py` line measured on a B200 in round 2 (profiles/r2e_bench.json)."""
-    d = json.load(open(os.path.join(ROOT, "profiles", "r2e_bench.json")))
+    """A default `python bench.py` line measured on a B200 in round 2 (profiles/r2r_bench.json)."""
+    d = json.load(open(os.path.join(ROOT, "profiles", "r2r_bench.json")))
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
         assert k in d, k
@@ -38,6 +38,8 @@ def test_committed_b200_line_has_the_contract_keys():
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
     assert d["parity"]["ok"] and d["parity"]["max_rel_vs_dense_oracle"] <= 1e-10 and d["parity"]["walkers"] >= 8
     assert set(d["configs"]) == {"configs[1]", "configs[4]"} and d["e2e"]["steps"] >= 10
+    assert d["frozen_shared"]["max_rel_diff_vs_per_walker_factorisation"] <= 1e-10
+    assert d["roofline"]["traffic"] and 0 < d["roofline"]["int8_mma_issued_frac"] <= 1
     r = d["roofline"]
     assert r["bound"] in ("hbm", "tensor") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
