@@ -455,6 +455,155 @@ void run_ts(int sms) {
   printf("chip TS 128x64x32 i8 on %d SMs: %.2f ms -> %.1f TOP/s\n", sms, ms, 2.0 * 128 * N * 32 * 26.0 * big * sms / ms * 1e-9);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// CTA pair (cta_group::2): one MMA of M = 256 (128 rows from each CTA's shared memory) x N = 64 (32 B rows from each
+// CTA) x K = 32, issued by the leader CTA; accumulators in each CTA's own TMEM.  Correctness against the CPU GEMM and
+// the dispatch pace of the 26-pair issue pattern.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_i8_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+    pair_kernel(const int8_t* A /*256x32*/, const int8_t* B /*64x32*/, int32_t* D /*256x64*/, int chunks, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t rank = cluster_ctarank();
+  const Variant v{6, 32, 1, 256, 16, 1};
+  // per CTA: A rows 128*rank.., B rows 32*rank..  (same shared-memory offsets in both CTAs)
+  uint8_t* sA = smem;            // 6 slabs of 4 KB (only slab 0 carries the test data; the others feed the pace loop)
+  uint8_t* sB = smem + 6 * 4096; // 6 slabs of 1 KB
+  for (int i = tid; i < 6 * 4096 + 6 * 1024; i += blockDim.x) smem[i] = (uint8_t)(i * 5 + 1);
+  __syncthreads();
+  for (int i = tid; i < 128 * 32; i += blockDim.x) sA[slab_off(v, i / 32, i % 32)] = (uint8_t)A[(128 * rank + i / 32) * 32 + i % 32];
+  for (int i = tid; i < 32 * 32; i += blockDim.x) sB[slab_off(v, i / 32, i % 32)] = (uint8_t)B[(32 * rank + i / 32) * 32 + i % 32];
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (tid == 0) {
+    mbar_init(smem_u32(&bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc2(smem_u32(&tmem_base), 512);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tb = tmem_base;
+  const uint32_t idesc = make_idesc_i8(256, 64);
+  long long t0 = 0;
+  if (rank == 0 && warp == 1) {
+    const bool leader = elect_one();
+    if (leader) umma_i8_2cta(tb, make_desc(smem_u32(sA), 16, 256, 6), make_desc(smem_u32(sB), 16, 256, 6), idesc, 0);
+    t0 = clock64();
+    for (int c = 0; c < chunks; ++c) {   // pace: 26-pair pattern into accumulators 1..6 (accumulator 0 keeps the test result)
+      if (leader) {
+#pragma unroll
+        for (int sa = 0; sa < 6; ++sa)
+#pragma unroll
+          for (int sb = 0; sb < 6; ++sb) {
+            if (sa + sb >= 7) continue;
+            umma_i8_2cta(tb + (uint32_t)(1 + (sa + sb) % 6) * 64, make_desc(smem_u32(sA) + sa * 4096, 16, 256, 6),
+                         make_desc(smem_u32(sB) + sb * 1024, 16, 256, 6), idesc, 1);
+          }
+      }
+      __syncwarp();
+    }
+    if (leader) umma_commit_2cta(smem_u32(&bar));
+    __syncwarp();
+  }
+  mbar_wait(smem_u32(&bar), 0);
+  if (rank == 0 && tid == 32) out[0] = clock64() - t0;
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  for (int c0 = 0; c0 < 64; c0 += 16) {
+    uint32_t r[16];
+    tmem_ld16(tb + ((uint32_t)(warp * 32) << 16) + c0, r);
+    tmem_ld_wait();
+    for (int j = 0; j < 16; ++j) D[(size_t)(128 * rank + tid) * 64 + c0 + j] = (int32_t)r[j];
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();
+  if (warp == 0) tmem_dealloc2(tb, 512);
+}
+
+void run_pair(int sms) {
+  std::vector<int8_t> A(256 * 32), B(64 * 32);
+  srand(99);
+  for (auto& x : A) x = (int8_t)(rand() % 256 - 128);
+  for (auto& x : B) x = (int8_t)(rand() % 256 - 128);
+  int8_t *dA, *dB;
+  int32_t* dD;
+  long long* dout;
+  CK(cudaMalloc(&dA, A.size()));
+  CK(cudaMalloc(&dB, B.size()));
+  CK(cudaMalloc(&dD, sizeof(int32_t) * 256 * 64));
+  CK(cudaMalloc(&dout, 64));
+  CK(cudaMemcpy(dA, A.data(), A.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, B.data(), B.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemset(dD, 0xff, sizeof(int32_t) * 256 * 64));
+  CK(cudaFuncSetAttribute(pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  const int chunks = 256;
+  pair_kernel<<<2, 128, 32 * 1024>>>(dA, dB, dD, chunks, dout);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    printf("cta_group::2: CUDA error %s\n", cudaGetErrorString(e));
+    exit(1);
+  }
+  std::vector<int32_t> D(256 * 64);
+  long long h[1];
+  CK(cudaMemcpy(D.data(), dD, sizeof(int32_t) * 256 * 64, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(h, dout, 8, cudaMemcpyDeviceToHost));
+  long long bad = 0;
+  for (int i = 0; i < 256; ++i)
+    for (int j = 0; j < 64; ++j) {
+      int32_t ref = 0;
+      for (int k = 0; k < 32; ++k) ref += (int32_t)A[i * 32 + k] * (int32_t)B[j * 32 + k];
+      if (ref != D[i * 64 + j]) ++bad;
+    }
+  printf("cta_group::2 MMA 256x64x32 i8 (A rows 128/CTA, B rows 32/CTA): %s (%lld mismatches of %d)\n", bad ? "WRONG" : "exact", bad,
+         256 * 64);
+  printf("pace cta_group::2 256x64x32 i8, 26-pair pattern: %.1f cycles per MMA = %.1f per 128x64x32 equivalent (1-CTA SS form: 52.4)\n",
+         (double)h[0] / (chunks * 26.0), (double)h[0] / (chunks * 26.0) / 2);
+  cudaEvent_t a, b;
+  CK(cudaEventCreate(&a));
+  CK(cudaEventCreate(&b));
+  const int big = 40000, nblk = sms & ~1;
+  pair_kernel<<<nblk, 128, 32 * 1024>>>(dA, dB, dD, 100, dout);
+  CK(cudaEventRecord(a));
+  pair_kernel<<<nblk, 128, 32 * 1024>>>(dA, dB, dD, big, dout);
+  CK(cudaEventRecord(b));
+  CK(cudaDeviceSynchronize());
+  float ms;
+  CK(cudaEventElapsedTime(&ms, a, b));
+  printf("chip cta_group::2 256x64x32 i8 on %d SMs: %.2f ms -> %.1f TOP/s\n", nblk, ms,
+         2.0 * 256 * 64 * 32 * 26.0 * big * (nblk / 2) / ms * 1e-9);
+}
+
 int main() {
   int dev = 0;
   CK(cudaSetDevice(dev));
@@ -512,6 +661,7 @@ int main() {
     cudaFree(dA); cudaFree(dB); cudaFree(dD);
   }
 
+  run_pair(prop.multiProcessorCount);
   run_ts(prop.multiProcessorCount);
   run_pace<64>(prop.multiProcessorCount);
   run_pace<128>(prop.multiProcessorCount);
