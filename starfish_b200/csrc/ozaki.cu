@@ -142,6 +142,22 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// registers -> TMEM: lane i of the warp writes 16 consecutive 32-bit columns of TMEM lane (quarter base + i)  (SASS STTM)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint4& a, const uint4& b, const uint4& c, const uint4& d) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w), "r"(c.x), "r"(c.y), "r"(c.z), "r"(c.w),
+      "r"(d.x), "r"(d.y), "r"(d.z), "r"(d.w)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
 // UMMA shared-memory matrix descriptor, K-major, SWIZZLE_32B (layout code 6), descriptor version 1:
 // start address, LBO (unused for swizzled K-major; canonical value 1) and SBO in 16-byte units.
@@ -229,6 +245,76 @@ __device__ __forceinline__ uint32_t oz_issue_chunk(uint32_t fa, uint32_t fb, uin
   }
   touched |= local;
   return n;
+}
+
+// ---- epilogue (4 warps; warp q owns tile rows 32q..32q+31 = its TMEM lane quarter).
+// Two thread mappings: TMEM hands a thread ONE ROW (lane = row, 16 columns per load), global memory wants a
+// warp on one row (lane = column pair, 512 contiguous bytes).  The C tile is therefore fetched in the global
+// mapping BEFORE the accumulators are ready (32 independent 16-byte loads per thread, in flight under the
+// main loop), the recombined update goes through a warp-private transpose buffer, the accumulators are handed
+// back to the MMA warp, and the read-modify-write finishes with coalesced streaming stores while the next
+// tile's MMAs already run.
+__device__ __forceinline__ void oz_epilogue(const CholParams& p, const OzParams& oz, int s, int l0, int l1, int jt0, int njt,
+                                            int strip, uint32_t tmem, uint32_t tbuf0, int q, int lane, uint32_t meta,
+                                            uint32_t accfull, uint32_t tmem_empty, const volatile uint32_t* touched_p) {
+  const double* rs = oz.rscale + (long long)s * p.Np;
+  const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+  const uint32_t tbuf = tbuf0 + (uint32_t)q * (32 * OZ_TROW);
+  int k = 0;
+  for (int l = l0; l < l1; ++l) {
+    const OzTile t = oz_tile(l, jt0, njt, strip);
+    if (!t.live) continue;
+    const double ri = rs[t.r0 + q * 32 + lane];                                         // row scale, TMEM mapping
+    const double2 rj = *reinterpret_cast<const double2*>(rs + t.c0 + 2 * lane);        // column scales, global mapping
+    double* Cw = p.W + (long long)s * p.strideW + (long long)(t.r0 + q * 32) * p.Np + t.c0 + 2 * lane;
+    double2 creg[32];
+#pragma unroll
+    for (int r = 0; r < 32; ++r) creg[r] = __ldcs(reinterpret_cast<const double2*>(Cw + (long long)r * p.Np));
+    mbar_wait(meta, k & 1);
+    const uint32_t touched = *touched_p;
+    mbar_wait(accfull, k & 1);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+    for (int cb = 0; cb < OZ_BN / 16; ++cb) {
+      double acc[16];
+      uint32_t v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] = 0.0;
+#pragma unroll
+      for (int d = OZ_NACC - 1; d >= 0; --d) {   // Horner from the least significant anti-diagonal
+        if ((touched >> d) & 1u) {
+          tmem_ld16(tlane + d * OZ_BN + cb * 16, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] = fma(acc[j], 0.00390625, i2d(v[j]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] *= 0.00390625;
+        }
+      }
+      const uint32_t dst = tbuf + (uint32_t)lane * OZ_TROW + (uint32_t)cb * 128;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(dst + 16 * j), "d"(acc[2 * j] * ri), "d"(acc[2 * j + 1] * ri)
+                     : "memory");
+    }
+    // accumulators drained: hand TMEM back to the MMA warp (which orders its next MMAs after this arrive)
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tmem_empty);
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+      double tx, ty;
+      asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(tx), "=d"(ty) : "r"(tbuf + (uint32_t)r * OZ_TROW + 16 * lane) : "memory");
+      double2 c = creg[r];
+      c.x = fma(-tx, rj.x, c.x);
+      c.y = fma(-ty, rj.y, c.y);
+      __stcs(reinterpret_cast<double2*>(Cw + (long long)r * p.Np), c);
+    }
+    __syncwarp();  // the transpose buffer is rewritten by the next tile
+    ++k;
+  }
+
 }
 
 template <bool TS>
@@ -347,75 +433,240 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
       atomicAdd(oz.stats + 1, (unsigned long long)k * nch * 26ull);
     }
   } else {
-    // ---- epilogue (4 warps; warp q owns tile rows 32q..32q+31 = its TMEM lane quarter).
-    // Two thread mappings: TMEM hands a thread ONE ROW (lane = row, 16 columns per load), global memory wants a
-    // warp on one row (lane = column pair, 512 contiguous bytes).  The C tile is therefore fetched in the global
-    // mapping BEFORE the accumulators are ready (32 independent 16-byte loads per thread, in flight under the
-    // main loop), the recombined update goes through a warp-private transpose buffer, the accumulators are handed
-    // back to the MMA warp, and the read-modify-write finishes with coalesced streaming stores while the next
-    // tile's MMAs already run.
-    const int q = warp & 3;
-    const double* rs = oz.rscale + (long long)s * p.Np;
-    const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
-    const uint32_t tbuf = tbuf0 + (uint32_t)q * (32 * OZ_TROW);
-    int k = 0;
-    for (int l = l0; l < l1; ++l) {
-      const OzTile t = oz_tile(l, jt0, njt, strip);
-      if (!t.live) continue;
-      const double ri = rs[t.r0 + q * 32 + lane];                                         // row scale, TMEM mapping
-      const double2 rj = *reinterpret_cast<const double2*>(rs + t.c0 + 2 * lane);        // column scales, global mapping
-      double* Cw = p.W + (long long)s * p.strideW + (long long)(t.r0 + q * 32) * p.Np + t.c0 + 2 * lane;
-      double2 creg[32];
-#pragma unroll
-      for (int r = 0; r < 32; ++r) creg[r] = __ldcs(reinterpret_cast<const double2*>(Cw + (long long)r * p.Np));
-      mbar_wait(meta, k & 1);
-      const uint32_t touched = touched_s;
-      mbar_wait(accfull, k & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-      for (int cb = 0; cb < OZ_BN / 16; ++cb) {
-        double acc[16];
-        uint32_t v[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = 0.0;
-#pragma unroll
-        for (int d = OZ_NACC - 1; d >= 0; --d) {   // Horner from the least significant anti-diagonal
-          if ((touched >> d) & 1u) {
-            tmem_ld16(tlane + d * OZ_BN + cb * 16, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 16; ++j) acc[j] = fma(acc[j], 0.00390625, i2d(v[j]));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) acc[j] *= 0.00390625;
-          }
-        }
-        const uint32_t dst = tbuf + (uint32_t)lane * OZ_TROW + (uint32_t)cb * 128;
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(dst + 16 * j), "d"(acc[2 * j] * ri), "d"(acc[2 * j + 1] * ri)
-                       : "memory");
-      }
-      // accumulators drained: hand TMEM back to the MMA warp (which orders its next MMAs after this arrive)
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty);
-#pragma unroll
-      for (int r = 0; r < 32; ++r) {
-        double tx, ty;
-        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(tx), "=d"(ty) : "r"(tbuf + (uint32_t)r * OZ_TROW + 16 * lane) : "memory");
-        double2 c = creg[r];
-        c.x = fma(-tx, rj.x, c.x);
-        c.y = fma(-ty, rj.y, c.y);
-        __stcs(reinterpret_cast<double2*>(Cw + (long long)r * p.Np), c);
-      }
-      __syncwarp();  // the transpose buffer is rewritten by the next tile
-      ++k;
-    }
+    oz_epilogue(p, oz, s, l0, l1, jt0, njt, strip, tmem, tbuf0, warp & 3, lane, meta, accfull, tmem_empty, &touched_s);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, OZ_TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// The same update with the A operand fed to TMEM by LOADER WARPS (registers -> TMEM, tcgen05.st) instead of
+// tcgen05.cp.  Why: the 128×64×32 int8 MMA needs 32 tensor cycles, but with both operands in shared memory it reads
+// 6 KB per MMA (48 cycles at 128 B/clk), and the TS form of syrk_i8_kernel pays 6 × 4 KB of tcgen05.cp per chunk at
+// 64 B/clk IN the tensor pipe's issue order (26·32 + 384 cycles per chunk = 46.8 per MMA; measured 48.2,
+// tools/exp/umma_i8_probe.cu).  A register -> TMEM store runs beside the MMAs (256 B/clk), so the issue stream holds
+// MMAs only and the tensor pipe sees its 32-cycle floor; shared memory carries B (2 KB per MMA) plus one LDS pass
+// over A (24 KB per chunk): 76 of the 106 KB a chunk's 832 cycles can deliver.
+//
+// TMEM: 7 accumulators × 64 columns, then a ring of four 16-column A buffers (448..511); a buffer holds TWO digit
+// slabs (8 columns each).  The slabs of a chunk are paired {0,5}, {1,4}, {2,3} — 8, 9 and 9 of the 26 MMAs — so the
+// MMA warp consumes a buffer every ≈ 280 cycles and the loaders may run three buffers ahead.
+// Warp groups (setmaxnreg needs aligned groups of four warps): 0-3 epilogue (240 registers), 4-7 loaders — thread =
+// operand row = TMEM lane, 12 conflict-free 16-byte shared loads and three 16-column stores per chunk —, 8 = bulk-copy
+// producer, 9 = MMA issuer, 10-11 idle.
+// Barriers: full/empty per stage (empty = 1 commit of the MMA warp + the 4 loader warps), afull/aempty per A buffer.
+// ------------------------------------------------------------------------------------------------
+constexpr int OZ_ST_THREADS = 384;
+constexpr int OZ_ABUF = 4;                       // TMEM A buffers of 16 columns
+constexpr int OZ_NBARS_ST = 2 * OZ_STAGES + 2 * OZ_ABUF + 3;
+
+// MMAs of one slab pair PR = {PR, 5−PR}; A from the TMEM buffer at column `acol`
+template <int PR>
+__device__ __forceinline__ uint32_t oz_issue_pair(uint32_t fa, uint32_t fb, uint32_t& touched, uint32_t tmem, uint32_t acol,
+                                                  uint64_t bd0) {
+  uint32_t local = 0, n = 0;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int sa = h ? 5 - PR : PR;
+    if (!((fa >> sa) & 1u)) continue;
+#pragma unroll
+    for (int sb = 0; sb < OZ_S; ++sb) {
+      if (sa + sb >= OZ_NACC) continue;
+      if (!((fb >> sb) & 1u)) continue;
+      const uint32_t d = sa + sb;
+      const uint32_t acc = ((touched | local) >> d) & 1u;
+      umma_i8_ts(tmem + d * OZ_BN, acol + h * (OZ_KC / 4), bd0 + (uint64_t)(sb * (OZ_GROUP_BYTES >> 4)), OZ_IDESC, acc);
+      local |= 1u << d;
+      ++n;
+    }
+  }
+  touched |= local;
+  return n;
+}
+template <int PR>
+__device__ __forceinline__ uint32_t oz_issue_pair_dispatch(uint32_t fa, uint32_t fb, uint32_t& touched, uint32_t tmem,
+                                                           uint32_t acol, uint64_t bd0) {
+  // compile-time masks for the dominant digit patterns (see syrk_i8_kernel)
+  if (fa == 0x3fu && fb == 0x3fu) return oz_issue_pair<PR>(0x3fu, 0x3fu, touched, tmem, acol, bd0);
+  if (fa == 0x3eu && fb == 0x3eu) return oz_issue_pair<PR>(0x3eu, 0x3eu, touched, tmem, acol, bd0);
+  if (fa == 0x3eu && fb == 0x3fu) return oz_issue_pair<PR>(0x3eu, 0x3fu, touched, tmem, acol, bd0);
+  if (fa == 0x3fu && fb == 0x3eu) return oz_issue_pair<PR>(0x3fu, 0x3eu, touched, tmem, acol, bd0);
+  return oz_issue_pair<PR>(fa, fb, touched, tmem, acol, bd0);
+}
+
+__global__ void __launch_bounds__(OZ_ST_THREADS, 1)
+    syrk_i8_st_kernel(CholParams p, OzParams oz, int nch, int jt0, int njt, int strip, int ntiles, int tpc) {
+  const int s = blockIdx.z;
+  if (p.info[s] != 0) return;
+  const int l0 = blockIdx.x * tpc;
+  const int l1 = min(ntiles, l0 + tpc);
+
+  extern __shared__ uint8_t oz_smem_raw[];
+  __shared__ uint64_t bars[OZ_NBARS_ST];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ uint32_t touched_s;
+  const uint32_t ring = (smem_u32(oz_smem_raw) + 1023u) & ~1023u;
+  const uint32_t tbuf0 = ring + OZ_STAGES * OZ_STAGE_BYTES;
+  const uint32_t bar0 = smem_u32(bars);                       // full[s] at +8s, empty[s] at +8(STAGES+s)
+  const uint32_t afull0 = bar0 + 16 * OZ_STAGES;              // afull[i] at +8i, aempty[i] at +8(ABUF+i)
+  const uint32_t aempty0 = afull0 + 8 * OZ_ABUF;
+  const uint32_t accfull = aempty0 + 8 * OZ_ABUF, tmem_empty = accfull + 8, meta = accfull + 16;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < OZ_STAGES; ++i) {
+      mbar_init(bar0 + 8 * i, 1);
+      mbar_init(bar0 + 8 * (OZ_STAGES + i), 5);  // the MMA warp's commit + the four loader warps
+    }
+#pragma unroll
+    for (int i = 0; i < OZ_ABUF; ++i) {
+      mbar_init(afull0 + 8 * i, 4);              // one arrival per loader warp
+      mbar_init(aempty0 + 8 * i, 1);
+    }
+    mbar_init(accfull, 1);
+    mbar_init(tmem_empty, 4);
+    mbar_init(meta, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 9) tmem_alloc(smem_u32(&tmem_base_s), OZ_TMEM_COLS);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+
+  const int8_t* Ps = oz.P + (long long)s * oz.strideP;
+  const long long chunk_bytes = (long long)(p.Np / 8) * OZ_ROWGROUP_BYTES;
+
+  if (warp < 4) {
+    setmaxnreg_inc<240>();
+    oz_epilogue(p, oz, s, l0, l1, jt0, njt, strip, tmem, tbuf0, warp, lane, meta, accfull, tmem_empty, &touched_s);
+  } else if (warp < 8) {
+    setmaxnreg_dec<96>();
+    // ---- loaders: thread = row of the A tile = TMEM lane.  The two 16-byte halves of a row sit swapped in shared
+    // memory for rows 4-7 of a group (32-byte swizzle); reading the LOGICAL halves in order makes the eight lanes of
+    // a quarter-warp cover all 32 banks (the physical order would put rows r and r+4 on the same banks).
+    const int q = warp & 3, row = q * 32 + lane;
+    const uint32_t aoff = (uint32_t)(row >> 3) * OZ_ROWGROUP_BYTES + (uint32_t)(row & 7) * OZ_KC;
+    const uint32_t h0 = (uint32_t)((row & 7) >> 2) * 16, h1 = h0 ^ 16;
+    const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16) + OZ_TMEM_A;
+    int g = 0, ga = 0;  // chunks, A buffers handled so far
+    for (int l = l0; l < l1; ++l) {
+      const OzTile t = oz_tile(l, jt0, njt, strip);
+      if (!t.live) continue;
+      for (int c = 0; c < nch; ++c, ++g) {
+        const int st = g % OZ_STAGES;
+        mbar_wait(bar0 + 8 * st, (g / OZ_STAGES) & 1);
+        const uint32_t base = ring + st * OZ_STAGE_BYTES + aoff;
+        uint4 lo[OZ_S], hi[OZ_S];
+#pragma unroll
+        for (int sa = 0; sa < OZ_S; ++sa) {
+          lo[sa] = lds128(base + sa * OZ_GROUP_BYTES + h0);
+          hi[sa] = lds128(base + sa * OZ_GROUP_BYTES + h1);
+        }
+#pragma unroll
+        for (int pr = 0; pr < 3; ++pr, ++ga) {
+          const int slot = ga % OZ_ABUF;
+          if (ga >= OZ_ABUF) mbar_wait(aempty0 + 8 * slot, ((ga / OZ_ABUF) - 1) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          tmem_st16(tl + 16 * slot, lo[pr], hi[pr], lo[5 - pr], hi[5 - pr]);
+          tmem_st_wait();
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(afull0 + 8 * slot);
+        }
+        // every shared-memory read of this stage has been consumed by a store above
+        if (lane == 0) mbar_arrive(bar0 + 8 * (OZ_STAGES + st));
+      }
+    }
+  } else {
+    setmaxnreg_dec<96>();
+    if (warp == 8) {
+      if (lane == 0) {  // ---- producer (as in syrk_i8_kernel)
+        int g = 0;
+        for (int l = l0; l < l1; ++l) {
+          const OzTile t = oz_tile(l, jt0, njt, strip);
+          if (!t.live) continue;
+          const int8_t* srcA = Ps + (long long)(t.r0 / 8) * OZ_ROWGROUP_BYTES;
+          const int8_t* srcB = Ps + (long long)(t.c0 / 8) * OZ_ROWGROUP_BYTES;
+          for (int c = 0; c < nch; ++c, ++g) {
+            const int st = g % OZ_STAGES;
+            if (g >= OZ_STAGES) mbar_wait(bar0 + 8 * (OZ_STAGES + st), ((g / OZ_STAGES) - 1) & 1);
+            const uint32_t full = bar0 + 8 * st;
+            const uint32_t dst = ring + st * OZ_STAGE_BYTES;
+            mbar_arrive_expect_tx(full, OZ_STAGE_BYTES);
+            bulk_g2s(dst, srcA + c * chunk_bytes, OZ_A_BYTES, full);
+            bulk_g2s(dst + OZ_A_BYTES, srcB + c * chunk_bytes, OZ_B_BYTES, full);
+          }
+        }
+      }
+    } else if (warp == 9) {
+      // ---- MMA issuer: per chunk three A buffers, 8 + 9 + 9 MMAs, B from the shared-memory stage
+      const bool leader = elect_one();
+      const uint8_t* Fs = oz.F + (long long)s * oz.strideF;
+      const int nrb = p.Np / 64;
+      unsigned long long issued = 0;
+      int g = 0, ga = 0, k = 0;
+      for (int l = l0; l < l1; ++l) {
+        const OzTile t = oz_tile(l, jt0, njt, strip);
+        if (!t.live) continue;
+        uint32_t fa0 = 0, fb0 = 0, fa1 = 0, fb1 = 0;
+        if (lane < nch) {
+          const uint8_t* f = Fs + (long long)lane * nrb;
+          fa0 = f[t.r0 / 64] | f[t.r0 / 64 + 1];
+          fb0 = f[t.c0 / 64];
+        }
+        if (lane + 32 < nch) {
+          const uint8_t* f = Fs + (long long)(lane + 32) * nrb;
+          fa1 = f[t.r0 / 64] | f[t.r0 / 64 + 1];
+          fb1 = f[t.c0 / 64];
+        }
+        if (k > 0) {
+          mbar_wait(tmem_empty, (k - 1) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        uint32_t touched = 0;
+        for (int c = 0; c < nch; ++c, ++g) {
+          const int st = g % OZ_STAGES;
+          const uint32_t fa = __shfl_sync(0xffffffffu, c < 32 ? fa0 : fa1, c & 31);
+          const uint32_t fb = __shfl_sync(0xffffffffu, c < 32 ? fb0 : fb1, c & 31);
+          mbar_wait(bar0 + 8 * st, (g / OZ_STAGES) & 1);
+          const uint64_t bd0 = oz_desc(ring + st * OZ_STAGE_BYTES + OZ_A_BYTES);
+#pragma unroll
+          for (int pr = 0; pr < 3; ++pr, ++ga) {
+            const int slot = ga % OZ_ABUF;
+            mbar_wait(afull0 + 8 * slot, (ga / OZ_ABUF) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t acol = tmem + OZ_TMEM_A + 16 * slot;
+            if (leader) {
+              if (pr == 0) issued += oz_issue_pair_dispatch<0>(fa, fb, touched, tmem, acol, bd0);
+              else if (pr == 1) issued += oz_issue_pair_dispatch<1>(fa, fb, touched, tmem, acol, bd0);
+              else issued += oz_issue_pair_dispatch<2>(fa, fb, touched, tmem, acol, bd0);
+              umma_commit(aempty0 + 8 * slot);
+            }
+            __syncwarp();
+          }
+          if (leader) umma_commit(bar0 + 8 * (OZ_STAGES + st));
+          __syncwarp();
+        }
+        if (leader) {
+          touched_s = touched;
+          mbar_arrive(meta);
+          umma_commit(accfull);
+        }
+        __syncwarp();
+        ++k;
+      }
+      if (leader && oz.stats) {
+        atomicAdd(oz.stats, issued);
+        atomicAdd(oz.stats + 1, (unsigned long long)k * nch * 26ull);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 9) tmem_dealloc(tmem, OZ_TMEM_COLS);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -500,21 +751,22 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(CholParams p, OzParams oz
 }  // namespace
 
 namespace {
-// A operand from TMEM (tcgen05.cp + .ts MMAs) instead of shared memory: measured 418 vs 398 evals/s on the 256-walker
-// step (profiles/r2g_i8_ss_vs_ts.txt) — the copy replaces 26 shared-memory reads of A slabs by 6, which matters once
-// the chip runs at its power cap.  The SS form stays selectable in an experiments build.
-bool g_oz_ts = true;
+// Where the A operand of the int8 MMAs comes from: 0 = shared memory (SS form), 1 = TMEM filled by tcgen05.cp
+// (418 vs 398 evals/s for the SS form, profiles/r2g_i8_ss_vs_ts.txt), 2 = TMEM filled by loader warps with tcgen05.st
+// (syrk_i8_st_kernel).  Modes 0 and 1 stay selectable in an experiments build.
+int g_oz_mode = 2;
 int g_oz_tpc = 8;      // most tiles a CTA works through
 }
-void ozaki_set_ts(bool on) { g_oz_ts = on; }
+void ozaki_set_mode(int m) { g_oz_mode = m; }
 void ozaki_set_tpc(int n) { g_oz_tpc = n < 1 ? 1 : n; }
 
 cudaError_t ozaki_init() {
   cudaError_t e = cudaFuncSetAttribute((const void*)syrk_i8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        OZ_SMEM_BYTES);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute((const void*)syrk_i8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              OZ_SMEM_BYTES);
+  e = cudaFuncSetAttribute((const void*)syrk_i8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute((const void*)syrk_i8_st_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES);
 }
 
 size_t oz_panel_bytes_per_slot(int Np, int outer_tiles) {
@@ -538,7 +790,9 @@ cudaError_t launch_syrk_i8(const CholParams& p, const OzParams& oz, int K, int j
   int tpc = (int)std::min<long long>(g_oz_tpc, std::max<long long>(1, total / (4LL * sms)));
   tpc = std::min(tpc, ntiles);
   const dim3 grid((ntiles + tpc - 1) / tpc, 1, B);
-  if (g_oz_ts)
+  if (g_oz_mode == 2)
+    syrk_i8_st_kernel<<<grid, OZ_ST_THREADS, OZ_SMEM_BYTES, st>>>(p, oz, K / OZ_KC, jt0, njt, strip, ntiles, tpc);
+  else if (g_oz_mode == 1)
     syrk_i8_kernel<true><<<grid, OZ_THREADS, OZ_SMEM_BYTES, st>>>(p, oz, K / OZ_KC, jt0, njt, strip, ntiles, tpc);
   else
     syrk_i8_kernel<false><<<grid, OZ_THREADS, OZ_SMEM_BYTES, st>>>(p, oz, K / OZ_KC, jt0, njt, strip, ntiles, tpc);

@@ -604,7 +604,173 @@ void run_pair(int sms) {
          2.0 * 256 * 64 * 32 * 26.0 * big * (nblk / 2) / ms * 1e-9);
 }
 
+// ------------------------------------------------------------------------------------------------
+// What bounds the TS form once the A copies leave the tensor pipe's issue stream?  A resident in TMEM, B from shared
+// memory, the 26-pair pattern per chunk, one CTA per SM, cycles per MMA by clock64 around the whole loop:
+//   MODE 0  MMAs only, accumulate flag a literal
+//   MODE 1  MMAs only, accumulate flag from a run-time bit mask (the kernel's `touched` logic)
+//   MODE 2  MODE 0 + per chunk four mbarrier try_waits on completed barriers and four commits (the handshake traffic
+//           of syrk_i8_st_kernel without anybody on the other side)
+//   MODE 3  two issuing warps, alternating chunks, literal flag
+//   MODE 4  MODE 0 + four loader warps streaming LDS.128 -> tcgen05.st into the A columns (no handshake): does the
+//           register -> TMEM path disturb the MMAs?
+//   MODE 5  MODE 2 with the try_waits issued one step ahead (result consumed after the MMAs)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint4& a, const uint4& b, const uint4& c, const uint4& d) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w), "r"(c.x), "r"(c.y), "r"(c.z), "r"(c.w),
+      "r"(d.x), "r"(d.y), "r"(d.z), "r"(d.w)
+      : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+template <int MODE>
+__global__ void __launch_bounds__(320, 1) issue_kernel(int chunks, int nstage, uint32_t touched0, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar, done[8], stop;
+  __shared__ uint32_t tmem_base;
+  constexpr int N = 64, A_BYTES = 16 * 1536, B_BYTES = (N / 8) * 1536, STAGE = A_BYTES + B_BYTES;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < nstage * STAGE; i += blockDim.x) smem[i] = (uint8_t)(i * 7 + 3);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (tid == 0) {
+    mbar_init(smem_u32(&bar), MODE == 3 ? 2 : 1);
+    for (int i = 0; i < 8; ++i) mbar_init(smem_u32(&done[i]), 1);
+    mbar_init(smem_u32(&stop), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_base), 512);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tb = tmem_base;
+  const uint32_t idesc = make_idesc_i8(M_, N);
+  if (warp == 1 || (MODE == 3 && warp == 2)) {
+    const bool leader = elect_one();
+    uint32_t touched = touched0;
+    const long long t0 = clock64();
+    uint32_t hs = 0;  // handshake counter (MODE 2/5)
+    bool ok_next = true;
+    for (int c = (MODE == 3 ? warp - 1 : 0); c < chunks; c += (MODE == 3 ? 2 : 1)) {
+      const uint32_t b0 = smem_u32(smem) + (c % nstage) * STAGE + A_BYTES;
+      const uint64_t bd0 = desc_sw32(b0);
+      if (MODE == 2) {
+        // nobody ever arrives on done[0..4]: a wait for parity 1 of a fresh barrier succeeds at once
+        mbar_wait(smem_u32(&done[4]), 1);  // parity 1 of a fresh barrier: complete
+      }
+#pragma unroll
+      for (int pr = 0; pr < 3; ++pr) {
+        if (MODE == 2) {
+          mbar_wait(smem_u32(&done[(hs++) & 3]), 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        if (MODE == 5) {
+          while (!ok_next) ok_next = mbar_test(smem_u32(&done[hs & 3]), 1);
+          ++hs;
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          ok_next = mbar_test(smem_u32(&done[hs & 3]), 1);
+        }
+        if (leader) {
+          uint32_t local = 0;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int sa = h ? 5 - pr : pr;
+#pragma unroll
+            for (int sb = 0; sb < 6; ++sb) {
+              if (sa + sb >= 7) continue;
+              const uint32_t d = sa + sb;
+              uint32_t acc = 1;
+              if (MODE == 1) { acc = ((touched | local) >> d) & 1u; local |= 1u << d; }
+              umma_i8_ts(tb + d * N, tb + 448 + ((c * 3 + pr) & 3) * 16 + h * 8, bd0 + sb * 16, idesc, acc);
+            }
+          }
+          touched |= local;
+          if (MODE == 2 || MODE == 5) umma_commit(smem_u32(&done[5 + ((hs) & 1)]));
+        }
+        __syncwarp();
+      }
+      if (MODE == 2 || MODE == 5) {
+        if (leader) umma_commit(smem_u32(&done[7]));
+        __syncwarp();
+      }
+    }
+    if (leader) umma_commit(smem_u32(&bar));
+    __syncwarp();
+    mbar_wait(smem_u32(&bar), 0);
+    if (leader && warp == 1) out[0] = clock64() - t0;
+    if (leader && warp == 1) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&stop)) : "memory");
+  } else if (MODE == 4 && warp >= 6) {
+    // loader warps: free-running LDS -> tcgen05.st into the A columns until the MMA warp is done
+    const int q = warp & 3, row = q * 32 + lane;
+    const uint32_t aoff = (uint32_t)(row >> 3) * 1536 + (uint32_t)(row & 7) * 32;
+    const uint32_t h0 = (uint32_t)((row & 7) >> 2) * 16, h1 = h0 ^ 16;
+    const uint32_t tl = tb + ((uint32_t)(q * 32) << 16) + 448;
+    long long n = 0;
+    for (int c = 0; !mbar_test(smem_u32(&stop), 0); ++c) {
+      const uint32_t base = smem_u32(smem) + (c % nstage) * STAGE + aoff;
+      uint4 lo[6], hi[6];
+#pragma unroll
+      for (int sa = 0; sa < 6; ++sa) {
+        lo[sa] = lds128(base + sa * 256 + h0);
+        hi[sa] = lds128(base + sa * 256 + h1);
+      }
+#pragma unroll
+      for (int pr = 0; pr < 3; ++pr) {
+        tmem_st16(tl + 16 * ((c * 3 + pr) & 3), lo[pr], hi[pr], lo[5 - pr], hi[5 - pr]);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      }
+      ++n;
+    }
+    if (tid == 6 * 32) out[1] = n;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, 512);
+}
+
+template <int MODE>
+void run_issue_mode(int sms, const char* what) {
+  long long* dout;
+  CK(cudaMalloc(&dout, 64));
+  CK(cudaMemset(dout, 0, 64));
+  CK(cudaFuncSetAttribute(issue_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  const int STAGE = 16 * 1536 + 8 * 1536, nstage = 4, chunks = 512;
+  issue_kernel<MODE><<<1, 320, nstage * STAGE + 1024>>>(chunks, nstage, 0u, dout);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("issue mode %d: CUDA error %s\n", MODE, cudaGetErrorString(e)); exit(1); }
+  long long h[2];
+  CK(cudaMemcpy(h, dout, 16, cudaMemcpyDeviceToHost));
+  cudaEvent_t a, b;
+  CK(cudaEventCreate(&a));
+  CK(cudaEventCreate(&b));
+  const int big = 20000;
+  issue_kernel<MODE><<<sms, 320, nstage * STAGE + 1024>>>(100, nstage, 0u, dout);
+  CK(cudaEventRecord(a));
+  issue_kernel<MODE><<<sms, 320, nstage * STAGE + 1024>>>(big, nstage, 0u, dout);
+  CK(cudaEventRecord(b));
+  CK(cudaDeviceSynchronize());
+  float ms;
+  CK(cudaEventElapsedTime(&ms, a, b));
+  printf("issue pace mode %d (%s): %.1f cycles per MMA on one SM", MODE, what, (double)h[0] / (chunks * 26.0));
+  if (MODE == 4) printf(" (loaders: %.2f chunks of A stored per MMA chunk)", (double)h[1] / chunks);
+  printf("; chip %.1f TOP/s\n", 2.0 * 128 * 64 * 32 * 26.0 * big * sms / ms * 1e-9);
+  cudaFree(dout);
+}
+void run_issue(int sms) {
+  run_issue_mode<0>(sms, "TS MMAs only, literal accumulate flag");
+  run_issue_mode<1>(sms, "TS MMAs only, run-time accumulate flag");
+  run_issue_mode<2>(sms, "+ 4 try_waits and 4 commits per chunk");
+  run_issue_mode<5>(sms, "+ 4 try_waits one step ahead and 4 commits per chunk");
+  run_issue_mode<3>(sms, "two issuing warps, alternating chunks");
+  run_issue_mode<4>(sms, "+ free-running loader warps LDS -> tcgen05.st");
+}
+
 int main() {
+  setvbuf(stdout, NULL, _IONBF, 0);
   int dev = 0;
   CK(cudaSetDevice(dev));
   cudaDeviceProp prop;
@@ -661,6 +827,7 @@ int main() {
     cudaFree(dA); cudaFree(dB); cudaFree(dD);
   }
 
+  run_issue(prop.multiProcessorCount);
   run_pair(prop.multiProcessorCount);
   run_ts(prop.multiProcessorCount);
   run_pace<64>(prop.multiProcessorCount);

@@ -18,10 +18,11 @@ except Exception as e:
 PY
   tail -3 gpurun_out/${TAG}_bench_$1.err
 }
-run_bench ss "SFB_NOP=1"
-if [ -f starfish_b200/libsfb200_exp.so ]; then
-  SFB200_LIB=$PWD/starfish_b200/libsfb200_exp.so SFB_OZ_TS=1 timeout 300 python -m pytest tests/test_gpu_ozaki.py -q -x > gpurun_out/${TAG}_pytest_ts.log 2>&1; echo "pytest TS rc=$?"; tail -2 gpurun_out/${TAG}_pytest_ts.log
-  run_bench ts "SFB200_LIB=$PWD/starfish_b200/libsfb200_exp.so SFB_OZ_TS=1"
+run_bench default "SFB_NOP=1"
+if [ -f starfish_b200/libsfb200_exp.so ]; then   # A/B of the A-operand modes (experiments build): 1 = tcgen05.cp, 0 = shared memory
+  for m in ${OZ_MODES:-1}; do
+    run_bench mode$m "SFB200_LIB=$PWD/starfish_b200/libsfb200_exp.so SFB_OZ_MODE=$m"
+  done
 fi
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv \
   --log-file gpurun_out/${TAG}_launches.csv python bench.py --solver dense_i8 --walkers 32 --steps 1 --warmup 0 --no-e2e --no-cpu-baseline --no-model --no-structured --no-configs --no-alt --no-frozen > gpurun_out/${TAG}_l.log 2>&1; echo "ncu launches rc=$?"
