@@ -20,20 +20,21 @@
 // tests/test_gpu_ozaki.py; 5 accumulators give 1e-7 — the anti-diagonal count, not the digit count, is what
 // matters).  The epilogue recombines Σ_d 256^(−d)·S_d by Horner in fp64 and applies C −= 2^(e_i−7)·2^(e_j−7)·(…).
 //
-// Data layout.  The sliced panels of the current outer block live in P (per slot), pre-tiled so that an operand
-// tile is ONE contiguous block and already in the canonical K-major shared-memory layout of the MMA:
-//     P[chunk c (32 k)][row group g = row/8][slice t][row%8][32 bytes]        (NCH × Np/8 × 6 × 256 B)
-// -> the A operand (128 rows, all slices) of a chunk is 24 KB contiguous, the B operand (64 rows) 12 KB: two 1-D
-// bulk async copies (cp.async.bulk, SASS UBLKCP) per pipeline stage, no tensor map.  Inside a 256-byte row group
-// the two 16-byte halves of a row are XOR-swapped by bit 2 of the row (the 32-byte swizzle pattern, applied by
-// the slicing kernel), and the 8-row groups of one slice are 6·256 = 1536 B apart: UMMA descriptor
-// {SWIZZLE_32B, SBO = 1536}.
+// Data layout.  The sliced panels of the current outer block live in P (per slot), pre-tiled so that every digit
+// slab of an operand tile is ONE contiguous block, already in the canonical K-major shared-memory layout of the MMA:
+//     P[chunk c (32 k)][slice t][row group g = row/8][row%8][32 bytes]        (NCH × 6 × Np/8 × 256 B)
+// -> one digit slab of the A operand (128 rows) of a chunk is 4 KB contiguous, of the B operand (64 rows) 2 KB: one
+// 1-D bulk async copy (cp.async.bulk, SASS UBLKCP) per NON-ZERO slab and pipeline stage, no tensor map.  Inside a
+// 256-byte row group the two 16-byte halves of a row are XOR-swapped by bit 2 of the row (the 32-byte swizzle pattern,
+// applied by the slicing kernel), consecutive 8-row groups are 256 B apart: UMMA descriptor {SWIZZLE_32B, SBO = 256}.
+// In shared memory the six B slabs of a stage lie back to back, so a run of consecutive B slabs is one operand of
+// N = 64·len rows (oz_issue_chunk).
 //
-// Kernel shape: 192 threads = warp 0 bulk-copy producer (one lane), warp 1 MMA issuer (one elected lane) + TMEM
-// allocator, warps 2-5 epilogue (TMEM lane quarter = warp%4).  5-stage ring of 36 KB, full/empty mbarriers,
-// tcgen05.commit releases a stage / signals the epilogue.  The epilogue warps prefetch the C tile (coalesced,
-// into registers) while the main loop runs, transpose the recombined update through the idle ring and finish
-// the read-modify-write with coalesced streaming stores.
+// Kernel shape: 192 threads = warp 0 bulk-copy producer, warp 1 MMA issuer (one elected lane) + TMEM allocator,
+// warps 2-5 epilogue (TMEM lane quarter = warp%4).  4-stage ring of 36 KB, full/empty mbarriers, tcgen05.commit
+// releases a stage / signals the epilogue.  The epilogue warps prefetch the C tile (coalesced, into registers) while
+// the main loop runs, transpose the recombined update through a padded buffer and finish the read-modify-write with
+// coalesced streaming stores.
 #include <algorithm>
 #include <cstdint>
 
@@ -116,19 +117,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// shared memory -> TMEM, 128 lanes × 256 bits (one K-major 128×32-byte operand slab; SASS UTCCP)
-__device__ __forceinline__ void utccp_128x256b(uint32_t taddr, uint64_t sdesc) {
-  asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
-}
-// D[tmem] (+)= A[tmem]·B[smem]ᵀ
-__device__ __forceinline__ void umma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
-                                           uint32_t accumulate) {
-  asm volatile(
-      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tmem_d),
-      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 // exact int32 -> double on the full-rate fp64 add pipe: (2^52 + 2^31 + v) − (2^52 + 2^31)
 __device__ __forceinline__ double i2d(uint32_t v) {
   return __hiloint2double(0x43300000, (int)(v ^ 0x80000000u)) - 4503601774854144.0;
@@ -142,32 +130,17 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// registers -> TMEM: lane i of the warp writes 16 consecutive 32-bit columns of TMEM lane (quarter base + i)  (SASS STTM)
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint4& a, const uint4& b, const uint4& c, const uint4& d) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
-      "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w), "r"(c.x), "r"(c.y), "r"(c.z), "r"(c.w),
-      "r"(d.x), "r"(d.y), "r"(d.z), "r"(d.w)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
-  return v;
-}
-template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
-template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
 
 // UMMA shared-memory matrix descriptor, K-major, SWIZZLE_32B (layout code 6), descriptor version 1:
 // start address, LBO (unused for swizzled K-major; canonical value 1) and SBO in 16-byte units.
 __device__ __forceinline__ uint64_t oz_desc(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)1 << 16) | ((uint64_t)(OZ_ROWGROUP_BYTES >> 4) << 32) |
+  return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)1 << 16) | ((uint64_t)(OZ_GROUP_BYTES >> 4) << 32) |
          ((uint64_t)1 << 46) | ((uint64_t)6 << 61);
 }
-// instruction descriptor: D = S32 (2 << 4), A = B = signed int8 (1 << 7, 1 << 10), both K-major, N >> 3, M >> 4
-constexpr uint32_t OZ_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BN >> 3) << 17) |
-                              ((uint32_t)(OZ_BM >> 4) << 24);
+// instruction descriptor: D = S32 (2 << 4), A = B = signed int8 (1 << 7, 1 << 10), both K-major, M >> 4 at bit 24; the
+// N >> 3 field (bit 17) is added per MMA (oz_idesc)
+constexpr uint32_t OZ_IDESC_BASE = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BM >> 4) << 24);
 
 // ------------------------------------------------------------------------------------------------
 // syrk on the int8 path: C[r0.., c0..] −= Σ_{chunks} (sliced L rows r0..) · (sliced L rows c0..)ᵀ.
@@ -180,7 +153,7 @@ constexpr uint32_t OZ_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(O
 //            row tile jt0+y, 64-column block x; tiles above the diagonal of their tile column (y < x/2) are skipped
 //   triangle trailing update of every tile column >= jt0: l in [0, T(T+1)), decoded to (row tile t, 64-column block)
 // Roles: warp 0 = bulk-copy producer (runs ahead across tile boundaries), warp 1 = MMA issuer (waits for the previous
-// tile's accumulators to be drained), warps 2-5 = epilogue.
+// tile's accumulators to be drained, clears them with two MMAs against an all-zero A slab), warps 2-5 = epilogue.
 // ------------------------------------------------------------------------------------------------
 struct OzTile { int r0, c0, live; };
 
@@ -202,49 +175,64 @@ __device__ __forceinline__ OzTile oz_tile(int l, int jt0, int njt, int strip) {
   return t;
 }
 
+constexpr int OZ_SLAB_A = OZ_BM * OZ_KC;             // 4096: one digit slab of the A operand (128 rows × 32 B)
+constexpr int OZ_SLAB_B = OZ_BN * OZ_KC;             // 2048
 constexpr uint32_t OZ_TROW = 66 * 8;                 // padded row of the transpose buffer (528 B: conflict-free 16-byte accesses)
 constexpr int OZ_TBUF_BYTES = 4 * 32 * OZ_TROW;     // 4 epilogue warps × 32 rows
-constexpr int OZ_SMEM_BYTES = OZ_STAGES * OZ_STAGE_BYTES + OZ_TBUF_BYTES + 1024;  // + alignment slack
-constexpr uint32_t OZ_TMEM_A = OZ_NACC * OZ_BN;     // first TMEM column of the A operand (TS form): 448..495
+constexpr int OZ_ZERO_BYTES = OZ_SLAB_A;            // an all-zero A slab (clears the accumulators at the start of a tile)
+constexpr int OZ_SMEM_BYTES = OZ_STAGES * OZ_STAGE_BYTES + OZ_TBUF_BYTES + OZ_ZERO_BYTES + 1024;  // + alignment slack
 
-// One 32-deep chunk: the six A slices shared memory -> TMEM once (TS form; the SS form re-reads each A slice for every
-// pair), then one int8 MMA per digit pair (sa, sb), sa + sb <= 6, into the accumulator of anti-diagonal sa + sb.
-// fa / fb: bit t set = digit slab t of the A / B operand block has a non-zero entry; a product with an all-zero slab
-// contributes nothing and is skipped (exactly).  Called with literal masks the tests fold away at compile time.
-// Copies and MMAs of one thread execute in issue order, so this chunk's copies follow the previous chunk's MMAs
-// without a wait.  Returns the number of MMAs issued.
-template <bool TS>
-__device__ __forceinline__ uint32_t oz_issue_chunk(uint32_t fa, uint32_t fb, uint32_t& touched, uint32_t tmem,
-                                                   uint64_t ad0, uint64_t bd0) {
-  if constexpr (TS) {
-#pragma unroll
-    for (int sa = 0; sa < OZ_S; ++sa)
-      if ((fa >> sa) & 1u)
-        utccp_128x256b(tmem + OZ_TMEM_A + sa * (OZ_KC / 4), ad0 + (uint64_t)(sa * (OZ_GROUP_BYTES >> 4)));
-  }
-  uint32_t local = 0, n = 0;  // accumulators touched by this chunk so far (compile-time known for literal masks)
+__device__ __forceinline__ uint32_t oz_idesc(uint32_t n) { return OZ_IDESC_BASE | ((n >> 3) << 17); }
+
+// One 32-deep chunk.  A digit slab of A (128 rows) meets every digit slab of B (64 rows) whose anti-diagonal sa + sb
+// stays <= 6; the B slabs of a stage lie back to back (2 KB each, 8-row groups 256 B apart) and the accumulators of
+// consecutive anti-diagonals are adjacent in TMEM, so a RUN of consecutive B slabs is ONE MMA of N = 64·len columns
+// against accumulators sa+sb0 … sa+sb0+len−1.  Why it matters: a 128×64×32 int8 MMA needs 32 tensor cycles but reads
+// 6 KB of shared memory (48 cycles at 128 B/clk; 52 measured), and feeding A through TMEM (tcgen05.cp, 64 B/clk, in
+// the tensor pipe's issue order) costs 384 cycles per chunk on top of 26·32.  At N >= 128 the shared-memory traffic
+// per MMA (4 KB + 2 KB·len) fits under its 32·len tensor cycles: 9 MMAs per chunk (3+3, 3+3, 3+2, 4, 3, 2 slabs) at the
+// floor of 832 cycles, both operands from shared memory, no TMEM operand at all (tools/exp/umma_i8_probe.cu: 65.5 /
+// 128.1 cycles for N = 128 / 256).  Runs of 5 and 6 slabs are split 3+2 / 3+3 so that no single-slab MMA remains.
+// fa / fb: bit t set = digit slab t of the A / B operand block has a non-zero entry (and was loaded); products with
+// an all-zero slab are skipped — exactly.  Every MMA accumulates (the accumulators are cleared per tile), so with
+// literal masks the whole schedule folds at compile time.  Returns the number of slab products issued.
+__device__ __forceinline__ uint32_t oz_issue_chunk(uint32_t fa, uint32_t fb, uint32_t tmem, uint64_t ad0, uint64_t bd0) {
+  uint32_t n = 0;
 #pragma unroll
   for (int sa = 0; sa < OZ_S; ++sa) {
+    if (!((fa >> sa) & 1u)) continue;
+    const uint32_t m = fb & ((1u << (OZ_NACC - sa)) - 1u) & 0x3fu;
+    const uint64_t ad = ad0 + (uint64_t)(sa * (OZ_SLAB_A >> 4));
 #pragma unroll
-    for (int sb = 0; sb < OZ_S; ++sb) {
-      if (sa + sb >= OZ_NACC) continue;
-      if (!(((fa >> sa) & 1u) && ((fb >> sb) & 1u))) continue;
-      // the start-address field counts 16-byte units and never leaves its 14-bit range inside the ring, so the
-      // other slices' descriptors are the stage's plus a constant
-      const uint64_t bd = bd0 + (uint64_t)(sb * (OZ_GROUP_BYTES >> 4));
-      const uint32_t d = sa + sb;
-      const uint32_t acc = ((touched | local) >> d) & 1u;   // the first product into an accumulator overwrites it
-      if constexpr (TS) {
-        umma_i8_ts(tmem + d * OZ_BN, tmem + OZ_TMEM_A + sa * (OZ_KC / 4), bd, OZ_IDESC, acc);
-      } else {
-        umma_i8(tmem + d * OZ_BN, ad0 + (uint64_t)(sa * (OZ_GROUP_BYTES >> 4)), bd, OZ_IDESC, acc);
+    for (int s = 0; s < OZ_S; ++s) {
+      const uint32_t b0 = (m >> s) & 1u, prev = s ? (m >> (s - 1)) & 1u : 0u;
+      if (!(b0 && !prev)) continue;             // a run of set bits starts at s
+      uint32_t len = 1, run = 1;
+#pragma unroll
+      for (int t = s + 1; t < OZ_S; ++t) {
+        run &= (m >> t) & 1u;
+        len += run;
       }
-      local |= 1u << d;
-      ++n;
+      const uint64_t bd = bd0 + (uint64_t)(s * (OZ_SLAB_B >> 4));
+      const uint32_t d = tmem + (uint32_t)(sa + s) * OZ_BN;
+      if (len <= 4) {
+        umma_i8(d, ad, bd, oz_idesc(len * OZ_BN), 1);
+      } else {
+        umma_i8(d, ad, bd, oz_idesc(3 * OZ_BN), 1);
+        umma_i8(d + 3 * OZ_BN, ad, bd + (uint64_t)(3 * (OZ_SLAB_B >> 4)), oz_idesc((len - 3) * OZ_BN), 1);
+      }
+      n += len;
     }
   }
-  touched |= local;
   return n;
+}
+// accumulators that receive a product for digit-slab masks (fa, fb)
+__device__ __forceinline__ uint32_t oz_touched(uint32_t fa, uint32_t fb) {
+  uint32_t t = 0;
+#pragma unroll
+  for (int sa = 0; sa < OZ_S; ++sa)
+    if ((fa >> sa) & 1u) t |= (fb & ((1u << (OZ_NACC - sa)) - 1u)) << sa;
+  return t & 0x7fu;
 }
 
 // ---- epilogue (4 warps; warp q owns tile rows 32q..32q+31 = its TMEM lane quarter).
@@ -317,7 +305,6 @@ __device__ __forceinline__ void oz_epilogue(const CholParams& p, const OzParams&
 
 }
 
-template <bool TS>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
     syrk_i8_kernel(CholParams p, OzParams oz, int nch, int jt0, int njt, int strip, int ntiles, int tpc) {
   const int s = blockIdx.z;
@@ -331,7 +318,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
   __shared__ uint32_t touched_s;
   const uint32_t ring = (smem_u32(oz_smem_raw) + 1023u) & ~1023u;
   const uint32_t tbuf0 = ring + OZ_STAGES * OZ_STAGE_BYTES;
-  const uint32_t bar0 = smem_u32(bars);  // full[s] at +8s, empty[s] at +8(STAGES+s), then accfull, tmem_empty
+  const uint32_t zero0 = tbuf0 + OZ_TBUF_BYTES;
+  const uint32_t bar0 = smem_u32(bars);  // full[s] at +8s, empty[s] at +8(STAGES+s), then accfull, tmem_empty, meta
   const uint32_t accfull = bar0 + 16 * OZ_STAGES, tmem_empty = accfull + 8, meta = accfull + 16;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -342,6 +330,9 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
     mbar_init(meta, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  for (int i = tid; i < OZ_ZERO_BYTES / 16; i += OZ_THREADS)
+    asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(zero0 + 16 * i), "r"(0) : "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the zero slab is read by the tensor pipe (async proxy)
   if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), OZ_TMEM_COLS);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -349,40 +340,21 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
   const uint32_t tmem = tmem_base_s;
 
   const int8_t* Ps = oz.P + (long long)s * oz.strideP;
-  const long long chunk_bytes = (long long)(p.Np / 8) * OZ_ROWGROUP_BYTES;
+  const uint8_t* Fs = oz.F + (long long)s * oz.strideF;
+  const int nrb = p.Np / 64;
+  const long long slice_bytes = (long long)p.Np * OZ_KC;       // one digit slab of one chunk, all rows
+  const long long chunk_bytes = OZ_S * slice_bytes;
 
-  if (warp == 0) {
-    if (lane == 0) {  // ---- producer: two contiguous bulk copies per chunk, continuous over the CTA's tiles
-      int g = 0;      // chunks issued so far (ring position)
-      for (int l = l0; l < l1; ++l) {
-        const OzTile t = oz_tile(l, jt0, njt, strip);
-        if (!t.live) continue;
-        const int8_t* srcA = Ps + (long long)(t.r0 / 8) * OZ_ROWGROUP_BYTES;
-        const int8_t* srcB = Ps + (long long)(t.c0 / 8) * OZ_ROWGROUP_BYTES;
-        for (int c = 0; c < nch; ++c, ++g) {
-          const int st = g % OZ_STAGES;
-          if (g >= OZ_STAGES) mbar_wait(bar0 + 8 * (OZ_STAGES + st), ((g / OZ_STAGES) - 1) & 1);
-          const uint32_t full = bar0 + 8 * st;
-          const uint32_t dst = ring + st * OZ_STAGE_BYTES;
-          mbar_arrive_expect_tx(full, OZ_STAGE_BYTES);
-          bulk_g2s(dst, srcA + c * chunk_bytes, OZ_A_BYTES, full);
-          bulk_g2s(dst + OZ_A_BYTES, srcB + c * chunk_bytes, OZ_B_BYTES, full);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ---- MMA issuer: 26 int8 MMAs per chunk into 7 accumulators.  The whole warp runs the loop (descriptor
-    // arithmetic stays warp-uniform, i.e. in uniform registers); one elected lane issues.
+  if (warp <= 1) {
+    // producer (warp 0) and MMA issuer (warp 1) walk the same tiles and chunks with the same digit-slab flags:
+    // lane j holds the flags of chunks j and j+32 of the current tile (written by the slicing kernel), fetched once
+    // per tile; whole warps run the loops (uniform control flow), one elected lane issues.
     const bool leader = elect_one();
-    const uint8_t* Fs = oz.F + (long long)s * oz.strideF;
-    const int nrb = p.Np / 64;
     unsigned long long issued = 0;
     int g = 0, k = 0;  // ring position, live tiles done
     for (int l = l0; l < l1; ++l) {
       const OzTile t = oz_tile(l, jt0, njt, strip);
       if (!t.live) continue;
-      // which digit slabs of this tile's operands are not identically zero, chunk by chunk (written by the slicing
-      // kernel; lane j holds chunks j and j+32) — fetched while the previous tile's accumulators are being drained
       uint32_t fa0 = 0, fb0 = 0, fa1 = 0, fb1 = 0;
       if (lane < nch) {
         const uint8_t* f = Fs + (long long)lane * nrb;
@@ -394,41 +366,72 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
         fa1 = f[t.r0 / 64] | f[t.r0 / 64 + 1];
         fb1 = f[t.c0 / 64];
       }
-      if (k > 0) {  // the epilogue must have drained the accumulators of the previous tile
-        mbar_wait(tmem_empty, (k - 1) & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      }
-      uint32_t touched = 0;  // accumulators that have received a product in this tile
-      for (int c = 0; c < nch; ++c, ++g) {
-        const int st = g % OZ_STAGES;
-        const uint32_t fa = __shfl_sync(0xffffffffu, c < 32 ? fa0 : fa1, c & 31);
-        const uint32_t fb = __shfl_sync(0xffffffffu, c < 32 ? fb0 : fb1, c & 31);
-        mbar_wait(bar0 + 8 * st, (g / OZ_STAGES) & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a0 = ring + st * OZ_STAGE_BYTES, b0 = a0 + OZ_A_BYTES;
-        const uint64_t ad0 = oz_desc(a0), bd0 = oz_desc(b0);
+      if (warp == 0) {
+        // ---- producer: one bulk copy per non-zero digit slab (4 KB of A, 2 KB of B), continuous over the CTA's tiles
+        const int8_t* srcA = Ps + (long long)(t.r0 / 8) * OZ_GROUP_BYTES;
+        const int8_t* srcB = Ps + (long long)(t.c0 / 8) * OZ_GROUP_BYTES;
+        for (int c = 0; c < nch; ++c, ++g) {
+          const int st = g % OZ_STAGES;
+          const uint32_t fa = __shfl_sync(0xffffffffu, c < 32 ? fa0 : fa1, c & 31);
+          const uint32_t fb = __shfl_sync(0xffffffffu, c < 32 ? fb0 : fb1, c & 31);
+          if (g >= OZ_STAGES) mbar_wait(bar0 + 8 * (OZ_STAGES + st), ((g / OZ_STAGES) - 1) & 1);
+          if (leader) {
+            const uint32_t full = bar0 + 8 * st;
+            const uint32_t dst = ring + st * OZ_STAGE_BYTES;
+            mbar_arrive_expect_tx(full, (uint32_t)__popc(fa) * OZ_SLAB_A + (uint32_t)__popc(fb) * OZ_SLAB_B);
+            const int8_t* a = srcA + c * chunk_bytes;
+            const int8_t* b = srcB + c * chunk_bytes;
+#pragma unroll
+            for (int sl = 0; sl < OZ_S; ++sl) {
+              if ((fa >> sl) & 1u) bulk_g2s(dst + sl * OZ_SLAB_A, a + sl * slice_bytes, OZ_SLAB_A, full);
+              if ((fb >> sl) & 1u) bulk_g2s(dst + OZ_A_BYTES + sl * OZ_SLAB_B, b + sl * slice_bytes, OZ_SLAB_B, full);
+            }
+          }
+          __syncwarp();
+        }
+      } else {
+        // ---- MMA issuer
+        if (k > 0) {  // the epilogue must have drained the accumulators of the previous tile
+          mbar_wait(tmem_empty, (k - 1) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        if (leader) {  // clear the seven accumulators: zero A slab × whatever the ring holds (448 columns)
+          umma_i8(tmem, oz_desc(zero0), oz_desc(ring), oz_idesc(256), 0);
+          umma_i8(tmem + 256, oz_desc(zero0), oz_desc(ring), oz_idesc(192), 0);
+        }
+        uint32_t touched = 0;  // accumulators that receive a product in this tile (the epilogue skips the others)
+        for (int c = 0; c < nch; ++c, ++g) {
+          const int st = g % OZ_STAGES;
+          const uint32_t fa = __shfl_sync(0xffffffffu, c < 32 ? fa0 : fa1, c & 31);
+          const uint32_t fb = __shfl_sync(0xffffffffu, c < 32 ? fb0 : fb1, c & 31);
+          mbar_wait(bar0 + 8 * st, (g / OZ_STAGES) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a0 = ring + st * OZ_STAGE_BYTES;
+          const uint64_t ad0 = oz_desc(a0), bd0 = oz_desc(a0 + OZ_A_BYTES);
+          touched |= oz_touched(fa, fb);
+          if (leader) {
+            // The digit patterns that dominate (nothing zero / leading slab zero, for either operand) get fully
+            // unrolled code with compile-time masks: a single thread issues every MMA of the CTA, so run-time tests per
+            // product would make the issue loop the bottleneck.  Anything else takes the generic path.
+            if (fa == 0x3fu && fb == 0x3fu) issued += oz_issue_chunk(0x3fu, 0x3fu, tmem, ad0, bd0);
+            else if (fa == 0x3eu && fb == 0x3eu) issued += oz_issue_chunk(0x3eu, 0x3eu, tmem, ad0, bd0);
+            else if (fa == 0x3eu && fb == 0x3fu) issued += oz_issue_chunk(0x3eu, 0x3fu, tmem, ad0, bd0);
+            else if (fa == 0x3fu && fb == 0x3eu) issued += oz_issue_chunk(0x3fu, 0x3eu, tmem, ad0, bd0);
+            else issued += oz_issue_chunk(fa, fb, tmem, ad0, bd0);
+            umma_commit(bar0 + 8 * (OZ_STAGES + st));  // stage free once these MMAs have read it
+          }
+          __syncwarp();
+        }
         if (leader) {
-          // The two digit patterns that dominate (nothing zero / leading slab zero), for either operand, get fully
-          // unrolled code with compile-time masks: a single thread issues every MMA of the CTA, so per-product
-          // run-time tests would make the issue loop the bottleneck.  Anything else takes the generic path.
-          if (fa == 0x3fu && fb == 0x3fu) issued += oz_issue_chunk<TS>(0x3fu, 0x3fu, touched, tmem, ad0, bd0);
-          else if (fa == 0x3eu && fb == 0x3eu) issued += oz_issue_chunk<TS>(0x3eu, 0x3eu, touched, tmem, ad0, bd0);
-          else if (fa == 0x3eu && fb == 0x3fu) issued += oz_issue_chunk<TS>(0x3eu, 0x3fu, touched, tmem, ad0, bd0);
-          else if (fa == 0x3fu && fb == 0x3eu) issued += oz_issue_chunk<TS>(0x3fu, 0x3eu, touched, tmem, ad0, bd0);
-          else issued += oz_issue_chunk<TS>(fa, fb, touched, tmem, ad0, bd0);
-          umma_commit(bar0 + 8 * (OZ_STAGES + st));  // stage free once these MMAs (and copies) have read it
+          touched_s = touched;
+          mbar_arrive(meta);                 // release: the epilogue reads touched_s after acquiring this barrier
+          umma_commit(accfull);
         }
         __syncwarp();
       }
-      if (leader) {
-        touched_s = touched;               // which accumulators hold a sum (the others are stale: treated as zero)
-        mbar_arrive(meta);                 // release: the epilogue reads touched_s after acquiring this barrier
-        umma_commit(accfull);
-      }
-      __syncwarp();
       ++k;
     }
-    if (leader && oz.stats) {
+    if (warp == 1 && leader && oz.stats) {
       atomicAdd(oz.stats, issued);
       atomicAdd(oz.stats + 1, (unsigned long long)k * nch * 26ull);
     }
@@ -438,235 +441,6 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, OZ_TMEM_COLS);
-}
-
-// ------------------------------------------------------------------------------------------------
-// The same update with the A operand fed to TMEM by LOADER WARPS (registers -> TMEM, tcgen05.st) instead of
-// tcgen05.cp.  Why: the 128×64×32 int8 MMA needs 32 tensor cycles, but with both operands in shared memory it reads
-// 6 KB per MMA (48 cycles at 128 B/clk), and the TS form of syrk_i8_kernel pays 6 × 4 KB of tcgen05.cp per chunk at
-// 64 B/clk IN the tensor pipe's issue order (26·32 + 384 cycles per chunk = 46.8 per MMA; measured 48.2,
-// tools/exp/umma_i8_probe.cu).  A register -> TMEM store runs beside the MMAs (256 B/clk), so the issue stream holds
-// MMAs only and the tensor pipe sees its 32-cycle floor; shared memory carries B (2 KB per MMA) plus one LDS pass
-// over A (24 KB per chunk): 76 of the 106 KB a chunk's 832 cycles can deliver.
-//
-// TMEM: 7 accumulators × 64 columns, then a ring of four 16-column A buffers (448..511); a buffer holds TWO digit
-// slabs (8 columns each).  The slabs of a chunk are paired {0,5}, {1,4}, {2,3} — 8, 9 and 9 of the 26 MMAs — so the
-// MMA warp consumes a buffer every ≈ 280 cycles and the loaders may run three buffers ahead.
-// Warp groups (setmaxnreg needs aligned groups of four warps): 0-3 epilogue (240 registers), 4-7 loaders — thread =
-// operand row = TMEM lane, 12 conflict-free 16-byte shared loads and three 16-column stores per chunk —, 8 = bulk-copy
-// producer, 9 = MMA issuer, 10-11 idle.
-// Barriers: full/empty per stage (empty = 1 commit of the MMA warp + the 4 loader warps), afull/aempty per A buffer.
-// ------------------------------------------------------------------------------------------------
-constexpr int OZ_ST_THREADS = 384;
-constexpr int OZ_ABUF = 4;                       // TMEM A buffers of 16 columns
-constexpr int OZ_NBARS_ST = 2 * OZ_STAGES + 2 * OZ_ABUF + 3;
-
-// MMAs of one slab pair PR = {PR, 5−PR}; A from the TMEM buffer at column `acol`
-template <int PR>
-__device__ __forceinline__ uint32_t oz_issue_pair(uint32_t fa, uint32_t fb, uint32_t& touched, uint32_t tmem, uint32_t acol,
-                                                  uint64_t bd0) {
-  uint32_t local = 0, n = 0;
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int sa = h ? 5 - PR : PR;
-    if (!((fa >> sa) & 1u)) continue;
-#pragma unroll
-    for (int sb = 0; sb < OZ_S; ++sb) {
-      if (sa + sb >= OZ_NACC) continue;
-      if (!((fb >> sb) & 1u)) continue;
-      const uint32_t d = sa + sb;
-      const uint32_t acc = ((touched | local) >> d) & 1u;
-      umma_i8_ts(tmem + d * OZ_BN, acol + h * (OZ_KC / 4), bd0 + (uint64_t)(sb * (OZ_GROUP_BYTES >> 4)), OZ_IDESC, acc);
-      local |= 1u << d;
-      ++n;
-    }
-  }
-  touched |= local;
-  return n;
-}
-template <int PR>
-__device__ __forceinline__ uint32_t oz_issue_pair_dispatch(uint32_t fa, uint32_t fb, uint32_t& touched, uint32_t tmem,
-                                                           uint32_t acol, uint64_t bd0) {
-  // compile-time masks for the dominant digit patterns (see syrk_i8_kernel)
-  if (fa == 0x3fu && fb == 0x3fu) return oz_issue_pair<PR>(0x3fu, 0x3fu, touched, tmem, acol, bd0);
-  if (fa == 0x3eu && fb == 0x3eu) return oz_issue_pair<PR>(0x3eu, 0x3eu, touched, tmem, acol, bd0);
-  if (fa == 0x3eu && fb == 0x3fu) return oz_issue_pair<PR>(0x3eu, 0x3fu, touched, tmem, acol, bd0);
-  if (fa == 0x3fu && fb == 0x3eu) return oz_issue_pair<PR>(0x3fu, 0x3eu, touched, tmem, acol, bd0);
-  return oz_issue_pair<PR>(fa, fb, touched, tmem, acol, bd0);
-}
-
-__global__ void __launch_bounds__(OZ_ST_THREADS, 1)
-    syrk_i8_st_kernel(CholParams p, OzParams oz, int nch, int jt0, int njt, int strip, int ntiles, int tpc) {
-  const int s = blockIdx.z;
-  if (p.info[s] != 0) return;
-  const int l0 = blockIdx.x * tpc;
-  const int l1 = min(ntiles, l0 + tpc);
-
-  extern __shared__ uint8_t oz_smem_raw[];
-  __shared__ uint64_t bars[OZ_NBARS_ST];
-  __shared__ uint32_t tmem_base_s;
-  __shared__ uint32_t touched_s;
-  const uint32_t ring = (smem_u32(oz_smem_raw) + 1023u) & ~1023u;
-  const uint32_t tbuf0 = ring + OZ_STAGES * OZ_STAGE_BYTES;
-  const uint32_t bar0 = smem_u32(bars);                       // full[s] at +8s, empty[s] at +8(STAGES+s)
-  const uint32_t afull0 = bar0 + 16 * OZ_STAGES;              // afull[i] at +8i, aempty[i] at +8(ABUF+i)
-  const uint32_t aempty0 = afull0 + 8 * OZ_ABUF;
-  const uint32_t accfull = aempty0 + 8 * OZ_ABUF, tmem_empty = accfull + 8, meta = accfull + 16;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-  if (tid == 0) {
-#pragma unroll
-    for (int i = 0; i < OZ_STAGES; ++i) {
-      mbar_init(bar0 + 8 * i, 1);
-      mbar_init(bar0 + 8 * (OZ_STAGES + i), 5);  // the MMA warp's commit + the four loader warps
-    }
-#pragma unroll
-    for (int i = 0; i < OZ_ABUF; ++i) {
-      mbar_init(afull0 + 8 * i, 4);              // one arrival per loader warp
-      mbar_init(aempty0 + 8 * i, 1);
-    }
-    mbar_init(accfull, 1);
-    mbar_init(tmem_empty, 4);
-    mbar_init(meta, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 9) tmem_alloc(smem_u32(&tmem_base_s), OZ_TMEM_COLS);
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem = tmem_base_s;
-
-  const int8_t* Ps = oz.P + (long long)s * oz.strideP;
-  const long long chunk_bytes = (long long)(p.Np / 8) * OZ_ROWGROUP_BYTES;
-
-  if (warp < 4) {
-    setmaxnreg_inc<240>();
-    oz_epilogue(p, oz, s, l0, l1, jt0, njt, strip, tmem, tbuf0, warp, lane, meta, accfull, tmem_empty, &touched_s);
-  } else if (warp < 8) {
-    setmaxnreg_dec<96>();
-    // ---- loaders: thread = row of the A tile = TMEM lane.  The two 16-byte halves of a row sit swapped in shared
-    // memory for rows 4-7 of a group (32-byte swizzle); reading the LOGICAL halves in order makes the eight lanes of
-    // a quarter-warp cover all 32 banks (the physical order would put rows r and r+4 on the same banks).
-    const int q = warp & 3, row = q * 32 + lane;
-    const uint32_t aoff = (uint32_t)(row >> 3) * OZ_ROWGROUP_BYTES + (uint32_t)(row & 7) * OZ_KC;
-    const uint32_t h0 = (uint32_t)((row & 7) >> 2) * 16, h1 = h0 ^ 16;
-    const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16) + OZ_TMEM_A;
-    int g = 0, ga = 0;  // chunks, A buffers handled so far
-    for (int l = l0; l < l1; ++l) {
-      const OzTile t = oz_tile(l, jt0, njt, strip);
-      if (!t.live) continue;
-      for (int c = 0; c < nch; ++c, ++g) {
-        const int st = g % OZ_STAGES;
-        mbar_wait(bar0 + 8 * st, (g / OZ_STAGES) & 1);
-        const uint32_t base = ring + st * OZ_STAGE_BYTES + aoff;
-        uint4 lo[OZ_S], hi[OZ_S];
-#pragma unroll
-        for (int sa = 0; sa < OZ_S; ++sa) {
-          lo[sa] = lds128(base + sa * OZ_GROUP_BYTES + h0);
-          hi[sa] = lds128(base + sa * OZ_GROUP_BYTES + h1);
-        }
-#pragma unroll
-        for (int pr = 0; pr < 3; ++pr, ++ga) {
-          const int slot = ga % OZ_ABUF;
-          if (ga >= OZ_ABUF) mbar_wait(aempty0 + 8 * slot, ((ga / OZ_ABUF) - 1) & 1);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          tmem_st16(tl + 16 * slot, lo[pr], hi[pr], lo[5 - pr], hi[5 - pr]);
-          tmem_st_wait();
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) mbar_arrive(afull0 + 8 * slot);
-        }
-        // every shared-memory read of this stage has been consumed by a store above
-        if (lane == 0) mbar_arrive(bar0 + 8 * (OZ_STAGES + st));
-      }
-    }
-  } else {
-    setmaxnreg_dec<96>();
-    if (warp == 8) {
-      if (lane == 0) {  // ---- producer (as in syrk_i8_kernel)
-        int g = 0;
-        for (int l = l0; l < l1; ++l) {
-          const OzTile t = oz_tile(l, jt0, njt, strip);
-          if (!t.live) continue;
-          const int8_t* srcA = Ps + (long long)(t.r0 / 8) * OZ_ROWGROUP_BYTES;
-          const int8_t* srcB = Ps + (long long)(t.c0 / 8) * OZ_ROWGROUP_BYTES;
-          for (int c = 0; c < nch; ++c, ++g) {
-            const int st = g % OZ_STAGES;
-            if (g >= OZ_STAGES) mbar_wait(bar0 + 8 * (OZ_STAGES + st), ((g / OZ_STAGES) - 1) & 1);
-            const uint32_t full = bar0 + 8 * st;
-            const uint32_t dst = ring + st * OZ_STAGE_BYTES;
-            mbar_arrive_expect_tx(full, OZ_STAGE_BYTES);
-            bulk_g2s(dst, srcA + c * chunk_bytes, OZ_A_BYTES, full);
-            bulk_g2s(dst + OZ_A_BYTES, srcB + c * chunk_bytes, OZ_B_BYTES, full);
-          }
-        }
-      }
-    } else if (warp == 9) {
-      // ---- MMA issuer: per chunk three A buffers, 8 + 9 + 9 MMAs, B from the shared-memory stage
-      const bool leader = elect_one();
-      const uint8_t* Fs = oz.F + (long long)s * oz.strideF;
-      const int nrb = p.Np / 64;
-      unsigned long long issued = 0;
-      int g = 0, ga = 0, k = 0;
-      for (int l = l0; l < l1; ++l) {
-        const OzTile t = oz_tile(l, jt0, njt, strip);
-        if (!t.live) continue;
-        uint32_t fa0 = 0, fb0 = 0, fa1 = 0, fb1 = 0;
-        if (lane < nch) {
-          const uint8_t* f = Fs + (long long)lane * nrb;
-          fa0 = f[t.r0 / 64] | f[t.r0 / 64 + 1];
-          fb0 = f[t.c0 / 64];
-        }
-        if (lane + 32 < nch) {
-          const uint8_t* f = Fs + (long long)(lane + 32) * nrb;
-          fa1 = f[t.r0 / 64] | f[t.r0 / 64 + 1];
-          fb1 = f[t.c0 / 64];
-        }
-        if (k > 0) {
-          mbar_wait(tmem_empty, (k - 1) & 1);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        }
-        uint32_t touched = 0;
-        for (int c = 0; c < nch; ++c, ++g) {
-          const int st = g % OZ_STAGES;
-          const uint32_t fa = __shfl_sync(0xffffffffu, c < 32 ? fa0 : fa1, c & 31);
-          const uint32_t fb = __shfl_sync(0xffffffffu, c < 32 ? fb0 : fb1, c & 31);
-          mbar_wait(bar0 + 8 * st, (g / OZ_STAGES) & 1);
-          const uint64_t bd0 = oz_desc(ring + st * OZ_STAGE_BYTES + OZ_A_BYTES);
-#pragma unroll
-          for (int pr = 0; pr < 3; ++pr, ++ga) {
-            const int slot = ga % OZ_ABUF;
-            mbar_wait(afull0 + 8 * slot, (ga / OZ_ABUF) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t acol = tmem + OZ_TMEM_A + 16 * slot;
-            if (leader) {
-              if (pr == 0) issued += oz_issue_pair_dispatch<0>(fa, fb, touched, tmem, acol, bd0);
-              else if (pr == 1) issued += oz_issue_pair_dispatch<1>(fa, fb, touched, tmem, acol, bd0);
-              else issued += oz_issue_pair_dispatch<2>(fa, fb, touched, tmem, acol, bd0);
-              umma_commit(aempty0 + 8 * slot);
-            }
-            __syncwarp();
-          }
-          if (leader) umma_commit(bar0 + 8 * (OZ_STAGES + st));
-          __syncwarp();
-        }
-        if (leader) {
-          touched_s = touched;
-          mbar_arrive(meta);
-          umma_commit(accfull);
-        }
-        __syncwarp();
-        ++k;
-      }
-      if (leader && oz.stats) {
-        atomicAdd(oz.stats, issued);
-        atomicAdd(oz.stats + 1, (unsigned long long)k * nch * 26ull);
-      }
-    }
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 9) tmem_dealloc(tmem, OZ_TMEM_COLS);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -729,10 +503,11 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(CholParams p, OzParams oz
     }
     const int r8 = row & 7;
     const int half = ((kb >> 4) ^ (r8 >> 2)) & 1;         // 32-byte swizzle: 16-byte halves swapped for rows 4-7
-    int8_t* dst = oz.P + (long long)s * oz.strideP +
-                  ((long long)chunk * (p.Np / 8) + (row >> 3)) * OZ_ROWGROUP_BYTES + r8 * OZ_KC + half * 16 + (kb & 15);
+    const long long slice_bytes = (long long)p.Np * OZ_KC;
+    int8_t* dst = oz.P + (long long)s * oz.strideP + (long long)chunk * OZ_S * slice_bytes +
+                  (long long)(row >> 3) * OZ_GROUP_BYTES + r8 * OZ_KC + half * 16 + (kb & 15);
 #pragma unroll
-    for (int t = 0; t < OZ_S; ++t) *reinterpret_cast<uint32_t*>(dst + t * OZ_GROUP_BYTES) = packed[t];
+    for (int t = 0; t < OZ_S; ++t) *reinterpret_cast<uint32_t*>(dst + t * slice_bytes) = packed[t];
   }
   // OR over the 8 lanes of a chunk, then over the CTA's 8 warps
   nz |= __shfl_xor_sync(0xffffffffu, nz, 1);
@@ -751,22 +526,12 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(CholParams p, OzParams oz
 }  // namespace
 
 namespace {
-// Where the A operand of the int8 MMAs comes from: 0 = shared memory (SS form), 1 = TMEM filled by tcgen05.cp
-// (418 vs 398 evals/s for the SS form, profiles/r2g_i8_ss_vs_ts.txt), 2 = TMEM filled by loader warps with tcgen05.st
-// (syrk_i8_st_kernel).  Modes 0 and 1 stay selectable in an experiments build.
-int g_oz_mode = 2;
 int g_oz_tpc = 8;      // most tiles a CTA works through
 }
-void ozaki_set_mode(int m) { g_oz_mode = m; }
 void ozaki_set_tpc(int n) { g_oz_tpc = n < 1 ? 1 : n; }
 
 cudaError_t ozaki_init() {
-  cudaError_t e = cudaFuncSetAttribute((const void*)syrk_i8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       OZ_SMEM_BYTES);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute((const void*)syrk_i8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute((const void*)syrk_i8_st_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES);
+  return cudaFuncSetAttribute((const void*)syrk_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES);
 }
 
 size_t oz_panel_bytes_per_slot(int Np, int outer_tiles) {
@@ -790,12 +555,7 @@ cudaError_t launch_syrk_i8(const CholParams& p, const OzParams& oz, int K, int j
   int tpc = (int)std::min<long long>(g_oz_tpc, std::max<long long>(1, total / (4LL * sms)));
   tpc = std::min(tpc, ntiles);
   const dim3 grid((ntiles + tpc - 1) / tpc, 1, B);
-  if (g_oz_mode == 2)
-    syrk_i8_st_kernel<<<grid, OZ_ST_THREADS, OZ_SMEM_BYTES, st>>>(p, oz, K / OZ_KC, jt0, njt, strip, ntiles, tpc);
-  else if (g_oz_mode == 1)
-    syrk_i8_kernel<true><<<grid, OZ_THREADS, OZ_SMEM_BYTES, st>>>(p, oz, K / OZ_KC, jt0, njt, strip, ntiles, tpc);
-  else
-    syrk_i8_kernel<false><<<grid, OZ_THREADS, OZ_SMEM_BYTES, st>>>(p, oz, K / OZ_KC, jt0, njt, strip, ntiles, tpc);
+  syrk_i8_kernel<<<grid, OZ_THREADS, OZ_SMEM_BYTES, st>>>(p, oz, K / OZ_KC, jt0, njt, strip, ntiles, tpc);
   return cudaGetLastError();
 }
 }  // namespace

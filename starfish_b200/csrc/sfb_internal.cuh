@@ -118,7 +118,6 @@ struct OzParams {
   unsigned long long* stats;  // optional [2]: int8 MMAs issued / MMAs a dense digit pattern would issue
 };
 cudaError_t ozaki_init();
-void ozaki_set_mode(int m);  // A operand of the int8 MMAs: 0 shared memory, 1 TMEM via tcgen05.cp, 2 TMEM via loader warps (default)
 void ozaki_set_tpc(int n);   // most tiles per CTA (experiments)
 size_t oz_panel_bytes_per_slot(int Np, int outer_tiles);
 size_t oz_flag_bytes_per_slot(int Np, int outer_tiles);

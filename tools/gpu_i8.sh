@@ -1,5 +1,5 @@
 #!/bin/bash
-# int8 (Ozaki) trailing update: parity tests, short bench of the int8 mode, optional TS-form A/B (experiments build), launch list
+# int8 (Ozaki) trailing update: parity tests, short bench of the int8 mode, launch list
 set -u
 TAG=${1:-i8}
 mkdir -p gpurun_out
@@ -19,11 +19,6 @@ PY
   tail -3 gpurun_out/${TAG}_bench_$1.err
 }
 run_bench default "SFB_NOP=1"
-if [ -f starfish_b200/libsfb200_exp.so ]; then   # A/B of the A-operand modes (experiments build): 1 = tcgen05.cp, 0 = shared memory
-  for m in ${OZ_MODES:-1}; do
-    run_bench mode$m "SFB200_LIB=$PWD/starfish_b200/libsfb200_exp.so SFB_OZ_MODE=$m"
-  done
-fi
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv \
   --log-file gpurun_out/${TAG}_launches.csv python bench.py --solver dense_i8 --walkers 32 --steps 1 --warmup 0 --no-e2e --no-cpu-baseline --no-model --no-structured --no-configs --no-alt --no-frozen > gpurun_out/${TAG}_l.log 2>&1; echo "ncu launches rc=$?"
 python tools/ncu_summary.py launches gpurun_out/${TAG}_launches.csv | head -9
