@@ -674,6 +674,7 @@ int sfb_create(int device, int N, int M, int Kmax, int Bmax, int workspace_walke
   if (const char* dbg = getenv("SFB_DEBUG_MODE")) h->debug_mode = atoi(dbg);
   if (const char* ot = getenv("SFB_OUTER_TILES")) h->outer_tiles = std::max(1, atoi(ot));
   if (const char* v = getenv("SFB_OZ_TPC")) ozaki_set_tpc(atoi(v));
+  if (const char* v = getenv("SFB_OZ_PAIR")) ozaki_set_pair(atoi(v) != 0);
   if (const char* v = getenv("SFB_POTRF_BLOCKED")) potrf_set_blocked(atoi(v) != 0);
   if (const char* v = getenv("SFB_LANES")) h->nlanes = std::max(1, std::min(kMaxLanes, atoi(v)));
 #endif

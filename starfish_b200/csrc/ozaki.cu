@@ -84,6 +84,23 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// the same copy delivered to the same shared-memory offset of every CTA in `mask` of the cluster; each destination
+// CTA's mbarrier (same offset) receives the complete_tx
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
                : "memory");
@@ -105,6 +122,12 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_
 // tcgen05.fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// the same arrival on the mbarrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
@@ -242,14 +265,14 @@ __device__ __forceinline__ uint32_t oz_touched(uint32_t fa, uint32_t fb) {
 // main loop), the recombined update goes through a warp-private transpose buffer, the accumulators are handed
 // back to the MMA warp, and the read-modify-write finishes with coalesced streaming stores while the next
 // tile's MMAs already run.
-__device__ __forceinline__ void oz_epilogue(const CholParams& p, const OzParams& oz, int s, int l0, int l1, int jt0, int njt,
+__device__ __forceinline__ void oz_epilogue(const CholParams& p, const OzParams& oz, int s, int l0, int l1, int lstep, int jt0, int njt,
                                             int strip, uint32_t tmem, uint32_t tbuf0, int q, int lane, uint32_t meta,
                                             uint32_t accfull, uint32_t tmem_empty, const volatile uint32_t* touched_p) {
   const double* rs = oz.rscale + (long long)s * p.Np;
   const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
   const uint32_t tbuf = tbuf0 + (uint32_t)q * (32 * OZ_TROW);
   int k = 0;
-  for (int l = l0; l < l1; ++l) {
+  for (int l = l0; l < l1; l += lstep) {
     const OzTile t = oz_tile(l, jt0, njt, strip);
     if (!t.live) continue;
     const double ri = rs[t.r0 + q * 32 + lane];                                         // row scale, TMEM mapping
@@ -305,12 +328,21 @@ __device__ __forceinline__ void oz_epilogue(const CholParams& p, const OzParams&
 
 }
 
+// PAIR: launched as clusters of two CTAs that work on the two 64-column halves (l = 2m, 2m+1) of the same 128×128 tile
+// in lockstep.  They need the SAME A operand, so each CTA fetches every other non-zero A slab and the copy is delivered
+// to both (bulk copy with .multicast::cluster): 24 instead of 36 KB per CTA and chunk cross the L2 -> SM fabric, which
+// is what bounds this kernel once the MMAs run at their floor (8.7 TB/s of operand traffic, ring of 4 stages starved:
+// profiles/r2x).  A stage is refilled only after BOTH CTAs have read it: the MMA warps commit to the `empty` barrier
+// of both CTAs (count 2).  tpc counts tile PAIRS per cluster then.
+template <bool PAIR>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
     syrk_i8_kernel(CholParams p, OzParams oz, int nch, int jt0, int njt, int strip, int ntiles, int tpc) {
   const int s = blockIdx.z;
   if (p.info[s] != 0) return;
-  const int l0 = blockIdx.x * tpc;
-  const int l1 = min(ntiles, l0 + tpc);
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int lstep = PAIR ? 2 : 1;
+  const int l0 = PAIR ? 2 * ((int)(blockIdx.x >> 1) * tpc) + (int)rank : blockIdx.x * tpc;
+  const int l1 = PAIR ? min(ntiles, 2 * ((int)(blockIdx.x >> 1) * tpc + tpc)) : min(ntiles, l0 + tpc);
 
   extern __shared__ uint8_t oz_smem_raw[];
   __shared__ uint64_t bars[2 * OZ_STAGES + 3];
@@ -325,7 +357,11 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
 
   if (tid == 0) {
 #pragma unroll
-    for (int i = 0; i < 2 * OZ_STAGES + 1; ++i) mbar_init(bar0 + 8 * i, 1);
+    for (int i = 0; i < OZ_STAGES; ++i) {
+      mbar_init(bar0 + 8 * i, 1);
+      mbar_init(bar0 + 8 * (OZ_STAGES + i), PAIR ? 2 : 1);  // a commit from the MMA warp of every CTA that reads the stage
+    }
+    mbar_init(accfull, 1);
     mbar_init(tmem_empty, 4);  // one arrival per epilogue warp
     mbar_init(meta, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -336,6 +372,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
   if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), OZ_TMEM_COLS);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer's barriers exist before a multicast copy or commit can reach them
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_base_s;
 
@@ -352,7 +389,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
     const bool leader = elect_one();
     unsigned long long issued = 0;
     int g = 0, k = 0;  // ring position, live tiles done
-    for (int l = l0; l < l1; ++l) {
+    for (int l = l0; l < l1; l += lstep) {
       const OzTile t = oz_tile(l, jt0, njt, strip);
       if (!t.live) continue;
       uint32_t fa0 = 0, fb0 = 0, fa1 = 0, fb1 = 0;
@@ -383,7 +420,10 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
             const int8_t* b = srcB + c * chunk_bytes;
 #pragma unroll
             for (int sl = 0; sl < OZ_S; ++sl) {
-              if ((fa >> sl) & 1u) bulk_g2s(dst + sl * OZ_SLAB_A, a + sl * slice_bytes, OZ_SLAB_A, full);
+              if ((fa >> sl) & 1u) {
+                if (!PAIR) bulk_g2s(dst + sl * OZ_SLAB_A, a + sl * slice_bytes, OZ_SLAB_A, full);
+                else if ((uint32_t)(sl & 1) == rank) bulk_g2s_mc(dst + sl * OZ_SLAB_A, a + sl * slice_bytes, OZ_SLAB_A, full, 3);
+              }
               if ((fb >> sl) & 1u) bulk_g2s(dst + OZ_A_BYTES + sl * OZ_SLAB_B, b + sl * slice_bytes, OZ_SLAB_B, full);
             }
           }
@@ -418,7 +458,9 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
             else if (fa == 0x3eu && fb == 0x3fu) issued += oz_issue_chunk(0x3eu, 0x3fu, tmem, ad0, bd0);
             else if (fa == 0x3fu && fb == 0x3eu) issued += oz_issue_chunk(0x3fu, 0x3eu, tmem, ad0, bd0);
             else issued += oz_issue_chunk(fa, fb, tmem, ad0, bd0);
-            umma_commit(bar0 + 8 * (OZ_STAGES + st));  // stage free once these MMAs have read it
+            // stage free once these MMAs have read it (in both CTAs of a pair: the peer's copies land here too)
+            if (PAIR) umma_commit_mc(bar0 + 8 * (OZ_STAGES + st), 3);
+            else umma_commit(bar0 + 8 * (OZ_STAGES + st));
           }
           __syncwarp();
         }
@@ -436,10 +478,11 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
       atomicAdd(oz.stats + 1, (unsigned long long)k * nch * 26ull);
     }
   } else {
-    oz_epilogue(p, oz, s, l0, l1, jt0, njt, strip, tmem, tbuf0, warp & 3, lane, meta, accfull, tmem_empty, &touched_s);
+    oz_epilogue(p, oz, s, l0, l1, lstep, jt0, njt, strip, tmem, tbuf0, warp & 3, lane, meta, accfull, tmem_empty, &touched_s);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // no exit while the peer may still signal this CTA's barriers
   if (warp == 1) tmem_dealloc(tmem, OZ_TMEM_COLS);
 }
 
@@ -527,11 +570,17 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(CholParams p, OzParams oz
 
 namespace {
 int g_oz_tpc = 8;      // most tiles a CTA works through
+bool g_oz_pair = true; // clusters of two CTAs sharing the A operand by multicast (off: experiments build, A/B)
 }
+void ozaki_set_pair(bool on) { g_oz_pair = on; }
 void ozaki_set_tpc(int n) { g_oz_tpc = n < 1 ? 1 : n; }
 
 cudaError_t ozaki_init() {
-  return cudaFuncSetAttribute((const void*)syrk_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES);
+  cudaError_t e = cudaFuncSetAttribute((const void*)syrk_i8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       OZ_SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute((const void*)syrk_i8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              OZ_SMEM_BYTES);
 }
 
 size_t oz_panel_bytes_per_slot(int Np, int outer_tiles) {
@@ -554,9 +603,28 @@ cudaError_t launch_syrk_i8(const CholParams& p, const OzParams& oz, int K, int j
   long long total = (long long)ntiles * B;
   int tpc = (int)std::min<long long>(g_oz_tpc, std::max<long long>(1, total / (4LL * sms)));
   tpc = std::min(tpc, ntiles);
-  const dim3 grid((ntiles + tpc - 1) / tpc, 1, B);
-  syrk_i8_kernel<<<grid, OZ_THREADS, OZ_SMEM_BYTES, st>>>(p, oz, K / OZ_KC, jt0, njt, strip, ntiles, tpc);
-  return cudaGetLastError();
+  if (!g_oz_pair) {
+    const dim3 grid((ntiles + tpc - 1) / tpc, 1, B);
+    syrk_i8_kernel<false><<<grid, OZ_THREADS, OZ_SMEM_BYTES, st>>>(p, oz, K / OZ_KC, jt0, njt, strip, ntiles, tpc);
+    return cudaGetLastError();
+  }
+  // clusters of two: tile l = 2m + rank; ntiles is even in both enumerations and the halves of a 128×128 tile are
+  // adjacent.  tpc tile pairs per cluster = tpc tiles per CTA.
+  const int npairs = ntiles / 2;
+  tpc = std::min(tpc, npairs);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * ((npairs + tpc - 1) / tpc), 1, B);
+  cfg.blockDim = dim3(OZ_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = OZ_SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, syrk_i8_kernel<true>, p, oz, K / OZ_KC, jt0, njt, strip, ntiles, tpc);
 }
 }  // namespace
 

@@ -119,6 +119,7 @@ struct OzParams {
 };
 cudaError_t ozaki_init();
 void ozaki_set_tpc(int n);   // most tiles per CTA (experiments)
+void ozaki_set_pair(bool on);  // CTA pairs sharing the A operand by multicast (default) or independent CTAs (experiments)
 size_t oz_panel_bytes_per_slot(int Np, int outer_tiles);
 size_t oz_flag_bytes_per_slot(int Np, int outer_tiles);
 cudaError_t launch_oz_rowscale(const CholParams& p, const OzParams& oz, int B, cudaStream_t st);
