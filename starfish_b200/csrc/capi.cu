@@ -235,9 +235,9 @@ int ensure_ozaki(sfb_ctx* h) {
   if (cudaMalloc((void**)&h->ozP, 2 * h->oz_bytes * (size_t)h->slots) != cudaSuccess ||
       cudaMalloc((void**)&h->oz_rscale, sizeof(double) * (size_t)h->Np * h->slots) != cudaSuccess ||
       cudaMalloc((void**)&h->ozF, 2 * h->oz_fbytes * (size_t)h->slots) != cudaSuccess ||
-      cudaMalloc((void**)&h->oz_stats, 2 * sizeof(unsigned long long)) != cudaSuccess)
+      cudaMalloc((void**)&h->oz_stats, 8 * sizeof(unsigned long long)) != cudaSuccess)
     return fail(h, SFB_ERR_NOMEM, "int8 solver: sliced-panel workspace allocation failed");
-  SFB_CUDA(h, cudaMemset(h->oz_stats, 0, 2 * sizeof(unsigned long long)));
+  SFB_CUDA(h, cudaMemset(h->oz_stats, 0, 8 * sizeof(unsigned long long)));
   SFB_CUDA(h, ozaki_init());
   return SFB_OK;
 }
@@ -1171,11 +1171,18 @@ int sfb_i8_mma_counts(sfb_t* h, unsigned long long* issued, unsigned long long* 
   if (!h->oz_stats) return SFB_OK;
   DeviceGuard guard(h->device);
   for (int i = 0; i < kMaxLanes; ++i) SFB_CUDA(h, cudaStreamSynchronize(h->streams[i]));
-  unsigned long long v[2];
+  unsigned long long v[8];
   SFB_CUDA(h, cudaMemcpy(v, h->oz_stats, sizeof(v), cudaMemcpyDeviceToHost));
   SFB_CUDA(h, cudaMemset(h->oz_stats, 0, sizeof(v)));
   *issued = v[0];
   *dense = v[1];
+#ifdef SFB_EXPERIMENTS  // where the MMA warp of the int8 update spends its time (clock64 sums over all CTAs)
+  if (getenv("SFB_OZ_TIMING") && v[5])
+    fprintf(stderr, "[sfb] int8 MMA warp: %.0f cycles per tile = %.1f %% waiting for operands + %.1f %% waiting for the epilogue "
+            "to drain the accumulators + %.1f %% issuing; %llu tiles, %.1f slab products per chunk\n",
+            (double)v[2] / v[5], 100.0 * v[3] / v[2], 100.0 * v[4] / v[2], 100.0 * (v[2] - v[3] - v[4]) / v[2], v[5],
+            26.0 * v[0] / v[1]);
+#endif
   return SFB_OK;
 }
 

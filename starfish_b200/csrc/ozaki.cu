@@ -30,8 +30,8 @@
 // In shared memory the six B slabs of a stage lie back to back, so a run of consecutive B slabs is one operand of
 // N = 64·len rows (oz_issue_chunk).
 //
-// Kernel shape: 192 threads = warp 0 bulk-copy producer, warp 1 MMA issuer (one elected lane) + TMEM allocator,
-// warps 2-5 epilogue (TMEM lane quarter = warp%4).  4-stage ring of 36 KB, full/empty mbarriers, tcgen05.commit
+// Kernel shape: 320 threads = warp 0 bulk-copy producer, warp 1 MMA issuer (one elected lane) + TMEM allocator,
+// warps 2-9 epilogue (TMEM lane quarter = warp%4, two warps per quarter).  4-stage ring of 36 KB, full/empty mbarriers, tcgen05.commit
 // releases a stage / signals the epilogue.  The epilogue warps prefetch the C tile (coalesced, into registers) while
 // the main loop runs, transpose the recombined update through a padded buffer and finish the read-modify-write with
 // coalesced streaming stores.
@@ -54,7 +54,7 @@ constexpr int OZ_ROWGROUP_BYTES = OZ_S * OZ_GROUP_BYTES;     // 1536: all slices
 constexpr int OZ_A_BYTES = (OZ_BM / 8) * OZ_ROWGROUP_BYTES;  // 24576
 constexpr int OZ_B_BYTES = (OZ_BN / 8) * OZ_ROWGROUP_BYTES;  // 12288
 constexpr int OZ_STAGE_BYTES = OZ_A_BYTES + OZ_B_BYTES;      // 36864
-constexpr int OZ_THREADS = 192;
+constexpr int OZ_THREADS = 320;      // producer warp, MMA warp, eight epilogue warps
 constexpr uint32_t OZ_TMEM_COLS = 512;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -176,7 +176,7 @@ constexpr uint32_t OZ_IDESC_BASE = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32
 //            row tile jt0+y, 64-column block x; tiles above the diagonal of their tile column (y < x/2) are skipped
 //   triangle trailing update of every tile column >= jt0: l in [0, T(T+1)), decoded to (row tile t, 64-column block)
 // Roles: warp 0 = bulk-copy producer (runs ahead across tile boundaries), warp 1 = MMA issuer (waits for the previous
-// tile's accumulators to be drained, clears them with two MMAs against an all-zero A slab), warps 2-5 = epilogue.
+// tile's accumulators to be drained, clears them with two MMAs against an all-zero A slab), warps 2-9 = epilogue.
 // ------------------------------------------------------------------------------------------------
 struct OzTile { int r0, c0, live; };
 
@@ -200,8 +200,9 @@ __device__ __forceinline__ OzTile oz_tile(int l, int jt0, int njt, int strip) {
 
 constexpr int OZ_SLAB_A = OZ_BM * OZ_KC;             // 4096: one digit slab of the A operand (128 rows × 32 B)
 constexpr int OZ_SLAB_B = OZ_BN * OZ_KC;             // 2048
-constexpr uint32_t OZ_TROW = 66 * 8;                 // padded row of the transpose buffer (528 B: conflict-free 16-byte accesses)
-constexpr int OZ_TBUF_BYTES = 4 * 32 * OZ_TROW;     // 4 epilogue warps × 32 rows
+constexpr uint32_t OZ_TROW = 34 * 8;                 // padded row of a transpose buffer (32 doubles + 16 B: conflict-free 16-byte accesses)
+constexpr int OZ_EPI_WARPS = 8;
+constexpr int OZ_TBUF_BYTES = OZ_EPI_WARPS * 32 * OZ_TROW;     // one 32 × 32 buffer per epilogue warp
 constexpr int OZ_ZERO_BYTES = OZ_SLAB_A;            // an all-zero A slab (clears the accumulators at the start of a tile)
 constexpr int OZ_SMEM_BYTES = OZ_STAGES * OZ_STAGE_BYTES + OZ_TBUF_BYTES + OZ_ZERO_BYTES + 1024;  // + alignment slack
 
@@ -258,74 +259,110 @@ __device__ __forceinline__ uint32_t oz_touched(uint32_t fa, uint32_t fb) {
   return t & 0x7fu;
 }
 
-// ---- epilogue (4 warps; warp q owns tile rows 32q..32q+31 = its TMEM lane quarter).
-// Two thread mappings: TMEM hands a thread ONE ROW (lane = row, 16 columns per load), global memory wants a
-// warp on one row (lane = column pair, 512 contiguous bytes).  The C tile is therefore fetched in the global
-// mapping BEFORE the accumulators are ready (32 independent 16-byte loads per thread, in flight under the
-// main loop), the recombined update goes through a warp-private transpose buffer, the accumulators are handed
-// back to the MMA warp, and the read-modify-write finishes with coalesced streaming stores while the next
-// tile's MMAs already run.
+// ---- epilogue (8 warps; warp (q, hh) owns tile rows 32q..32q+31 — its TMEM lane quarter — and columns 32hh..32hh+31).
+// Two thread mappings: TMEM hands a thread ONE ROW (lane = row, 16 columns per load), global memory wants
+// neighbouring lanes on one row (half a warp = 256 contiguous bytes of a row, two rows per instruction).  The C tile
+// is therefore fetched in the global mapping BEFORE the accumulators are ready (16 independent 16-byte loads per
+// thread, in flight under the main loop), the recombined update goes through a warp-private padded transpose buffer,
+// the accumulators are handed back to the MMA warp, and the read-modify-write finishes with coalesced streaming
+// stores while the next tile's MMAs already run.  The drain (accfull -> tmem_empty) is the serial part of a tile — the
+// MMA warp waits for it — hence eight warps on it and the next accumulator's TMEM load in flight under the Horner step.
 __device__ __forceinline__ void oz_epilogue(const CholParams& p, const OzParams& oz, int s, int l0, int l1, int lstep, int jt0, int njt,
-                                            int strip, uint32_t tmem, uint32_t tbuf0, int q, int lane, uint32_t meta,
+                                            int strip, uint32_t tmem, uint32_t tbuf0, int ew, int lane, uint32_t meta,
                                             uint32_t accfull, uint32_t tmem_empty, const volatile uint32_t* touched_p) {
+  const int q = ew & 3, hh = ew >> 2;   // TMEM lane quarter (must equal warp id % 4), column half
   const double* rs = oz.rscale + (long long)s * p.Np;
-  const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
-  const uint32_t tbuf = tbuf0 + (uint32_t)q * (32 * OZ_TROW);
+  const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(hh * 32);
+  const uint32_t tbuf = tbuf0 + (uint32_t)ew * (32 * OZ_TROW);
+  const int grow = lane >> 4, gcol = 2 * (lane & 15);   // global mapping: instruction i covers rows 2i, 2i+1
   int k = 0;
   for (int l = l0; l < l1; l += lstep) {
     const OzTile t = oz_tile(l, jt0, njt, strip);
     if (!t.live) continue;
-    const double ri = rs[t.r0 + q * 32 + lane];                                         // row scale, TMEM mapping
-    const double2 rj = *reinterpret_cast<const double2*>(rs + t.c0 + 2 * lane);        // column scales, global mapping
-    double* Cw = p.W + (long long)s * p.strideW + (long long)(t.r0 + q * 32) * p.Np + t.c0 + 2 * lane;
-    double2 creg[32];
+    const double ri = rs[t.r0 + q * 32 + lane];                                                 // row scale, TMEM mapping
+    const double2 rj = *reinterpret_cast<const double2*>(rs + t.c0 + hh * 32 + gcol);          // column scales, global mapping
+    double* Cw = p.W + (long long)s * p.strideW + (long long)(t.r0 + q * 32 + grow) * p.Np + t.c0 + hh * 32 + gcol;
+    double2 creg[16];
 #pragma unroll
-    for (int r = 0; r < 32; ++r) creg[r] = __ldcs(reinterpret_cast<const double2*>(Cw + (long long)r * p.Np));
+    for (int i = 0; i < 16; ++i) creg[i] = __ldcs(reinterpret_cast<const double2*>(Cw + (long long)(2 * i) * p.Np));
     mbar_wait(meta, k & 1);
     const uint32_t touched = *touched_p;
     mbar_wait(accfull, k & 1);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-    for (int cb = 0; cb < OZ_BN / 16; ++cb) {
-      double acc[16];
-      uint32_t v[16];
+    if (touched == 0x7fu) {
+      // every accumulator holds a sum (the common case): software-pipelined, the load of anti-diagonal d−1 is in
+      // flight while d is folded in
 #pragma unroll
-      for (int j = 0; j < 16; ++j) acc[j] = 0.0;
+      for (int cb = 0; cb < 2; ++cb) {
+        double acc[16];
+        uint32_t va[16], vb[16];
+        tmem_ld16(tlane + (OZ_NACC - 1) * OZ_BN + cb * 16, va);
 #pragma unroll
-      for (int d = OZ_NACC - 1; d >= 0; --d) {   // Horner from the least significant anti-diagonal
-        if ((touched >> d) & 1u) {
-          tmem_ld16(tlane + d * OZ_BN + cb * 16, v);
+        for (int j = 0; j < 16; ++j) acc[j] = 0.0;
+#pragma unroll
+        for (int d = OZ_NACC - 1; d >= 0; --d) {   // Horner from the least significant anti-diagonal
           tmem_ld_wait();
+          if (((OZ_NACC - 1 - d) & 1) == 0) {
+            if (d > 0) tmem_ld16(tlane + (d - 1) * OZ_BN + cb * 16, vb);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) acc[j] = fma(acc[j], 0.00390625, i2d(v[j]));
-        } else {
+            for (int j = 0; j < 16; ++j) acc[j] = fma(acc[j], 0.00390625, i2d(va[j]));
+          } else {
+            if (d > 0) tmem_ld16(tlane + (d - 1) * OZ_BN + cb * 16, va);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) acc[j] *= 0.00390625;
+            for (int j = 0; j < 16; ++j) acc[j] = fma(acc[j], 0.00390625, i2d(vb[j]));
+          }
         }
-      }
-      const uint32_t dst = tbuf + (uint32_t)lane * OZ_TROW + (uint32_t)cb * 128;
+        const uint32_t dst = tbuf + (uint32_t)lane * OZ_TROW + (uint32_t)cb * 128;
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(dst + 16 * j), "d"(acc[2 * j] * ri), "d"(acc[2 * j + 1] * ri)
-                     : "memory");
+        for (int j = 0; j < 8; ++j)
+          asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(dst + 16 * j), "d"(acc[2 * j] * ri), "d"(acc[2 * j + 1] * ri)
+                       : "memory");
+      }
+    } else {
+#pragma unroll 1
+      for (int cb = 0; cb < 2; ++cb) {
+        double acc[16];
+        uint32_t v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = 0.0;
+#pragma unroll
+        for (int d = OZ_NACC - 1; d >= 0; --d) {
+          if ((touched >> d) & 1u) {   // an accumulator without a product holds zeros: skip its load
+            tmem_ld16(tlane + d * OZ_BN + cb * 16, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j] = fma(acc[j], 0.00390625, i2d(v[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j] *= 0.00390625;
+          }
+        }
+        const uint32_t dst = tbuf + (uint32_t)lane * OZ_TROW + (uint32_t)cb * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(dst + 16 * j), "d"(acc[2 * j] * ri), "d"(acc[2 * j + 1] * ri)
+                       : "memory");
+      }
     }
     // accumulators drained: hand TMEM back to the MMA warp (which orders its next MMAs after this arrive)
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncwarp();
     if (lane == 0) mbar_arrive(tmem_empty);
 #pragma unroll
-    for (int r = 0; r < 32; ++r) {
+    for (int i = 0; i < 16; ++i) {
       double tx, ty;
-      asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(tx), "=d"(ty) : "r"(tbuf + (uint32_t)r * OZ_TROW + 16 * lane) : "memory");
-      double2 c = creg[r];
+      asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];"
+                   : "=d"(tx), "=d"(ty)
+                   : "r"(tbuf + (uint32_t)(2 * i + grow) * OZ_TROW + 8 * (uint32_t)gcol)
+                   : "memory");
+      double2 c = creg[i];
       c.x = fma(-tx, rj.x, c.x);
       c.y = fma(-ty, rj.y, c.y);
-      __stcs(reinterpret_cast<double2*>(Cw + (long long)r * p.Np), c);
+      __stcs(reinterpret_cast<double2*>(Cw + (long long)(2 * i) * p.Np), c);
     }
     __syncwarp();  // the transpose buffer is rewritten by the next tile
     ++k;
   }
-
 }
 
 // PAIR: launched as clusters of two CTAs that work on the two 64-column halves (l = 2m, 2m+1) of the same 128×128 tile
@@ -362,7 +399,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
       mbar_init(bar0 + 8 * (OZ_STAGES + i), PAIR ? 2 : 1);  // a commit from the MMA warp of every CTA that reads the stage
     }
     mbar_init(accfull, 1);
-    mbar_init(tmem_empty, 4);  // one arrival per epilogue warp
+    mbar_init(tmem_empty, OZ_EPI_WARPS);  // one arrival per epilogue warp
     mbar_init(meta, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -388,6 +425,10 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
     // per tile; whole warps run the loops (uniform control flow), one elected lane issues.
     const bool leader = elect_one();
     unsigned long long issued = 0;
+#ifdef SFB_EXPERIMENTS
+    long long t_full = 0, t_drain = 0;
+    const long long t_begin = clock64();
+#endif
     int g = 0, k = 0;  // ring position, live tiles done
     for (int l = l0; l < l1; l += lstep) {
       const OzTile t = oz_tile(l, jt0, njt, strip);
@@ -431,10 +472,16 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
         }
       } else {
         // ---- MMA issuer
+#ifdef SFB_EXPERIMENTS
+        const long long tt0 = clock64();
+#endif
         if (k > 0) {  // the epilogue must have drained the accumulators of the previous tile
           mbar_wait(tmem_empty, (k - 1) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
+#ifdef SFB_EXPERIMENTS
+        t_drain += clock64() - tt0;
+#endif
         if (leader) {  // clear the seven accumulators: zero A slab × whatever the ring holds (448 columns)
           umma_i8(tmem, oz_desc(zero0), oz_desc(ring), oz_idesc(256), 0);
           umma_i8(tmem + 256, oz_desc(zero0), oz_desc(ring), oz_idesc(192), 0);
@@ -444,7 +491,13 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
           const int st = g % OZ_STAGES;
           const uint32_t fa = __shfl_sync(0xffffffffu, c < 32 ? fa0 : fa1, c & 31);
           const uint32_t fb = __shfl_sync(0xffffffffu, c < 32 ? fb0 : fb1, c & 31);
+#ifdef SFB_EXPERIMENTS
+          const long long tf0 = clock64();
+#endif
           mbar_wait(bar0 + 8 * st, (g / OZ_STAGES) & 1);
+#ifdef SFB_EXPERIMENTS
+          t_full += clock64() - tf0;
+#endif
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t a0 = ring + st * OZ_STAGE_BYTES;
           const uint64_t ad0 = oz_desc(a0), bd0 = oz_desc(a0 + OZ_A_BYTES);
@@ -476,9 +529,17 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
     if (warp == 1 && leader && oz.stats) {
       atomicAdd(oz.stats, issued);
       atomicAdd(oz.stats + 1, (unsigned long long)k * nch * 26ull);
+#ifdef SFB_EXPERIMENTS
+      atomicAdd(oz.stats + 2, (unsigned long long)(clock64() - t_begin));
+      atomicAdd(oz.stats + 3, (unsigned long long)t_full);
+      atomicAdd(oz.stats + 4, (unsigned long long)t_drain);
+      atomicAdd(oz.stats + 5, (unsigned long long)k);
+#endif
     }
   } else {
-    oz_epilogue(p, oz, s, l0, l1, lstep, jt0, njt, strip, tmem, tbuf0, warp & 3, lane, meta, accfull, tmem_empty, &touched_s);
+    // warps 2..9: TMEM lane quarter = warp % 4 (hardware rule), column half = (warp − 2) / 4
+    oz_epilogue(p, oz, s, l0, l1, lstep, jt0, njt, strip, tmem, tbuf0, (warp & 3) + 4 * ((warp - 2) >> 2), lane, meta, accfull,
+                tmem_empty, &touched_s);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
