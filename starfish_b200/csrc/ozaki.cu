@@ -31,7 +31,7 @@
 // N = 64·len rows (oz_issue_chunk).
 //
 // Kernel shape: 320 threads = warp 0 bulk-copy producer, warp 1 MMA issuer (one elected lane) + TMEM allocator,
-// warps 2-9 epilogue (TMEM lane quarter = warp%4, two warps per quarter).  4-stage ring of 36 KB, full/empty mbarriers, tcgen05.commit
+// warps 2-9 epilogue (TMEM lane quarter = warp%4, two warps per quarter).  5-stage ring of 36 KB, full/empty mbarriers, tcgen05.commit
 // releases a stage / signals the epilogue.  The epilogue warps prefetch the C tile (coalesced, into registers) while
 // the main loop runs, transpose the recombined update through a padded buffer and finish the read-modify-write with
 // coalesced streaming stores.
@@ -48,7 +48,7 @@ constexpr int OZ_S = kOzSlices;      // 6
 constexpr int OZ_NACC = 7;           // anti-diagonals 0..6
 constexpr int OZ_KC = kOzChunk;      // 32
 constexpr int OZ_BM = 128, OZ_BN = 64;
-constexpr int OZ_STAGES = 4;
+constexpr int OZ_STAGES = 5;
 constexpr int OZ_GROUP_BYTES = 8 * OZ_KC;                    // 256: 8 rows × 32 B of one slice
 constexpr int OZ_ROWGROUP_BYTES = OZ_S * OZ_GROUP_BYTES;     // 1536: all slices of 8 rows
 constexpr int OZ_A_BYTES = (OZ_BM / 8) * OZ_ROWGROUP_BYTES;  // 24576
@@ -200,9 +200,9 @@ __device__ __forceinline__ OzTile oz_tile(int l, int jt0, int njt, int strip) {
 
 constexpr int OZ_SLAB_A = OZ_BM * OZ_KC;             // 4096: one digit slab of the A operand (128 rows × 32 B)
 constexpr int OZ_SLAB_B = OZ_BN * OZ_KC;             // 2048
-constexpr uint32_t OZ_TROW = 34 * 8;                 // padded row of a transpose buffer (32 doubles + 16 B: conflict-free 16-byte accesses)
+constexpr uint32_t OZ_TROW = 18 * 8;                 // padded row of a transpose buffer (16 doubles + 16 B: conflict-free 16-byte accesses)
 constexpr int OZ_EPI_WARPS = 8;
-constexpr int OZ_TBUF_BYTES = OZ_EPI_WARPS * 32 * OZ_TROW;     // one 32 × 32 buffer per epilogue warp
+constexpr int OZ_TBUF_BYTES = OZ_EPI_WARPS * 32 * OZ_TROW;     // one 32 × 16 buffer per epilogue warp
 constexpr int OZ_ZERO_BYTES = OZ_SLAB_A;            // an all-zero A slab (clears the accumulators at the start of a tile)
 constexpr int OZ_SMEM_BYTES = OZ_STAGES * OZ_STAGE_BYTES + OZ_TBUF_BYTES + OZ_ZERO_BYTES + 1024;  // + alignment slack
 
@@ -261,12 +261,54 @@ __device__ __forceinline__ uint32_t oz_touched(uint32_t fa, uint32_t fb) {
 
 // ---- epilogue (8 warps; warp (q, hh) owns tile rows 32q..32q+31 — its TMEM lane quarter — and columns 32hh..32hh+31).
 // Two thread mappings: TMEM hands a thread ONE ROW (lane = row, 16 columns per load), global memory wants
-// neighbouring lanes on one row (half a warp = 256 contiguous bytes of a row, two rows per instruction).  The C tile
-// is therefore fetched in the global mapping BEFORE the accumulators are ready (16 independent 16-byte loads per
-// thread, in flight under the main loop), the recombined update goes through a warp-private padded transpose buffer,
-// the accumulators are handed back to the MMA warp, and the read-modify-write finishes with coalesced streaming
-// stores while the next tile's MMAs already run.  The drain (accfull -> tmem_empty) is the serial part of a tile — the
-// MMA warp waits for it — hence eight warps on it and the next accumulator's TMEM load in flight under the Horner step.
+// neighbouring lanes on one row (8 lanes = 128 contiguous bytes of a row, four rows per instruction).  The C tile is
+// therefore fetched in the global mapping BEFORE the accumulators are ready (16 independent 16-byte loads per thread,
+// in flight under the main loop), the recombined update goes through a warp-private padded transpose buffer in two
+// rounds of 16 columns (a 32 × 16 buffer per warp keeps shared memory free for a fifth pipeline stage), the
+// accumulators are handed back to the MMA warp, and the read-modify-write finishes with coalesced streaming stores
+// while the next tile's MMAs already run.  The drain (accfull -> tmem_empty) is the serial part of a tile — the MMA
+// warp waits for it — hence eight warps on it and the next accumulator's TMEM load in flight under the Horner step.
+__device__ __forceinline__ void oz_drain16(uint32_t taddr, uint32_t touched, double ri, uint32_t dst) {
+  double acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = 0.0;
+  if (touched == 0x7fu) {
+    // every accumulator holds a sum (the common case): software-pipelined loads
+    uint32_t va[16], vb[16];
+    tmem_ld16(taddr + (OZ_NACC - 1) * OZ_BN, va);
+#pragma unroll
+    for (int d = OZ_NACC - 1; d >= 0; --d) {   // Horner from the least significant anti-diagonal
+      tmem_ld_wait();
+      if (((OZ_NACC - 1 - d) & 1) == 0) {
+        if (d > 0) tmem_ld16(taddr + (d - 1) * OZ_BN, vb);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = fma(acc[j], 0.00390625, i2d(va[j]));
+      } else {
+        if (d > 0) tmem_ld16(taddr + (d - 1) * OZ_BN, va);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = fma(acc[j], 0.00390625, i2d(vb[j]));
+      }
+    }
+  } else {
+    uint32_t v[16];
+#pragma unroll
+    for (int d = OZ_NACC - 1; d >= 0; --d) {
+      if ((touched >> d) & 1u) {   // an accumulator without a product holds zeros: skip its load
+        tmem_ld16(taddr + d * OZ_BN, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = fma(acc[j], 0.00390625, i2d(v[j]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] *= 0.00390625;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(dst + 16 * j), "d"(acc[2 * j] * ri), "d"(acc[2 * j + 1] * ri) : "memory");
+}
+
 __device__ __forceinline__ void oz_epilogue(const CholParams& p, const OzParams& oz, int s, int l0, int l1, int lstep, int jt0, int njt,
                                             int strip, uint32_t tmem, uint32_t tbuf0, int ew, int lane, uint32_t meta,
                                             uint32_t accfull, uint32_t tmem_empty, const volatile uint32_t* touched_p) {
@@ -274,92 +316,51 @@ __device__ __forceinline__ void oz_epilogue(const CholParams& p, const OzParams&
   const double* rs = oz.rscale + (long long)s * p.Np;
   const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(hh * 32);
   const uint32_t tbuf = tbuf0 + (uint32_t)ew * (32 * OZ_TROW);
-  const int grow = lane >> 4, gcol = 2 * (lane & 15);   // global mapping: instruction i covers rows 2i, 2i+1
+  const int grow = lane >> 3, gcol = 2 * (lane & 7);   // global mapping: instruction g of a round covers rows 4g..4g+3
+  const uint32_t tdst = tbuf + (uint32_t)lane * OZ_TROW;                       // TMEM mapping: my row
+  const uint32_t tsrc = tbuf + (uint32_t)grow * OZ_TROW + 8 * (uint32_t)gcol;  // global mapping
   int k = 0;
   for (int l = l0; l < l1; l += lstep) {
     const OzTile t = oz_tile(l, jt0, njt, strip);
     if (!t.live) continue;
     const double ri = rs[t.r0 + q * 32 + lane];                                                 // row scale, TMEM mapping
-    const double2 rj = *reinterpret_cast<const double2*>(rs + t.c0 + hh * 32 + gcol);          // column scales, global mapping
     double* Cw = p.W + (long long)s * p.strideW + (long long)(t.r0 + q * 32 + grow) * p.Np + t.c0 + hh * 32 + gcol;
-    double2 creg[16];
+    const double2 rj0 = *reinterpret_cast<const double2*>(rs + t.c0 + hh * 32 + gcol);         // column scales, global mapping
+    const double2 rj1 = *reinterpret_cast<const double2*>(rs + t.c0 + hh * 32 + 16 + gcol);
+    double2 creg[16];   // [round cb][row group g]: rows 4g + grow, columns 16·cb + gcol
 #pragma unroll
-    for (int i = 0; i < 16; ++i) creg[i] = __ldcs(reinterpret_cast<const double2*>(Cw + (long long)(2 * i) * p.Np));
+    for (int i = 0; i < 16; ++i)
+      creg[i] = __ldcs(reinterpret_cast<const double2*>(Cw + (long long)(4 * (i & 7)) * p.Np + 16 * (i >> 3)));
     mbar_wait(meta, k & 1);
     const uint32_t touched = *touched_p;
     mbar_wait(accfull, k & 1);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if (touched == 0x7fu) {
-      // every accumulator holds a sum (the common case): software-pipelined, the load of anti-diagonal d−1 is in
-      // flight while d is folded in
+    // round 0: columns 0..15 of this warp's 32
+    oz_drain16(tlane, touched, ri, tdst);
+    __syncwarp();
 #pragma unroll
-      for (int cb = 0; cb < 2; ++cb) {
-        double acc[16];
-        uint32_t va[16], vb[16];
-        tmem_ld16(tlane + (OZ_NACC - 1) * OZ_BN + cb * 16, va);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = 0.0;
-#pragma unroll
-        for (int d = OZ_NACC - 1; d >= 0; --d) {   // Horner from the least significant anti-diagonal
-          tmem_ld_wait();
-          if (((OZ_NACC - 1 - d) & 1) == 0) {
-            if (d > 0) tmem_ld16(tlane + (d - 1) * OZ_BN + cb * 16, vb);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) acc[j] = fma(acc[j], 0.00390625, i2d(va[j]));
-          } else {
-            if (d > 0) tmem_ld16(tlane + (d - 1) * OZ_BN + cb * 16, va);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) acc[j] = fma(acc[j], 0.00390625, i2d(vb[j]));
-          }
-        }
-        const uint32_t dst = tbuf + (uint32_t)lane * OZ_TROW + (uint32_t)cb * 128;
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(dst + 16 * j), "d"(acc[2 * j] * ri), "d"(acc[2 * j + 1] * ri)
-                       : "memory");
-      }
-    } else {
-#pragma unroll 1
-      for (int cb = 0; cb < 2; ++cb) {
-        double acc[16];
-        uint32_t v[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = 0.0;
-#pragma unroll
-        for (int d = OZ_NACC - 1; d >= 0; --d) {
-          if ((touched >> d) & 1u) {   // an accumulator without a product holds zeros: skip its load
-            tmem_ld16(tlane + d * OZ_BN + cb * 16, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 16; ++j) acc[j] = fma(acc[j], 0.00390625, i2d(v[j]));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) acc[j] *= 0.00390625;
-          }
-        }
-        const uint32_t dst = tbuf + (uint32_t)lane * OZ_TROW + (uint32_t)cb * 128;
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(dst + 16 * j), "d"(acc[2 * j] * ri), "d"(acc[2 * j + 1] * ri)
-                       : "memory");
-      }
+    for (int g = 0; g < 8; ++g) {
+      double tx, ty;
+      asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(tx), "=d"(ty) : "r"(tsrc + (uint32_t)(4 * g) * OZ_TROW) : "memory");
+      creg[g].x = fma(-tx, rj0.x, creg[g].x);
+      creg[g].y = fma(-ty, rj0.y, creg[g].y);
     }
-    // accumulators drained: hand TMEM back to the MMA warp (which orders its next MMAs after this arrive)
+    __syncwarp();
+    // round 1: columns 16..31; afterwards the accumulators are drained
+    oz_drain16(tlane + 16, touched, ri, tdst);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncwarp();
-    if (lane == 0) mbar_arrive(tmem_empty);
+    if (lane == 0) mbar_arrive(tmem_empty);   // TMEM back to the MMA warp (which orders its next MMAs after this arrive)
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
+    for (int g = 0; g < 8; ++g) {
       double tx, ty;
-      asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];"
-                   : "=d"(tx), "=d"(ty)
-                   : "r"(tbuf + (uint32_t)(2 * i + grow) * OZ_TROW + 8 * (uint32_t)gcol)
-                   : "memory");
-      double2 c = creg[i];
-      c.x = fma(-tx, rj.x, c.x);
-      c.y = fma(-ty, rj.y, c.y);
-      __stcs(reinterpret_cast<double2*>(Cw + (long long)(2 * i) * p.Np), c);
+      asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(tx), "=d"(ty) : "r"(tsrc + (uint32_t)(4 * g) * OZ_TROW) : "memory");
+      creg[8 + g].x = fma(-tx, rj1.x, creg[8 + g].x);
+      creg[8 + g].y = fma(-ty, rj1.y, creg[8 + g].y);
     }
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      __stcs(reinterpret_cast<double2*>(Cw + (long long)(4 * (i & 7)) * p.Np + 16 * (i >> 3)), creg[i]);
     __syncwarp();  // the transpose buffer is rewritten by the next tile
     ++k;
   }
