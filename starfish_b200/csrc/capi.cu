@@ -259,7 +259,7 @@ int run_cholesky(sfb_ctx* h, int lane, int slot0, int nb, double* lnL_out, int* 
   p.info = h->info_ws + slot0;
   p.k0 = 0;
   const int nt = h->Np / kTile;
-  OzParams oz{nullptr, 0, nullptr, nullptr, 0, nullptr};
+  OzParams oz{nullptr, 0, nullptr, nullptr, 0, nullptr, 0};
   if (i8) {
     int rc = ensure_ozaki(h);
     if (rc != SFB_OK) return rc;
@@ -675,6 +675,7 @@ int sfb_create(int device, int N, int M, int Kmax, int Bmax, int workspace_walke
   if (const char* ot = getenv("SFB_OUTER_TILES")) h->outer_tiles = std::max(1, atoi(ot));
   if (const char* v = getenv("SFB_OZ_TPC")) ozaki_set_tpc(atoi(v));
   if (const char* v = getenv("SFB_OZ_PAIR")) ozaki_set_pair(atoi(v) != 0);
+  if (const char* v = getenv("SFB_OZ_DEBUG")) ozaki_set_debug(atoi(v));
   if (const char* v = getenv("SFB_POTRF_BLOCKED")) potrf_set_blocked(atoi(v) != 0);
   if (const char* v = getenv("SFB_LANES")) h->nlanes = std::max(1, std::min(kMaxLanes, atoi(v)));
 #endif

@@ -75,6 +75,16 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// one look, never suspends (mbarrier.test_wait): used to learn a barrier's state ahead of time
+__device__ __forceinline__ bool mbar_test_nb(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_test(bar, parity)) {
   }
@@ -250,6 +260,14 @@ __device__ __forceinline__ uint32_t oz_issue_chunk(uint32_t fa, uint32_t fb, uin
   }
   return n;
 }
+// number of slab products for digit-slab masks (fa, fb)
+__device__ __forceinline__ uint32_t oz_products(uint32_t fa, uint32_t fb) {
+  uint32_t n = 0;
+#pragma unroll
+  for (int sa = 0; sa < OZ_S; ++sa)
+    if ((fa >> sa) & 1u) n += __popc(fb & ((1u << (OZ_NACC - sa)) - 1u) & 0x3fu);
+  return n;
+}
 // accumulators that receive a product for digit-slab masks (fa, fb)
 __device__ __forceinline__ uint32_t oz_touched(uint32_t fa, uint32_t fb) {
   uint32_t t = 0;
@@ -329,8 +347,17 @@ __device__ __forceinline__ void oz_epilogue(const CholParams& p, const OzParams&
     const double2 rj1 = *reinterpret_cast<const double2*>(rs + t.c0 + hh * 32 + 16 + gcol);
     double2 creg[16];   // [round cb][row group g]: rows 4g + grow, columns 16·cb + gcol
 #pragma unroll
-    for (int i = 0; i < 16; ++i)
+    for (int i = 0; i < 16; ++i) {
+#ifdef SFB_EXPERIMENTS
+      if (oz.dbg & 2) { creg[i] = make_double2(0.0, 0.0); continue; }
+#endif
       creg[i] = __ldcs(reinterpret_cast<const double2*>(Cw + (long long)(4 * (i & 7)) * p.Np + 16 * (i >> 3)));
+    }
+#ifdef SFB_EXPERIMENTS
+    if (oz.dbg & 4) {
+      while (!mbar_test_nb(meta, k & 1)) __nanosleep(256);
+    }
+#endif
     mbar_wait(meta, k & 1);
     const uint32_t touched = *touched_p;
     mbar_wait(accfull, k & 1);
@@ -359,8 +386,12 @@ __device__ __forceinline__ void oz_epilogue(const CholParams& p, const OzParams&
       creg[8 + g].y = fma(-ty, rj1.y, creg[8 + g].y);
     }
 #pragma unroll
-    for (int i = 0; i < 16; ++i)
+    for (int i = 0; i < 16; ++i) {
+#ifdef SFB_EXPERIMENTS
+      if ((oz.dbg & 2) && creg[i].x != 12345.678) continue;
+#endif
       __stcs(reinterpret_cast<double2*>(Cw + (long long)(4 * (i & 7)) * p.Np + 16 * (i >> 3)), creg[i]);
+    }
     __syncwarp();  // the transpose buffer is rewritten by the next tile
     ++k;
   }
@@ -430,7 +461,10 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
     long long t_full = 0, t_drain = 0;
     const long long t_begin = clock64();
 #endif
-    int g = 0, k = 0;  // ring position, live tiles done
+    int g = 0, k = 0;  // ring position (producer), live tiles done
+    int st = 0;        // ring position of the MMA warp: stage and the parity of its `full` barrier
+    uint32_t par = 0;
+    const uint64_t desc_ring = oz_desc(ring);
     for (int l = l0; l < l1; l += lstep) {
       const OzTile t = oz_tile(l, jt0, njt, strip);
       if (!t.live) continue;
@@ -451,8 +485,11 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
         const int8_t* srcB = Ps + (long long)(t.c0 / 8) * OZ_GROUP_BYTES;
         for (int c = 0; c < nch; ++c, ++g) {
           const int st = g % OZ_STAGES;
-          const uint32_t fa = __shfl_sync(0xffffffffu, c < 32 ? fa0 : fa1, c & 31);
-          const uint32_t fb = __shfl_sync(0xffffffffu, c < 32 ? fb0 : fb1, c & 31);
+          uint32_t fa = __shfl_sync(0xffffffffu, c < 32 ? fa0 : fa1, c & 31);
+          uint32_t fb = __shfl_sync(0xffffffffu, c < 32 ? fb0 : fb1, c & 31);
+#ifdef SFB_EXPERIMENTS
+          if (oz.dbg & 1) fa = fb = 0x3fu;
+#endif
           if (g >= OZ_STAGES) mbar_wait(bar0 + 8 * (OZ_STAGES + st), ((g / OZ_STAGES) - 1) & 1);
           if (leader) {
             const uint32_t full = bar0 + 8 * st;
@@ -487,36 +524,58 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
           umma_i8(tmem, oz_desc(zero0), oz_desc(ring), oz_idesc(256), 0);
           umma_i8(tmem + 256, oz_desc(zero0), oz_desc(ring), oz_idesc(192), 0);
         }
-        uint32_t touched = 0;  // accumulators that receive a product in this tile (the epilogue skips the others)
-        for (int c = 0; c < nch; ++c, ++g) {
-          const int st = g % OZ_STAGES;
-          const uint32_t fa = __shfl_sync(0xffffffffu, c < 32 ? fa0 : fa1, c & 31);
-          const uint32_t fb = __shfl_sync(0xffffffffu, c < 32 ? fb0 : fb1, c & 31);
+        // accumulators that receive a product in this tile (the epilogue skips the others)
+        uint32_t touched = __reduce_or_sync(0xffffffffu, oz_touched(fa0, fb0) | oz_touched(fa1, fb1));
+        if (oz.stats) issued += __reduce_add_sync(0xffffffffu, oz_products(fa0, fb0) + oz_products(fa1, fb1));
 #ifdef SFB_EXPERIMENTS
+        if (oz.dbg & 1) touched = 0x7fu;
+#endif
+        // The loop is software-pipelined around the single issuing thread: the flags of chunk c+1 and a first,
+        // non-blocking look at its `full` barrier are taken BEFORE the MMAs of chunk c are issued, so the ~100-cycle
+        // barrier test overlaps the (back-pressured) MMA issue instead of standing between two chunks' MMAs, where
+        // the tensor pipe's short queue would run dry.
+        uint32_t fa = __shfl_sync(0xffffffffu, fa0, 0), fb = __shfl_sync(0xffffffffu, fb0, 0);
+        bool ready = mbar_test_nb(bar0 + 8 * st, par);
+        for (int c = 0; c < nch; ++c) {
+#ifdef SFB_EXPERIMENTS
+          if (oz.dbg & 1) fa = fb = 0x3fu;
           const long long tf0 = clock64();
 #endif
-          mbar_wait(bar0 + 8 * st, (g / OZ_STAGES) & 1);
+          while (!ready) ready = mbar_test(bar0 + 8 * st, par);
 #ifdef SFB_EXPERIMENTS
           t_full += clock64() - tf0;
 #endif
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t a0 = ring + st * OZ_STAGE_BYTES;
-          const uint64_t ad0 = oz_desc(a0), bd0 = oz_desc(a0 + OZ_A_BYTES);
-          touched |= oz_touched(fa, fb);
+          // descriptors of the stage: start-address field = (ring + st·STAGE) >> 4, never leaves its 14 bits
+          const uint64_t ad0 = desc_ring + (uint64_t)((uint32_t)st * (OZ_STAGE_BYTES >> 4));
+          const uint64_t bd0 = ad0 + (uint64_t)(OZ_A_BYTES >> 4);
+          const uint32_t empty_bar = bar0 + 8 * (OZ_STAGES + st);
+          // ring position of the next chunk (no division in the loop)
+          const int c1 = c + 1;
+          const int st1 = (st + 1 == OZ_STAGES) ? 0 : st + 1;
+          const uint32_t par1 = (st + 1 == OZ_STAGES) ? par ^ 1u : par;
+          uint32_t fan = 0, fbn = 0;
+          bool readyn = false;
+          if (c1 < nch) {
+            fan = __shfl_sync(0xffffffffu, c1 < 32 ? fa0 : fa1, c1 & 31);
+            fbn = __shfl_sync(0xffffffffu, c1 < 32 ? fb0 : fb1, c1 & 31);
+            readyn = mbar_test_nb(bar0 + 8 * st1, par1);
+          }
           if (leader) {
             // The digit patterns that dominate (nothing zero / leading slab zero, for either operand) get fully
             // unrolled code with compile-time masks: a single thread issues every MMA of the CTA, so run-time tests per
             // product would make the issue loop the bottleneck.  Anything else takes the generic path.
-            if (fa == 0x3fu && fb == 0x3fu) issued += oz_issue_chunk(0x3fu, 0x3fu, tmem, ad0, bd0);
-            else if (fa == 0x3eu && fb == 0x3eu) issued += oz_issue_chunk(0x3eu, 0x3eu, tmem, ad0, bd0);
-            else if (fa == 0x3eu && fb == 0x3fu) issued += oz_issue_chunk(0x3eu, 0x3fu, tmem, ad0, bd0);
-            else if (fa == 0x3fu && fb == 0x3eu) issued += oz_issue_chunk(0x3fu, 0x3eu, tmem, ad0, bd0);
-            else issued += oz_issue_chunk(fa, fb, tmem, ad0, bd0);
+            if (fa == 0x3fu && fb == 0x3fu) oz_issue_chunk(0x3fu, 0x3fu, tmem, ad0, bd0);
+            else if (fa == 0x3eu && fb == 0x3eu) oz_issue_chunk(0x3eu, 0x3eu, tmem, ad0, bd0);
+            else if (fa == 0x3eu && fb == 0x3fu) oz_issue_chunk(0x3eu, 0x3fu, tmem, ad0, bd0);
+            else if (fa == 0x3fu && fb == 0x3eu) oz_issue_chunk(0x3fu, 0x3eu, tmem, ad0, bd0);
+            else oz_issue_chunk(fa, fb, tmem, ad0, bd0);
             // stage free once these MMAs have read it (in both CTAs of a pair: the peer's copies land here too)
-            if (PAIR) umma_commit_mc(bar0 + 8 * (OZ_STAGES + st), 3);
-            else umma_commit(bar0 + 8 * (OZ_STAGES + st));
+            if (PAIR) umma_commit_mc(empty_bar, 3);
+            else umma_commit(empty_bar);
           }
           __syncwarp();
+          fa = fan; fb = fbn; ready = readyn; st = st1; par = par1;
         }
         if (leader) {
           touched_s = touched;
@@ -635,6 +694,8 @@ int g_oz_tpc = 8;      // most tiles a CTA works through
 bool g_oz_pair = true; // clusters of two CTAs sharing the A operand by multicast (off: experiments build, A/B)
 }
 void ozaki_set_pair(bool on) { g_oz_pair = on; }
+namespace { int g_oz_dbg = 0; }
+void ozaki_set_debug(int d) { g_oz_dbg = d; }
 void ozaki_set_tpc(int n) { g_oz_tpc = n < 1 ? 1 : n; }
 
 cudaError_t ozaki_init() {
@@ -662,12 +723,14 @@ cudaError_t launch_syrk_i8(const CholParams& p, const OzParams& oz, int K, int j
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
+  OzParams ozd = oz;
+  ozd.dbg = g_oz_dbg;
   long long total = (long long)ntiles * B;
   int tpc = (int)std::min<long long>(g_oz_tpc, std::max<long long>(1, total / (4LL * sms)));
   tpc = std::min(tpc, ntiles);
   if (!g_oz_pair) {
     const dim3 grid((ntiles + tpc - 1) / tpc, 1, B);
-    syrk_i8_kernel<false><<<grid, OZ_THREADS, OZ_SMEM_BYTES, st>>>(p, oz, K / OZ_KC, jt0, njt, strip, ntiles, tpc);
+    syrk_i8_kernel<false><<<grid, OZ_THREADS, OZ_SMEM_BYTES, st>>>(p, ozd, K / OZ_KC, jt0, njt, strip, ntiles, tpc);
     return cudaGetLastError();
   }
   // clusters of two: tile l = 2m + rank; ntiles is even in both enumerations and the halves of a 128×128 tile are
@@ -686,7 +749,7 @@ cudaError_t launch_syrk_i8(const CholParams& p, const OzParams& oz, int K, int j
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, syrk_i8_kernel<true>, p, oz, K / OZ_KC, jt0, njt, strip, ntiles, tpc);
+  return cudaLaunchKernelEx(&cfg, syrk_i8_kernel<true>, p, ozd, K / OZ_KC, jt0, njt, strip, ntiles, tpc);
 }
 }  // namespace
 

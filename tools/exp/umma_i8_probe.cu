@@ -769,6 +769,131 @@ void run_issue(int sms) {
   run_issue_mode<4>(sms, "+ free-running loader warps LDS -> tcgen05.st");
 }
 
+// ------------------------------------------------------------------------------------------------
+// Wide-run schedule of syrk_i8_kernel: per chunk 9 SS MMAs — A slab sa (4 KB) against runs of consecutive B slabs
+// (3+3, 3+3, 3+2, 4, 3, 2 slabs -> N = 128..256), operands resident in shared memory.
+//   MODE 0  MMAs only
+//   MODE 1  + a producer warp streaming 36 KB of bulk copies per chunk from global memory into the ring (full/empty
+//           barriers as in the kernel): what the shared-memory writes of the operand stream cost the MMAs
+//   MODE 2  MODE 0 with single-slab MMAs only (26 per chunk, N = 64) for reference
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t desc_sw32_sbo256(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)1 << 16) | ((uint64_t)16 << 32) | ((uint64_t)1 << 46) | ((uint64_t)6 << 61);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+template <int MODE>
+__global__ void __launch_bounds__(128, 1) wide_kernel(int chunks, const uint8_t* src, int fstages, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int NST = 5, STAGE = 36864, A_BYTES = 24576;
+  __shared__ uint64_t full[NST], empty[NST], bar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < NST * STAGE; i += blockDim.x) smem[i] = (uint8_t)(i * 7 + 3);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (tid == 0) {
+    mbar_init(smem_u32(&bar), 1);
+    for (int i = 0; i < NST; ++i) { mbar_init(smem_u32(&full[i]), 1); mbar_init(smem_u32(&empty[i]), 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_base), 512);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tb = tmem_base;
+  if (warp == 2 && MODE == 1) {
+    if (elect_one()) {
+      for (int c = 0; c < chunks; ++c) {
+        const int st = c % NST;
+        if (c >= NST) mbar_wait(smem_u32(&empty[st]), ((c / NST) - 1) & 1);
+        const uint32_t fb = smem_u32(&full[st]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"(STAGE) : "memory");
+        const uint8_t* g = src + (size_t)(((size_t)blockIdx.x * 37 + c) % fstages) * STAGE;
+        for (int sl = 0; sl < 6; ++sl) {
+          bulk_g2s(smem_u32(smem) + st * STAGE + sl * 4096, g + sl * 4096, 4096, fb);
+          bulk_g2s(smem_u32(smem) + st * STAGE + A_BYTES + sl * 2048, g + A_BYTES + sl * 2048, 2048, fb);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const bool leader = elect_one();
+    const long long t0 = clock64();
+    for (int c = 0; c < chunks; ++c) {
+      const int st = c % NST;
+      if (MODE == 1) {
+        mbar_wait(smem_u32(&full[st]), (c / NST) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
+      const uint32_t a0 = smem_u32(smem) + st * STAGE, b0 = a0 + A_BYTES;
+      const uint64_t ad0 = desc_sw32_sbo256(a0), bd0 = desc_sw32_sbo256(b0);
+      if (leader) {
+        if (MODE == 2) {
+#pragma unroll
+          for (int sa = 0; sa < 6; ++sa)
+#pragma unroll
+            for (int sb = 0; sb < 6; ++sb) {
+              if (sa + sb >= 7) continue;
+              umma_i8(tb + (uint32_t)(sa + sb) * 64, ad0 + sa * 256, bd0 + sb * 128, make_idesc_i8(128, 64), 1);
+            }
+        } else {
+          // (sa, sb0, len)
+          constexpr int R[9][3] = {{0, 0, 3}, {0, 3, 3}, {1, 0, 3}, {1, 3, 3}, {2, 0, 3}, {2, 3, 2}, {3, 0, 4}, {4, 0, 3}, {5, 0, 2}};
+#pragma unroll
+          for (int i = 0; i < 9; ++i)
+            umma_i8(tb + (uint32_t)(R[i][0] + R[i][1]) * 64, ad0 + R[i][0] * 256, bd0 + R[i][1] * 128, make_idesc_i8(128, R[i][2] * 64), 1);
+        }
+        if (MODE == 1) umma_commit(smem_u32(&empty[st]));
+      }
+      __syncwarp();
+    }
+    if (leader) umma_commit(smem_u32(&bar));
+    __syncwarp();
+    mbar_wait(smem_u32(&bar), 0);
+    if (leader) out[0] = clock64() - t0;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, 512);
+}
+template <int MODE>
+void run_wide_mode(int sms, const uint8_t* src, int fstages, const char* what) {
+  long long* dout;
+  CK(cudaMalloc(&dout, 64));
+  CK(cudaMemset(dout, 0, 64));
+  const int smem_bytes = 5 * 36864 + 1024;
+  CK(cudaFuncSetAttribute(wide_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  const int chunks = 2048;
+  wide_kernel<MODE><<<1, 128, smem_bytes>>>(chunks, src, fstages, dout);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("wide mode %d: CUDA error %s\n", MODE, cudaGetErrorString(e)); exit(1); }
+  long long h1[1], h2[1];
+  CK(cudaMemcpy(h1, dout, 8, cudaMemcpyDeviceToHost));
+  wide_kernel<MODE><<<sms, 128, smem_bytes>>>(chunks, src, fstages, dout);
+  CK(cudaDeviceSynchronize());
+  wide_kernel<MODE><<<sms, 128, smem_bytes>>>(chunks, src, fstages, dout);
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(h2, dout, 8, cudaMemcpyDeviceToHost));
+  printf("wide-run schedule mode %d (%s; operand footprint %.0f MB): %.0f cycles per chunk on one SM, %.0f with all %d SMs running (floor 832)\n",
+         MODE, what, fstages * 36864e-6, (double)h1[0] / chunks, (double)h2[0] / chunks, sms);
+  cudaFree(dout);
+}
+void run_wide(int sms) {
+  uint8_t* src;
+  const int fmax = 148 * 64;
+  const size_t bytes = (size_t)fmax * 36864;
+  CK(cudaMalloc(&src, bytes));
+  CK(cudaMemset(src, 1, bytes));
+  run_wide_mode<0>(sms, src, fmax, "9 wide SS MMAs, operands resident");
+  run_wide_mode<2>(sms, src, fmax, "26 single-slab SS MMAs, operands resident");
+  run_wide_mode<1>(sms, src, fmax, "9 wide SS MMAs + 36 KB of bulk copies per chunk");   // 350 MB: from HBM
+  run_wide_mode<1>(sms, src, 1024, "9 wide SS MMAs + 36 KB of bulk copies per chunk");   // 38 MB: from L2
+  run_wide_mode<1>(sms, src, 256, "9 wide SS MMAs + 36 KB of bulk copies per chunk");    // 9 MB: from L2, many readers per line
+  cudaFree(src);
+}
+
 int main() {
   setvbuf(stdout, NULL, _IONBF, 0);
   int dev = 0;
@@ -827,6 +952,7 @@ int main() {
     cudaFree(dA); cudaFree(dB); cudaFree(dD);
   }
 
+  run_wide(prop.multiProcessorCount);
   run_issue(prop.multiProcessorCount);
   run_pair(prop.multiProcessorCount);
   run_ts(prop.multiProcessorCount);
