@@ -312,13 +312,11 @@ int run_cholesky(sfb_ctx* h, int lane, int slot0, int nb, double* lnL_out, int* 
       }
       if (!last) {
         {
+          // trsm; in int8 mode the same kernel writes the fixed-point restatement of the panel it just solved ->
+          // chunks [4c, 4c+4) of this block's buffer
           ProfScope ps(h, hi, SFB_K_TRSM, nb * (rem * kTile * kTile));  // useful FLOPs of a triangular solve
-          SFB_CUDA(h, launch_trsm(p, h->maps, slot0, nb, hi));
-          h->launches++;
-        }
-        if (i8) {  // fixed-point restatement of the panel just solved -> chunks [4c, 4c+4) of this block's buffer
-          ProfScope ps(h, hi, SFB_K_OZ_SLICE, nb * rem * kTile * (8.0 + kOzSlices));
-          SFB_CUDA(h, launch_oz_slice(p, oz, c * (kTile / kOzChunk), nb, hi));
+          if (i8) SFB_CUDA(h, launch_trsm_slice(p, h->maps, oz, c * (kTile / kOzChunk), slot0, nb, hi));
+          else SFB_CUDA(h, launch_trsm(p, h->maps, slot0, nb, hi));
           h->launches++;
         }
       }

@@ -310,12 +310,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2)
 // M is lower triangular: output columns [32·wn, 32·wn+32) only need k < 32·(wn+1), so each warp skips the
 // k-slabs beyond its columns.
 // ------------------------------------------------------------------------------------------------
+// SLICE (int8 trailing update): the CTA also writes the fixed-point slices and digit-slab flags of its 64 × 128
+// block (oz_slice_block) from a shared-memory copy of the tile, so the panel is not read back from global memory by
+// a separate kernel.
+constexpr int TRSM_TILE_LD = 128 + 4;            // doubles per row of the staged tile (row stride = 8 words mod 32 banks)
+constexpr int TRSM_TILE_OFF = 2048;              // behind the 4 × 64 partial sums of the rhs reduction
+static_assert(TRSM_TILE_OFF + 64 * TRSM_TILE_LD * 8 <= STAGES * STAGE_BYTES, "staged tile must fit the idle ring");
+template <bool SLICE>
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
     trsm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmM, CholParams p,
-                int slot0) {
+                int slot0, OzParams oz, int ch0) {
   const int rb = blockIdx.x, s = blockIdx.y;
   if (p.info[s] != 0) return;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint32_t wmask[8][4];
   double* Wm = p.W + (long long)s * p.strideW;
   const long long ld = p.Np;
   const int r0 = p.k0 + kTile + rb * 64;
@@ -345,6 +353,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2)
       Cg[(long long)mt * 8 * ld + cb + 4] = acc[mt][nt][1];
       part[mt] = fma(acc[mt][nt][0], z0, part[mt]);
       part[mt] = fma(acc[mt][nt][1], z1, part[mt]);
+      if (SLICE) {
+        double* tl = reinterpret_cast<double*>(smem_raw + TRSM_TILE_OFF) + (wm * 32 + mt * 8 + rho) * TRSM_TILE_LD + cb + t;
+        tl[0] = acc[mt][nt][0];
+        tl[4] = acc[mt][nt][1];
+      }
     }
   }
   // reduce over the 4 lanes sharing a row, then over the 4 column-warps in a fixed order
@@ -362,6 +375,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2)
     double sum = ((red[r] + red[64 + r]) + red[128 + r]) + red[192 + r];
     p.rhs[(long long)s * p.Np + r0 + r] -= sum;
   }
+  if (SLICE)  // the barrier above also covers the staged tile
+    oz_slice_block(oz, s, p.Np, r0, ch0, reinterpret_cast<const double*>(smem_raw + TRSM_TILE_OFF), TRSM_TILE_LD, wmask);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1098,7 +1113,8 @@ cudaError_t kernels_init() {
   // L1 — and is therefore not done.)
   struct Item { const void* fn; int bytes; };
   const Item items[] = {{(const void*)syrk_kernel, GEMM_SMEM_BYTES},
-                        {(const void*)trsm_kernel, GEMM_SMEM_BYTES},
+                        {(const void*)trsm_kernel<false>, GEMM_SMEM_BYTES},
+                        {(const void*)trsm_kernel<true>, GEMM_SMEM_BYTES},
                         {(const void*)potrf_diag2_kernel, (int)kPotrf2Smem},
                         {(const void*)solve_lower_kernel, 200 * 1024}};
   for (const Item& it : items) {
@@ -1134,7 +1150,16 @@ cudaError_t launch_potrf_diag(const CholParams& p, int B, int last, double* lnL_
 cudaError_t launch_trsm(const CholParams& p, const GemmMaps& m, int slot0, int B, cudaStream_t st) {
   const int rows = p.Np - p.k0 - kTile;
   if (rows <= 0) return cudaSuccess;
-  trsm_kernel<<<dim3(rows / 64, B), GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(*m.W, *m.Minv, p, slot0);
+  trsm_kernel<false><<<dim3(rows / 64, B), GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(*m.W, *m.Minv, p, slot0, OzParams{}, 0);
+  return cudaGetLastError();
+}
+
+// trsm + fixed-point slices of the panel it produces (chunks [chunk0, chunk0+4) of oz.P, flags in oz.F)
+cudaError_t launch_trsm_slice(const CholParams& p, const GemmMaps& m, const OzParams& oz, int chunk0, int slot0, int B,
+                              cudaStream_t st) {
+  const int rows = p.Np - p.k0 - kTile;
+  if (rows <= 0) return cudaSuccess;
+  trsm_kernel<true><<<dim3(rows / 64, B), GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(*m.W, *m.Minv, p, slot0, oz, chunk0);
   return cudaGetLastError();
 }
 

@@ -26,7 +26,7 @@
 // -> one digit slab of the A operand (128 rows) of a chunk is 4 KB contiguous, of the B operand (64 rows) 2 KB: one
 // 1-D bulk async copy (cp.async.bulk, SASS UBLKCP) per NON-ZERO slab and pipeline stage, no tensor map.  Inside a
 // 256-byte row group the two 16-byte halves of a row are XOR-swapped by bit 2 of the row (the 32-byte swizzle pattern,
-// applied by the slicing kernel), consecutive 8-row groups are 256 B apart: UMMA descriptor {SWIZZLE_32B, SBO = 256}.
+// applied where the slices are written: oz_slice_block in sfb_internal.cuh, called from trsm_kernel), consecutive 8-row groups are 256 B apart: UMMA descriptor {SWIZZLE_32B, SBO = 256}.
 // In shared memory the six B slabs of a stage lie back to back, so a run of consecutive B slabs is one operand of
 // N = 64·len rows (oz_issue_chunk).
 //
@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
 
   if (warp <= 1) {
     // producer (warp 0) and MMA issuer (warp 1) walk the same tiles and chunks with the same digit-slab flags:
-    // lane j holds the flags of chunks j and j+32 of the current tile (written by the slicing kernel), fetched once
+    // lane j holds the flags of chunks j and j+32 of the current tile (written with the slices by trsm_kernel), fetched once
     // per tile; whole warps run the loops (uniform control flow), one elected lane issues.
     const bool leader = elect_one();
     unsigned long long issued = 0;
@@ -624,69 +624,6 @@ __global__ void oz_rowscale_kernel(CholParams p, OzParams oz) {
   oz.rscale[(long long)s * p.Np + i] = r;
 }
 
-// ------------------------------------------------------------------------------------------------
-// slice the panel just produced by trsm (rows k0+128.., columns k0..k0+127) into chunks [ch0, ch0+4) of P.
-// A CTA takes 64 rows (one flag block), a warp 8 of them; per row lane l owns k = 4l..4l+3 (one coalesced 1 KB row
-// read), six packed 4-byte stores.  Per (64-row block, chunk) the CTA also records which digit slabs are not
-// identically zero (F): |L_ik| is usually far below its row's scale away from the band, so the leading digit slab
-// of most operand blocks is all zero and the update kernel skips every product with it.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) oz_slice_kernel(CholParams p, OzParams oz, int ch0) {
-  const int s = blockIdx.y;
-  if (p.info[s] != 0) return;
-  __shared__ uint32_t wmask[8][4];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int row_base = p.k0 + kTile + blockIdx.x * 64;
-  const int chunk = ch0 + (lane >> 3);
-  const int kb = (4 * lane) & 31;                       // byte inside the 32-byte row
-  uint32_t nz = 0;                                      // bit t: slab t of this lane's chunk has a non-zero digit
-  for (int i = 0; i < 8; ++i) {
-    const int row = row_base + warp * 8 + i;
-    const double* src = p.W + (long long)s * p.strideW + (long long)row * p.Np + p.k0 + 4 * lane;
-    const double2 v01 = *reinterpret_cast<const double2*>(src);
-    const double2 v23 = *reinterpret_cast<const double2*>(src + 2);
-    const double inv = 1099511627776.0 / oz.rscale[(long long)s * p.Np + row];  // 2^40 / 2^(e−7) = 2^(47−e)
-    const double lim = 140737488355327.0;                                       // 2^47 − 1
-    long long qv[4];
-    qv[0] = __double2ll_rn(fmin(fmax(v01.x * inv, -lim), lim));
-    qv[1] = __double2ll_rn(fmin(fmax(v01.y * inv, -lim), lim));
-    qv[2] = __double2ll_rn(fmin(fmax(v23.x * inv, -lim), lim));
-    qv[3] = __double2ll_rn(fmin(fmax(v23.y * inv, -lim), lim));
-    uint32_t packed[OZ_S];
-#pragma unroll
-    for (int t = OZ_S - 1; t >= 0; --t) {  // least significant digit first
-      uint32_t w = 0;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const long long dgt = (long long)(int8_t)(qv[e] & 0xff);
-        qv[e] = (qv[e] - dgt) >> 8;
-        w |= ((uint32_t)dgt & 0xffu) << (8 * e);
-      }
-      packed[t] = w;
-      nz |= (w != 0u) << t;
-    }
-    const int r8 = row & 7;
-    const int half = ((kb >> 4) ^ (r8 >> 2)) & 1;         // 32-byte swizzle: 16-byte halves swapped for rows 4-7
-    const long long slice_bytes = (long long)p.Np * OZ_KC;
-    int8_t* dst = oz.P + (long long)s * oz.strideP + (long long)chunk * OZ_S * slice_bytes +
-                  (long long)(row >> 3) * OZ_GROUP_BYTES + r8 * OZ_KC + half * 16 + (kb & 15);
-#pragma unroll
-    for (int t = 0; t < OZ_S; ++t) *reinterpret_cast<uint32_t*>(dst + t * slice_bytes) = packed[t];
-  }
-  // OR over the 8 lanes of a chunk, then over the CTA's 8 warps
-  nz |= __shfl_xor_sync(0xffffffffu, nz, 1);
-  nz |= __shfl_xor_sync(0xffffffffu, nz, 2);
-  nz |= __shfl_xor_sync(0xffffffffu, nz, 4);
-  if ((lane & 7) == 0) wmask[warp][lane >> 3] = nz;
-  __syncthreads();
-  if (threadIdx.x < 4) {
-    uint32_t m = 0;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) m |= wmask[w][threadIdx.x];
-    oz.F[(long long)s * oz.strideF + (long long)(ch0 + threadIdx.x) * (p.Np / 64) + row_base / 64] = (uint8_t)m;
-  }
-}
-
 }  // namespace
 
 namespace {
@@ -755,13 +692,6 @@ cudaError_t launch_syrk_i8(const CholParams& p, const OzParams& oz, int K, int j
 
 cudaError_t launch_oz_rowscale(const CholParams& p, const OzParams& oz, int B, cudaStream_t st) {
   oz_rowscale_kernel<<<dim3((p.Np + 255) / 256, B), 256, 0, st>>>(p, oz);
-  return cudaGetLastError();
-}
-
-cudaError_t launch_oz_slice(const CholParams& p, const OzParams& oz, int chunk0, int B, cudaStream_t st) {
-  const int rows = p.Np - p.k0 - kTile;
-  if (rows <= 0) return cudaSuccess;
-  oz_slice_kernel<<<dim3(rows / 64, B), 256, 0, st>>>(p, oz, chunk0);
   return cudaGetLastError();
 }
 

@@ -125,10 +125,83 @@ void ozaki_set_pair(bool on);  // CTA pairs sharing the A operand by multicast (
 size_t oz_panel_bytes_per_slot(int Np, int outer_tiles);
 size_t oz_flag_bytes_per_slot(int Np, int outer_tiles);
 cudaError_t launch_oz_rowscale(const CholParams& p, const OzParams& oz, int B, cudaStream_t st);
-cudaError_t launch_oz_slice(const CholParams& p, const OzParams& oz, int chunk0, int B, cudaStream_t st);
 cudaError_t launch_oz_syrk_strip(const CholParams& p, const OzParams& oz, int K, int jt0, int njt, int B,
                                  cudaStream_t st);
 cudaError_t launch_oz_syrk_tri(const CholParams& p, const OzParams& oz, int K, int jt0, int B, cudaStream_t st);
+
+#ifdef __CUDACC__
+// Fixed-point slices of one 64-row × 128-column block of the panel (rows row_base.., four 32-k chunks ch0..ch0+3) for
+// the int8 trailing update (layout and arithmetic: ozaki.cu).  256 threads: a warp takes 8 rows; per row lane l owns
+// k = 4l..4l+3 (32 contiguous bytes of `src`, which may be global memory — the panel as trsm left it — or the shared
+// memory tile trsm still holds), six packed 4-byte stores.  Per chunk the CTA also records which digit slabs are not
+// identically zero (F): |L_ik| is usually far below its row's scale away from the band, so the leading digit slab of
+// most operand blocks is all zero and the update kernel skips every copy and product with it.
+__device__ __forceinline__ void oz_slice_block(const OzParams& oz, int s, int Np, int row_base, int ch0, const double* src,
+                                               long long src_ld, uint32_t (*wmask)[4]) {
+  constexpr int OZ_S = kOzSlices, OZ_KC = kOzChunk, OZ_GROUP_BYTES = 8 * kOzChunk;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int chunk = ch0 + (lane >> 3);
+  const int kb = (4 * lane) & 31;                       // byte inside the 32-byte row
+  uint32_t nz = 0;                                      // bit t: slab t of this lane's chunk has a non-zero digit
+  int rs_hi8[8];                                        // exponent words of the eight rows' scales, fetched together
+#pragma unroll
+  for (int i = 0; i < 8; ++i) rs_hi8[i] = __double2hiint(__ldg(oz.rscale + (long long)s * Np + row_base + warp * 8 + i));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = row_base + warp * 8 + i;
+    const double* sp = src + (long long)(warp * 8 + i) * src_ld + 4 * lane;
+    const double2 v01 = *reinterpret_cast<const double2*>(sp);
+    const double2 v23 = *reinterpret_cast<const double2*>(sp + 2);
+    // 2^40 / rscale = 2^(47−e), exact: rscale is a power of two, so only its exponent field is needed
+    const double inv = __hiloint2double((2 * 1023 + 40 - ((rs_hi8[i] >> 20) & 0x7ff)) << 20, 0);
+    // q = rint(L·2^(47−e)) by the magic-number add (|q| < 2^51): the integer sits in the mantissa of x + 1.5·2^52.
+    // Balanced radix-256 digits b_t ∈ [−128, 127] of q = Σ b_t·256^t, all six at once: u = q + Σ 128·256^t has the
+    // UNSIGNED bytes b_t + 128 (the representation is unique), and x − 128 = x XOR 0x80 as an int8.  Representable
+    // range |q| <= 0x7f7f7f7f7f7f; |L_ik| < 2^(e−1) keeps |q| < 2^46.
+    const double lim = 139637976727423.0;                                       // 0x7f7f7f7f7f7f
+    const double magic = 6755399441055744.0;                                    // 1.5·2^52 = 0x4338000000000000
+    const long long fix = 0x808080808080ll - 0x4338000000000000ll;
+    unsigned long long u[4];
+    u[0] = (unsigned long long)(__double_as_longlong(fmin(fmax(v01.x * inv, -lim), lim) + magic) + fix) ^ 0x808080808080ull;
+    u[1] = (unsigned long long)(__double_as_longlong(fmin(fmax(v01.y * inv, -lim), lim) + magic) + fix) ^ 0x808080808080ull;
+    u[2] = (unsigned long long)(__double_as_longlong(fmin(fmax(v23.x * inv, -lim), lim) + magic) + fix) ^ 0x808080808080ull;
+    u[3] = (unsigned long long)(__double_as_longlong(fmin(fmax(v23.y * inv, -lim), lim) + magic) + fix) ^ 0x808080808080ull;
+    uint32_t packed[OZ_S];
+#pragma unroll
+    for (int t = 0; t < OZ_S; ++t) {       // slab t = digit 5 − t (t = 0 most significant): byte 5 − t of each element
+      const int bt = OZ_S - 1 - t;
+      uint32_t x0, x1, x2, x3;
+      if (bt < 4) { x0 = (uint32_t)u[0]; x1 = (uint32_t)u[1]; x2 = (uint32_t)u[2]; x3 = (uint32_t)u[3]; }
+      else { x0 = (uint32_t)(u[0] >> 32); x1 = (uint32_t)(u[1] >> 32); x2 = (uint32_t)(u[2] >> 32); x3 = (uint32_t)(u[3] >> 32); }
+      const uint32_t sel = (uint32_t)(bt & 3) | ((uint32_t)(4 + (bt & 3)) << 4);
+      const uint32_t w = __byte_perm(__byte_perm(x0, x1, sel), __byte_perm(x2, x3, sel), 0x5410);
+      packed[t] = w;
+      nz |= (w != 0u) << t;
+    }
+    const int r8 = row & 7;
+    const int half = ((kb >> 4) ^ (r8 >> 2)) & 1;         // 32-byte swizzle: 16-byte halves swapped for rows 4-7
+    const long long slice_bytes = (long long)Np * OZ_KC;
+    int8_t* dst = oz.P + (long long)s * oz.strideP + (long long)chunk * OZ_S * slice_bytes +
+                  (long long)(row >> 3) * OZ_GROUP_BYTES + r8 * OZ_KC + half * 16 + (kb & 15);
+#pragma unroll
+    for (int t = 0; t < OZ_S; ++t) *reinterpret_cast<uint32_t*>(dst + t * slice_bytes) = packed[t];
+  }
+  // OR over the 8 lanes of a chunk, then over the CTA's 8 warps
+  nz |= __shfl_xor_sync(0xffffffffu, nz, 1);
+  nz |= __shfl_xor_sync(0xffffffffu, nz, 2);
+  nz |= __shfl_xor_sync(0xffffffffu, nz, 4);
+  if ((lane & 7) == 0) wmask[warp][lane >> 3] = nz;
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) m |= wmask[w][threadIdx.x];
+    oz.F[(long long)s * oz.strideF + (long long)(ch0 + threadIdx.x) * (Np / 64) + row_base / 64] = (uint8_t)m;
+  }
+}
+#endif
+cudaError_t launch_trsm_slice(const CholParams& p, const GemmMaps& m, const OzParams& oz, int chunk0, int slot0, int B,
+                              cudaStream_t st);
 
 }  // namespace sfb
 
