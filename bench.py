@@ -328,19 +328,22 @@ def roofline_block(prof, solver, peaks, issued_frac=1.0):
         i8 = ach * I8_PRODUCTS * issued_frac   # int8 TOP/s actually executed on the tensor pipe
         peak = 2.0 * peaks["bf16_tflops_sustained"] if peaks.get("bf16_tflops_sustained") else 2.0 * 1400.0
         common.update({
-            "kernel": "syrk_i8_kernel (trailing update A_ij -= L_ik L_jk^T as 26 exact int8 MMAs per fp64 product "
-                      "term: tcgen05.mma kind::i8, 7 int32 TMEM accumulators, fp64 recombination)",
+            "kernel": "syrk_i8_kernel (trailing update A_ij -= L_ik L_jk^T as 26 exact int8 digit-slab products per "
+                      "fp64 product term, issued as 9 wide tcgen05.mma kind::i8 per 32-deep chunk (runs of "
+                      "consecutive slabs, N = 128..256), 7 int32 TMEM accumulators, fp64 recombination; CTA pairs "
+                      "share the A operand by multicast bulk copies)",
             "achieved": i8, "peak": peak, "frac": i8 / peak,
             "achieved_fp64_equivalent_tflops": ach, "fp64_dmma_peak_tflops": FP64_DMMA_PEAK_TFLOPS,
             "int8_mma_issued_frac": issued_frac,
             "speedup_over_fp64_tensor_peak": ach / FP64_DMMA_PEAK_TFLOPS,
             "peak_source": "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (int8 dense rate = 2 x bf16 on sm_100a; the "
                            "file has no int8 entry" + ("" if peaks.get("bf16_tflops_sustained") else "; FALLBACK 1.4 PF") +
-                           "); this kernel's 128x64 MMA shape is shared-memory-bandwidth-bound at 0.61 of the int8 "
-                           "issue peak (tools/exp/umma_i8_probe.cu: 2789 of 4596 TOP/s measured on the chip)",
-            "algorithmic_work": "n(n+1)K fp64 FLOP per trailing update x 26 int8 MMA terms x int8_mma_issued_frac "
-                                "(products with an all-zero digit slab are skipped — exact; the fraction is measured "
-                                "by the kernel itself over the profiled step)"})
+                           "); in isolation the kernel's MMA schedule runs at the tensor floor (832 cycles per "
+                           "dense chunk, profiles/r3e_umma_i8_wide_run_probe.txt); in the step it is paced by operand "
+                           "delivery (36 KB per chunk and SM, ~10 TB/s L2 -> SM) and the per-tile TMEM drain",
+            "algorithmic_work": "n(n+1)K fp64 FLOP per trailing update x 26 int8 slab products x int8_mma_issued_frac "
+                                "(products with an all-zero digit slab are skipped — exact; the fraction is counted "
+                                "by the kernel from the digit-slab flags over the profiled step)"})
     else:
         common.update({
             "kernel": "syrk_kernel (trailing update A_ij -= L_ik L_jk^T, DMMA m8n8k4 fp64)",
