@@ -1181,6 +1181,8 @@ int sfb_i8_mma_counts(sfb_t* h, unsigned long long* issued, unsigned long long* 
             "to drain the accumulators + %.1f %% issuing; %llu tiles, %.1f slab products per chunk\n",
             (double)v[2] / v[5], 100.0 * v[3] / v[2], 100.0 * v[4] / v[2], 100.0 * (v[2] - v[3] - v[4]) / v[2], v[5],
             26.0 * v[0] / v[1]);
+  if (getenv("SFB_OZ_TIMING") && v[7])
+    fprintf(stderr, "[sfb] int8 producer warp: %.1f %% of its time waiting for a free stage\n", 100.0 * v[6] / v[7]);
 #endif
   return SFB_OK;
 }

@@ -30,8 +30,8 @@
 // In shared memory the six B slabs of a stage lie back to back, so a run of consecutive B slabs is one operand of
 // N = 64·len rows (oz_issue_chunk).
 //
-// Kernel shape: 320 threads = warp 0 bulk-copy producer, warp 1 MMA issuer (one elected lane) + TMEM allocator,
-// warps 2-9 epilogue (TMEM lane quarter = warp%4, two warps per quarter).  5-stage ring of 36 KB, full/empty mbarriers, tcgen05.commit
+// Kernel shape: 352 threads = warp 0 bulk-copy producer (A), warp 1 MMA issuer (one elected lane) + TMEM allocator,
+// warps 2-9 epilogue (TMEM lane quarter = warp%4, two warps per quarter), warp 10 bulk-copy producer (B).  5-stage ring of 36 KB, full/empty mbarriers, tcgen05.commit
 // releases a stage / signals the epilogue.  The epilogue warps prefetch the C tile (coalesced, into registers) while
 // the main loop runs, transpose the recombined update through a padded buffer and finish the read-modify-write with
 // coalesced streaming stores.
@@ -54,7 +54,8 @@ constexpr int OZ_ROWGROUP_BYTES = OZ_S * OZ_GROUP_BYTES;     // 1536: all slices
 constexpr int OZ_A_BYTES = (OZ_BM / 8) * OZ_ROWGROUP_BYTES;  // 24576
 constexpr int OZ_B_BYTES = (OZ_BN / 8) * OZ_ROWGROUP_BYTES;  // 12288
 constexpr int OZ_STAGE_BYTES = OZ_A_BYTES + OZ_B_BYTES;      // 36864
-constexpr int OZ_THREADS = 320;      // producer warp, MMA warp, eight epilogue warps
+constexpr int OZ_THREADS = 352;      // producer warp (A), MMA warp, eight epilogue warps, second producer warp (B)
+constexpr int OZ_PRODB_WARP = 10;
 constexpr uint32_t OZ_TMEM_COLS = 512;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -230,35 +231,50 @@ __device__ __forceinline__ uint32_t oz_idesc(uint32_t n) { return OZ_IDESC_BASE 
 // fa / fb: bit t set = digit slab t of the A / B operand block has a non-zero entry (and was loaded); products with
 // an all-zero slab are skipped — exactly.  Every MMA accumulates (the accumulators are cleared per tile), so with
 // literal masks the whole schedule folds at compile time.  Returns the number of slab products issued.
-__device__ __forceinline__ uint32_t oz_issue_chunk(uint32_t fa, uint32_t fb, uint32_t tmem, uint64_t ad0, uint64_t bd0) {
-  uint32_t n = 0;
+// PHASE 0 issues the MMAs of 1 and 2 slabs, PHASE 1 those of 3 and 4, each in ascending length: the tensor pipe's queue
+// holds about two MMAs beyond the one executing (profiles/r3t_umma_i8_queue_slack_probe.txt: 165 cycles of issue-thread
+// work between two chunks are hidden when a chunk ends with a 2- and a 3-slab MMA), so a chunk should END with its
+// longest MMAs — that is the time the issue thread has to get from one chunk's last MMA to the next one's first.
+template <int PHASE>
+__device__ __forceinline__ void oz_issue_chunk(uint32_t fa, uint32_t fb, uint32_t tmem, uint64_t ad0, uint64_t bd0) {
 #pragma unroll
-  for (int sa = 0; sa < OZ_S; ++sa) {
-    if (!((fa >> sa) & 1u)) continue;
-    const uint32_t m = fb & ((1u << (OZ_NACC - sa)) - 1u) & 0x3fu;
-    const uint64_t ad = ad0 + (uint64_t)(sa * (OZ_SLAB_A >> 4));
+  for (int want = 2 * PHASE + 1; want <= 2 * PHASE + 2; ++want) {
 #pragma unroll
-    for (int s = 0; s < OZ_S; ++s) {
-      const uint32_t b0 = (m >> s) & 1u, prev = s ? (m >> (s - 1)) & 1u : 0u;
-      if (!(b0 && !prev)) continue;             // a run of set bits starts at s
-      uint32_t len = 1, run = 1;
+    for (int sa = 0; sa < OZ_S; ++sa) {
+      if (!((fa >> sa) & 1u)) continue;
+      const uint32_t m = fb & ((1u << (OZ_NACC - sa)) - 1u) & 0x3fu;
+      const uint64_t ad = ad0 + (uint64_t)(sa * (OZ_SLAB_A >> 4));
 #pragma unroll
-      for (int t = s + 1; t < OZ_S; ++t) {
-        run &= (m >> t) & 1u;
-        len += run;
+      for (int s = 0; s < OZ_S; ++s) {
+        const uint32_t b0 = (m >> s) & 1u, prev = s ? (m >> (s - 1)) & 1u : 0u;
+        if (!(b0 && !prev)) continue;             // a run of set bits starts at s
+        uint32_t len = 1, run = 1;
+#pragma unroll
+        for (int t = s + 1; t < OZ_S; ++t) {
+          run &= (m >> t) & 1u;
+          len += run;
+        }
+        const uint64_t bd = bd0 + (uint64_t)(s * (OZ_SLAB_B >> 4));
+        const uint32_t d = tmem + (uint32_t)(sa + s) * OZ_BN;
+        if (len <= 4) {
+          if (len == (uint32_t)want) umma_i8(d, ad, bd, oz_idesc(len * OZ_BN), 1);
+        } else {   // 5 -> 2 + 3, 6 -> 3 + 3
+          if (len - 3 == (uint32_t)want) umma_i8(d, ad, bd, oz_idesc((len - 3) * OZ_BN), 1);
+          if (want == 3)
+            umma_i8(d + (len - 3) * OZ_BN, ad, bd + (uint64_t)((len - 3) * (OZ_SLAB_B >> 4)), oz_idesc(3 * OZ_BN), 1);
+        }
       }
-      const uint64_t bd = bd0 + (uint64_t)(s * (OZ_SLAB_B >> 4));
-      const uint32_t d = tmem + (uint32_t)(sa + s) * OZ_BN;
-      if (len <= 4) {
-        umma_i8(d, ad, bd, oz_idesc(len * OZ_BN), 1);
-      } else {
-        umma_i8(d, ad, bd, oz_idesc(3 * OZ_BN), 1);
-        umma_i8(d + 3 * OZ_BN, ad, bd + (uint64_t)(3 * (OZ_SLAB_B >> 4)), oz_idesc((len - 3) * OZ_BN), 1);
-      }
-      n += len;
     }
   }
-  return n;
+}
+// the four patterns that make up the bench ensemble with compile-time masks, anything else generic
+template <int PHASE>
+__device__ __forceinline__ void oz_issue_dispatch(uint32_t fa, uint32_t fb, uint32_t tmem, uint64_t ad0, uint64_t bd0) {
+  if (fa == 0x3fu && fb == 0x3fu) oz_issue_chunk<PHASE>(0x3fu, 0x3fu, tmem, ad0, bd0);
+  else if (fa == 0x3eu && fb == 0x3eu) oz_issue_chunk<PHASE>(0x3eu, 0x3eu, tmem, ad0, bd0);
+  else if (fa == 0x3eu && fb == 0x3fu) oz_issue_chunk<PHASE>(0x3eu, 0x3fu, tmem, ad0, bd0);
+  else if (fa == 0x3fu && fb == 0x3eu) oz_issue_chunk<PHASE>(0x3fu, 0x3eu, tmem, ad0, bd0);
+  else oz_issue_chunk<PHASE>(fa, fb, tmem, ad0, bd0);
 }
 // number of slab products for digit-slab masks (fa, fb)
 __device__ __forceinline__ uint32_t oz_products(uint32_t fa, uint32_t fb) {
@@ -451,8 +467,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
   const long long slice_bytes = (long long)p.Np * OZ_KC;       // one digit slab of one chunk, all rows
   const long long chunk_bytes = OZ_S * slice_bytes;
 
-  if (warp <= 1) {
-    // producer (warp 0) and MMA issuer (warp 1) walk the same tiles and chunks with the same digit-slab flags:
+  if (warp <= 1 || warp == OZ_PRODB_WARP) {
+    // the producers (warp 0: A slabs, warp 10: B slabs) and the MMA issuer (warp 1) walk the same tiles and chunks with the same digit-slab flags:
     // lane j holds the flags of chunks j and j+32 of the current tile (written with the slices by trsm_kernel), fetched once
     // per tile; whole warps run the loops (uniform control flow), one elected lane issues.
     const bool leader = elect_one();
@@ -479,34 +495,45 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
         fa1 = f[t.r0 / 64] | f[t.r0 / 64 + 1];
         fb1 = f[t.c0 / 64];
       }
-      if (warp == 0) {
-        // ---- producer: one bulk copy per non-zero digit slab (4 KB of A, 2 KB of B), continuous over the CTA's tiles
-        const int8_t* srcA = Ps + (long long)(t.r0 / 8) * OZ_GROUP_BYTES;
-        const int8_t* srcB = Ps + (long long)(t.c0 / 8) * OZ_GROUP_BYTES;
+      if (warp != 1) {
+        // ---- producers: one bulk copy per non-zero digit slab (4 KB of A, 2 KB of B), continuous over the CTA's tiles.
+        // Issuing a copy costs the lone thread ~10 dependent instructions; twelve per chunk made ONE producer the
+        // pace-setter of the whole kernel (it waited for a free stage only 20 % of its time while the MMA warp waited
+        // for operands 24 % of its own).  Hence two: warp 0 posts the stage's byte count and fetches A, warp 10 fetches
+        // B (its complete_tx may reach the barrier before the expect_tx: the phase cannot complete until warp 0 arrives).
+        const bool prod_a = (warp == 0);
+        const int8_t* src = Ps + (long long)((prod_a ? t.r0 : t.c0) / 8) * OZ_GROUP_BYTES;
         for (int c = 0; c < nch; ++c, ++g) {
-          const int st = g % OZ_STAGES;
           uint32_t fa = __shfl_sync(0xffffffffu, c < 32 ? fa0 : fa1, c & 31);
           uint32_t fb = __shfl_sync(0xffffffffu, c < 32 ? fb0 : fb1, c & 31);
 #ifdef SFB_EXPERIMENTS
           if (oz.dbg & 1) fa = fb = 0x3fu;
+          const long long te0 = clock64();
 #endif
-          if (g >= OZ_STAGES) mbar_wait(bar0 + 8 * (OZ_STAGES + st), ((g / OZ_STAGES) - 1) & 1);
+          if (g >= OZ_STAGES) mbar_wait(bar0 + 8 * (OZ_STAGES + st), par ^ 1u);
+#ifdef SFB_EXPERIMENTS
+          t_full += clock64() - te0;   // producer: time waiting for a free stage
+#endif
           if (leader) {
             const uint32_t full = bar0 + 8 * st;
             const uint32_t dst = ring + st * OZ_STAGE_BYTES;
-            mbar_arrive_expect_tx(full, (uint32_t)__popc(fa) * OZ_SLAB_A + (uint32_t)__popc(fb) * OZ_SLAB_B);
-            const int8_t* a = srcA + c * chunk_bytes;
-            const int8_t* b = srcB + c * chunk_bytes;
+            if (prod_a) {
+              mbar_arrive_expect_tx(full, (uint32_t)__popc(fa) * OZ_SLAB_A + (uint32_t)__popc(fb) * OZ_SLAB_B);
 #pragma unroll
-            for (int sl = 0; sl < OZ_S; ++sl) {
-              if ((fa >> sl) & 1u) {
-                if (!PAIR) bulk_g2s(dst + sl * OZ_SLAB_A, a + sl * slice_bytes, OZ_SLAB_A, full);
-                else if ((uint32_t)(sl & 1) == rank) bulk_g2s_mc(dst + sl * OZ_SLAB_A, a + sl * slice_bytes, OZ_SLAB_A, full, 3);
+              for (int sl = 0; sl < OZ_S; ++sl) {
+                if (!((fa >> sl) & 1u)) continue;
+                if (!PAIR) bulk_g2s(dst + sl * OZ_SLAB_A, src + sl * slice_bytes, OZ_SLAB_A, full);
+                else if ((uint32_t)(sl & 1) == rank) bulk_g2s_mc(dst + sl * OZ_SLAB_A, src + sl * slice_bytes, OZ_SLAB_A, full, 3);
               }
-              if ((fb >> sl) & 1u) bulk_g2s(dst + OZ_A_BYTES + sl * OZ_SLAB_B, b + sl * slice_bytes, OZ_SLAB_B, full);
+            } else {
+#pragma unroll
+              for (int sl = 0; sl < OZ_S; ++sl)
+                if ((fb >> sl) & 1u) bulk_g2s(dst + OZ_A_BYTES + sl * OZ_SLAB_B, src + sl * slice_bytes, OZ_SLAB_B, full);
             }
           }
           __syncwarp();
+          src += chunk_bytes;
+          if (++st == OZ_STAGES) { st = 0; par ^= 1u; }
         }
       } else {
         // ---- MMA issuer
@@ -531,9 +558,9 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
         if (oz.dbg & 1) touched = 0x7fu;
 #endif
         // The loop is software-pipelined around the single issuing thread: the flags of chunk c+1 and a first,
-        // non-blocking look at its `full` barrier are taken BEFORE the MMAs of chunk c are issued, so the ~100-cycle
-        // barrier test overlaps the (back-pressured) MMA issue instead of standing between two chunks' MMAs, where
-        // the tensor pipe's short queue would run dry.
+        // non-blocking look at its `full` barrier are taken BETWEEN the short and the long MMAs of chunk c, i.e. while
+        // the issue is back-pressured anyway, instead of standing between two chunks' MMAs, where the tensor pipe's
+        // short queue would run dry.
         uint32_t fa = __shfl_sync(0xffffffffu, fa0, 0), fb = __shfl_sync(0xffffffffu, fb0, 0);
         bool ready = mbar_test_nb(bar0 + 8 * st, par);
         for (int c = 0; c < nch; ++c) {
@@ -550,7 +577,11 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
           const uint64_t ad0 = desc_ring + (uint64_t)((uint32_t)st * (OZ_STAGE_BYTES >> 4));
           const uint64_t bd0 = ad0 + (uint64_t)(OZ_A_BYTES >> 4);
           const uint32_t empty_bar = bar0 + 8 * (OZ_STAGES + st);
-          // ring position of the next chunk (no division in the loop)
+          // The digit patterns that dominate (nothing zero / leading slab zero, for either operand) get fully unrolled
+          // code with compile-time masks: a single thread issues every MMA of the CTA, so run-time tests per product
+          // would make the issue loop the bottleneck.  Anything else takes the generic path.
+          if (leader) oz_issue_dispatch<0>(fa, fb, tmem, ad0, bd0);   // short MMAs first
+          // ring position, flags and barrier state of the next chunk — while the queue is full (no division in the loop)
           const int c1 = c + 1;
           const int st1 = (st + 1 == OZ_STAGES) ? 0 : st + 1;
           const uint32_t par1 = (st + 1 == OZ_STAGES) ? par ^ 1u : par;
@@ -562,14 +593,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
             readyn = mbar_test_nb(bar0 + 8 * st1, par1);
           }
           if (leader) {
-            // The digit patterns that dominate (nothing zero / leading slab zero, for either operand) get fully
-            // unrolled code with compile-time masks: a single thread issues every MMA of the CTA, so run-time tests per
-            // product would make the issue loop the bottleneck.  Anything else takes the generic path.
-            if (fa == 0x3fu && fb == 0x3fu) oz_issue_chunk(0x3fu, 0x3fu, tmem, ad0, bd0);
-            else if (fa == 0x3eu && fb == 0x3eu) oz_issue_chunk(0x3eu, 0x3eu, tmem, ad0, bd0);
-            else if (fa == 0x3eu && fb == 0x3fu) oz_issue_chunk(0x3eu, 0x3fu, tmem, ad0, bd0);
-            else if (fa == 0x3fu && fb == 0x3eu) oz_issue_chunk(0x3fu, 0x3eu, tmem, ad0, bd0);
-            else oz_issue_chunk(fa, fb, tmem, ad0, bd0);
+            oz_issue_dispatch<1>(fa, fb, tmem, ad0, bd0);               // the chunk ends with its longest MMAs
             // stage free once these MMAs have read it (in both CTAs of a pair: the peer's copies land here too)
             if (PAIR) umma_commit_mc(empty_bar, 3);
             else umma_commit(empty_bar);
@@ -586,6 +610,12 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
       }
       ++k;
     }
+#ifdef SFB_EXPERIMENTS
+    if (warp == OZ_PRODB_WARP && leader && oz.stats) {
+      atomicAdd(oz.stats + 6, (unsigned long long)t_full);
+      atomicAdd(oz.stats + 7, (unsigned long long)(clock64() - t_begin));
+    }
+#endif
     if (warp == 1 && leader && oz.stats) {
       atomicAdd(oz.stats, issued);
       atomicAdd(oz.stats + 1, (unsigned long long)k * nch * 26ull);

@@ -786,7 +786,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                : "memory");
 }
 template <int MODE>
-__global__ void __launch_bounds__(128, 1) wide_kernel(int chunks, const uint8_t* src, int fstages, long long* out) {
+__global__ void __launch_bounds__(128, 1) wide_kernel(int chunks, const uint8_t* src, int fstages, long long* out, int gap = 0) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int NST = 5, STAGE = 36864, A_BYTES = 24576;
   __shared__ uint64_t full[NST], empty[NST], bar;
@@ -848,6 +848,11 @@ __global__ void __launch_bounds__(128, 1) wide_kernel(int chunks, const uint8_t*
         if (MODE == 1) umma_commit(smem_u32(&empty[st]));
       }
       __syncwarp();
+      if (gap > 0) {  // issue-thread work between two chunks' MMAs (how much does the tensor pipe's queue hide?)
+        const long long g0 = clock64();
+        while (clock64() - g0 < gap) {
+        }
+      }
     }
     if (leader) umma_commit(smem_u32(&bar));
     __syncwarp();
@@ -880,6 +885,24 @@ void run_wide_mode(int sms, const uint8_t* src, int fstages, const char* what) {
          MODE, what, fstages * 36864e-6, (double)h1[0] / chunks, (double)h2[0] / chunks, sms);
   cudaFree(dout);
 }
+void run_wide_gap(int sms, const uint8_t* src) {
+  long long* dout;
+  CK(cudaMalloc(&dout, 64));
+  const int smem_bytes = 5 * 36864 + 1024;
+  CK(cudaFuncSetAttribute(wide_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  const int chunks = 2048;
+  const int gaps[] = {0, 50, 100, 150, 200, 300, 400, 600};
+  printf("wide-run schedule, a busy-wait of G cycles between two chunks' MMAs (cycles per chunk; 832 + G would mean nothing is hidden):");
+  for (int g : gaps) {
+    wide_kernel<0><<<sms, 128, smem_bytes>>>(chunks, src, 1024, dout, g);
+    CK(cudaDeviceSynchronize());
+    long long h[1];
+    CK(cudaMemcpy(h, dout, 8, cudaMemcpyDeviceToHost));
+    printf("  G=%d: %.0f", g, (double)h[0] / chunks);
+  }
+  printf("\n");
+  cudaFree(dout);
+}
 void run_wide(int sms) {
   uint8_t* src;
   const int fmax = 148 * 64;
@@ -891,6 +914,7 @@ void run_wide(int sms) {
   run_wide_mode<1>(sms, src, fmax, "9 wide SS MMAs + 36 KB of bulk copies per chunk");   // 350 MB: from HBM
   run_wide_mode<1>(sms, src, 1024, "9 wide SS MMAs + 36 KB of bulk copies per chunk");   // 38 MB: from L2
   run_wide_mode<1>(sms, src, 256, "9 wide SS MMAs + 36 KB of bulk copies per chunk");    // 9 MB: from L2, many readers per line
+  run_wide_gap(sms, src);
   cudaFree(src);
 }
 
