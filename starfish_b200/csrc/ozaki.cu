@@ -270,6 +270,7 @@ __device__ __forceinline__ void oz_issue_chunk(uint32_t fa, uint32_t fb, uint32_
 // the four patterns that make up the bench ensemble with compile-time masks, anything else generic
 template <int PHASE>
 __device__ __forceinline__ void oz_issue_dispatch(uint32_t fa, uint32_t fb, uint32_t tmem, uint64_t ad0, uint64_t bd0) {
+  if (fa == 0u || fb == 0u) return;   // an all-zero operand block (exact zeros outside a band): nothing to issue
   if (fa == 0x3fu && fb == 0x3fu) oz_issue_chunk<PHASE>(0x3fu, 0x3fu, tmem, ad0, bd0);
   else if (fa == 0x3eu && fb == 0x3eu) oz_issue_chunk<PHASE>(0x3eu, 0x3eu, tmem, ad0, bd0);
   else if (fa == 0x3eu && fb == 0x3fu) oz_issue_chunk<PHASE>(0x3eu, 0x3fu, tmem, ad0, bd0);
@@ -443,7 +444,11 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
   if (tid == 0) {
 #pragma unroll
     for (int i = 0; i < OZ_STAGES; ++i) {
-      mbar_init(bar0 + 8 * i, 1);
+      // BOTH producers arrive on `full` every round, each with its own byte count — also when it has nothing to fetch.
+      // (With a single arrival, a producer whose byte count is zero for a while — operand blocks of exact zeros in a
+      // banded matrix — is not needed for the phase to complete, falls two phases behind on a stage and then misreads
+      // the parity of `empty`: a deadlock that only timing had hidden.)
+      mbar_init(bar0 + 8 * i, 2);
       mbar_init(bar0 + 8 * (OZ_STAGES + i), PAIR ? 2 : 1);  // a commit from the MMA warp of every CTA that reads the stage
     }
     mbar_init(accfull, 1);
@@ -499,8 +504,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
         // ---- producers: one bulk copy per non-zero digit slab (4 KB of A, 2 KB of B), continuous over the CTA's tiles.
         // Issuing a copy costs the lone thread ~10 dependent instructions; twelve per chunk made ONE producer the
         // pace-setter of the whole kernel (it waited for a free stage only 20 % of its time while the MMA warp waited
-        // for operands 24 % of its own).  Hence two: warp 0 posts the stage's byte count and fetches A, warp 10 fetches
-        // B (its complete_tx may reach the barrier before the expect_tx: the phase cannot complete until warp 0 arrives).
+        // for operands 24 % of its own).  Hence two: warp 0 fetches A, warp 10 fetches B; each posts its own byte count
+        // on the stage's `full` barrier (two arrivals per phase).
         const bool prod_a = (warp == 0);
         const int8_t* src = Ps + (long long)((prod_a ? t.r0 : t.c0) / 8) * OZ_GROUP_BYTES;
         for (int c = 0; c < nch; ++c, ++g) {
@@ -518,7 +523,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
             const uint32_t full = bar0 + 8 * st;
             const uint32_t dst = ring + st * OZ_STAGE_BYTES;
             if (prod_a) {
-              mbar_arrive_expect_tx(full, (uint32_t)__popc(fa) * OZ_SLAB_A + (uint32_t)__popc(fb) * OZ_SLAB_B);
+              mbar_arrive_expect_tx(full, (uint32_t)__popc(fa) * OZ_SLAB_A);
 #pragma unroll
               for (int sl = 0; sl < OZ_S; ++sl) {
                 if (!((fa >> sl) & 1u)) continue;
@@ -526,6 +531,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
                 else if ((uint32_t)(sl & 1) == rank) bulk_g2s_mc(dst + sl * OZ_SLAB_A, src + sl * slice_bytes, OZ_SLAB_A, full, 3);
               }
             } else {
+              mbar_arrive_expect_tx(full, (uint32_t)__popc(fb) * OZ_SLAB_B);
 #pragma unroll
               for (int sl = 0; sl < OZ_S; ++sl)
                 if ((fb >> sl) & 1u) bulk_g2s(dst + OZ_A_BYTES + sl * OZ_SLAB_B, src + sl * slice_bytes, OZ_SLAB_B, full);
