@@ -166,3 +166,32 @@ def test_zero_digit_slabs_are_skipped_exactly():
     print("issued / dense-pattern int8 MMAs:", fracs)
     assert fracs[0] > 0.95 and fracs[1] < 0.75
     eng.close()
+
+
+@pytest.mark.timeout(120)
+def test_banded_matrices_with_all_zero_operand_blocks_many_rounds():
+    """Global kernel only (M = 0): S is banded, so most 64 x 32 operand blocks of the factor are EXACT zeros — the
+    producers of the update kernel have nothing to fetch for long stretches and the MMA warp nothing to issue.  A
+    producer that is not needed for a pipeline stage to complete must still keep in step with it (it once fell two
+    barrier phases behind and the kernel deadlocked, seen only at bench size): many walkers, repeated calls, int8 mode,
+    results against the independent checker and bit-identical between calls."""
+    B = 24
+    d = synth.stage_inputs_direct(4096, B, n_comp=0, n_local=0)
+    eng = _engine(4096, 0, 1, B)
+    eng.set_solver("dense_i8")
+    eng.set_data(d["wave"], d["sigma"], d["data_flux"])
+    first = None
+    for _ in range(6):
+        lnL, info = eng.log_likelihood(None, None, d["model_flux"], glob=d["glob"])
+        lnL, info = lnL.cpu().numpy(), info.cpu().numpy()
+        assert (info == 0).all()
+        if first is None:
+            first = lnL.copy()
+            for b in (0, B // 2, B - 1):
+                ref = SO.stage_log_likelihood(d["wave"], d["sigma"], d["data_flux"], None, None, d["model_flux"][b],
+                                              d["glob"][b], d["loc"][b][: d["nloc"][b]])
+                assert abs(lnL[b] - ref) <= LNL_RTOL * max(1.0, abs(ref)), (b, lnL[b], ref)
+        assert np.array_equal(lnL, first)
+    issued, dense = eng.i8_mma_counts()
+    assert issued < 0.05 * dense       # almost every product has an all-zero slab
+    eng.close()
