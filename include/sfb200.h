@@ -235,6 +235,8 @@ int sfb_sync(sfb_t* h);
  * stream and brackets every launch with CUDA events.  sfb_profile_read fills, per kernel class,
  * out[3*c+0] = number of launches, out[3*c+1] = total device milliseconds, out[3*c+2] = algorithmic work
  * (bytes for SFB_K_BUILD, FLOPs otherwise), and resets the counters.  `n` = capacity of out in doubles.
+ * SFB_K_OZ_SLICE stays in the enumeration for layout compatibility; it no longer receives launches (the fixed-point
+ * slices of the int8 solver are written by the SFB_K_TRSM kernel).
  */
 enum sfb_kernel_class { SFB_K_BUILD = 0, SFB_K_POTRF_DIAG = 1, SFB_K_TRSM = 2, SFB_K_SYRK = 3, SFB_K_UPSTREAM = 4,
                         SFB_K_BAND_BUILD = 5, SFB_K_BAND_CHOL = 6, SFB_K_OZ_SLICE = 7, SFB_K_FWD_ROWS = 8, SFB_K_NCLASS = 9 };
