@@ -14,8 +14,8 @@
 //   L_ik·L_jk ≈ 2^(e_i+e_j−14) · Σ_{d=0..6} 256^(−d) · S_d ,   S_d = Σ_k Σ_{s+t=d} b_iks·b_jkt
 //
 // Every S_d is exact in int32 (|S_d| ≤ 6·2^14·1024 < 2^27 for K ≤ 1024), so one TMEM accumulator per
-// anti-diagonal d: 7 accumulators × 64 columns = 448 of the 512 TMEM columns for a 128×64 tile, fed by 26 int8
-// MMAs per 32-deep k-chunk (pairs s,t ≤ 5, s+t ≤ 6).  What is dropped is the anti-diagonals d ≥ 7 and the
+// anti-diagonal d: 7 accumulators × 64 columns = 448 of the 512 TMEM columns for a 128×64 tile, fed by 26 digit-slab
+// products per 32-deep k-chunk (pairs s,t ≤ 5, s+t ≤ 6; issued as 9 wide MMAs, oz_issue_chunk).  What is dropped is the anti-diagonals d ≥ 7 and the
 // rounding of q: measured |ΔlnL|/|lnL| ≤ 1.6e-12 against the dense oracle up to cond 7e5 (tools/ozaki_experiment.py,
 // tests/test_gpu_ozaki.py; 5 accumulators give 1e-7 — the anti-diagonal count, not the digit count, is what
 // matters).  The epilogue recombines Σ_d 256^(−d)·S_d by Horner in fp64 and applies C −= 2^(e_i−7)·2^(e_j−7)·(…).
@@ -26,12 +26,14 @@
 // -> one digit slab of the A operand (128 rows) of a chunk is 4 KB contiguous, of the B operand (64 rows) 2 KB: one
 // 1-D bulk async copy (cp.async.bulk, SASS UBLKCP) per NON-ZERO slab and pipeline stage, no tensor map.  Inside a
 // 256-byte row group the two 16-byte halves of a row are XOR-swapped by bit 2 of the row (the 32-byte swizzle pattern,
-// applied where the slices are written: oz_slice_block in sfb_internal.cuh, called from trsm_kernel), consecutive 8-row groups are 256 B apart: UMMA descriptor {SWIZZLE_32B, SBO = 256}.
+// applied where the slices are written: oz_slice_block in sfb_internal.cuh, called from trsm_kernel), consecutive
+// 8-row groups are 256 B apart: UMMA descriptor {SWIZZLE_32B, SBO = 256}.
 // In shared memory the six B slabs of a stage lie back to back, so a run of consecutive B slabs is one operand of
 // N = 64·len rows (oz_issue_chunk).
 //
 // Kernel shape: 352 threads = warp 0 bulk-copy producer (A), warp 1 MMA issuer (one elected lane) + TMEM allocator,
-// warps 2-9 epilogue (TMEM lane quarter = warp%4, two warps per quarter), warp 10 bulk-copy producer (B).  5-stage ring of 36 KB, full/empty mbarriers, tcgen05.commit
+// warps 2-9 epilogue (TMEM lane quarter = warp%4, two warps per quarter), warp 10 bulk-copy producer (B); launched as
+// clusters of two CTAs that share the A operand.  5-stage ring of 36 KB, full/empty mbarriers, tcgen05.commit
 // releases a stage / signals the epilogue.  The epilogue warps prefetch the C tile (coalesced, into registers) while
 // the main loop runs, transpose the recombined update through a padded buffer and finish the read-modify-write with
 // coalesced streaming stores.
