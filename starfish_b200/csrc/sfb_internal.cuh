@@ -142,31 +142,48 @@ __device__ __forceinline__ void oz_slice_block(const OzParams& oz, int s, int Np
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int chunk = ch0 + (lane >> 3);
   const int kb = (4 * lane) & 31;                       // byte inside the 32-byte row
-  uint32_t nz = 0;                                      // bit t: slab t of this lane's chunk has a non-zero digit
+  uint32_t orw[OZ_S];                                   // OR of this lane's packed digits per slab (zero <=> all digits zero)
+#pragma unroll
+  for (int t = 0; t < OZ_S; ++t) orw[t] = 0u;
   int rs_hi8[8];                                        // exponent words of the eight rows' scales, fetched together
 #pragma unroll
   for (int i = 0; i < 8; ++i) rs_hi8[i] = __double2hiint(__ldg(oz.rscale + (long long)s * Np + row_base + warp * 8 + i));
+  // The warp's eight rows are ONE 8-row group of P (row_base is a multiple of 64): per slab one pointer, per row an
+  // immediate offset.  32-byte swizzle: the 16-byte halves of a row are swapped for rows 4-7 of the group.
+  const long long slice_bytes = (long long)Np * OZ_KC;
+  int8_t* dst[OZ_S];
+  {
+    int8_t* d0 = oz.P + (long long)s * oz.strideP + (long long)chunk * OZ_S * slice_bytes +
+                 (long long)((row_base + warp * 8) >> 3) * OZ_GROUP_BYTES + (kb & 15) + 16 * ((kb >> 4) & 1);
+#pragma unroll
+    for (int t = 0; t < OZ_S; ++t) dst[t] = d0 + t * slice_bytes;
+  }
+  const int flip = 16 - 32 * ((kb >> 4) & 1);           // rows 4-7: the other half (+16 or −16 bytes)
+  const double* sp0 = src + (long long)(warp * 8) * src_ld + 4 * lane;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const int row = row_base + warp * 8 + i;
-    const double* sp = src + (long long)(warp * 8 + i) * src_ld + 4 * lane;
+    if (i == 4) {
+#pragma unroll
+      for (int t = 0; t < OZ_S; ++t) dst[t] += flip;
+    }
+    const double* sp = sp0 + (long long)i * src_ld;
     const double2 v01 = *reinterpret_cast<const double2*>(sp);
     const double2 v23 = *reinterpret_cast<const double2*>(sp + 2);
     // 2^40 / rscale = 2^(47−e), exact: rscale is a power of two, so only its exponent field is needed
     const double inv = __hiloint2double((2 * 1023 + 40 - ((rs_hi8[i] >> 20) & 0x7ff)) << 20, 0);
-    // q = rint(L·2^(47−e)) by the magic-number add (|q| < 2^51): the integer sits in the mantissa of x + 1.5·2^52.
+    // q = rint(L·2^(47−e)) by the magic-number add: the integer sits in the mantissa of x + 1.5·2^52.
     // Balanced radix-256 digits b_t ∈ [−128, 127] of q = Σ b_t·256^t, all six at once: u = q + Σ 128·256^t has the
-    // UNSIGNED bytes b_t + 128 (the representation is unique), and x − 128 = x XOR 0x80 as an int8.  Representable
-    // range |q| <= 0x7f7f7f7f7f7f; |L_ik| < 2^(e−1) keeps |q| < 2^46.
+    // UNSIGNED bytes b_t + 128 (the representation is unique), and x − 128 = x XOR 0x80 as an int8.  The bias is
+    // folded into the magic constant (1.5·2^52 + 0x808080808080 is an integer below 2^53, hence exact), so the low
+    // 48 bits of the sum's bit pattern ARE u — no integer arithmetic at all; the XOR is applied to the packed words.
+    // Representable range |q| <= 0x7f7f7f7f7f7f; |L_ik| < 2^(e−1) keeps |q| < 2^46.
     const double lim = 139637976727423.0;                                       // 0x7f7f7f7f7f7f
-    const double magic = 6755399441055744.0;                                    // 1.5·2^52 = 0x4338000000000000
-    const long long fix = 0x808080808080ll - 0x4338000000000000ll;
+    const double magic = 6755399441055744.0 + 141289400074368.0;                // 1.5·2^52 + 0x808080808080
     unsigned long long u[4];
-    u[0] = (unsigned long long)(__double_as_longlong(fmin(fmax(v01.x * inv, -lim), lim) + magic) + fix) ^ 0x808080808080ull;
-    u[1] = (unsigned long long)(__double_as_longlong(fmin(fmax(v01.y * inv, -lim), lim) + magic) + fix) ^ 0x808080808080ull;
-    u[2] = (unsigned long long)(__double_as_longlong(fmin(fmax(v23.x * inv, -lim), lim) + magic) + fix) ^ 0x808080808080ull;
-    u[3] = (unsigned long long)(__double_as_longlong(fmin(fmax(v23.y * inv, -lim), lim) + magic) + fix) ^ 0x808080808080ull;
-    uint32_t packed[OZ_S];
+    u[0] = (unsigned long long)__double_as_longlong(fmin(fmax(v01.x * inv, -lim), lim) + magic);
+    u[1] = (unsigned long long)__double_as_longlong(fmin(fmax(v01.y * inv, -lim), lim) + magic);
+    u[2] = (unsigned long long)__double_as_longlong(fmin(fmax(v23.x * inv, -lim), lim) + magic);
+    u[3] = (unsigned long long)__double_as_longlong(fmin(fmax(v23.y * inv, -lim), lim) + magic);
 #pragma unroll
     for (int t = 0; t < OZ_S; ++t) {       // slab t = digit 5 − t (t = 0 most significant): byte 5 − t of each element
       const int bt = OZ_S - 1 - t;
@@ -174,19 +191,15 @@ __device__ __forceinline__ void oz_slice_block(const OzParams& oz, int s, int Np
       if (bt < 4) { x0 = (uint32_t)u[0]; x1 = (uint32_t)u[1]; x2 = (uint32_t)u[2]; x3 = (uint32_t)u[3]; }
       else { x0 = (uint32_t)(u[0] >> 32); x1 = (uint32_t)(u[1] >> 32); x2 = (uint32_t)(u[2] >> 32); x3 = (uint32_t)(u[3] >> 32); }
       const uint32_t sel = (uint32_t)(bt & 3) | ((uint32_t)(4 + (bt & 3)) << 4);
-      const uint32_t w = __byte_perm(__byte_perm(x0, x1, sel), __byte_perm(x2, x3, sel), 0x5410);
-      packed[t] = w;
-      nz |= (w != 0u) << t;
+      const uint32_t w = __byte_perm(__byte_perm(x0, x1, sel), __byte_perm(x2, x3, sel), 0x5410) ^ 0x80808080u;
+      orw[t] |= w;
+      *reinterpret_cast<uint32_t*>(dst[t] + i * OZ_KC) = w;
     }
-    const int r8 = row & 7;
-    const int half = ((kb >> 4) ^ (r8 >> 2)) & 1;         // 32-byte swizzle: 16-byte halves swapped for rows 4-7
-    const long long slice_bytes = (long long)Np * OZ_KC;
-    int8_t* dst = oz.P + (long long)s * oz.strideP + (long long)chunk * OZ_S * slice_bytes +
-                  (long long)(row >> 3) * OZ_GROUP_BYTES + r8 * OZ_KC + half * 16 + (kb & 15);
-#pragma unroll
-    for (int t = 0; t < OZ_S; ++t) *reinterpret_cast<uint32_t*>(dst + t * slice_bytes) = packed[t];
   }
-  // OR over the 8 lanes of a chunk, then over the CTA's 8 warps
+  // bit t: slab t of this lane's chunk has a non-zero digit; OR over the 8 lanes of a chunk, then over the CTA's 8 warps
+  uint32_t nz = 0;
+#pragma unroll
+  for (int t = 0; t < OZ_S; ++t) nz |= (orw[t] != 0u) << t;
   nz |= __shfl_xor_sync(0xffffffffu, nz, 1);
   nz |= __shfl_xor_sync(0xffffffffu, nz, 2);
   nz |= __shfl_xor_sync(0xffffffffu, nz, 4);
