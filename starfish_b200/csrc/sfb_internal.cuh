@@ -176,14 +176,16 @@ __device__ __forceinline__ void oz_slice_block(const OzParams& oz, int s, int Np
     // UNSIGNED bytes b_t + 128 (the representation is unique), and x − 128 = x XOR 0x80 as an int8.  The bias is
     // folded into the magic constant (1.5·2^52 + 0x808080808080 is an integer below 2^53, hence exact), so the low
     // 48 bits of the sum's bit pattern ARE u — no integer arithmetic at all; the XOR is applied to the packed words.
-    // Representable range |q| <= 0x7f7f7f7f7f7f; |L_ik| < 2^(e−1) keeps |q| < 2^46.
-    const double lim = 139637976727423.0;                                       // 0x7f7f7f7f7f7f
+    // Representable range |q| <= 0x7f7f7f7f7f7f, and no clamp: the pivots of an accepted factorisation satisfy
+    // Σ_k L_ik² <= C_ii(1+ε), so |L_ik| < 2^(e−1) and |q| < 2^46(1+ε) — a matrix that violates it has been flagged by
+    // potrf_diag before this panel is sliced (every kernel returns on info != 0), and whatever bit pattern an
+    // out-of-range or non-finite value produces is still six int8 digits (fmin/fmax cost more than everything else here).
     const double magic = 6755399441055744.0 + 141289400074368.0;                // 1.5·2^52 + 0x808080808080
     unsigned long long u[4];
-    u[0] = (unsigned long long)__double_as_longlong(fmin(fmax(v01.x * inv, -lim), lim) + magic);
-    u[1] = (unsigned long long)__double_as_longlong(fmin(fmax(v01.y * inv, -lim), lim) + magic);
-    u[2] = (unsigned long long)__double_as_longlong(fmin(fmax(v23.x * inv, -lim), lim) + magic);
-    u[3] = (unsigned long long)__double_as_longlong(fmin(fmax(v23.y * inv, -lim), lim) + magic);
+    u[0] = (unsigned long long)__double_as_longlong(fma(v01.x, inv, magic));
+    u[1] = (unsigned long long)__double_as_longlong(fma(v01.y, inv, magic));
+    u[2] = (unsigned long long)__double_as_longlong(fma(v23.x, inv, magic));
+    u[3] = (unsigned long long)__double_as_longlong(fma(v23.y, inv, magic));
 #pragma unroll
     for (int t = 0; t < OZ_S; ++t) {       // slab t = digit 5 − t (t = 0 most significant): byte 5 − t of each element
       const int bt = OZ_S - 1 - t;
