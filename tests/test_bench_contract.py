@@ -29,8 +29,8 @@ def test_reference_arm_json_line():
 
 
 def test_committed_b200_line_has_the_contract_keys():
-    """A default `python bench.py` line measured on a B200 at the end of round 2 (profiles/r4e_bench.json)."""
-    d = json.load(open(os.path.join(ROOT, "profiles", "r4e_bench.json")))
+    """A default `python bench.py` line measured on a B200 at the end of round 2 (profiles/r4i_bench.json)."""
+    d = json.load(open(os.path.join(ROOT, "profiles", "r4i_bench.json")))
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
         assert k in d, k
