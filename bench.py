@@ -633,9 +633,9 @@ def run_b200(args, rank, world, local_rank, cpu_sample):
                   "api": "sfb_loglike(shared_hyper=1): the reference's frozen global_cov/local_cov mode "
                          "(spectrum_model.py:341-363); S built and factorised once, all walkers' right-hand sides "
                          "solved together, M x M capacitance system per walker"}
-        if rank == 0:
+        if rank == 0:   # rank 0 alone: the local call only — step_frozen() ends in the all-gather and would wait for the others
             eng.profile(True)
-            step_frozen()
+            eng.log_likelihood_resident(nb, X, A, F, g1, n1, l1, lnL, info, shared_hyper=True)
             frozen["kernels"] = kernel_shares(eng.profile_read())
             eng.profile(False)
 

@@ -44,3 +44,27 @@ def test_committed_b200_line_has_the_contract_keys():
     assert r["bound"] in ("hbm", "tensor") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+
+
+def test_no_collective_inside_rank0_only_blocks():
+    """bench.py under torchrun: a step function that ends in the lnL all-gather must never be called from a block only
+    rank 0 executes (rank 0 would wait for the others for ever — seen once with the frozen-groups leg at 2 GPUs)."""
+    src = open(os.path.join(ROOT, "bench.py")).read().splitlines()
+    collective = ("step_frozen(", "step_device(", "step_model(", "gather(", "allgather_lnl(", "gather_lnl(")
+    i = 0
+    found = []
+    while i < len(src):
+        line = src[i]
+        stripped = line.lstrip()
+        if stripped.startswith("if rank == 0"):
+            indent = len(line) - len(stripped)
+            j = i + 1
+            while j < len(src) and (not src[j].strip() or len(src[j]) - len(src[j].lstrip()) > indent):
+                code = src[j].split("#")[0]
+                if any(c in code for c in collective) and "def " not in code:
+                    found.append((j + 1, src[j].strip()))
+                j += 1
+            i = j
+        else:
+            i += 1
+    assert not found, found
