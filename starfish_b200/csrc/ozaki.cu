@@ -366,17 +366,8 @@ __device__ __forceinline__ void oz_epilogue(const CholParams& p, const OzParams&
     const double2 rj1 = *reinterpret_cast<const double2*>(rs + t.c0 + hh * 32 + 16 + gcol);
     double2 creg[16];   // [round cb][row group g]: rows 4g + grow, columns 16·cb + gcol
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-#ifdef SFB_EXPERIMENTS
-      if (oz.dbg & 2) { creg[i] = make_double2(0.0, 0.0); continue; }
-#endif
+    for (int i = 0; i < 16; ++i)
       creg[i] = __ldcs(reinterpret_cast<const double2*>(Cw + (long long)(4 * (i & 7)) * p.Np + 16 * (i >> 3)));
-    }
-#ifdef SFB_EXPERIMENTS
-    if (oz.dbg & 4) {
-      while (!mbar_test_nb(meta, k & 1)) __nanosleep(256);
-    }
-#endif
     mbar_wait(meta, k & 1);
     const uint32_t touched = *touched_p;
     mbar_wait(accfull, k & 1);
@@ -405,12 +396,8 @@ __device__ __forceinline__ void oz_epilogue(const CholParams& p, const OzParams&
       creg[8 + g].y = fma(-ty, rj1.y, creg[8 + g].y);
     }
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-#ifdef SFB_EXPERIMENTS
-      if ((oz.dbg & 2) && creg[i].x != 12345.678) continue;
-#endif
+    for (int i = 0; i < 16; ++i)
       __stcs(reinterpret_cast<double2*>(Cw + (long long)(4 * (i & 7)) * p.Np + 16 * (i >> 3)), creg[i]);
-    }
     __syncwarp();  // the transpose buffer is rewritten by the next tile
     ++k;
   }

@@ -116,7 +116,7 @@ struct OzParams {
   uint8_t* F;            // per slot: [chunk][row/64] bit t = digit slab t of that 64-row × 32-k block is not all zero
   long long strideF;     // bytes per slot
   unsigned long long* stats;  // optional [2]: int8 MMAs issued / MMAs a dense digit pattern would issue
-  int dbg;               // experiments build only: 1 = treat every digit slab as non-zero, 2 = epilogue without global traffic
+  int dbg;               // experiments build only: 1 = treat every digit slab as non-zero (timing of the dense schedule)
 };
 void ozaki_set_debug(int d);
 cudaError_t ozaki_init();
