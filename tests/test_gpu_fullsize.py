@@ -42,6 +42,33 @@ def test_config3_n8192_global_local_emulator():
     eng.close()
 
 
+@pytest.mark.timeout(300)
+def test_n8192_two_walkers_against_the_dense_oracle_itself():
+    """Headline size, DIRECT comparison: two bench walkers at N=8192 (M=6, K=2) against oracle/starfish_oracle.py — the
+    numpy kernels and scipy cho_factor/cho_solve of the reference path, no banded shortcut in between — for both
+    trailing-update modes of the dense solver."""
+    from oracle import starfish_oracle as O
+
+    B = 2
+    d = synth.stage_inputs_direct(8192, B)
+    eng = _engine(8192, 6, 2, B, workspace_walkers=2)
+    eng.set_data(d["wave"], d["sigma"], d["data_flux"])
+    ref = []
+    for b in range(B):
+        wcov = np.linalg.inv(d["A"][b])       # the oracle takes Σ_w; the stage carries A = Σ_w⁻¹ (as the reference codes it)
+        ref.append(O.stage_log_likelihood(d["wave"], d["sigma"], d["data_flux"], d["X"][b], wcov, d["model_flux"][b],
+                                          d["glob"][b], d["loc"][b][: d["nloc"][b]]))
+    ref = np.array(ref)
+    for solver in ("dense_i8", "dense"):
+        eng.set_solver(solver)
+        lnL, info = eng.log_likelihood(d["X"], d["A"], d["model_flux"], glob=d["glob"], loc=d["loc"])
+        assert (info.cpu().numpy() == 0).all()
+        rel = np.abs(lnL.cpu().numpy() - ref) / np.maximum(1.0, np.abs(ref))
+        print(f"N=8192 {solver}: max |lnL - dense oracle| / |lnL| = {rel.max():.2e}")
+        assert rel.max() <= LNL_RTOL, (solver, rel)
+    eng.close()
+
+
 def test_config2_n4096_global_only():
     """configs[1]: N=4096, global kernel + σ² only (X = NULL)."""
     B = 8
